@@ -1,0 +1,175 @@
+/*
+ * l3ac_b200 -- C ABI of the B200 (sm_100a) kernels behind the L3AC encode/quantize/decode hot path.
+ *
+ * The reference (zhai-lw/L3AC) has no FFI: its hot path is the body of two Python methods,
+ *   L3AC.encode_audio   l3ac/__init__.py:108-114
+ *   L3AC.decode_audio   l3ac/__init__.py:116-121
+ * which call stock ATen operators.  This header is the operator-level boundary that replaces
+ * those ATen call sites; each entry point cites the reference operator(s) it stands in for
+ * (paths relative to the reference tree).  INTEGRATION.md shows the ctypes binding and how the
+ * reference's `L3AC` class would call it.
+ *
+ * Conventions
+ *  - Plain C: raw device pointers, sizes, a `cudaStream_t` passed as `void*`.  No torch types.
+ *  - The library allocates nothing and keeps no global state: outputs and workspaces are
+ *    caller-allocated device buffers; all work is enqueued on the given stream (graph-capturable).
+ *  - Activations are time-major / channels-last: a (B, T, C) tensor is B*T rows of C contiguous
+ *    values.  (The reference is channels-first (B, C, T) in the conv stack; the host layer
+ *    converts at the two ends of the path only.)
+ *  - Return value: 0 = ok; <0 = argument validation error (L3AC_E*); >0 = cudaError_t.
+ */
+#ifndef L3AC_B200_H_
+#define L3AC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define L3AC_OK 0
+#define L3AC_EINVAL (-1)        /* bad argument (NULL pointer, size out of range)   */
+#define L3AC_EUNSUPPORTED (-2)  /* valid request this build has no kernel for       */
+#define L3AC_EDRIVER (-3)       /* CUDA driver entry point unavailable (TMA encode) */
+
+/* activation element types for `out_dtype` */
+#define L3AC_F32 0
+#define L3AC_BF16 1
+
+/* epilogue activations of the GEMM entry points */
+#define L3AC_ACT_NONE 0
+#define L3AC_ACT_SNAKE 1 /* snake(x; alpha) then optional per-column affine (the folded GRN)      */
+#define L3AC_ACT_GEGLU 2 /* columns come in (value, gate) pairs: out[n/2] = v * gelu_erf(g)       */
+#define L3AC_ACT_GELU 3
+#define L3AC_ACT_TANH 4
+
+typedef void* l3ac_stream_t; /* cudaStream_t */
+
+int l3ac_abi_version(void);
+const char* l3ac_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------
+ * Encoder stem.  Replaces V3FirstBlock.forward (l3ac/tconv/__init__.py:16-22) incl. BaseBlock
+ * (l3ac/tconv/base.py:27-45) and trend_pool (l3ac/tconv/base.py:8-14):
+ *   5 x [TrendPool(k) -> Conv1d(1->4,k7)] -> cat(20) -> 1x1 20->80 -> GELU -> cat(x) -> 1x1 81->C.
+ * audio (B,T) fp32 -> out (B,T,C) fp32.  pool kernels are fixed (1,5,11,21,45).  C must be 24.
+ *   branch_w [5][4][7], branch_b [20], w1 [80][20], b1 [80], w2 [C][81], b2 [C]  (all folded fp32)
+ * ------------------------------------------------------------------------------------------ */
+int l3ac_stem(const float* audio, int B, int T, const float* branch_w, const float* branch_b,
+              const float* w1, const float* b1, const float* w2, const float* b2, int C, float* out,
+              l3ac_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * ConvUnit prologue.  Replaces dw_conv + permute + norm of ConvUnit.forward
+ * (l3ac/modules.py:33-35; F.layer_norm at l3ac/layers.py:80): depthwise Conv1d(C,C,k7,pad 3) then
+ * LayerNorm over C.  x (B,T,C) fp32 -> out (B,T,C) fp32|bf16.  dw_w is [7][C] (tap-major).
+ * ------------------------------------------------------------------------------------------ */
+int l3ac_dwconv7_ln(const float* x, int B, int T, int C, const float* dw_w, const float* dw_b,
+                    const float* ln_w, const float* ln_b, float eps, void* out, int out_dtype,
+                    l3ac_stream_t stream);
+
+/* LayerNorm over the last dim.  Replaces channels-first ChannelNorm (l3ac/layers.py:50-56) after the
+ * strided convs and nn.LayerNorm inside local_attention's LocalMHA / FeedForward. */
+int l3ac_layernorm(const float* x, long long M, int C, const float* w, const float* b, float eps,
+                   void* out, int out_dtype, l3ac_stream_t stream);
+
+/* Elementwise snake (l3ac/layers.py:29-33), per-channel alpha [C]. */
+int l3ac_snake(const float* x, long long M, int C, const float* alpha, void* out, int out_dtype,
+               l3ac_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * GEMM / conv-as-GEMM with fused epilogue.  Replaces nn.Linear / nn.Conv1d call sites:
+ *   pw_conv1 / pw_conv2 (l3ac/modules.py:36,39), strided down convs (modules.py:97; local_trans.py:136),
+ *   k3 edge convs (modules.py:110,150), 1x1 up convs (modules.py:161), LegacyUnit convs
+ *   (modules.py:55,57), to_qkv / to_out / FeedForward linears (local_attention, call site
+ *   local_trans.py:34-39), with snake + GRN (layers.py:29-33,112-115), GEGLU and Residual
+ *   (xtract/nn/layers.py:59-62) fused.
+ *
+ *   out[m, n] = epi( bias[n] + sum_{s<taps} sum_{k<K} A[b, t + tap_shift0 + s*tap_step, k] * W[n, s*K + k] )
+ *   with m = b*T + t; rows outside [0,T) read as zero (the conv's zero padding).
+ *   epi: act (see L3AC_ACT_*), then `+ residual[m, n]` if residual != NULL.
+ *   For L3AC_ACT_SNAKE: v = snake(v, alpha[n]); if scale: v = v*scale[n] + shift[n].
+ *   For L3AC_ACT_GEGLU: N counts the interleaved (value,gate) columns; out has N/2 columns.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct l3ac_gemm_desc {
+    const void* A;         /* [B*T, lda]: fp32 (l3ac_gemm_f32) or bf16 (l3ac_gemm_bf16_tc)          */
+    const void* W;         /* [N, taps*K]  same element type as A                                   */
+    const float* bias;     /* [N] or NULL                                                           */
+    const float* alpha;    /* [N] (ACT_SNAKE)                                                       */
+    const float* scale;    /* [N] or NULL (ACT_SNAKE)                                               */
+    const float* shift;    /* [N] or NULL (ACT_SNAKE)                                               */
+    const float* residual; /* [B*T, ldr] fp32 or NULL                                               */
+    void* out;             /* [B*T, ldo] fp32 or bf16                                               */
+    long long lda, ldr, ldo; /* row pitches in elements                                            */
+    int B, T, K, N;
+    int taps, tap_shift0, tap_step;
+    int act, out_dtype;
+} l3ac_gemm_desc;
+
+/* fp32 SIMT reference-precision path (used for the encoder side and for the fp32 mode). */
+int l3ac_gemm_f32(const l3ac_gemm_desc* d, l3ac_stream_t stream);
+
+/* bf16 x bf16 -> fp32 tcgen05/TMEM path fed by TMA.  A and W are bf16; lda and taps*K must be
+ * multiples of 8 (16-byte TMA pitch).  `ws` is reserved (pass NULL). */
+int l3ac_gemm_bf16_tc(const l3ac_gemm_desc* d, l3ac_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Block-local causal attention.  Replaces LocalAttention.forward of local-attention==1.11.2 as
+ * configured at l3ac/local_trans.py:34-38 (causal, look_backward=1, exact_windowsize=False, autopad)
+ * plus the DynamicPositionBias gather (local_trans.py:43):
+ *   query p attends keys [ (floor(p/w)-1)*w clipped at 0 , p ];  logit = q.k/sqrt(D) + bias[h][p-k].
+ * qkv (B,T,3*H*D) fp32 packed [q | k | v], each (H,D)-major -> out (B,T,H*D).  bias_table [H][2w].
+ * D must be 32.
+ * ------------------------------------------------------------------------------------------ */
+int l3ac_local_attention_f32(const float* qkv, const float* bias_table, int B, int T, int H, int D,
+                             int window, float* out, l3ac_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * FSQ bottleneck.  Replaces VQEmbed.forward (l3ac/vq/__init__.py:25-30) = project_in ->
+ * SuperFSQ.forward (l3ac/vq/fsq.py:30-68; tanh_act l3ac/vq/fsq_act.py:38-39) -> project_out, and
+ * VQEmbed.to_features (l3ac/vq/__init__.py:20-23; fsq.py:70-81).
+ *   x (M,F) fp32;  w_in [D][F], b_in [D], w_out [F][D], b_out [F];  levels: HOST array of D ints, D<=8.
+ *   q_feature (M,F) fp32, indices (M) int32, level_indices (M,D) fp32 (may be NULL), z (M,D) (may be NULL).
+ * l3ac_fsq_quantize_latents takes the D-dim latents directly (bit-exactness check of the quantiser).
+ * ------------------------------------------------------------------------------------------ */
+int l3ac_fsq_quantize(const float* x, long long M, int F, const float* w_in, const float* b_in,
+                      const float* w_out, const float* b_out, const int* levels, int D, float* q_feature,
+                      int32_t* indices, float* level_indices, float* z, l3ac_stream_t stream);
+int l3ac_fsq_quantize_latents(const float* z, long long M, const int* levels, int D, float* q_z,
+                              int32_t* indices, float* level_indices, l3ac_stream_t stream);
+int l3ac_fsq_dequantize(const void* indices, int indices_are_i64, long long M, int F, const float* w_out,
+                        const float* b_out, const int* levels, int D, float* q_feature,
+                        l3ac_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Linear x`scale` upsampling along time (nn.Upsample(mode='linear', align_corners=False),
+ * l3ac/modules.py:162, l3ac/local_trans.py:121) with the following channels-first ChannelNorm
+ * (l3ac/modules.py:163, l3ac/layers.py:50-56) fused when cn_w != NULL.
+ * x (B,T,C) fp32 -> out (B,T*scale,C) fp32.
+ * ------------------------------------------------------------------------------------------ */
+int l3ac_upsample_linear_cn(const float* x, int B, int T, int C, int scale, const float* cn_w,
+                            const float* cn_b, float eps, float* out, l3ac_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * EnhanceBlock (l3ac/tconv/__init__.py:30-44): 4 x [TrendPool(k in 1,3,5,9) -> Conv1d(1->1,k7,dil 1,2,3,5)]
+ * on channel 0 -> InstanceNorm1d(4, affine, eps 1e-5, stats over all T) -> Conv1d(4->C,1x1) -> x + y*x.
+ * Two passes: `stats` writes per-(b,chunk) partial sums, `apply` reduces them and gates.
+ * partials: l3ac_enhance_partials_floats(B,T) floats.  conv_w [4][7], conv_b [4], in_w/in_b [4],
+ * merge_w [C][4], merge_b [C].  out (B,T,C) fp32|bf16.
+ * ------------------------------------------------------------------------------------------ */
+long long l3ac_enhance_partials_floats(int B, int T);
+int l3ac_enhance_stats(const float* x, int B, int T, int C, const float* conv_w, const float* conv_b,
+                       float* partials, l3ac_stream_t stream);
+int l3ac_enhance_apply(const float* x, int B, int T, int C, const float* conv_w, const float* conv_b,
+                       const float* in_w, const float* in_b, const float* merge_w, const float* merge_b,
+                       const float* partials, void* out, int out_dtype, l3ac_stream_t stream);
+
+/* Decoder tail (l3ac/modules.py:192-194): Snake(C) -> Conv1d(C->1,k7,pad 3) -> tanh.
+ * x (B,T,C) fp32 -> out (B,T) fp32.  w is [7][C] (tap-major). */
+int l3ac_tail_conv_tanh(const float* x, int B, int T, int C, const float* alpha, const float* w, float bias,
+                        float* out, l3ac_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* L3AC_B200_H_ */

@@ -1,0 +1,57 @@
+// Shared device/host helpers for the l3ac_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/l3ac_b200.h"
+
+#define L3AC_CHECK_ARG(cond)            \
+    do {                                \
+        if (!(cond)) return L3AC_EINVAL; \
+    } while (0)
+
+// Kernel launches are asynchronous; report launch-configuration errors to the caller.
+static inline int l3ac_launch_status() {
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? L3AC_OK : (int)e;
+}
+
+static inline int l3ac_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// shared argument validation of the two GEMM entry points (defined in gemm_f32.cu)
+int l3ac_validate_gemm_desc(const l3ac_gemm_desc* d);
+
+namespace l3ac {
+
+constexpr float kEps = 1e-8f;   // l3ac/xtract/nn/utils.py:33 (float32(1e-8))
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// x + sin^2(alpha x) / (alpha + 1e-8)      (l3ac/layers.py:29-33)
+__device__ __forceinline__ float snake_f(float x, float alpha, float inv_alpha) {
+    float s = sinf(alpha * x);
+    return x + inv_alpha * (s * s);
+}
+
+// exact-erf GELU (nn.GELU() default / F.gelu default)
+__device__ __forceinline__ float gelu_erf(float x) {
+    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+// Output-type adapters used by kernels that can emit fp32 or bf16 activations.
+template <typename T> __device__ __forceinline__ T cvt_out(float v);
+template <> __device__ __forceinline__ float cvt_out<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 cvt_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+}  // namespace l3ac

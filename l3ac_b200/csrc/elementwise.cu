@@ -1,0 +1,509 @@
+// HBM-bound stencil / normalisation kernels of the L3AC conv stack (channels-last activations).
+//   dwconv7 + LayerNorm      ConvUnit prologue          l3ac/modules.py:33-35
+//   LayerNorm                ChannelNorm / nn.LayerNorm l3ac/layers.py:50-56
+//   snake                    Snake1d                    l3ac/layers.py:29-47
+//   linear upsample (+CN)    nn.Upsample + ChannelNorm  l3ac/modules.py:160-164
+//   EnhanceBlock             stats + apply              l3ac/tconv/__init__.py:30-44
+//   tail                     Snake -> Conv(C->1,k7) -> tanh   l3ac/modules.py:192-194
+#include "common.cuh"
+
+namespace l3ac {
+
+// ------------------------------------------------------------------------------------------
+// depthwise conv k7 (pad 3) + LayerNorm over C.  One warp per (b, t) row; lane owns channels
+// lane, lane+32, ...  Weights are staged in shared memory ([7][C] taps, bias, ln w/b).
+// ------------------------------------------------------------------------------------------
+template <int CPL, typename OutT>
+__global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* __restrict__ x, int B, int T, int C,
+                                                         const float* __restrict__ dw_w,
+                                                         const float* __restrict__ dw_b,
+                                                         const float* __restrict__ ln_w,
+                                                         const float* __restrict__ ln_b, float eps,
+                                                         OutT* __restrict__ out) {
+    extern __shared__ float sm[];
+    float* s_w = sm;             // [7][C]
+    float* s_b = sm + 7 * C;     // [C]
+    float* s_lw = s_b + C;       // [C]
+    float* s_lb = s_lw + C;      // [C]
+    for (int i = threadIdx.x; i < 7 * C; i += blockDim.x) s_w[i] = dw_w[i];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        s_b[i] = dw_b[i];
+        s_lw[i] = ln_w[i];
+        s_lb[i] = ln_b[i];
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const long long rows = (long long)B * T;
+    for (long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows;
+         row += (long long)gridDim.x * warps_per_block) {
+        const int t = (int)(row % T);
+        const float* xr = x + row * C;
+        float acc[CPL];
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+            const int c = lane + 32 * i;
+            acc[i] = (c < C) ? s_b[c] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            const int tt = t + j - 3;
+            if (tt < 0 || tt >= T) continue;   // warp-uniform
+            const float* xs = xr + (long long)(j - 3) * C;
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+                const int c = lane + 32 * i;
+                if (c < C) acc[i] = fmaf(s_w[j * C + c], __ldg(xs + c), acc[i]);
+            }
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) s += (lane + 32 * i < C) ? acc[i] : 0.f;
+        const float mean = warp_sum(s) / (float)C;
+        float v = 0.f;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+            const float dlt = acc[i] - mean;
+            v += (lane + 32 * i < C) ? dlt * dlt : 0.f;
+        }
+        const float rstd = 1.0f / sqrtf(warp_sum(v) / (float)C + eps);
+        OutT* orow = out + row * C;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+            const int c = lane + 32 * i;
+            if (c < C) orow[c] = cvt_out<OutT>((acc[i] - mean) * rstd * s_lw[c] + s_lb[c]);
+        }
+    }
+}
+
+template <int CPL, typename OutT>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, long long M, int C,
+                                                        const float* __restrict__ w,
+                                                        const float* __restrict__ b, float eps,
+                                                        OutT* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    for (long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M;
+         row += (long long)gridDim.x * warps_per_block) {
+        const float* xr = x + row * C;
+        float v[CPL];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+            const int c = lane + 32 * i;
+            v[i] = (c < C) ? xr[c] : 0.f;
+            s += v[i];
+        }
+        const float mean = warp_sum(s) / (float)C;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+            const float dlt = v[i] - mean;
+            q += (lane + 32 * i < C) ? dlt * dlt : 0.f;
+        }
+        const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
+        OutT* orow = out + row * C;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+            const int c = lane + 32 * i;
+            if (c < C) orow[c] = cvt_out<OutT>((v[i] - mean) * rstd * __ldg(w + c) + __ldg(b + c));
+        }
+    }
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) snake_kernel(const float* __restrict__ x, long long n, int C,
+                                                    const float* __restrict__ alpha, OutT* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const float a = __ldg(alpha + c);
+        out[i] = cvt_out<OutT>(snake_f(x[i], a, 1.0f / (a + kEps)));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// linear upsample x`scale` along time (+ optional LayerNorm over C).  One warp per output row.
+// Index math follows ATen's area_pixel_compute_source_index (align_corners=False):
+//   src = max(0, (1/scale) * (j + 0.5) - 0.5), i0 = floor(src), i1 = min(i0 + 1, T - 1), lam = src - i0.
+// ------------------------------------------------------------------------------------------
+template <int CPL>
+__global__ void __launch_bounds__(256) upsample_cn_kernel(const float* __restrict__ x, int B, int T, int C,
+                                                          int scale, const float* __restrict__ cn_w,
+                                                          const float* __restrict__ cn_b, float eps,
+                                                          float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const int To = T * scale;
+    const long long rows = (long long)B * To;
+    const float rscale = (float)(1.0 / (double)scale);
+    for (long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows;
+         row += (long long)gridDim.x * warps_per_block) {
+        const int b = (int)(row / To);
+        const int j = (int)(row % To);
+        float src = __fsub_rn(__fmul_rn(rscale, (float)j + 0.5f), 0.5f);
+        src = src < 0.f ? 0.f : src;
+        int i0 = (int)src;
+        if (i0 > T - 1) i0 = T - 1;
+        const int i1 = i0 + (i0 < T - 1 ? 1 : 0);
+        const float l1 = src - (float)i0;
+        const float l0 = 1.0f - l1;
+        const float* x0 = x + ((long long)b * T + i0) * C;
+        const float* x1 = x + ((long long)b * T + i1) * C;
+        float v[CPL];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+            const int c = lane + 32 * i;
+            v[i] = (c < C) ? __fmaf_rn(l1, __ldg(x1 + c), __fmul_rn(l0, __ldg(x0 + c))) : 0.f;
+            s += v[i];
+        }
+        float* orow = out + row * C;
+        if (cn_w == nullptr) {
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+                const int c = lane + 32 * i;
+                if (c < C) orow[c] = v[i];
+            }
+            continue;
+        }
+        const float mean = warp_sum(s) / (float)C;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+            const float dlt = v[i] - mean;
+            q += (lane + 32 * i < C) ? dlt * dlt : 0.f;
+        }
+        const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+            const int c = lane + 32 * i;
+            if (c < C) orow[c] = (v[i] - mean) * rstd * __ldg(cn_w + c) + __ldg(cn_b + c);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// EnhanceBlock.  Branch j in {0..3}: pool kernel k_j in {1,3,5,9}, conv dilation d_j in {1,2,3,5}.
+//   p_j = trend_pool(x[:, 0], k_j)  (k=1: identity without abs; else avg_k(max_k(|x|)), max ignores
+//   out-of-range samples, avg zero-pads and always divides by k), zero outside [0,T) for the conv.
+//   y_j[t] = cb_j + sum_i cw_j[i] * p_j[t + (i-3) d_j]
+// kReach = 8 (pool) + 15 (conv) = 23 samples on each side of a tile.
+// ------------------------------------------------------------------------------------------
+constexpr int kEnhReach = 23;
+constexpr int kEnhChunk = 1024;   // time steps per stats block (partials granularity)
+constexpr int kEnhTile = 128;     // time steps per apply block
+
+// Computes y_j[t0 + i] for i in [0, CH) into ys[j][i] (shared, [4][CH]).  xs/ms/ps: [CH + 2*kEnhReach].
+template <int CH>
+__device__ __forceinline__ void enhance_branches(const float* __restrict__ xb /* x + b*T*C */, int T, int C, int t0,
+                                                 const float* __restrict__ conv_w,
+                                                 const float* __restrict__ conv_b, float* xs, float* ms, float* ps,
+                                                 float* ys) {
+    constexpr int R = kEnhReach;
+    constexpr int W = CH + 2 * R;
+    for (int i = threadIdx.x; i < W; i += blockDim.x) {
+        const int t = t0 - R + i;
+        xs[i] = (t >= 0 && t < T) ? __ldg(xb + (long long)t * C) : 0.f;
+    }
+    __syncthreads();
+    const int pool_k[4] = {1, 3, 5, 9};
+    const int dil[4] = {1, 2, 3, 5};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int k = pool_k[j], half = k >> 1, d = dil[j];
+        const float* src = xs;
+        if (k > 1) {
+            for (int i = threadIdx.x; i < W; i += blockDim.x) {
+                const int t = t0 - R + i;
+                float m = 0.f;
+                if (t >= 0 && t < T && i >= half && i < W - half) {
+                    for (int e = -half; e <= half; ++e) m = fmaxf(m, fabsf(xs[i + e]));   // OOB xs are 0 <= |x|
+                }
+                ms[i] = m;
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < W; i += blockDim.x) {
+                const int t = t0 - R + i;
+                float a = 0.f;
+                if (t >= 0 && t < T && i >= 2 * half && i < W - 2 * half) {
+                    for (int e = -half; e <= half; ++e) a += ms[i + e];
+                    a = a / (float)k;
+                }
+                ps[i] = a;
+            }
+            __syncthreads();
+            src = ps;
+        }
+        float w[7];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) w[i] = __ldg(conv_w + j * 7 + i);
+        const float cb = __ldg(conv_b + j);
+        for (int i = threadIdx.x; i < CH; i += blockDim.x) {
+            float acc = cb;
+#pragma unroll
+            for (int q = 0; q < 7; ++q) acc = fmaf(w[q], src[i + R + (q - 3) * d], acc);
+            ys[j * CH + i] = acc;
+        }
+        __syncthreads();
+    }
+}
+
+// partials layout: [B][nchunk][8] = (sum_j, sumsq_j) for j = 0..3
+__global__ void __launch_bounds__(256) enhance_stats_kernel(const float* __restrict__ x, int B, int T, int C,
+                                                            const float* __restrict__ conv_w,
+                                                            const float* __restrict__ conv_b,
+                                                            float* __restrict__ partials) {
+    constexpr int CH = kEnhChunk;
+    __shared__ float xs[CH + 2 * kEnhReach], ms[CH + 2 * kEnhReach], ps[CH + 2 * kEnhReach];
+    __shared__ float ys[4 * CH];
+    __shared__ float red[8][8];
+    const int b = blockIdx.y, chunk = blockIdx.x, t0 = chunk * CH;
+    enhance_branches<CH>(x + (long long)b * T * C, T, C, t0, conv_w, conv_b, xs, ms, ps, ys);
+    float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+    for (int i = threadIdx.x; i < CH; i += blockDim.x) {
+        if (t0 + i < T) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float y = ys[j * CH + i];
+                s[j] += y;
+                q[j] = fmaf(y, y, q[j]);
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        s[j] = warp_sum(s[j]);
+        q[j] = warp_sum(q[j]);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            red[warp][2 * j] = s[j];
+            red[warp][2 * j + 1] = q[j];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        float a = 0.f;
+        for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) a += red[wv][threadIdx.x];
+        partials[((long long)b * gridDim.x + chunk) * 8 + threadIdx.x] = a;
+    }
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) enhance_apply_kernel(const float* __restrict__ x, int B, int T, int C,
+                                                            const float* __restrict__ conv_w,
+                                                            const float* __restrict__ conv_b,
+                                                            const float* __restrict__ in_w,
+                                                            const float* __restrict__ in_b,
+                                                            const float* __restrict__ merge_w,
+                                                            const float* __restrict__ merge_b,
+                                                            const float* __restrict__ partials, int nchunk,
+                                                            OutT* __restrict__ out) {
+    constexpr int CH = kEnhTile;
+    __shared__ float xs[CH + 2 * kEnhReach], ms[CH + 2 * kEnhReach], ps[CH + 2 * kEnhReach];
+    __shared__ float ys[4 * CH];
+    __shared__ float s_scale[4], s_shift[4];
+    const int b = blockIdx.y, t0 = blockIdx.x * CH;
+    if (threadIdx.x < 4) {
+        const int j = threadIdx.x;
+        double s = 0.0, q = 0.0;
+        for (int c = 0; c < nchunk; ++c) {
+            s += (double)partials[((long long)b * nchunk + c) * 8 + 2 * j];
+            q += (double)partials[((long long)b * nchunk + c) * 8 + 2 * j + 1];
+        }
+        const double mean = s / (double)T;
+        double var = q / (double)T - mean * mean;   // biased variance (InstanceNorm1d)
+        if (var < 0.0) var = 0.0;
+        const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+        const float g = in_w[j] * rstd;
+        s_scale[j] = g;
+        s_shift[j] = in_b[j] - (float)mean * g;
+    }
+    enhance_branches<CH>(x + (long long)b * T * C, T, C, t0, conv_w, conv_b, xs, ms, ps, ys);
+    // (enhance_branches ends with __syncthreads, so s_scale/s_shift are visible)
+    for (int i = threadIdx.x; i < 4 * CH; i += blockDim.x) {
+        const int j = i / CH;
+        ys[i] = fmaf(ys[i], s_scale[j], s_shift[j]);
+    }
+    __syncthreads();
+    const int nt = min(CH, T - t0);
+    const long long base = ((long long)b * T + t0) * C;
+    for (int e = threadIdx.x; e < nt * C; e += blockDim.x) {
+        const int i = e / C, c = e - i * C;
+        const float4 mw = __ldg(reinterpret_cast<const float4*>(merge_w) + c);
+        float y = __ldg(merge_b + c);
+        y = fmaf(mw.x, ys[i], y);
+        y = fmaf(mw.y, ys[CH + i], y);
+        y = fmaf(mw.z, ys[2 * CH + i], y);
+        y = fmaf(mw.w, ys[3 * CH + i], y);
+        const float xv = x[base + e];
+        out[base + e] = cvt_out<OutT>(fmaf(y, xv, xv));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// decoder tail: snake -> conv(C->1, k7, pad 3) -> tanh.  Block = 256 output samples.
+// ------------------------------------------------------------------------------------------
+constexpr int kTailTile = 256;
+constexpr int kTailMaxC = 32;
+
+__global__ void __launch_bounds__(kTailTile) tail_kernel(const float* __restrict__ x, int B, int T, int C,
+                                                         const float* __restrict__ alpha,
+                                                         const float* __restrict__ w, float bias,
+                                                         float* __restrict__ out) {
+    __shared__ float s[(kTailTile + 6) * (kTailMaxC + 1)];
+    __shared__ float s_w[7 * kTailMaxC];
+    const int b = blockIdx.y, t0 = blockIdx.x * kTailTile;
+    const int ld = C + 1;
+    for (int i = threadIdx.x; i < 7 * C; i += blockDim.x) s_w[i] = w[i];
+    const float* xb = x + (long long)b * T * C;
+    for (int e = threadIdx.x; e < (kTailTile + 6) * C; e += blockDim.x) {
+        const int i = e / C, c = e - i * C;
+        const int t = t0 - 3 + i;
+        float v = 0.f;
+        if (t >= 0 && t < T) {
+            const float a = __ldg(alpha + c);
+            v = snake_f(__ldg(xb + (long long)t * C + c), a, 1.0f / (a + kEps));
+        }
+        s[i * ld + c] = v;
+    }
+    __syncthreads();
+    const int t = t0 + threadIdx.x;
+    if (t < T) {
+        float acc = bias;
+        for (int j = 0; j < 7; ++j) {
+            const float* sr = s + (threadIdx.x + j) * ld;
+            for (int c = 0; c < C; ++c) acc = fmaf(s_w[j * C + c], sr[c], acc);
+        }
+        out[(long long)b * T + t] = tanhf(acc);
+    }
+}
+
+static inline int grid_for_rows(long long rows, int rows_per_block) {
+    long long g = (rows + rows_per_block - 1) / rows_per_block;
+    const long long cap = 148LL * 32;   // persistent-style cap: 32 blocks per SM worth of waves
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace l3ac
+
+using namespace l3ac;
+
+#define DISPATCH_CPL(C, ...)                                        \
+    do {                                                            \
+        const int cpl_ = ((C) + 31) / 32;                           \
+        if (cpl_ <= 1) { constexpr int CPL = 1; __VA_ARGS__; }      \
+        else if (cpl_ <= 2) { constexpr int CPL = 2; __VA_ARGS__; } \
+        else if (cpl_ <= 3) { constexpr int CPL = 3; __VA_ARGS__; } \
+        else if (cpl_ <= 4) { constexpr int CPL = 4; __VA_ARGS__; } \
+        else if (cpl_ <= 6) { constexpr int CPL = 6; __VA_ARGS__; } \
+        else if (cpl_ <= 8) { constexpr int CPL = 8; __VA_ARGS__; } \
+        else { constexpr int CPL = 16; __VA_ARGS__; }               \
+    } while (0)
+
+extern "C" int l3ac_dwconv7_ln(const float* x, int B, int T, int C, const float* dw_w, const float* dw_b,
+                               const float* ln_w, const float* ln_b, float eps, void* out, int out_dtype,
+                               l3ac_stream_t stream) {
+    L3AC_CHECK_ARG(x && dw_w && dw_b && ln_w && ln_b && out);
+    L3AC_CHECK_ARG(B > 0 && T > 0 && C > 0 && C <= 512);
+    L3AC_CHECK_ARG(out_dtype == L3AC_F32 || out_dtype == L3AC_BF16);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long rows = (long long)B * T;
+    const int grid = grid_for_rows(rows, 8);
+    const size_t smem = (size_t)10 * C * sizeof(float);
+    DISPATCH_CPL(C, {
+        if (out_dtype == L3AC_F32)
+            dwconv7_ln_kernel<CPL, float><<<grid, 256, smem, st>>>(x, B, T, C, dw_w, dw_b, ln_w, ln_b, eps, (float*)out);
+        else
+            dwconv7_ln_kernel<CPL, __nv_bfloat16>
+                <<<grid, 256, smem, st>>>(x, B, T, C, dw_w, dw_b, ln_w, ln_b, eps, (__nv_bfloat16*)out);
+    });
+    return l3ac_launch_status();
+}
+
+extern "C" int l3ac_layernorm(const float* x, long long M, int C, const float* w, const float* b, float eps,
+                              void* out, int out_dtype, l3ac_stream_t stream) {
+    L3AC_CHECK_ARG(x && w && b && out);
+    L3AC_CHECK_ARG(M > 0 && C > 0 && C <= 512);
+    L3AC_CHECK_ARG(out_dtype == L3AC_F32 || out_dtype == L3AC_BF16);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = grid_for_rows(M, 8);
+    DISPATCH_CPL(C, {
+        if (out_dtype == L3AC_F32)
+            layernorm_kernel<CPL, float><<<grid, 256, 0, st>>>(x, M, C, w, b, eps, (float*)out);
+        else
+            layernorm_kernel<CPL, __nv_bfloat16><<<grid, 256, 0, st>>>(x, M, C, w, b, eps, (__nv_bfloat16*)out);
+    });
+    return l3ac_launch_status();
+}
+
+extern "C" int l3ac_snake(const float* x, long long M, int C, const float* alpha, void* out, int out_dtype,
+                          l3ac_stream_t stream) {
+    L3AC_CHECK_ARG(x && alpha && out && M > 0 && C > 0);
+    L3AC_CHECK_ARG(out_dtype == L3AC_F32 || out_dtype == L3AC_BF16);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n = M * C;
+    const int grid = grid_for_rows(n, 256 * 4);
+    if (out_dtype == L3AC_F32)
+        snake_kernel<float><<<grid, 256, 0, st>>>(x, n, C, alpha, (float*)out);
+    else
+        snake_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, n, C, alpha, (__nv_bfloat16*)out);
+    return l3ac_launch_status();
+}
+
+extern "C" int l3ac_upsample_linear_cn(const float* x, int B, int T, int C, int scale, const float* cn_w,
+                                       const float* cn_b, float eps, float* out, l3ac_stream_t stream) {
+    L3AC_CHECK_ARG(x && out && B > 0 && T > 0 && C > 0 && C <= 512 && scale >= 1);
+    L3AC_CHECK_ARG((cn_w == nullptr) == (cn_b == nullptr));
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long rows = (long long)B * T * scale;
+    const int grid = grid_for_rows(rows, 8);
+    DISPATCH_CPL(C, { upsample_cn_kernel<CPL><<<grid, 256, 0, st>>>(x, B, T, C, scale, cn_w, cn_b, eps, out); });
+    return l3ac_launch_status();
+}
+
+extern "C" long long l3ac_enhance_partials_floats(int B, int T) {
+    return (long long)B * l3ac_cdiv(T, kEnhChunk) * 8;
+}
+
+extern "C" int l3ac_enhance_stats(const float* x, int B, int T, int C, const float* conv_w, const float* conv_b,
+                                  float* partials, l3ac_stream_t stream) {
+    L3AC_CHECK_ARG(x && conv_w && conv_b && partials && B > 0 && B <= 65535 && T > 0 && C > 0);
+    dim3 grid(l3ac_cdiv(T, kEnhChunk), B);
+    enhance_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, B, T, C, conv_w, conv_b, partials);
+    return l3ac_launch_status();
+}
+
+extern "C" int l3ac_enhance_apply(const float* x, int B, int T, int C, const float* conv_w, const float* conv_b,
+                                  const float* in_w, const float* in_b, const float* merge_w,
+                                  const float* merge_b, const float* partials, void* out, int out_dtype,
+                                  l3ac_stream_t stream) {
+    L3AC_CHECK_ARG(x && conv_w && conv_b && in_w && in_b && merge_w && merge_b && partials && out);
+    L3AC_CHECK_ARG(B > 0 && B <= 65535 && T > 0 && C > 0);
+    L3AC_CHECK_ARG(out_dtype == L3AC_F32 || out_dtype == L3AC_BF16);
+    L3AC_CHECK_ARG((reinterpret_cast<uintptr_t>(merge_w) & 15) == 0);
+    dim3 grid(l3ac_cdiv(T, kEnhTile), B);
+    const int nchunk = l3ac_cdiv(T, kEnhChunk);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (out_dtype == L3AC_F32)
+        enhance_apply_kernel<float><<<grid, 256, 0, st>>>(x, B, T, C, conv_w, conv_b, in_w, in_b, merge_w, merge_b,
+                                                          partials, nchunk, (float*)out);
+    else
+        enhance_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, B, T, C, conv_w, conv_b, in_w, in_b, merge_w,
+                                                                  merge_b, partials, nchunk, (__nv_bfloat16*)out);
+    return l3ac_launch_status();
+}
+
+extern "C" int l3ac_tail_conv_tanh(const float* x, int B, int T, int C, const float* alpha, const float* w,
+                                   float bias, float* out, l3ac_stream_t stream) {
+    L3AC_CHECK_ARG(x && alpha && w && out && B > 0 && B <= 65535 && T > 0 && C > 0 && C <= kTailMaxC);
+    dim3 grid(l3ac_cdiv(T, kTailTile), B);
+    tail_kernel<<<grid, kTailTile, 0, (cudaStream_t)stream>>>(x, B, T, C, alpha, w, bias, out);
+    return l3ac_launch_status();
+}
