@@ -1,0 +1,350 @@
+"""Forward engine: packs reference-format weights once, then runs encode / decode as kernel sequences.
+
+The composition follows the reference forward op by op (citations per method); the arithmetic lives in
+``libl3ac_b200.so``.  Weight packing (weight-norm folding ``w = g v / ||v||``, tap-major conv layouts,
+GEGLU column interleave, the input-independent attention bias table, GRN folded to a per-channel affine)
+is one-time, input-independent preprocessing done with torch on the parameters' device.
+
+Precision modes
+  ``fp32``  every GEMM on the fp32 SIMT path (parity mode, 1e-5 class).
+  ``bf16``  decode side (en_decoder + decoder) GEMM operands in bf16 on the tcgen05 path with fp32
+            accumulation and fp32 residual stream; the encode side stays fp32 because token indices
+            flip under bf16 rounding (93.6 % agreement at bf16, 100 % at fp32 class).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+from .config import ModelConfig
+from .spec import HEADS, is_compressed
+
+EPS = 1e-8          # ChannelNorm eps, l3ac/xtract/nn/utils.py:33
+LN_EPS = 1e-5       # nn.LayerNorm default inside local_attention
+FF_PAD = 352        # FeedForward inner 341 padded to a multiple of 16 bf16 elements / 32 B
+
+
+def fold_weight_norm(sd, prefix: str) -> torch.Tensor:
+    """Effective weight of a weight-normed layer (l3ac/layers.py:17-18): g * v / ||v||, norm over dims != 0."""
+    if prefix + ".weight" in sd:
+        return sd[prefix + ".weight"].float()
+    g = sd[prefix + ".parametrizations.weight.original0"].float()
+    v = sd[prefix + ".parametrizations.weight.original1"].float()
+    norm = v.flatten(1).norm(dim=1).reshape(g.shape)
+    return v * (g / norm)
+
+
+def _taps_major(w: torch.Tensor) -> torch.Tensor:
+    """Conv1d weight (Co, Ci, k) -> GEMM weight (Co, k*Ci) with the tap index outermost."""
+    return w.permute(0, 2, 1).reshape(w.shape[0], -1).contiguous()
+
+
+class _Linear:
+    """A packed GEMM weight: fp32 master + optional bf16 copy for the tcgen05 path."""
+
+    def __init__(self, w: torch.Tensor, bias: Optional[torch.Tensor], bf16: bool):
+        self.w32 = w.contiguous().float()
+        self.w16 = self.w32.to(torch.bfloat16).contiguous() if bf16 else None
+        self.bias = None if bias is None else bias.contiguous().float()
+
+    def weight_for(self, a: torch.Tensor) -> torch.Tensor:
+        return self.w32 if a.dtype == torch.float32 else self.w16
+
+
+class Engine:
+    def __init__(self, mc: ModelConfig, weights: Dict[str, Dict[str, torch.Tensor]], device, precision: str = "bf16",
+                 max_chunk_seconds: float = 160.0):
+        if precision not in ("fp32", "bf16"):
+            raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
+        if not mc.en_coder_dynamic_pos:
+            raise NotImplementedError("rotary position path (en_coder_dynamic_pos=false) is not built yet")
+        if mc.decoder_last_layer != "legacy" or mc.base_unit != "normal" or not mc.use_norm or not mc.use_snake_act:
+            raise NotImplementedError("only the layer options used by the four named configs are built")
+        if mc.en_coder_cache_size != 0:
+            raise NotImplementedError("en_coder_cache_size must be 0 (the reference asserts the same)")
+        self.mc = mc
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("l3ac_b200 runs on CUDA devices only; move the network with .cuda() first")
+        self.precision = precision
+        self.max_chunk_samples = int(max_chunk_seconds * 16000)
+        self.dec_dtype = torch.bfloat16 if precision == "bf16" else torch.float32
+        w = {m: {k: v.detach().to(self.device) for k, v in sd.items()} for m, sd in weights.items()}
+        with torch.no_grad():
+            self._pack_encoder(w["encoder"])
+            self._pack_en_encoder(w["en_encoder"])
+            self._pack_quantizer(w["quantizer"])
+            self._pack_en_decoder(w["en_decoder"])
+            self._pack_decoder(w["decoder"])
+
+    # ------------------------------------------------------------------ packing
+    def _conv_unit(self, sd, p, bf16):
+        dw = fold_weight_norm(sd, f"{p}.dw_conv")                      # (C, 1, 7)
+        gamma, beta = sd[f"{p}.grn.gamma"].float().flatten(), sd[f"{p}.grn.beta"].float().flatten()
+        return dict(
+            dw_w=dw[:, 0, :].t().contiguous(), dw_b=sd[f"{p}.dw_conv.bias"].float().contiguous(),
+            ln_w=sd[f"{p}.norm.weight"].float().contiguous(), ln_b=sd[f"{p}.norm.bias"].float().contiguous(),
+            pw1=_Linear(fold_weight_norm(sd, f"{p}.pw_conv1"), sd[f"{p}.pw_conv1.bias"], bf16),
+            alpha=sd[f"{p}.act.alpha"].float().flatten().contiguous(),
+            # GRN (l3ac/layers.py:112-115): n_x = g/(g+1e-8) == 1 to within 1e-8/g, so gamma*(x*n_x)+beta+x is the
+            # per-channel affine (1+gamma) x + beta (absolute deviation <= 1e-8*|gamma|).
+            scale=(1.0 + gamma).contiguous(), shift=beta.contiguous(),
+            pw2=_Linear(fold_weight_norm(sd, f"{p}.pw_conv2"), sd[f"{p}.pw_conv2.bias"], bf16),
+        )
+
+    def _pack_encoder(self, sd):
+        mc = self.mc
+        bw = torch.stack([fold_weight_norm(sd, f"blocks.0.blocks.{i}.1")[:, 0, :] for i in range(5)])   # (5,4,7)
+        bb = torch.cat([sd[f"blocks.0.blocks.{i}.1.bias"].float() for i in range(5)])
+        self.stem = dict(
+            branch_w=bw.contiguous(), branch_b=bb.contiguous(),
+            w1=fold_weight_norm(sd, "blocks.0.conv_1")[:, :, 0].contiguous(), b1=sd["blocks.0.conv_1.bias"].float(),
+            w2=fold_weight_norm(sd, "blocks.0.conv_2")[:, :, 0].contiguous(), b2=sd["blocks.0.conv_2.bias"].float())
+        self.enc_stages = []
+        blk = 1
+        for i, stride in enumerate(mc.compress_rates):
+            units = [self._conv_unit(sd, f"blocks.{blk}.{j}.module", False) for j in range(mc.encoder_depths[i])]
+            blk += 1
+            down = _Linear(_taps_major(fold_weight_norm(sd, f"blocks.{blk}.0")), sd[f"blocks.{blk}.0.bias"], False)
+            self.enc_stages.append(dict(units=units, stride=stride, down=down,
+                                        cn_w=sd[f"blocks.{blk}.1.weight"].float().contiguous(),
+                                        cn_b=sd[f"blocks.{blk}.1.bias"].float().contiguous()))
+            blk += 1
+        self.enc_last = [self._conv_unit(sd, f"blocks.{blk}.{j}.module", False) for j in range(mc.encoder_depths[-1])]
+        self.enc_out = _Linear(_taps_major(fold_weight_norm(sd, f"blocks.{blk + 1}")), sd[f"blocks.{blk + 1}.bias"], False)
+
+    def _local_trans(self, sd, p, depth, window, bf16):
+        """LocalTrans weights + the DynamicPositionBias table f[h][d], d = q_pos - k_pos in [0, 2w)
+        (l3ac/local_trans.py:30,43; the MLP input is the integer distance, so the table is input-independent)."""
+        q = f"{p}.dynamic_pos_bias.mlp"
+        d = torch.arange(2 * window, dtype=torch.float32, device=self.device)[:, None]
+        h = torch.nn.functional.silu(torch.nn.functional.linear(d, sd[f"{q}.0.weight"].float(), sd[f"{q}.0.bias"].float()))
+        h = torch.nn.functional.silu(torch.nn.functional.linear(h, sd[f"{q}.2.weight"].float(), sd[f"{q}.2.bias"].float()))
+        table = torch.nn.functional.linear(h, sd[f"{q}.4.weight"].float(), sd[f"{q}.4.bias"].float()).t().contiguous()
+        layers = []
+        for l in range(depth):
+            a, f = f"{p}.layers.{l}.0", f"{p}.layers.{l}.1"
+            w1 = sd[f"{f}.1.weight"].float()                       # (2*inner, dim): [value rows ; gate rows]
+            inner = w1.shape[0] // 2
+            dim = w1.shape[1]
+            w1i = torch.zeros((2 * FF_PAD, dim), device=self.device)
+            w1i[0:2 * inner:2] = w1[:inner]                        # interleave (value_i, gate_i) column pairs
+            w1i[1:2 * inner:2] = w1[inner:]
+            w2 = torch.zeros((dim, FF_PAD), device=self.device)
+            w2[:, :inner] = sd[f"{f}.4.weight"].float()
+            layers.append(dict(
+                ln1_w=sd[f"{a}.norm.weight"].float().contiguous(), ln1_b=sd[f"{a}.norm.bias"].float().contiguous(),
+                qkv=_Linear(sd[f"{a}.to_qkv.weight"], None, bf16), out=_Linear(sd[f"{a}.to_out.weight"], None, bf16),
+                ln2_w=sd[f"{f}.0.weight"].float().contiguous(), ln2_b=sd[f"{f}.0.bias"].float().contiguous(),
+                ff1=_Linear(w1i, None, bf16), ff2=_Linear(w2, None, bf16)))
+        return dict(layers=layers, window=window, table=table)
+
+    def _pack_en_encoder(self, sd):
+        mc = self.mc
+        w, r = mc.en_coder_window_size, mc.en_coder_compress_rate
+        if is_compressed(mc):
+            self.enc_trans_frame = self._local_trans(sd, "down_trans.trans", 3 // 2, w * r, False)
+            self.enc_trans_down = _Linear(_taps_major(fold_weight_norm(sd, "down_trans.down_layer")),
+                                          sd["down_trans.down_layer.bias"], False)
+            self.enc_trans_token = self._local_trans(sd, "local_trans", 3 - 3 // 2, w, False)
+        else:
+            self.enc_trans_frame = None
+            self.enc_trans_down = None
+            self.enc_trans_token = self._local_trans(sd, "local_trans", 1, w, False)
+
+    def _pack_quantizer(self, sd):
+        self.vq = dict(w_in=sd["project_in.weight"].float().contiguous(), b_in=sd["project_in.bias"].float().contiguous(),
+                       w_out=sd["project_out.weight"].float().contiguous(),
+                       b_out=sd["project_out.bias"].float().contiguous())
+
+    def _pack_en_decoder(self, sd):
+        mc = self.mc
+        bf16 = self.precision == "bf16"
+        w, r = mc.en_coder_window_size, mc.en_coder_compress_rate
+        if is_compressed(mc):
+            self.dec_trans_token = self._local_trans(sd, "local_trans", mc.en_coder_depth - 2, w, bf16)
+            self.dec_trans_frame = self._local_trans(sd, "up_trans.trans", 2, w * r, bf16)
+        else:
+            self.dec_trans_token = self._local_trans(sd, "local_trans", mc.en_coder_depth, w, bf16)
+            self.dec_trans_frame = None
+
+    def _pack_decoder(self, sd):
+        mc = self.mc
+        bf16 = self.precision == "bf16"
+        self.dec_in = _Linear(_taps_major(fold_weight_norm(sd, "blocks.0")), sd["blocks.0.bias"], bf16)
+        self.dec_stages = []
+        blk = 1
+        for i, stride in enumerate(mc.decode_rates):
+            units = [self._conv_unit(sd, f"blocks.{blk}.{j}.module", bf16) for j in range(mc.decoder_depths[i])]
+            blk += 1
+            e = f"blocks.{blk}"
+            enh = dict(
+                conv_w=torch.stack([fold_weight_norm(sd, f"{e}.blocks.{k}.1")[0, 0] for k in range(4)]).contiguous(),
+                conv_b=torch.cat([sd[f"{e}.blocks.{k}.1.bias"].float() for k in range(4)]).contiguous(),
+                in_w=sd[f"{e}.merge_layer.0.weight"].float().contiguous(),
+                in_b=sd[f"{e}.merge_layer.0.bias"].float().contiguous(),
+                merge_w=sd[f"{e}.merge_layer.1.weight"].float()[:, :, 0].contiguous(),
+                merge_b=sd[f"{e}.merge_layer.1.bias"].float().contiguous())
+            blk += 1
+            up = _Linear(fold_weight_norm(sd, f"blocks.{blk}.0")[:, :, 0], sd[f"blocks.{blk}.0.bias"], bf16)
+            self.dec_stages.append(dict(units=units, enh=enh, up=up, stride=stride,
+                                        cn_w=sd[f"blocks.{blk}.2.weight"].float().contiguous(),
+                                        cn_b=sd[f"blocks.{blk}.2.bias"].float().contiguous()))
+            blk += 1
+        p = f"blocks.{blk}.block"
+        self.dec_legacy = []
+        for j, dil in enumerate((1, 3, 9)):
+            q = f"{p}.0.{j}.module.block"
+            self.dec_legacy.append(dict(
+                dil=dil, alpha0=sd[f"{q}.0.alpha"].float().flatten().contiguous(),
+                conv=_Linear(_taps_major(fold_weight_norm(sd, f"{q}.1")), sd[f"{q}.1.bias"], bf16),
+                alpha1=sd[f"{q}.2.alpha"].float().flatten().contiguous(),
+                pw=_Linear(fold_weight_norm(sd, f"{q}.3")[:, :, 0], sd[f"{q}.3.bias"], bf16)))
+        self.dec_tail = dict(alpha=sd[f"{p}.1.alpha"].float().flatten().contiguous(),
+                             w=fold_weight_norm(sd, f"{p}.2")[0].t().contiguous(),       # (7, C)
+                             bias=float(sd[f"{p}.2.bias"].float().item()))
+
+    # ------------------------------------------------------------------ building blocks
+    @staticmethod
+    def _lin(a, lin: _Linear, B, T, K, **kw):
+        return ops.gemm(a, lin.weight_for(a), B=B, T=T, K=K, bias=lin.bias, **kw)
+
+    def _run_conv_unit(self, x, u, act_dtype):
+        """Residual(ConvUnit) -- l3ac/modules.py:32-44."""
+        B, T, C = x.shape
+        a = ops.dwconv7_ln(x, u["dw_w"], u["dw_b"], u["ln_w"], u["ln_b"], EPS, out_dtype=act_dtype)
+        h = self._lin(a, u["pw1"], B, T, C, act=ops.ACT_SNAKE, alpha=u["alpha"], scale=u["scale"], shift=u["shift"],
+                      out_dtype=act_dtype)
+        return self._lin(h, u["pw2"], B, T, 4 * C, residual=x)
+
+    def _run_local_trans(self, x, lt, act_dtype):
+        """LocalTrans.forward -- l3ac/local_trans.py:42-48 (LocalMHA prenorm + GEGLU FeedForward)."""
+        B, T, D = x.shape
+        for L in lt["layers"]:
+            a = ops.layernorm(x, L["ln1_w"], L["ln1_b"], LN_EPS, out_dtype=act_dtype)
+            qkv = self._lin(a, L["qkv"], B, T, D)                                   # fp32 (B,T,576)
+            o = ops.local_attention(qkv, lt["table"], HEADS, lt["window"])
+            if act_dtype != torch.float32:
+                o = o.to(act_dtype)
+            x = self._lin(o, L["out"], B, T, o.shape[-1], residual=x)
+            a = ops.layernorm(x, L["ln2_w"], L["ln2_b"], LN_EPS, out_dtype=act_dtype)
+            g = self._lin(a, L["ff1"], B, T, D, act=ops.ACT_GEGLU, out_dtype=act_dtype)   # (B,T,352)
+            x = self._lin(g, L["ff2"], B, T, FF_PAD, residual=x)
+        return x
+
+    # ------------------------------------------------------------------ encode
+    def encode_features(self, audio: torch.Tensor, taps: Optional[dict] = None) -> torch.Tensor:
+        """preprocess + encoder + en_encoder (l3ac/__init__.py:109-111) -> trans_feature (B, T_tok, F)."""
+        mc = self.mc
+        f32 = torch.float32
+        B, T0 = audio.shape
+        hop = mc.hop_length
+        T = math.ceil(T0 / hop) * hop                      # Codec.preprocess, l3ac/codec.py:79-84
+        if T != T0:
+            audio = torch.nn.functional.pad(audio, (0, T - T0))
+        x = ops.stem(audio.contiguous(), **self.stem)      # (B, T, 24)
+        if taps is not None:
+            taps["enc_stem"] = x
+        for si, st in enumerate(self.enc_stages):
+            for u in st["units"]:
+                x = self._run_conv_unit(x, u, f32)
+            B_, T_, C_ = x.shape
+            s = st["stride"]
+            x = self._lin(x, st["down"], B_, T_ // s, s * C_)                       # Conv1d(k=s, stride=s) as a GEMM
+            x = ops.layernorm(x, st["cn_w"], st["cn_b"], EPS)                       # channels-first ChannelNorm
+            if taps is not None:
+                taps[f"enc_down{si}"] = x
+        for u in self.enc_last:
+            x = self._run_conv_unit(x, u, f32)
+        B_, T_, C_ = x.shape
+        x = self._lin(x, self.enc_out, B_, T_, C_, taps=3, tap_shift0=-1)           # Conv1d(k3, pad 1)
+        if taps is not None:
+            taps["enc_feature"] = x
+        if self.enc_trans_frame is not None:                                        # l3ac/local_trans.py:138-142,161-165
+            x = self._run_local_trans(x, self.enc_trans_frame, f32)
+            r = mc.en_coder_compress_rate
+            x = self._lin(x, self.enc_trans_down, B_, T_ // r, r * x.shape[-1])
+        x = self._run_local_trans(x, self.enc_trans_token, f32)
+        return x
+
+    def quantize(self, trans_feature: torch.Tensor, want_z: bool = False):
+        """VQEmbed.forward -- l3ac/vq/__init__.py:25-30."""
+        return ops.fsq_quantize(trans_feature.contiguous(), self.vq["w_in"], self.vq["b_in"], self.vq["w_out"],
+                                self.vq["b_out"], self.mc.levels, want_z=want_z)
+
+    def dequantize(self, indices: torch.Tensor) -> torch.Tensor:
+        """VQEmbed.to_features -- l3ac/vq/__init__.py:20-23."""
+        return ops.fsq_dequantize(indices.contiguous(), self.vq["w_out"], self.vq["b_out"], self.mc.levels)
+
+    def _chunks(self, B: int, T: int):
+        per = max(1, self.max_chunk_samples // max(T, 1))
+        return [(i, min(B, i + per)) for i in range(0, B, per)]
+
+    def encode(self, audio: torch.Tensor, taps: Optional[dict] = None):
+        """L3AC.encode_audio -- l3ac/__init__.py:108-114."""
+        if audio.dim() != 2:
+            raise RuntimeError(f"encode_audio expects a (batch, samples) tensor, got shape {tuple(audio.shape)}")
+        audio = audio.to(device=self.device, dtype=torch.float32)
+        outs = []
+        for lo, hi in self._chunks(*audio.shape):
+            t = self.encode_features(audio[lo:hi], taps if (lo == 0 and hi == audio.shape[0]) else None)
+            if taps is not None:
+                taps["trans_feature"] = t
+            q, idx, lvl, z = self.quantize(t, want_z=taps is not None)
+            if taps is not None:
+                taps["z"] = z
+            outs.append((q, idx, lvl))
+        if len(outs) == 1:
+            q, idx, lvl = outs[0]
+        else:
+            q, idx, lvl = (torch.cat([o[i] for o in outs], dim=0) for i in range(3))
+        return q, {"indices": idx, "level_indices": lvl}
+
+    # ------------------------------------------------------------------ decode
+    def decode_features(self, feat: torch.Tensor, taps: Optional[dict] = None) -> torch.Tensor:
+        """en_decoder + decoder (l3ac/__init__.py:119-120).  feat (B, T_tok, F) fp32 -> audio (B, T)."""
+        mc = self.mc
+        adt = self.dec_dtype
+        x = self._run_local_trans(feat, self.dec_trans_token, adt)
+        if self.dec_trans_frame is not None:                                        # UpTransV2, l3ac/local_trans.py:123-126
+            x = ops.upsample_linear_cn(x, mc.en_coder_compress_rate)
+            x = self._run_local_trans(x, self.dec_trans_frame, adt)
+        if taps is not None:
+            taps["dec_feature"] = x
+        B, T, F = x.shape
+        a = x if adt == torch.float32 else x.to(adt)
+        x = self._lin(a, self.dec_in, B, T, F, taps=3, tap_shift0=-1)               # Conv1d(k3, pad 1)
+        for si, st in enumerate(self.dec_stages):
+            for u in st["units"]:
+                x = self._run_conv_unit(x, u, adt)
+            B, T, C = x.shape
+            a = ops.enhance(x, out_dtype=adt, **st["enh"])                          # EnhanceBlock
+            y = self._lin(a, st["up"], B, T, C)                                     # Conv1d 1x1
+            x = ops.upsample_linear_cn(y, st["stride"], st["cn_w"], st["cn_b"], EPS)   # Upsample + ChannelNorm
+            if taps is not None:
+                taps[f"dec_up{si}"] = x
+        B, T, C = x.shape
+        for u in self.dec_legacy:                                                   # Residual(LegacyUnit), modules.py:47-64
+            d = u["dil"]
+            a = ops.snake(x, u["alpha0"], out_dtype=adt)
+            h = self._lin(a, u["conv"], B, T, C, taps=7, tap_shift0=-3 * d, tap_step=d, act=ops.ACT_SNAKE,
+                          alpha=u["alpha1"], out_dtype=adt)
+            x = self._lin(h, u["pw"], B, T, C, residual=x)
+        return ops.tail_conv_tanh(x, self.dec_tail["alpha"], self.dec_tail["w"], self.dec_tail["bias"])
+
+    def decode(self, audio_feature: Optional[torch.Tensor] = None, indices: Optional[torch.Tensor] = None,
+               taps: Optional[dict] = None) -> torch.Tensor:
+        """L3AC.decode_audio -- l3ac/__init__.py:116-121."""
+        if audio_feature is None:
+            if indices is None:
+                # the reference fails inside quantizer.to_features(None) with AttributeError
+                raise AttributeError("decode_audio needs audio_feature or indices ('NoneType' has no attribute 'unsqueeze')")
+            audio_feature = self.dequantize(indices.to(self.device))
+        feat = audio_feature.to(device=self.device, dtype=torch.float32).contiguous()
+        B, T_tok, _ = feat.shape
+        outs = [self.decode_features(feat[lo:hi].contiguous(), taps if (lo == 0 and hi == B) else None)
+                for lo, hi in self._chunks(B, T_tok * self.mc.hop_length)]
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)

@@ -1,0 +1,211 @@
+"""Tensor-level wrappers over the C ABI (``include/l3ac_b200.h``).
+
+PyTorch is plumbing here: it owns device memory and the current stream; every computation below is a
+call into ``libl3ac_b200.so``.  Inputs must be contiguous CUDA tensors; outputs are fresh tensors on
+the same device.  Activations are channels-last ``(B, T, C)``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GEGLU, ACT_GELU, ACT_NONE, ACT_SNAKE, ACT_TANH, BF16, F32, GemmDesc, check  # noqa: F401
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(t: torch.Tensor):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _chk(t: torch.Tensor, dtype=torch.float32, name="tensor"):
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (l3ac_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t
+
+
+def _levels(levels: Sequence[int]):
+    return (C.c_int * len(levels))(*[int(v) for v in levels])
+
+
+def stem(audio: torch.Tensor, branch_w, branch_b, w1, b1, w2, b2) -> torch.Tensor:
+    _chk(audio, name="audio")
+    B, T = audio.shape
+    Cout = w2.shape[0]
+    out = torch.empty((B, T, Cout), device=audio.device, dtype=torch.float32)
+    with torch.cuda.device(audio.device):
+        check(_lib.load().l3ac_stem(_ptr(audio), B, T, _ptr(branch_w), _ptr(branch_b), _ptr(w1), _ptr(b1), _ptr(w2),
+                                    _ptr(b2), Cout, _ptr(out), _stream(audio)), "l3ac_stem")
+    return out
+
+
+def dwconv7_ln(x, dw_w, dw_b, ln_w, ln_b, eps: float, out_dtype=torch.float32) -> torch.Tensor:
+    _chk(x, name="x")
+    B, T, Cc = x.shape
+    out = torch.empty((B, T, Cc), device=x.device, dtype=out_dtype)
+    with torch.cuda.device(x.device):
+        check(_lib.load().l3ac_dwconv7_ln(_ptr(x), B, T, Cc, _ptr(dw_w), _ptr(dw_b), _ptr(ln_w), _ptr(ln_b), eps,
+                                          _ptr(out), _DT[out_dtype], _stream(x)), "l3ac_dwconv7_ln")
+    return out
+
+
+def layernorm(x, w, b, eps: float, out_dtype=torch.float32) -> torch.Tensor:
+    _chk(x, name="x")
+    Cc = x.shape[-1]
+    M = x.numel() // Cc
+    out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    with torch.cuda.device(x.device):
+        check(_lib.load().l3ac_layernorm(_ptr(x), M, Cc, _ptr(w), _ptr(b), eps, _ptr(out), _DT[out_dtype], _stream(x)),
+              "l3ac_layernorm")
+    return out
+
+
+def snake(x, alpha, out_dtype=torch.float32) -> torch.Tensor:
+    _chk(x, name="x")
+    Cc = x.shape[-1]
+    out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    with torch.cuda.device(x.device):
+        check(_lib.load().l3ac_snake(_ptr(x), x.numel() // Cc, Cc, _ptr(alpha), _ptr(out), _DT[out_dtype], _stream(x)),
+              "l3ac_snake")
+    return out
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, *, B: int, T: int, K: int, taps: int = 1, tap_shift0: int = 0,
+         tap_step: int = 1, bias=None, act: int = ACT_NONE, alpha=None, scale=None, shift=None, residual=None,
+         out_dtype=torch.float32, lda: Optional[int] = None) -> torch.Tensor:
+    """out[(b,t), n] = epi(bias[n] + sum_s sum_k a[b, t + shift_s, k] w[n, s*K + k])  (see the header).
+
+    ``a`` is any contiguous tensor whose memory is ``B*T`` rows of pitch ``lda`` (default ``K``); fp32 tensors take
+    the SIMT path, bf16 tensors the tcgen05 path.  Returns ``(B, T, N_out)``.
+    """
+    if a.dtype not in _DT or a.dtype != w.dtype:
+        raise ValueError(f"gemm operands must both be fp32 or both bf16, got {a.dtype} / {w.dtype}")
+    _chk(a, a.dtype, "a")
+    _chk(w, w.dtype, "w")
+    lda = K if lda is None else lda
+    if a.numel() != B * T * lda:
+        raise ValueError(f"a has {a.numel()} elements, expected B*T*lda = {B * T * lda}")
+    N = w.shape[0]
+    if w.shape[1] != taps * K:
+        raise ValueError(f"w must be (N, taps*K) = (N, {taps * K}), got {tuple(w.shape)}")
+    n_out = N // 2 if act == ACT_GEGLU else N
+    out = torch.empty((B, T, n_out), device=a.device, dtype=out_dtype)
+    if residual is not None:
+        _chk(residual, name="residual")
+        if residual.numel() != B * T * n_out:
+            raise ValueError("residual shape mismatch")
+    d = GemmDesc(A=_ptr(a), W=_ptr(w), bias=_ptr(bias), alpha=_ptr(alpha), scale=_ptr(scale), shift=_ptr(shift),
+                 residual=_ptr(residual), out=_ptr(out), lda=lda, ldr=n_out, ldo=n_out, B=B, T=T, K=K, N=N, taps=taps,
+                 tap_shift0=tap_shift0, tap_step=tap_step, act=act, out_dtype=_DT[out_dtype])
+    lib = _lib.load()
+    fn, what = (lib.l3ac_gemm_f32, "l3ac_gemm_f32") if a.dtype == torch.float32 else (lib.l3ac_gemm_bf16_tc,
+                                                                                      "l3ac_gemm_bf16_tc")
+    with torch.cuda.device(a.device):
+        check(fn(C.byref(d), _stream(a)), what)
+    return out
+
+
+def local_attention(qkv: torch.Tensor, bias_table: torch.Tensor, heads: int, window: int) -> torch.Tensor:
+    _chk(qkv, name="qkv")
+    _chk(bias_table, name="bias_table")
+    B, T, three_hd = qkv.shape
+    D = three_hd // (3 * heads)
+    if tuple(bias_table.shape) != (heads, 2 * window):
+        raise ValueError(f"bias_table must be (heads, 2*window), got {tuple(bias_table.shape)}")
+    out = torch.empty((B, T, heads * D), device=qkv.device, dtype=torch.float32)
+    with torch.cuda.device(qkv.device):
+        check(_lib.load().l3ac_local_attention_f32(_ptr(qkv), _ptr(bias_table), B, T, heads, D, window, _ptr(out),
+                                                   _stream(qkv)), "l3ac_local_attention_f32")
+    return out
+
+
+def fsq_quantize(x: torch.Tensor, w_in, b_in, w_out, b_out, levels: Sequence[int], want_z: bool = False):
+    _chk(x, name="x")
+    F = x.shape[-1]
+    lead = x.shape[:-1]
+    M = x.numel() // F
+    D = len(levels)
+    q = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+    idx = torch.empty(lead, device=x.device, dtype=torch.int32)
+    lvl = torch.empty((*lead, D), device=x.device, dtype=torch.float32)
+    z = torch.empty((*lead, D), device=x.device, dtype=torch.float32) if want_z else None
+    with torch.cuda.device(x.device):
+        check(_lib.load().l3ac_fsq_quantize(_ptr(x), M, F, _ptr(w_in), _ptr(b_in), _ptr(w_out), _ptr(b_out),
+                                            _levels(levels), D, _ptr(q), _ptr(idx), _ptr(lvl), _ptr(z), _stream(x)),
+              "l3ac_fsq_quantize")
+    return q, idx, lvl, z
+
+
+def fsq_quantize_latents(z: torch.Tensor, levels: Sequence[int]):
+    _chk(z, name="z")
+    D = len(levels)
+    if z.shape[-1] != D:
+        raise ValueError("last dim of z must equal len(levels)")
+    lead = z.shape[:-1]
+    q = torch.empty(z.shape, device=z.device, dtype=torch.float32)
+    idx = torch.empty(lead, device=z.device, dtype=torch.int32)
+    lvl = torch.empty(z.shape, device=z.device, dtype=torch.float32)
+    with torch.cuda.device(z.device):
+        check(_lib.load().l3ac_fsq_quantize_latents(_ptr(z), z.numel() // D, _levels(levels), D, _ptr(q), _ptr(idx),
+                                                    _ptr(lvl), _stream(z)), "l3ac_fsq_quantize_latents")
+    return q, idx, lvl
+
+
+def fsq_dequantize(indices: torch.Tensor, w_out, b_out, levels: Sequence[int]) -> torch.Tensor:
+    if indices.dtype not in (torch.int32, torch.int64):
+        raise ValueError(f"indices must be int32 or int64, got {indices.dtype}")
+    _chk(indices, indices.dtype, "indices")
+    F = w_out.shape[0]
+    out = torch.empty((*indices.shape, F), device=indices.device, dtype=torch.float32)
+    with torch.cuda.device(indices.device):
+        check(_lib.load().l3ac_fsq_dequantize(_ptr(indices), int(indices.dtype == torch.int64), indices.numel(), F,
+                                              _ptr(w_out), _ptr(b_out), _levels(levels), len(levels), _ptr(out),
+                                              _stream(indices)), "l3ac_fsq_dequantize")
+    return out
+
+
+def upsample_linear_cn(x: torch.Tensor, scale: int, cn_w=None, cn_b=None, eps: float = 1e-8) -> torch.Tensor:
+    _chk(x, name="x")
+    B, T, Cc = x.shape
+    out = torch.empty((B, T * scale, Cc), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        check(_lib.load().l3ac_upsample_linear_cn(_ptr(x), B, T, Cc, scale, _ptr(cn_w), _ptr(cn_b), eps, _ptr(out),
+                                                  _stream(x)), "l3ac_upsample_linear_cn")
+    return out
+
+
+def enhance(x: torch.Tensor, conv_w, conv_b, in_w, in_b, merge_w, merge_b, out_dtype=torch.float32) -> torch.Tensor:
+    _chk(x, name="x")
+    B, T, Cc = x.shape
+    lib = _lib.load()
+    partials = torch.empty(lib.l3ac_enhance_partials_floats(B, T), device=x.device, dtype=torch.float32)
+    out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    with torch.cuda.device(x.device):
+        st = _stream(x)
+        check(lib.l3ac_enhance_stats(_ptr(x), B, T, Cc, _ptr(conv_w), _ptr(conv_b), _ptr(partials), st),
+              "l3ac_enhance_stats")
+        check(lib.l3ac_enhance_apply(_ptr(x), B, T, Cc, _ptr(conv_w), _ptr(conv_b), _ptr(in_w), _ptr(in_b),
+                                     _ptr(merge_w), _ptr(merge_b), _ptr(partials), _ptr(out), _DT[out_dtype], st),
+              "l3ac_enhance_apply")
+    return out
+
+
+def tail_conv_tanh(x: torch.Tensor, alpha, w, bias: float) -> torch.Tensor:
+    _chk(x, name="x")
+    B, T, Cc = x.shape
+    out = torch.empty((B, T), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        check(_lib.load().l3ac_tail_conv_tanh(_ptr(x), B, T, Cc, _ptr(alpha), _ptr(w), float(bias), _ptr(out),
+                                              _stream(x)), "l3ac_tail_conv_tanh")
+    return out

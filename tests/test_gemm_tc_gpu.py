@@ -1,0 +1,84 @@
+"""GPU: the tcgen05/TMEM/TMA GEMM against an fp64 reference computed from the same bf16-rounded operands."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import max_abs
+from l3ac_b200 import ops
+from test_kernels_gpu import _gemm_ref, rnd
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("B,T,K,N,taps,shift0,step", [
+    (1, 128, 64, 32, 1, 0, 1),            # one tile, one k-block
+    (1, 300, 128, 64, 1, 0, 1),           # M tail
+    (1, 1000, 512, 2048, 1, 0, 1),        # pw_conv1 of the C=512 ConvUnit (BN=256, 8 N tiles)
+    (1, 700, 2048, 512, 1, 0, 1),         # pw_conv2 (32 k-blocks, deep pipeline wrap)
+    (2, 333, 96, 384, 1, 0, 1),           # K tail (96 = 64 + 32)
+    (2, 500, 24, 96, 1, 0, 1),            # K < 64
+    (2, 131, 192, 48, 1, 0, 1),           # N tail inside a 64-wide tile
+    (3, 150, 128, 512, 3, -1, 1),         # k3 conv, per-sample zero padding through TMA OOB fill
+    (2, 400, 24, 24, 7, -27, 9),          # dilated k7 LegacyUnit conv, K not a multiple of 64 per tap
+    (1, 260, 128, 576, 1, 0, 1),          # to_qkv: N = 576 -> BN 192
+    (1, 129, 352, 128, 1, 0, 1),          # FeedForward out, K = 352
+    (40, 1779, 256, 1024, 1, 0, 1),       # > 148 tiles per CTA wave: persistent loop + TMEM double buffering
+])
+def test_gemm_tc_matches_fp64(cuda_lib, B, T, K, N, taps, shift0, step):
+    a, w, bias = bf(rnd(B, T, K, seed=1)), bf(rnd(N, taps * K, seed=2, scale=0.1)), rnd(N, seed=3)
+    got = ops.gemm(a.to(DEV), w.to(DEV), B=B, T=T, K=K, taps=taps, tap_shift0=shift0, tap_step=step, bias=bias.to(DEV))
+    torch.cuda.synchronize()
+    if B * T * N > 2e7:      # big case: check a random subset of rows against the reference
+        rows = torch.randint(0, T, (64,))
+        want = _gemm_ref(a.float(), w.float(), bias, taps, shift0, step)[:, rows] if taps > 1 else \
+            (a.double()[:, rows] @ w.double().t() + bias.double())
+        got = got.cpu()[:, rows]
+    else:
+        want = _gemm_ref(a.float(), w.float(), bias, taps, shift0, step)
+        got = got.cpu()
+    tol = 2e-5 * max(1.0, float(want.abs().max())) * max(1.0, (taps * K) ** 0.5 / 8)
+    assert max_abs(got, want) < tol
+
+
+def test_gemm_tc_epilogues(cuda_lib):
+    B, T, K, N = 2, 300, 256, 1024
+    a, w, bias = bf(rnd(B, T, K, seed=1)), bf(rnd(N, K, seed=2, scale=0.05)), rnd(N, seed=3, scale=0.1)
+    alpha, gamma, beta = 0.5 + torch.rand(N), rnd(N, seed=4, scale=0.1), rnd(N, seed=5, scale=0.1)
+    res = rnd(B, T, N, seed=6)
+    lin = (a.double() @ w.double().t() + bias.double())
+    sn = lin + (alpha.double() + 1e-8).reciprocal() * torch.sin(alpha.double() * lin).pow(2)
+    want = sn * (1 + gamma.double()) + beta.double() + res.double()
+    got = ops.gemm(a.to(DEV), w.to(DEV), B=B, T=T, K=K, bias=bias.to(DEV), act=ops.ACT_SNAKE, alpha=alpha.to(DEV),
+                   scale=(1 + gamma).to(DEV), shift=beta.to(DEV), residual=res.to(DEV))
+    assert max_abs(got.cpu(), want) < 2e-4                      # __sinf in the fast epilogue
+    got16 = ops.gemm(a.to(DEV), w.to(DEV), B=B, T=T, K=K, bias=bias.to(DEV), act=ops.ACT_SNAKE, alpha=alpha.to(DEV),
+                     scale=(1 + gamma).to(DEV), shift=beta.to(DEV), out_dtype=torch.bfloat16)
+    want16 = sn * (1 + gamma.double()) + beta.double()
+    assert max_abs(got16.float().cpu(), want16) < 1e-2 * max(1.0, float(want16.abs().max()))
+    # GEGLU (interleaved columns), fp32 and bf16 outputs, N/2 = 352-style tail
+    N2 = 704
+    w2, = (bf(rnd(N2, K, seed=7, scale=0.05)),)
+    lin2 = a.double() @ w2.double().t()
+    want = lin2[..., 0::2] * F.gelu(lin2[..., 1::2])
+    got = ops.gemm(a.to(DEV), w2.to(DEV), B=B, T=T, K=K, act=ops.ACT_GEGLU)
+    assert max_abs(got.cpu(), want) < 2e-5 * max(1.0, float(want.abs().max())) * 4
+    got16 = ops.gemm(a.to(DEV), w2.to(DEV), B=B, T=T, K=K, act=ops.ACT_GEGLU, out_dtype=torch.bfloat16)
+    assert max_abs(got16.float().cpu(), want) < 1e-2 * max(1.0, float(want.abs().max()))
+
+
+def test_gemm_tc_linearity_at_full_size(cuda_lib):
+    """Size-independent property at the bench shape (B=16 x 8895 rows, C=256 MLP): GEMM(a1 + a2) == GEMM(a1) + GEMM(a2)."""
+    B, T, K, N = 16, 8895, 256, 1024
+    g = torch.Generator(device=DEV).manual_seed(0)
+    a1 = (torch.randint(-8, 9, (B, T, K), generator=g, device=DEV).float() / 8).to(torch.bfloat16)   # exactly representable
+    a2 = (torch.randint(-8, 9, (B, T, K), generator=g, device=DEV).float() / 8).to(torch.bfloat16)
+    w = (torch.randint(-4, 5, (N, K), generator=g, device=DEV).float() / 16).to(torch.bfloat16)
+    y1 = ops.gemm(a1, w, B=B, T=T, K=K)
+    y2 = ops.gemm(a2, w, B=B, T=T, K=K)
+    y12 = ops.gemm((a1.float() + a2.float()).to(torch.bfloat16), w, B=B, T=T, K=K)
+    assert torch.equal(y12, y1 + y2)          # all products/sums are exact in fp32 for these dyadic operands

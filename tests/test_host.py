@@ -1,0 +1,95 @@
+"""CPU: host-side logic -- config names and fields, checkpoint key inventory, C-ABI exports, error behaviour."""
+import ctypes
+import json
+import re
+from pathlib import Path
+
+import pytest
+import torch
+
+import l3ac_b200
+from helpers import CONFIGS, GOLDEN, model_config
+from l3ac_b200 import _lib
+from l3ac_b200.config import CONFIG_DIR, L3ACConfig, ModelConfig
+from l3ac_b200.spec import init_state_dicts, network_spec
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_list_models():
+    assert set(CONFIGS) <= set(l3ac_b200.list_models())
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_spec_matches_reference_checkpoint_keys(name):
+    """Key names and shapes equal the reference state_dicts (dumped from the reference by oracle/make_golden.py)."""
+    ref = json.loads((GOLDEN / "state_dict_keys.json").read_text())[name]
+    spec = network_spec(model_config(name))
+    assert set(spec) == set(ref)
+    for mod in spec:
+        assert {k: list(v[0]) for k, v in spec[mod].items()} == ref[mod], mod
+
+
+def test_config_fields_and_validation(tmp_path):
+    cfg = L3ACConfig(config_file=CONFIG_DIR / "1kbps.toml")
+    assert cfg.sample_rate == 16000 and cfg.model_name == "1kbps" and cfg.model_tag == "1kbps.v1"
+    mc = cfg.network_config
+    assert mc.feature_dim == 128 and mc.compress_rates == (6, 5, 3) and mc.hop_length == 270
+    assert mc.levels == (7, 7, 7, 7, 7, 7)
+    bad = tmp_path / "bad.toml"
+    bad.write_text('model_tag = "x"\n[network_config]\nfeature_dim = 128\n')
+    with pytest.raises(ValueError):
+        L3ACConfig(config_file=bad)
+    with pytest.raises(ValueError):
+        ModelConfig(compress_rates=(2, 2), encoder_dims=(8, 16), encoder_depths=(1, 1))
+
+
+def test_network_state_dict_round_trip(tmp_path):
+    mc = model_config("3kbps")
+    net = l3ac_b200.EnCodec(mc, seed=1)
+    assert list(net.trainable_modules) == ["encoder", "quantizer", "decoder", "en_encoder", "en_decoder"]
+    w = init_state_dicts(mc, seed=2, jitter=True)
+    net.load_state_dicts(w)
+    for mod, sd in w.items():
+        got = getattr(net, mod).state_dict()
+        assert list(got) == list(sd) and all(torch.equal(got[k], sd[k]) for k in sd)
+    net.save_model(model_path=tmp_path / "m")
+    net2 = l3ac_b200.EnCodec(mc, seed=5)
+    net2.load_model(model_path=tmp_path / "m")
+    assert torch.equal(net2.decoder.state_dict()["blocks.0.bias"], w["decoder"]["blocks.0.bias"])
+    padded, n = net.preprocess(torch.zeros(2, 1000))
+    assert n == 1000 and padded.shape == (2, 1056)
+
+
+def test_header_symbols_are_bound_and_exported():
+    """Every function the header declares has a ctypes prototype, and the built library exports it."""
+    header = (ROOT / "include" / "l3ac_b200.h").read_text()
+    declared = set(re.findall(r"\b(l3ac_[a-z0-9_]+)\s*\(", header)) - {"l3ac_gemm_desc"}
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    if not _lib.LIB_PATH.exists():
+        import __graft_entry__
+        __graft_entry__.build()
+    # dlopen needs libcuda only for kernel launches; resolving symbols works without a GPU
+    lib = ctypes.CDLL(str(_lib.LIB_PATH))
+    for name in declared:
+        assert hasattr(lib, name), f"{name} not exported"
+    assert lib.l3ac_abi_version() == 1
+
+
+def test_gemm_desc_layout_matches_header():
+    """The ctypes mirror of l3ac_gemm_desc has the C layout (8 pointers, 3 int64, 9 int32 -> 128 bytes)."""
+    assert ctypes.sizeof(_lib.GemmDesc) == 8 * 8 + 3 * 8 + 9 * 4 + 4
+    assert _lib.GemmDesc.lda.offset == 64 and _lib.GemmDesc.B.offset == 88 and _lib.GemmDesc.out_dtype.offset == 120
+
+
+def test_no_cpu_fallback():
+    """The product refuses to run without CUDA instead of silently computing on the host."""
+    net = l3ac_b200.EnCodec(model_config("1kbps"))
+    codec = l3ac_b200.L3AC(L3ACConfig(config_file=CONFIG_DIR / "1kbps.toml"))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            codec.encode_audio(torch.zeros(1, 16000))
+        with pytest.raises(RuntimeError):
+            net.engine
+    src = "".join(p.read_text() for p in (ROOT / "l3ac_b200").glob("*.py"))
+    assert "oracle" not in src.replace("# oracle", ""), "product code must not reference the oracle"

@@ -1,0 +1,208 @@
+"""GPU: per-kernel parity through the C ABI against the oracle's functions (CPU fp32) on seeded inputs."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import max_abs
+from l3ac_b200 import ops
+from oracle import l3ac_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def cl(x):      # (B, C, T) -> channels-last (B, T, C) on the GPU
+    return x.permute(0, 2, 1).contiguous().to(DEV)
+
+
+def cf(y):      # channels-last GPU tensor -> (B, C, T) on the CPU
+    return y.float().cpu().permute(0, 2, 1)
+
+
+def test_stem(cuda_lib):
+    B, T = 2, 1000
+    sd = {}
+    for i in range(5):
+        sd[f"s.blocks.{i}.1.weight"], sd[f"s.blocks.{i}.1.bias"] = rnd(4, 1, 7, seed=i, scale=0.3), rnd(4, seed=10 + i, scale=0.1)
+    sd["s.conv_1.weight"], sd["s.conv_1.bias"] = rnd(80, 20, 1, seed=20, scale=0.2), rnd(80, seed=21, scale=0.1)
+    sd["s.conv_2.weight"], sd["s.conv_2.bias"] = rnd(24, 81, 1, seed=22, scale=0.2), rnd(24, seed=23, scale=0.1)
+    x = rnd(B, 1, T, seed=30, scale=0.3)
+    want = O.first_block(sd, "s", x)
+    bw = torch.stack([sd[f"s.blocks.{i}.1.weight"][:, 0] for i in range(5)]).contiguous().to(DEV)
+    bb = torch.cat([sd[f"s.blocks.{i}.1.bias"] for i in range(5)]).to(DEV)
+    got = ops.stem(x[:, 0].contiguous().to(DEV), bw, bb, sd["s.conv_1.weight"][:, :, 0].contiguous().to(DEV),
+                   sd["s.conv_1.bias"].to(DEV), sd["s.conv_2.weight"][:, :, 0].contiguous().to(DEV), sd["s.conv_2.bias"].to(DEV))
+    assert max_abs(cf(got), want) < 2e-5
+
+
+@pytest.mark.parametrize("C,T", [(24, 300), (96, 77), (192, 50), (512, 40)])
+def test_dwconv7_ln(cuda_lib, C, T):
+    x = rnd(2, C, T, seed=1)
+    w, b = rnd(C, 1, 7, seed=2, scale=0.3), rnd(C, seed=3, scale=0.1)
+    lw, lb = 1 + rnd(C, seed=4, scale=0.1), rnd(C, seed=5, scale=0.1)
+    want = F.layer_norm(F.conv1d(x, w, b, padding=3, groups=C).permute(0, 2, 1), (C,), lw, lb, 1e-8)
+    got = ops.dwconv7_ln(cl(x), w[:, 0].t().contiguous().to(DEV), b.to(DEV), lw.to(DEV), lb.to(DEV), 1e-8)
+    assert max_abs(got.cpu(), want) < 2e-5
+    got16 = ops.dwconv7_ln(cl(x), w[:, 0].t().contiguous().to(DEV), b.to(DEV), lw.to(DEV), lb.to(DEV), 1e-8, torch.bfloat16)
+    assert max_abs(got16.float().cpu(), want) < 3e-2
+
+
+@pytest.mark.parametrize("C", [48, 128, 192])
+def test_layernorm_is_channel_norm(cuda_lib, C):
+    x = rnd(2, C, 33, seed=1)
+    w, b = 1 + rnd(C, seed=2, scale=0.1), rnd(C, seed=3, scale=0.1)
+    want = O.channel_norm_cf(x, w, b)
+    got = ops.layernorm(cl(x), w.to(DEV), b.to(DEV), 1e-8)
+    assert max_abs(cf(got), want) < 2e-5
+
+
+def _gemm_ref(a, w, bias, taps, shift0, step):
+    """a (B,T,K), w (N, taps*K): sum over taps of shifted rows (zero padded)."""
+    B, T, K = a.shape
+    out = torch.zeros(B, T, w.shape[0], dtype=torch.float64)
+    for s in range(taps):
+        sh = shift0 + s * step
+        shifted = torch.zeros_like(a, dtype=torch.float64)
+        lo, hi = max(0, -sh), min(T, T - sh)
+        if hi > lo:
+            shifted[:, lo:hi] = a[:, lo + sh:hi + sh].double()
+        out += shifted @ w[:, s * K:(s + 1) * K].double().t()
+    return out + (0 if bias is None else bias.double())
+
+
+@pytest.mark.parametrize("B,T,K,N,taps,shift0,step", [
+    (1, 300, 24, 96, 1, 0, 1), (2, 131, 96, 24, 1, 0, 1), (2, 200, 144, 48, 1, 0, 1),
+    (2, 150, 192, 128, 3, -1, 1), (2, 400, 24, 24, 7, -27, 9), (1, 260, 512, 2048, 1, 0, 1), (1, 129, 352, 128, 1, 0, 1)])
+def test_gemm_f32(cuda_lib, B, T, K, N, taps, shift0, step):
+    a, w, bias = rnd(B, T, K, seed=1), rnd(N, taps * K, seed=2, scale=0.1), rnd(N, seed=3)
+    want = _gemm_ref(a, w, bias, taps, shift0, step)
+    got = ops.gemm(a.to(DEV), w.to(DEV), B=B, T=T, K=K, taps=taps, tap_shift0=shift0, tap_step=step, bias=bias.to(DEV))
+    assert max_abs(got.cpu(), want) < 1e-4 * max(1.0, float(want.abs().max()))
+
+
+def test_gemm_f32_epilogues(cuda_lib):
+    B, T, K, N = 2, 100, 48, 192
+    a, w, bias = rnd(B, T, K, seed=1), rnd(N, K, seed=2, scale=0.2), rnd(N, seed=3, scale=0.1)
+    alpha, gamma, beta = 0.5 + torch.rand(N), rnd(N, seed=4, scale=0.1), rnd(N, seed=5, scale=0.1)
+    res = rnd(B, T, N, seed=6)
+    lin = F.linear(a, w, bias)
+    want = O.grn(O.snake(lin, alpha.view(1, 1, -1)), gamma.view(1, -1), beta.view(1, -1)) + res
+    got = ops.gemm(a.to(DEV), w.to(DEV), B=B, T=T, K=K, bias=bias.to(DEV), act=ops.ACT_SNAKE, alpha=alpha.to(DEV),
+                   scale=(1 + gamma).to(DEV), shift=beta.to(DEV), residual=res.to(DEV))
+    assert max_abs(got.cpu(), want) < 2e-5
+    # GEGLU with interleaved (value, gate) columns
+    val, gate = lin.chunk(2, dim=-1)
+    wi = torch.empty_like(w)
+    wi[0::2], wi[1::2] = w[:N // 2], w[N // 2:]
+    bi = torch.empty_like(bias)
+    bi[0::2], bi[1::2] = bias[:N // 2], bias[N // 2:]
+    got = ops.gemm(a.to(DEV), wi.to(DEV), B=B, T=T, K=K, bias=bi.to(DEV), act=ops.ACT_GEGLU)
+    assert max_abs(got.cpu(), val * F.gelu(gate)) < 2e-5
+
+
+@pytest.mark.parametrize("T,w", [(100, 40), (333, 100), (593, 250), (64, 200), (257, 64)])
+def test_local_attention(cuda_lib, T, w):
+    B, H, D = 2, 6, 32
+    qkv = rnd(B, T, 3 * H * D, seed=T)
+    table = rnd(H, 2 * w, seed=w, scale=0.5)
+    q, k, v = (t.reshape(B, T, H, D).transpose(1, 2).reshape(B * H, T, D) for t in qkv.chunk(3, dim=-1))
+    idx = (torch.arange(w, 2 * w)[:, None] - torch.arange(2 * w)[None, :]).abs()
+    bias = table[:, idx]                                                       # (H, w, 2w) as DynamicPositionBias builds it
+    want = O.local_attention(q, k, v, bias, w).reshape(B, H, T, D).transpose(1, 2).reshape(B, T, H * D)
+    got = ops.local_attention(qkv.to(DEV), table.to(DEV), H, w)
+    assert max_abs(got.cpu(), want) < 2e-5
+
+
+@pytest.mark.parametrize("levels", [(7, 7, 7, 7, 7, 7), (9, 9, 9, 7, 7, 7)])
+def test_fsq_bit_exact_from_reference_latents(cuda_lib, levels):
+    """Indices are bit-exact when the quantiser is fed the reference latents (north-star criterion)."""
+    z = rnd(20000, 6, seed=1, scale=1.5)
+    q_z, idx, lvl = O.fsq_quantize(z, levels)
+    gq, gidx, glvl = ops.fsq_quantize_latents(z.to(DEV), levels)
+    # exempt values within 1e-5 level units of a rounding tie (tanhf may differ by an ulp between libm and CUDA)
+    a = (torch.tanh(z.double()) + 1) / 2 * (torch.tensor(levels) - 1)
+    safe = ((a - a.floor() - 0.5).abs() > 1e-5).all(dim=-1)
+    assert safe.float().mean() > 0.999
+    assert torch.equal(gidx.cpu()[safe], idx[safe])
+    assert torch.equal(glvl.cpu()[safe], lvl[safe]) and torch.equal(gq.cpu()[safe], q_z[safe])
+    # whole codebook: dequantise every index and re-quantise its latents
+    n = int(torch.tensor(levels).prod())
+    all_idx = torch.arange(n, dtype=torch.int32)
+    w_out, b_out = rnd(128, 6, seed=2, scale=0.3), rnd(128, seed=3, scale=0.1)
+    feats = ops.fsq_dequantize(all_idx.to(DEV), w_out.to(DEV), b_out.to(DEV), levels)
+    want = F.linear(O.fsq_indices_to_codes(all_idx, levels), w_out, b_out)
+    assert max_abs(feats.cpu(), want) < 1e-6
+    feats64 = ops.fsq_dequantize(all_idx.long().to(DEV), w_out.to(DEV), b_out.to(DEV), levels)
+    assert torch.equal(feats64, feats)
+
+
+def test_fsq_quantize_full(cuda_lib):
+    levels = (7, 7, 7, 7, 7, 7)
+    sd = dict({"project_in.weight": rnd(6, 128, seed=1, scale=0.1), "project_in.bias": rnd(6, seed=2, scale=0.1),
+               "project_out.weight": rnd(128, 6, seed=3, scale=0.3), "project_out.bias": rnd(128, seed=4, scale=0.1)})
+    x = rnd(3, 211, 128, seed=5)
+    q, info, z = O.quantizer_forward(sd, {"vq_config": {"levels": levels}}, x)
+    gq, gidx, glvl, gz = ops.fsq_quantize(x.to(DEV), *(sd[k].to(DEV) for k in ("project_in.weight", "project_in.bias",
+                                                                               "project_out.weight", "project_out.bias")),
+                                          levels, want_z=True)
+    assert max_abs(gz.cpu(), z) < 1e-5
+    agree = (gidx.cpu() == info["indices"]).float().mean().item()
+    assert agree > 0.999
+    same = gidx.cpu() == info["indices"]
+    assert max_abs(gq.cpu()[same], q[same]) < 1e-5
+    # self-consistency: dequantising our indices gives our q_feature bit for bit
+    deq = ops.fsq_dequantize(gidx, sd["project_out.weight"].to(DEV), sd["project_out.bias"].to(DEV), levels)
+    assert torch.equal(deq, gq)
+
+
+@pytest.mark.parametrize("C,T,s", [(128, 50, 3), (256, 33, 5), (24, 100, 2), (96, 7, 4)])
+def test_upsample_linear_cn(cuda_lib, C, T, s):
+    x = rnd(2, C, T, seed=1)
+    w, b = 1 + rnd(C, seed=2, scale=0.1), rnd(C, seed=3, scale=0.1)
+    up = F.interpolate(x, scale_factor=s, mode="linear", align_corners=False)
+    got = ops.upsample_linear_cn(cl(x), s)
+    assert max_abs(cf(got), up) < 1e-6
+    got = ops.upsample_linear_cn(cl(x), s, w.to(DEV), b.to(DEV), 1e-8)
+    assert max_abs(cf(got), O.channel_norm_cf(up, w, b)) < 2e-5
+
+
+@pytest.mark.parametrize("C,T", [(48, 3000), (512, 130), (96, 1025)])
+def test_enhance_block(cuda_lib, C, T):
+    sd = {}
+    for k in range(4):
+        sd[f"e.blocks.{k}.1.weight"], sd[f"e.blocks.{k}.1.bias"] = rnd(1, 1, 7, seed=k, scale=0.4), rnd(1, seed=10 + k, scale=0.1)
+    sd["e.merge_layer.0.weight"], sd["e.merge_layer.0.bias"] = 1 + rnd(4, seed=20, scale=0.1), rnd(4, seed=21, scale=0.1)
+    sd["e.merge_layer.1.weight"], sd["e.merge_layer.1.bias"] = rnd(C, 4, 1, seed=22, scale=0.3), rnd(C, seed=23, scale=0.1)
+    x = rnd(2, C, T, seed=30)
+    want = O.enhance_block(sd, "e", x)
+    got = ops.enhance(cl(x), torch.stack([sd[f"e.blocks.{k}.1.weight"][0, 0] for k in range(4)]).contiguous().to(DEV),
+                      torch.cat([sd[f"e.blocks.{k}.1.bias"] for k in range(4)]).to(DEV), sd["e.merge_layer.0.weight"].to(DEV),
+                      sd["e.merge_layer.0.bias"].to(DEV), sd["e.merge_layer.1.weight"][:, :, 0].contiguous().to(DEV),
+                      sd["e.merge_layer.1.bias"].to(DEV))
+    assert max_abs(cf(got), want) < 5e-5
+
+
+def test_snake_and_tail(cuda_lib):
+    C, T = 24, 700
+    x = rnd(2, C, T, seed=1)
+    alpha = 0.5 + torch.rand(C)
+    got = ops.snake(cl(x), alpha.to(DEV))
+    assert max_abs(cf(got), O.snake(x, alpha.view(1, -1, 1))) < 1e-6
+    w, b = rnd(1, C, 7, seed=2, scale=0.2), rnd(1, seed=3, scale=0.1)
+    want = torch.tanh(F.conv1d(O.snake(x, alpha.view(1, -1, 1)), w, b, padding=3))[:, 0]
+    got = ops.tail_conv_tanh(cl(x), alpha.to(DEV), w[0].t().contiguous().to(DEV), float(b))
+    assert max_abs(got.cpu(), want) < 1e-5
+
+
+def test_argument_validation(cuda_lib):
+    with pytest.raises(ValueError):
+        ops.snake(torch.zeros(4, 4), torch.ones(4))                                        # CPU tensor
+    with pytest.raises(ValueError):
+        ops.gemm(torch.zeros(8, 8, device=DEV), torch.zeros(4, 9, device=DEV), B=1, T=8, K=8)   # bad weight shape
+    with pytest.raises(ValueError):
+        ops.fsq_quantize_latents(torch.zeros(4, 6, device=DEV), (1, 7, 7, 7, 7, 7))       # level < 2

@@ -1,0 +1,116 @@
+"""GPU: the full encode -> quantize -> decode path through the public API against the oracle and golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+import l3ac_b200
+from helpers import CONFIGS, golden_case, make_audio, max_abs, model_config, snr_db
+from l3ac_b200.config import CONFIG_DIR, L3ACConfig
+from l3ac_b200.spec import init_state_dicts
+from oracle import l3ac_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def build(name, weights, precision):
+    codec = l3ac_b200.L3AC(L3ACConfig(config_file=CONFIG_DIR / f"{name}.toml"), precision=precision)
+    codec.network.load_state_dicts(weights)
+    codec.network.cuda()
+    codec.network.eval()
+    return codec
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_fp32_mode_matches_golden(cuda_lib, name):
+    """fp32 mode against the reference's golden vectors: latents to 1e-5 class, indices equal away from rounding
+    ties, waveform to 1e-4 (the reference's own batch-shape noise is 7e-6)."""
+    mc, weights, audio, g = golden_case(name)
+    codec = build(name, weights, "fp32")
+    taps = {}
+    with torch.inference_mode():
+        q, idx = codec.network.engine.encode(audio.to(DEV), taps)
+        wav_from_ref_idx = codec.decode_audio(indices=torch.from_numpy(g["indices"]).to(DEV))
+        wav = codec.decode_audio(q)
+    z_err = max_abs(taps["z"].cpu(), torch.from_numpy(g["z"]))
+    agree = float((idx["indices"].cpu().numpy() == g["indices"]).mean())
+    stride = int(g["wav_stride"])
+    ref_wav = torch.from_numpy(g["wav"])
+    wav_err = max_abs(wav_from_ref_idx.cpu()[:, ::stride], ref_wav)
+    print(f"[{name}] z max-abs {z_err:.2e}  index agreement {agree:.5f}  wav max-abs {wav_err:.2e} "
+          f"snr {snr_db(ref_wav, wav_from_ref_idx.cpu()[:, ::stride]):.1f} dB")
+    assert z_err < 2e-4
+    assert agree >= 0.999
+    assert wav_err < 1e-4
+    assert idx["indices"].dtype == torch.int32 and idx["level_indices"].dtype == torch.float32
+    assert q.shape == (audio.shape[0], g["indices"].shape[1], 128) and wav.shape[1] == g["indices"].shape[1] * mc.hop_length
+    if agree == 1.0:
+        assert max_abs(wav.cpu()[:, ::stride], ref_wav) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["1kbps", "3kbps"])
+def test_bf16_mode_tolerance(cuda_lib, name):
+    """Default mode (bf16 tensor-core decode side, fp32 encode side): index agreement >= 99.9 %, waveform SNR stated."""
+    mc, weights, audio, g = golden_case(name)
+    codec = build(name, weights, "bf16")
+    with torch.inference_mode():
+        q, idx = codec.encode_audio(audio.to(DEV))
+        wav = codec.decode_audio(indices=torch.from_numpy(g["indices"]).to(DEV))
+    agree = float((idx["indices"].cpu().numpy() == g["indices"]).mean())
+    stride = int(g["wav_stride"])
+    ref_wav = torch.from_numpy(g["wav"])
+    snr = snr_db(ref_wav, wav.cpu()[:, ::stride])
+    err = max_abs(wav.cpu()[:, ::stride], ref_wav)
+    print(f"[{name}] bf16: index agreement {agree:.5f}  wav snr {snr:.1f} dB  max-abs {err:.3e}")
+    assert agree >= 0.999
+    assert snr > 18.0 and err < 0.3        # random-init nets are not contractive: SURVEY.md section 8d (iii)
+
+
+def test_api_surface_and_invariants(cuda_lib):
+    name = "1k5bps"
+    mc = model_config(name)
+    weights = init_state_dicts(mc, seed=11, jitter=True)
+    codec = build(name, weights, "fp32")
+    audio = make_audio(3, 1.7, seed=9).to(DEV)
+    with torch.inference_mode():
+        q, idx = codec.encode_audio(audio)
+        a = codec.decode_audio(q)                       # positional q_feature, README.md:61
+        b = codec.decode_audio(indices=idx["indices"])
+        c = codec.decode_audio(indices=idx["indices"].long())
+        assert torch.equal(a, b) and torch.equal(b, c)  # decode(q_feature) == decode(indices=) bit-exact
+        q1, idx1 = codec.encode_audio(audio[1:2])
+        assert torch.equal(idx1["indices"], idx["indices"][1:2])    # batch independence
+        out = codec.network(audio)
+        assert torch.equal(out["indices"], idx["indices"]) and out["generated_audio"].shape == audio.shape
+    with pytest.raises(RuntimeError):
+        codec.encode_audio(audio[0])                    # 1-D input, like the reference's conv shape error
+    with pytest.raises(AttributeError):
+        codec.decode_audio()
+    # oracle agreement on a ragged length (not a multiple of hop) and an empty-ish clip
+    orc = O.Oracle(mc.as_dict(), weights)
+    oq, oidx = orc.encode_audio(audio.cpu())
+    assert (oidx["indices"] == idx["indices"].cpu()).float().mean() >= 0.999
+    assert max_abs(orc.decode_audio(indices=idx["indices"].cpu()), b.cpu()) < 1e-4
+    short = make_audio(1, 0.01, seed=2).to(DEV)       # 160 samples -> one hop
+    with torch.inference_mode():
+        qs, ids = codec.encode_audio(short)
+    assert ids["indices"].shape == (1, 1)
+    assert torch.equal(ids["indices"].cpu(), orc.encode_audio(short.cpu())[1]["indices"])
+
+
+def test_round_trip_at_bench_size(cuda_lib):
+    """BASELINE config #2 shape (1kbps, 10 s clips, a micro-batch of it): properties that need no oracle run."""
+    codec = l3ac_b200.get_model("1kbps", pretrained=False)
+    codec.network.cuda()
+    audio = make_audio(8, 10.0, seed=3).to(DEV)
+    audio[4:] = audio[:4]                                   # duplicate clips must give identical results
+    with torch.inference_mode():
+        q, idx = codec.encode_audio(audio)
+        wav = codec.decode_audio(indices=idx["indices"])
+    assert idx["indices"].shape == (8, 593) and wav.shape == (8, 160110)
+    assert int(idx["indices"].min()) >= 0 and int(idx["indices"].max()) < 7 ** 6
+    assert torch.equal(idx["indices"][4:], idx["indices"][:4]) and torch.equal(wav[4:], wav[:4])
+    assert torch.isfinite(wav).all() and float(wav.abs().max()) <= 1.0
+    lv = idx["level_indices"].long()
+    basis = torch.tensor([1, 7, 49, 343, 2401, 16807], device=DEV)
+    assert torch.equal((lv * basis).sum(-1).int(), idx["indices"])   # mixed-radix checksum of the level digits
