@@ -35,6 +35,7 @@ extern "C" {
 /* activation element types for `out_dtype` */
 #define L3AC_F32 0
 #define L3AC_BF16 1
+#define L3AC_BF16X2 2 /* split pair: out = bf16(x) plane, out_lo = bf16(x - hi) plane (same shape and pitch) */
 
 /* epilogue activations of the GEMM entry points */
 #define L3AC_ACT_NONE 0
@@ -62,16 +63,21 @@ int l3ac_stem(const float* audio, int B, int T, const float* branch_w, const flo
 /* ------------------------------------------------------------------------------------------
  * ConvUnit prologue.  Replaces dw_conv + permute + norm of ConvUnit.forward
  * (l3ac/modules.py:33-35; F.layer_norm at l3ac/layers.py:80): depthwise Conv1d(C,C,k7,pad 3) then
- * LayerNorm over C.  x (B,T,C) fp32 -> out (B,T,C) fp32|bf16.  dw_w is [7][C] (tap-major).
+ * LayerNorm over C.  x (B,T,C) fp32 -> out (B,T,C) fp32|bf16|bf16 (hi,lo) pair.  dw_w is [7][C]
+ * (tap-major).  out_lo is the low-order plane for L3AC_BF16X2, NULL otherwise.
  * ------------------------------------------------------------------------------------------ */
 int l3ac_dwconv7_ln(const float* x, int B, int T, int C, const float* dw_w, const float* dw_b,
-                    const float* ln_w, const float* ln_b, float eps, void* out, int out_dtype,
+                    const float* ln_w, const float* ln_b, float eps, void* out, void* out_lo, int out_dtype,
                     l3ac_stream_t stream);
 
 /* LayerNorm over the last dim.  Replaces channels-first ChannelNorm (l3ac/layers.py:50-56) after the
  * strided convs and nn.LayerNorm inside local_attention's LocalMHA / FeedForward. */
 int l3ac_layernorm(const float* x, long long M, int C, const float* w, const float* b, float eps,
-                   void* out, int out_dtype, l3ac_stream_t stream);
+                   void* out, void* out_lo, int out_dtype, l3ac_stream_t stream);
+
+/* fp32 -> (hi, lo) bf16 planes with hi = bf16(x), lo = bf16(x - hi): the operand format of the split GEMM.
+ * n must be a multiple of 4. */
+int l3ac_split_bf16(const float* x, long long n, void* hi, void* lo, l3ac_stream_t stream);
 
 /* Elementwise snake (l3ac/layers.py:29-33), per-channel alpha [C]. */
 int l3ac_snake(const float* x, long long M, int C, const float* alpha, void* out, int out_dtype,
@@ -100,6 +106,9 @@ typedef struct l3ac_gemm_desc {
     const float* shift;    /* [N] or NULL (ACT_SNAKE)                                               */
     const float* residual; /* [B*T, ldr] fp32 or NULL                                               */
     void* out;             /* [B*T, ldo] fp32 or bf16                                               */
+    const void* A_lo;      /* tcgen05 path only: low-order bf16 plane of A (same layout) or NULL       */
+    const void* W_lo;      /* tcgen05 path only: low-order bf16 plane of W; given iff A_lo is given    */
+    void* out_lo;          /* low-order output plane when out_dtype == L3AC_BF16X2                    */
     long long lda, ldr, ldo; /* row pitches in elements                                            */
     int B, T, K, N;
     int taps, tap_shift0, tap_step;
@@ -110,7 +119,8 @@ typedef struct l3ac_gemm_desc {
 int l3ac_gemm_f32(const l3ac_gemm_desc* d, l3ac_stream_t stream);
 
 /* bf16 x bf16 -> fp32 tcgen05/TMEM path fed by TMA.  A and W are bf16; lda and taps*K must be
- * multiples of 8 (16-byte TMA pitch).  `ws` is reserved (pass NULL). */
+ * multiples of 8 (16-byte TMA pitch).  With A_lo/W_lo the product is the 3-term split
+ * A_hi*W_hi + A_lo*W_hi + A_hi*W_lo (fp32-class accuracy at bf16 tensor-core rate). */
 int l3ac_gemm_bf16_tc(const l3ac_gemm_desc* d, l3ac_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -9,7 +9,7 @@ from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent / "libl3ac_b200.so"
 
-F32, BF16 = 0, 1
+F32, BF16, BF16X2 = 0, 1, 2
 ACT_NONE, ACT_SNAKE, ACT_GEGLU, ACT_GELU, ACT_TANH = 0, 1, 2, 3, 4
 
 _p, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
@@ -19,6 +19,7 @@ class GemmDesc(C.Structure):
     """``l3ac_gemm_desc`` (include/l3ac_b200.h)."""
     _fields_ = [
         ("A", _p), ("W", _p), ("bias", _p), ("alpha", _p), ("scale", _p), ("shift", _p), ("residual", _p), ("out", _p),
+        ("A_lo", _p), ("W_lo", _p), ("out_lo", _p),
         ("lda", _ll), ("ldr", _ll), ("ldo", _ll),
         ("B", _i), ("T", _i), ("K", _i), ("N", _i),
         ("taps", _i), ("tap_shift0", _i), ("tap_step", _i),
@@ -31,8 +32,9 @@ PROTOTYPES = {
     "l3ac_abi_version": (_i, []),
     "l3ac_error_string": (C.c_char_p, [_i]),
     "l3ac_stem": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p]),
-    "l3ac_dwconv7_ln": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _f, _p, _i, _p]),
-    "l3ac_layernorm": (_i, [_p, _ll, _i, _p, _p, _f, _p, _i, _p]),
+    "l3ac_dwconv7_ln": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _f, _p, _p, _i, _p]),
+    "l3ac_layernorm": (_i, [_p, _ll, _i, _p, _p, _f, _p, _p, _i, _p]),
+    "l3ac_split_bf16": (_i, [_p, _ll, _p, _p, _p]),
     "l3ac_snake": (_i, [_p, _ll, _i, _p, _p, _i, _p]),
     "l3ac_gemm_f32": (_i, [C.POINTER(GemmDesc), _p]),
     "l3ac_gemm_bf16_tc": (_i, [C.POINTER(GemmDesc), _p]),

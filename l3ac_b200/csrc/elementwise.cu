@@ -9,6 +9,18 @@
 
 namespace l3ac {
 
+// Writes v as OutT; for the split pair (OutT = bf16 and lo != nullptr) also the low-order plane bf16(v - hi).
+template <typename OutT>
+__device__ __forceinline__ void store_act(OutT* hi, OutT* lo, long long i, float v) {
+    hi[i] = cvt_out<OutT>(v);
+}
+template <>
+__device__ __forceinline__ void store_act<__nv_bfloat16>(__nv_bfloat16* hi, __nv_bfloat16* lo, long long i, float v) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
 // ------------------------------------------------------------------------------------------
 // depthwise conv k7 (pad 3) + LayerNorm over C.  One warp per (b, t) row; lane owns channels
 // lane, lane+32, ...  Weights are staged in shared memory ([7][C] taps, bias, ln w/b).
@@ -19,7 +31,7 @@ __global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* __restrict
                                                          const float* __restrict__ dw_b,
                                                          const float* __restrict__ ln_w,
                                                          const float* __restrict__ ln_b, float eps,
-                                                         OutT* __restrict__ out) {
+                                                         OutT* __restrict__ out, OutT* __restrict__ out_lo) {
     extern __shared__ float sm[];
     float* s_w = sm;             // [7][C]
     float* s_b = sm + 7 * C;     // [C]
@@ -68,11 +80,10 @@ __global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* __restrict
             v += (lane + 32 * i < C) ? dlt * dlt : 0.f;
         }
         const float rstd = 1.0f / sqrtf(warp_sum(v) / (float)C + eps);
-        OutT* orow = out + row * C;
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
             const int c = lane + 32 * i;
-            if (c < C) orow[c] = cvt_out<OutT>((acc[i] - mean) * rstd * s_lw[c] + s_lb[c]);
+            if (c < C) store_act<OutT>(out, out_lo, row * C + c, (acc[i] - mean) * rstd * s_lw[c] + s_lb[c]);
         }
     }
 }
@@ -81,7 +92,7 @@ template <int CPL, typename OutT>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, long long M, int C,
                                                         const float* __restrict__ w,
                                                         const float* __restrict__ b, float eps,
-                                                        OutT* __restrict__ out) {
+                                                        OutT* __restrict__ out, OutT* __restrict__ out_lo) {
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     for (long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M;
@@ -103,12 +114,30 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
             q += (lane + 32 * i < C) ? dlt * dlt : 0.f;
         }
         const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
-        OutT* orow = out + row * C;
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
             const int c = lane + 32 * i;
-            if (c < C) orow[c] = cvt_out<OutT>((v[i] - mean) * rstd * __ldg(w + c) + __ldg(b + c));
+            if (c < C) store_act<OutT>(out, out_lo, row * C + c, (v[i] - mean) * rstd * __ldg(w + c) + __ldg(b + c));
         }
+    }
+}
+
+// fp32 -> (hi, lo) bf16 planes, 4 elements per thread
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ x, long long n4,
+                                                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+        const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+        const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+        const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y);
+        const __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
+        uint2 ph, pl;
+        ph.x = *reinterpret_cast<const uint32_t*>(&h01);
+        ph.y = *reinterpret_cast<const uint32_t*>(&h23);
+        pl.x = *reinterpret_cast<const uint32_t*>(&l01);
+        pl.y = *reinterpret_cast<const uint32_t*>(&l23);
+        reinterpret_cast<uint2*>(hi)[i] = ph;
+        reinterpret_cast<uint2*>(lo)[i] = pl;
     }
 }
 
@@ -142,7 +171,7 @@ __global__ void __launch_bounds__(256) upsample_cn_kernel(const float* __restric
          row += (long long)gridDim.x * warps_per_block) {
         const int b = (int)(row / To);
         const int j = (int)(row % To);
-        float src = __fsub_rn(__fmul_rn(rscale, (float)j + 0.5f), 0.5f);
+        float src = fmaf(rscale, (float)j + 0.5f, -0.5f);   // ATen contracts this to one fma
         src = src < 0.f ? 0.f : src;
         int i0 = (int)src;
         if (i0 > T - 1) i0 = T - 1;
@@ -408,38 +437,51 @@ using namespace l3ac;
     } while (0)
 
 extern "C" int l3ac_dwconv7_ln(const float* x, int B, int T, int C, const float* dw_w, const float* dw_b,
-                               const float* ln_w, const float* ln_b, float eps, void* out, int out_dtype,
-                               l3ac_stream_t stream) {
+                               const float* ln_w, const float* ln_b, float eps, void* out, void* out_lo,
+                               int out_dtype, l3ac_stream_t stream) {
     L3AC_CHECK_ARG(x && dw_w && dw_b && ln_w && ln_b && out);
     L3AC_CHECK_ARG(B > 0 && T > 0 && C > 0 && C <= 512);
-    L3AC_CHECK_ARG(out_dtype == L3AC_F32 || out_dtype == L3AC_BF16);
+    L3AC_CHECK_ARG(out_dtype == L3AC_F32 || out_dtype == L3AC_BF16 || out_dtype == L3AC_BF16X2);
+    L3AC_CHECK_ARG((out_dtype == L3AC_BF16X2) == (out_lo != nullptr));
     cudaStream_t st = (cudaStream_t)stream;
     const long long rows = (long long)B * T;
     const int grid = grid_for_rows(rows, 8);
     const size_t smem = (size_t)10 * C * sizeof(float);
     DISPATCH_CPL(C, {
         if (out_dtype == L3AC_F32)
-            dwconv7_ln_kernel<CPL, float><<<grid, 256, smem, st>>>(x, B, T, C, dw_w, dw_b, ln_w, ln_b, eps, (float*)out);
+            dwconv7_ln_kernel<CPL, float><<<grid, 256, smem, st>>>(x, B, T, C, dw_w, dw_b, ln_w, ln_b, eps, (float*)out,
+                                                                   nullptr);
         else
-            dwconv7_ln_kernel<CPL, __nv_bfloat16>
-                <<<grid, 256, smem, st>>>(x, B, T, C, dw_w, dw_b, ln_w, ln_b, eps, (__nv_bfloat16*)out);
+            dwconv7_ln_kernel<CPL, __nv_bfloat16><<<grid, 256, smem, st>>>(x, B, T, C, dw_w, dw_b, ln_w, ln_b, eps,
+                                                                           (__nv_bfloat16*)out, (__nv_bfloat16*)out_lo);
     });
     return l3ac_launch_status();
 }
 
 extern "C" int l3ac_layernorm(const float* x, long long M, int C, const float* w, const float* b, float eps,
-                              void* out, int out_dtype, l3ac_stream_t stream) {
+                              void* out, void* out_lo, int out_dtype, l3ac_stream_t stream) {
     L3AC_CHECK_ARG(x && w && b && out);
     L3AC_CHECK_ARG(M > 0 && C > 0 && C <= 512);
-    L3AC_CHECK_ARG(out_dtype == L3AC_F32 || out_dtype == L3AC_BF16);
+    L3AC_CHECK_ARG(out_dtype == L3AC_F32 || out_dtype == L3AC_BF16 || out_dtype == L3AC_BF16X2);
+    L3AC_CHECK_ARG((out_dtype == L3AC_BF16X2) == (out_lo != nullptr));
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = grid_for_rows(M, 8);
     DISPATCH_CPL(C, {
         if (out_dtype == L3AC_F32)
-            layernorm_kernel<CPL, float><<<grid, 256, 0, st>>>(x, M, C, w, b, eps, (float*)out);
+            layernorm_kernel<CPL, float><<<grid, 256, 0, st>>>(x, M, C, w, b, eps, (float*)out, nullptr);
         else
-            layernorm_kernel<CPL, __nv_bfloat16><<<grid, 256, 0, st>>>(x, M, C, w, b, eps, (__nv_bfloat16*)out);
+            layernorm_kernel<CPL, __nv_bfloat16><<<grid, 256, 0, st>>>(x, M, C, w, b, eps, (__nv_bfloat16*)out,
+                                                                       (__nv_bfloat16*)out_lo);
     });
+    return l3ac_launch_status();
+}
+
+extern "C" int l3ac_split_bf16(const float* x, long long n, void* hi, void* lo, l3ac_stream_t stream) {
+    L3AC_CHECK_ARG(x && hi && lo && n > 0 && n % 4 == 0);
+    L3AC_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(hi) & 7) == 0 &&
+                   (reinterpret_cast<uintptr_t>(lo) & 7) == 0);
+    split_bf16_kernel<<<grid_for_rows(n / 4, 256 * 2), 256, 0, (cudaStream_t)stream>>>(x, n / 4, (__nv_bfloat16*)hi,
+                                                                                      (__nv_bfloat16*)lo);
     return l3ac_launch_status();
 }
 

@@ -154,7 +154,7 @@ int l3ac_validate_gemm_desc(const l3ac_gemm_desc* d) {
     L3AC_CHECK_ARG(d && d->A && d->W && d->out);
     L3AC_CHECK_ARG(d->B > 0 && d->T > 0 && d->K > 0 && d->N > 0 && d->taps >= 1);
     L3AC_CHECK_ARG(d->lda >= d->K);
-    L3AC_CHECK_ARG(d->out_dtype == L3AC_F32 || d->out_dtype == L3AC_BF16);
+    L3AC_CHECK_ARG(d->out_dtype == L3AC_F32 || d->out_dtype == L3AC_BF16 || d->out_dtype == L3AC_BF16X2);
     L3AC_CHECK_ARG(d->act >= L3AC_ACT_NONE && d->act <= L3AC_ACT_TANH);
     if (d->act == L3AC_ACT_SNAKE) {
         L3AC_CHECK_ARG(d->alpha != nullptr);
@@ -170,6 +170,7 @@ int l3ac_validate_gemm_desc(const l3ac_gemm_desc* d) {
 extern "C" int l3ac_gemm_f32(const l3ac_gemm_desc* d, l3ac_stream_t stream) {
     const int rc = l3ac_validate_gemm_desc(d);
     if (rc != L3AC_OK) return rc;
+    if (d->A_lo || d->W_lo || d->out_dtype == L3AC_BF16X2) return L3AC_EUNSUPPORTED;   // split pairs are a tcgen05-path feature
     const long long M = (long long)d->B * d->T;
     L3AC_CHECK_ARG((M + kGemmBM - 1) / kGemmBM <= 2147483647LL);
     cudaStream_t st = (cudaStream_t)stream;

@@ -11,9 +11,15 @@
 //                                stages and publishes finished accumulators.
 //   warps 2..9  epilogue       : tcgen05.ld (32 lanes x 32 columns per instruction) -> bias / snake+affine / GEGLU /
 //                                residual -> global stores; overlaps the next tile's main loop.
+// Split mode (A_lo / W_lo given): operands are bf16 (hi, lo) pairs, x ~= hi + lo, and every k-block is issued three
+// times -- hi*hi + lo*hi + hi*lo -- into the same fp32 accumulator.  That recovers ~16 mantissa bits per operand
+// (fp32-class results) at bf16 tensor-core rate; the encode side needs it because token indices flip under plain
+// bf16 rounding.  The epilogue can emit the (hi, lo) pair of its output for the next split GEMM (L3AC_BF16X2).
 // Everything a conv layer needs beyond a GEMM (k-tap shifts with dilation, per-sample zero padding, strided
 // "patchify" convs as a reshape) is expressed through the TMA coordinates, never by reshaping data in HBM.
 #include <cuda.h>
+
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -27,7 +33,9 @@ constexpr int kMaxBN = 256;
 constexpr int kMaxStages = 8;
 constexpr int kThreads = 320;
 constexpr int kEpiThreads = 256;
-constexpr int kSmemBudget = 200 * 1024;
+constexpr int kSmemBudget = 176 * 1024;
+constexpr int kStagePitch = 36;                               // floats per staged row (32 + 4 pad)
+constexpr int kStageBytes = 8 * 32 * kStagePitch * 4;        // one 32-row slab per epilogue warp
 
 struct Params {
     const float* bias;
@@ -36,8 +44,10 @@ struct Params {
     const float* shift;
     const float* residual;
     void* out;
+    void* out_lo;
     long long ldr, ldo;
     int B, T, K, N, taps, tap_shift0, tap_step;
+    int split, thin;
     int BN, stages, flat;
     int tiles_per_b, num_m_tiles, num_n_tiles, k_blocks;
     int act, out_dtype;
@@ -133,23 +143,54 @@ __device__ __forceinline__ void tile_coords(const Params& p, int tile, int& m_ti
     n_tile = tile - m_tile * p.num_n_tiles;
 }
 
-__device__ __forceinline__ float epi_fast(float v, int act, float bias, float alpha, float inv_alpha, float scale,
-                                          float shift) {
-    v += bias;
-    if (act == L3AC_ACT_SNAKE) {
-        const float s = __sinf(alpha * v);
-        v = fmaf(inv_alpha, s * s, v);
-        v = fmaf(v, scale, shift);
-    } else if (act == L3AC_ACT_GELU) {
-        v = gelu_erf(v);
-    } else if (act == L3AC_ACT_TANH) {
-        v = tanhf(v);
+// First global row of an M tile and the number of valid rows in it (flat GEMMs run over B*T rows; conv GEMMs tile
+// every sample separately so that the TMA zero fill implements the per-sample padding).
+__device__ __forceinline__ void tile_rows(const Params& p, int m_tile, long long& row_base, int& rows_valid) {
+    if (p.flat) {
+        row_base = (long long)m_tile * kBM;
+        const long long left = (long long)p.B * p.T - row_base;
+        rows_valid = left < kBM ? (int)left : kBM;
+    } else {
+        const int b = m_tile / p.tiles_per_b;
+        const int t0 = (m_tile - b * p.tiles_per_b) * kBM;
+        row_base = (long long)b * p.T + t0;
+        rows_valid = min(kBM, p.T - t0);
     }
-    return v;
 }
 
+// x + sin^2(alpha x)/(alpha + 1e-8), then the folded GRN affine.  PRECISE selects sinf over the MUFU-based __sinf:
+// the split (fp32-class, encode side) GEMMs need it so that token indices are not perturbed; the bf16 decode side
+// only needs bf16-level accuracy.
+template <bool PRECISE>
+__device__ __forceinline__ float snake_affine(float v, float alpha, float inv_alpha, float scale, float shift) {
+    const float s = PRECISE ? sinf(alpha * v) : __sinf(alpha * v);
+    v = fmaf(inv_alpha, s * s, v);
+    return fmaf(v, scale, shift);
+}
+
+// Cold path: output/residual pitches or N that do not allow 16-byte vector access.  Kept out of line so that it
+// does not occupy instruction-cache space in the hot loop.
+template <int OUT>
+__device__ __noinline__ void store_scalar_tail(const Params& p, const float* stg_row, long long mm, int col, int n_out_total) {
+    for (int e = 0; e < 4; ++e) {
+        if (col + e >= n_out_total) break;
+        float x = stg_row[e];
+        if (p.residual) x += p.residual[mm * p.ldr + col + e];
+        if (OUT == L3AC_F32) {
+            reinterpret_cast<float*>(p.out)[mm * p.ldo + col + e] = x;
+        } else {
+            const __nv_bfloat16 h = __float2bfloat16_rn(x);
+            reinterpret_cast<__nv_bfloat16*>(p.out)[mm * p.ldo + col + e] = h;
+            if (OUT == L3AC_BF16X2)
+                reinterpret_cast<__nv_bfloat16*>(p.out_lo)[mm * p.ldo + col + e] = __float2bfloat16_rn(x - __bfloat162float(h));
+        }
+    }
+}
+
+template <int ACT, int OUT, bool RES, bool PRECISE>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const Params p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ CUtensorMap tmA_lo, const __grid_constant__ CUtensorMap tmW_lo, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -158,9 +199,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t a_base = smem_base;
     const uint32_t w_base = a_base + p.stages * kATileBytes;
     const uint32_t tail = w_base + p.stages * w_tile_bytes;     // 1024-aligned (both tile sizes are multiples of 1 KB)
-    // tail layout: params [5][256] floats, then barriers
+    // tail layout: params [5][256] floats, epilogue staging slabs, barriers
     float* s_par = reinterpret_cast<float*>(smem_gen + (tail - smem_base));
-    const uint32_t bar_base = tail + 5 * kMaxBN * 4;
+    float* s_stage = s_par + 5 * kMaxBN;
+    const uint32_t bar_base = tail + 5 * kMaxBN * 4 + kStageBytes;
     const uint32_t full_bar = bar_base;                          // [kMaxStages]
     const uint32_t empty_bar = bar_base + 8 * kMaxStages;        // [kMaxStages]
     const uint32_t tfull_bar = bar_base + 16 * kMaxStages;       // [2]
@@ -180,7 +222,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar + 8 * a, 1);
-            mbar_init(tempty_bar + 8 * a, kEpiThreads / 32);
+            mbar_init(tempty_bar + 8 * a, p.thin ? kEpiThreads / 64 : kEpiThreads / 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -195,7 +237,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_slot_gen;
 
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-    const int total_kb = p.taps * p.k_blocks;
+    const int terms = p.split ? 3 : 1;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -215,13 +257,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int s = 0; s < p.taps; ++s) {
                     const int shift = p.tap_shift0 + s * p.tap_step;
                     for (int kb = 0; kb < p.k_blocks; ++kb) {
-                        mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-                        mbar_arrive_expect_tx(full_bar + 8 * stage, tx_bytes);
-                        tma_load_3d(a_base + stage * kATileBytes, &tmA, kb * kBK, row0 + shift, b, full_bar + 8 * stage);
-                        tma_load_2d(w_base + stage * w_tile_bytes, &tmW, s * p.K + kb * kBK, n0, full_bar + 8 * stage);
-                        if (++stage == p.stages) {
-                            stage = 0;
-                            phase ^= 1;
+                        for (int term = 0; term < terms; ++term) {      // hi*hi, lo*hi, hi*lo
+                            mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                            mbar_arrive_expect_tx(full_bar + 8 * stage, tx_bytes);
+                            tma_load_3d(a_base + stage * kATileBytes, term == 1 ? &tmA_lo : &tmA, kb * kBK, row0 + shift, b,
+                                        full_bar + 8 * stage);
+                            tma_load_2d(w_base + stage * w_tile_bytes, term == 2 ? &tmW_lo : &tmW, s * p.K + kb * kBK, n0,
+                                        full_bar + 8 * stage);
+                            if (++stage == p.stages) {
+                                stage = 0;
+                                phase ^= 1;
+                            }
                         }
                     }
                 }
@@ -241,7 +287,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t d_tmem = tmem_base + acc * p.BN;
                 int it = 0;
                 for (int s = 0; s < p.taps; ++s) {
-                    for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
+                    for (int kbt = 0; kbt < p.k_blocks * terms; ++kbt, ++it) {
+                        const int kb = kbt / terms;
                         mbar_wait(full_bar + 8 * stage, phase);
                         tc_fence_after();
                         const uint64_t a_desc = make_sw128_desc(a_base + stage * kATileBytes);
@@ -259,7 +306,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 }
-                (void)total_kb;
                 tc_commit(tfull_bar + 8 * acc);
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
@@ -267,6 +313,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else {
         // ---------------------------------------------------------------------- epilogue (8 warps)
+        constexpr bool GEGLU = ACT == L3AC_ACT_GEGLU;
+        constexpr int WC = GEGLU ? 16 : 32;          // output columns per 32-column accumulator chunk
+        constexpr int VPR = WC / 4;                  // float4 per staged row
+        constexpr int RPI = 32 / VPR;                // rows covered by one warp-wide vector access
+        using OutElem = typename std::conditional<OUT == L3AC_F32, float, __nv_bfloat16>::type;
         const int ep_tid = threadIdx.x - 64;
         const int quad = warp & 3;            // TMEM lane quadrant this warp may access
         const int half = (warp - 2) >> 2;     // which half of the column chunks
@@ -276,140 +327,158 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float* s_ialpha = s_par + 2 * kMaxBN;
         float* s_scale = s_par + 3 * kMaxBN;
         float* s_shift = s_par + 4 * kMaxBN;
-        int acc = 0;
+        float* stg = s_stage + (warp - 2) * 32 * kStagePitch;
+        const int lane_r = lane / VPR, ci = lane % VPR;
+        const float* stg_rd = stg + lane_r * kStagePitch + 4 * ci;
+        float* stg_wr = stg + lane * kStagePitch;
+        const int n_out_total = GEGLU ? (p.N >> 1) : p.N;
+        const bool vec_ok = ((p.ldo & 3) == 0) && (!RES || (p.ldr & 3) == 0) && ((n_out_total & 3) == 0);
+        const long long out_step = (long long)RPI * p.ldo, res_step = (long long)RPI * p.ldr;
+        // Normal mode: all 8 warps work on one tile (two column halves).  Thin mode (one 32-column chunk, one N tile):
+        // the two groups of 4 warps take alternate tiles -- group h owns accumulator stage h -- which doubles the
+        // number of tiles whose (latency-bound) epilogue is in flight.
+        int acc = p.thin ? half : 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tile_step = p.thin ? 2 * gridDim.x : gridDim.x;
+        const int chunk0 = p.thin ? 0 : half;
+        bool params_loaded = false;
+        for (int tile = blockIdx.x + (p.thin ? half * gridDim.x : 0); tile < num_tiles; tile += tile_step) {
             int m_tile, n_tile;
             tile_coords(p, tile, m_tile, n_tile);
             const int n0 = n_tile * p.BN;
-            asm volatile("bar.sync 1, 256;" ::: "memory");     // previous tile's parameter reads are done
-            for (int i = ep_tid; i < p.BN; i += kEpiThreads) {
-                const int n = n0 + i;
-                const bool ok = n < p.N;
-                s_bias[i] = (ok && p.bias) ? __ldg(p.bias + n) : 0.f;
-                const float a = (ok && p.alpha) ? __ldg(p.alpha + n) : 1.f;
-                s_alpha[i] = a;
-                s_ialpha[i] = 1.0f / (a + kEps);
-                s_scale[i] = (ok && p.scale) ? __ldg(p.scale + n) : 1.f;
-                s_shift[i] = (ok && p.shift) ? __ldg(p.shift + n) : 0.f;
+            if (!p.thin || !params_loaded) {
+                // thin mode: every tile has n0 == 0, so the per-column parameters are staged once, by each group
+                // into identical values (benign duplicate writes), guarded by a per-group named barrier
+                if (p.thin) asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
+                else asm volatile("bar.sync 1, 256;" ::: "memory");     // previous tile's parameter reads are done
+                const int tid0 = p.thin ? (ep_tid & 127) : ep_tid;
+                const int nthr = p.thin ? 128 : kEpiThreads;
+                for (int i = tid0; i < p.BN; i += nthr) {
+                    const int n = n0 + i;
+                    const bool ok = n < p.N;
+                    s_bias[i] = (ok && p.bias) ? __ldg(p.bias + n) : 0.f;
+                    if (ACT == L3AC_ACT_SNAKE) {
+                        const float a = ok ? __ldg(p.alpha + n) : 1.f;
+                        s_alpha[i] = a;
+                        s_ialpha[i] = 1.0f / (a + kEps);
+                        s_scale[i] = (ok && p.scale) ? __ldg(p.scale + n) : 1.f;
+                        s_shift[i] = (ok && p.shift) ? __ldg(p.shift + n) : 0.f;
+                    }
+                }
+                if (p.thin) asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
+                else asm volatile("bar.sync 1, 256;" ::: "memory");
+                params_loaded = true;
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-
-            const int row = quad * 32 + lane;
-            long long m;
-            bool row_ok;
-            if (p.flat) {
-                m = (long long)m_tile * kBM + row;
-                row_ok = m < (long long)p.B * p.T;
-            } else {
-                const int b = m_tile / p.tiles_per_b;
-                const int t = (m_tile - b * p.tiles_per_b) * kBM + row;
-                row_ok = t < p.T;
-                m = (long long)b * p.T + t;
-            }
+            long long row_base;
+            int rows_valid;
+            tile_rows(p, m_tile, row_base, rows_valid);
+            const int slab_rows = rows_valid - quad * 32;          // valid rows in this warp's 32-row slab (may be <= 0)
+            const long long row_lane = row_base + quad * 32 + lane_r;
+            OutElem* out_lane = reinterpret_cast<OutElem*>(p.out) + row_lane * p.ldo + 4 * ci;
+            OutElem* lo_lane = OUT == L3AC_BF16X2 ? reinterpret_cast<OutElem*>(p.out_lo) + row_lane * p.ldo + 4 * ci : nullptr;
+            const float* res_lane = RES ? p.residual + row_lane * p.ldr + 4 * ci : nullptr;
 
             mbar_wait(tfull_bar + 8 * acc, acc_phase);
             tc_fence_after();
-            for (int c = half; c < n_chunks; c += 2) {
+            for (int c = chunk0; c < n_chunks; c += 2) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.BN + c * 32), v);
-                if (!row_ok) continue;
                 const int cb = c * 32;              // column offset inside the tile
-                const int nb = n0 + cb;             // global column
-                if (nb >= p.N) continue;
-                if (p.act == L3AC_ACT_GEGLU) {
-                    float r[16];
+                const int nb = n0 + cb;             // global (pre-activation) column
+                if (nb >= p.N) continue;            // warp-uniform
+                __syncwarp();                       // the previous chunk's staged rows have been read
+                // activation in registers (thread = one accumulator row), then stage the row in shared memory
+                // (pitch 36 floats: conflict-free float4 access both ways)
+                if (GEGLU) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float val = __uint_as_float(v[2 * i]) + s_bias[cb + 2 * i];
-                        const float gate = __uint_as_float(v[2 * i + 1]) + s_bias[cb + 2 * i + 1];
-                        r[i] = val * gelu_erf(gate);
-                    }
-                    const int no = nb >> 1;
-                    const int n_out = p.N >> 1;
-                    if (p.residual) {
-                        const float* rr = p.residual + m * p.ldr + no;
+                    for (int i = 0; i < 4; ++i) {
+                        float r[4];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (no + i < n_out) r[i] += rr[i];
-                    }
-                    if (p.out_dtype == L3AC_F32) {
-                        float* o = reinterpret_cast<float*>(p.out) + m * p.ldo + no;
-#pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (no + i < n_out) o[i] = r[i];
-                    } else {
-                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldo + no;
-                        if (no + 16 <= n_out && ((p.ldo | no) & 7) == 0) {
-                            uint4 pk[2];
-                            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(pk);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) h2[i] = __floats2bfloat162_rn(r[2 * i], r[2 * i + 1]);
-                            reinterpret_cast<uint4*>(o)[0] = pk[0];
-                            reinterpret_cast<uint4*>(o)[1] = pk[1];
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                if (no + i < n_out) o[i] = __float2bfloat16_rn(r[i]);
+                        for (int j = 0; j < 2; ++j) {
+                            const float4 b0 = *reinterpret_cast<const float4*>(s_bias + cb + 8 * i + 4 * j);
+                            r[2 * j] = (__uint_as_float(v[8 * i + 4 * j]) + b0.x) * gelu_erf(__uint_as_float(v[8 * i + 4 * j + 1]) + b0.y);
+                            r[2 * j + 1] = (__uint_as_float(v[8 * i + 4 * j + 2]) + b0.z) * gelu_erf(__uint_as_float(v[8 * i + 4 * j + 3]) + b0.w);
                         }
-                    }
-                    continue;
-                }
-                float r[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    r[i] = epi_fast(__uint_as_float(v[i]), p.act, s_bias[cb + i], s_alpha[cb + i], s_ialpha[cb + i],
-                                    s_scale[cb + i], s_shift[cb + i]);
-                const bool full = nb + 32 <= p.N;
-                if (p.residual) {
-                    const float* rr = p.residual + m * p.ldr + nb;
-                    if (full && ((p.ldr | nb) & 3) == 0) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float4 q4 = reinterpret_cast<const float4*>(rr)[i];
-                            r[4 * i] += q4.x;
-                            r[4 * i + 1] += q4.y;
-                            r[4 * i + 2] += q4.z;
-                            r[4 * i + 3] += q4.w;
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (nb + i < p.N) r[i] += rr[i];
-                    }
-                }
-                if (p.out_dtype == L3AC_F32) {
-                    float* o = reinterpret_cast<float*>(p.out) + m * p.ldo + nb;
-                    if (full && ((p.ldo | nb) & 3) == 0) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            reinterpret_cast<float4*>(o)[i] = make_float4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (nb + i < p.N) o[i] = r[i];
+                        *reinterpret_cast<float4*>(stg_wr + 4 * i) = make_float4(r[0], r[1], r[2], r[3]);
                     }
                 } else {
-                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldo + nb;
-                    if (full && ((p.ldo | nb) & 7) == 0) {
-                        uint4 pk[4];
-                        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(pk);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) h2[i] = __floats2bfloat162_rn(r[2 * i], r[2 * i + 1]);
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(s_bias + cb + 4 * i);
+                        float4 r = make_float4(__uint_as_float(v[4 * i]) + b4.x, __uint_as_float(v[4 * i + 1]) + b4.y,
+                                               __uint_as_float(v[4 * i + 2]) + b4.z, __uint_as_float(v[4 * i + 3]) + b4.w);
+                        if (ACT == L3AC_ACT_SNAKE) {
+                            const float4 a4 = *reinterpret_cast<const float4*>(s_alpha + cb + 4 * i);
+                            const float4 i4 = *reinterpret_cast<const float4*>(s_ialpha + cb + 4 * i);
+                            const float4 c4 = *reinterpret_cast<const float4*>(s_scale + cb + 4 * i);
+                            const float4 h4 = *reinterpret_cast<const float4*>(s_shift + cb + 4 * i);
+                            r.x = snake_affine<PRECISE>(r.x, a4.x, i4.x, c4.x, h4.x);
+                            r.y = snake_affine<PRECISE>(r.y, a4.y, i4.y, c4.y, h4.y);
+                            r.z = snake_affine<PRECISE>(r.z, a4.z, i4.z, c4.z, h4.z);
+                            r.w = snake_affine<PRECISE>(r.w, a4.w, i4.w, c4.w, h4.w);
+                        }
+                        *reinterpret_cast<float4*>(stg_wr + 4 * i) = r;
+                    }
+                }
+                __syncwarp();
+                // write the 32 x WC block row-contiguously: lane -> (row lane_r + it*RPI, float4 ci)
+                const int nbo = GEGLU ? (nb >> 1) : nb;    // first output column of this chunk
+                const int col = nbo + 4 * ci;
+                if (vec_ok) {
+                    const bool col_ok = col < n_out_total;
+                    float4 res[VPR];
+                    if (RES) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(o)[i] = pk[i];
-                    } else {
+                        for (int it = 0; it < VPR; ++it) {
+                            res[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (col_ok && lane_r + it * RPI < slab_rows)
+                                res[it] = __ldg(reinterpret_cast<const float4*>(res_lane + nbo + it * res_step));
+                        }
+                    }
 #pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (nb + i < p.N) o[i] = __float2bfloat16_rn(r[i]);
+                    for (int it = 0; it < VPR; ++it) {
+                        if (!(col_ok && lane_r + it * RPI < slab_rows)) continue;
+                        float4 val = *reinterpret_cast<const float4*>(stg_rd + it * RPI * kStagePitch);
+                        if (RES) {
+                            val.x += res[it].x; val.y += res[it].y; val.z += res[it].z; val.w += res[it].w;
+                        }
+                        OutElem* o = out_lane + nbo + it * out_step;
+                        if (OUT == L3AC_F32) {
+                            *reinterpret_cast<float4*>(o) = val;
+                        } else {
+                            const __nv_bfloat162 h01 = __floats2bfloat162_rn(val.x, val.y);
+                            const __nv_bfloat162 h23 = __floats2bfloat162_rn(val.z, val.w);
+                            uint2 pk;
+                            pk.x = *reinterpret_cast<const uint32_t*>(&h01);
+                            pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+                            *reinterpret_cast<uint2*>(o) = pk;
+                            if (OUT == L3AC_BF16X2) {
+                                const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+                                const __nv_bfloat162 l01 = __floats2bfloat162_rn(val.x - f01.x, val.y - f01.y);
+                                const __nv_bfloat162 l23 = __floats2bfloat162_rn(val.z - f23.x, val.w - f23.y);
+                                pk.x = *reinterpret_cast<const uint32_t*>(&l01);
+                                pk.y = *reinterpret_cast<const uint32_t*>(&l23);
+                                *reinterpret_cast<uint2*>(lo_lane + nbo + it * out_step) = pk;
+                            }
+                        }
+                    }
+                } else {
+                    for (int it = 0; it < VPR; ++it) {
+                        const int rl = lane_r + it * RPI;
+                        if (rl < slab_rows && col < n_out_total)
+                            store_scalar_tail<OUT>(p, stg_rd + it * RPI * kStagePitch, row_lane + it * RPI, col, n_out_total);
                     }
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
+            if (p.thin) {
+                acc_phase ^= 1;          // this group revisits its own accumulator stage every time
+            } else {
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
         }
     }
 
@@ -455,6 +524,33 @@ static int pick_bn(int N) {
     return best;
 }
 
+typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const Params);
+
+template <int ACT, int OUT, bool PRECISE>
+static KernelFn pick_res(bool res) {
+    return res ? (KernelFn)gemm_tc_kernel<ACT, OUT, true, PRECISE> : (KernelFn)gemm_tc_kernel<ACT, OUT, false, PRECISE>;
+}
+template <int ACT, bool PRECISE>
+static KernelFn pick_out(int out_dtype, bool res) {
+    switch (out_dtype) {
+        case L3AC_F32: return pick_res<ACT, L3AC_F32, PRECISE>(res);
+        case L3AC_BF16: return pick_res<ACT, L3AC_BF16, PRECISE>(res);
+        case L3AC_BF16X2: return pick_res<ACT, L3AC_BF16X2, PRECISE>(res);
+    }
+    return nullptr;
+}
+// One instantiation per (activation, output kind, residual): each kernel carries only the epilogue it needs, which
+// keeps the hot loop inside the instruction cache.  GELU / TANH epilogues exist on the fp32 SIMT path only.
+static KernelFn pick_kernel(int act, int out_dtype, bool res, bool split) {
+    switch (act) {
+        case L3AC_ACT_NONE: return pick_out<L3AC_ACT_NONE, false>(out_dtype, res);
+        case L3AC_ACT_GEGLU: return pick_out<L3AC_ACT_GEGLU, false>(out_dtype, res);
+        case L3AC_ACT_SNAKE:
+            return split ? pick_out<L3AC_ACT_SNAKE, true>(out_dtype, res) : pick_out<L3AC_ACT_SNAKE, false>(out_dtype, res);
+    }
+    return nullptr;
+}
+
 }  // namespace tc
 }  // namespace l3ac
 
@@ -463,6 +559,9 @@ using namespace l3ac::tc;
 extern "C" int l3ac_gemm_bf16_tc(const l3ac_gemm_desc* d, l3ac_stream_t stream) {
     const int rc = l3ac_validate_gemm_desc(d);
     if (rc != L3AC_OK) return rc;
+    const bool split = d->A_lo != nullptr;
+    L3AC_CHECK_ARG((d->A_lo == nullptr) == (d->W_lo == nullptr));
+    L3AC_CHECK_ARG(d->out_dtype != L3AC_BF16X2 || d->out_lo != nullptr);
     const long long ktot = (long long)d->taps * d->K;
     L3AC_CHECK_ARG(d->lda % 8 == 0 && ktot % 8 == 0);
     L3AC_CHECK_ARG((reinterpret_cast<uintptr_t>(d->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->W) & 15) == 0);
@@ -471,7 +570,8 @@ extern "C" int l3ac_gemm_bf16_tc(const l3ac_gemm_desc* d, l3ac_stream_t stream) 
 
     Params p{};
     p.bias = d->bias; p.alpha = d->alpha; p.scale = d->scale; p.shift = d->shift; p.residual = d->residual;
-    p.out = d->out; p.ldr = d->ldr; p.ldo = d->ldo;
+    p.out = d->out; p.out_lo = d->out_lo; p.ldr = d->ldr; p.ldo = d->ldo;
+    p.split = split ? 1 : 0;
     p.B = d->B; p.T = d->T; p.K = d->K; p.N = d->N;
     p.taps = d->taps; p.tap_shift0 = d->tap_shift0; p.tap_step = d->tap_step;
     p.act = d->act; p.out_dtype = d->out_dtype;
@@ -494,45 +594,53 @@ extern "C" int l3ac_gemm_bf16_tc(const l3ac_gemm_desc* d, l3ac_stream_t stream) 
         p.num_m_tiles = (int)mt;
     }
     p.num_n_tiles = (d->N + p.BN - 1) / p.BN;
+    p.thin = (p.BN == 32 && p.num_n_tiles == 1) ? 1 : 0;
     L3AC_CHECK_ARG((long long)p.num_m_tiles * p.num_n_tiles < (1LL << 31));
 
     // A: (k, t, b) bf16, row pitch lda.  Flat GEMMs view all B*T rows as one sample so tiles never straddle padding.
-    CUtensorMap tmA, tmW;
-    {
+    CUtensorMap tmA, tmW, tmA_lo, tmW_lo;
+    auto encode_a = [&](CUtensorMap* tm, const void* ptr) -> bool {
         const cuuint64_t rows = p.flat ? (cuuint64_t)M : (cuuint64_t)d->T;
         const cuuint64_t batches = p.flat ? 1 : (cuuint64_t)d->B;
         cuuint64_t dims[3] = {(cuuint64_t)d->K, rows, batches};
         cuuint64_t strides[2] = {(cuuint64_t)d->lda * 2, (cuuint64_t)d->lda * 2 * rows};
         cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)kBM, 1};
         cuuint32_t estr[3] = {1, 1, 1};
-        CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d->A), dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return L3AC_EINVAL;
-    }
-    {
+        return encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
+    auto encode_w = [&](CUtensorMap* tm, const void* ptr) -> bool {
         cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)d->N};
         cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
         cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)p.BN};
         cuuint32_t estr[2] = {1, 1};
-        CUresult r = encode(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->W), dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return L3AC_EINVAL;
+        return encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
+    if (!encode_a(&tmA, d->A) || !encode_w(&tmW, d->W)) return L3AC_EINVAL;
+    if (split) {
+        L3AC_CHECK_ARG((reinterpret_cast<uintptr_t>(d->A_lo) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->W_lo) & 15) == 0);
+        if (!encode_a(&tmA_lo, d->A_lo) || !encode_w(&tmW_lo, d->W_lo)) return L3AC_EINVAL;
+    } else {
+        tmA_lo = tmA;
+        tmW_lo = tmW;
     }
 
-    const size_t smem = 1024 /* alignment slack */ + (size_t)p.stages * stage_bytes + 5 * kMaxBN * 4 + 16 * kMaxStages + 64;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
+    const size_t smem = 1024 /* alignment slack */ + (size_t)p.stages * stage_bytes + 5 * kMaxBN * 4 + kStageBytes + 16 * kMaxStages + 64;
+    KernelFn fn = pick_kernel(d->act, d->out_dtype, d->residual != nullptr, split);
+    if (!fn) return L3AC_EUNSUPPORTED;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long tiles = (long long)p.num_m_tiles * p.num_n_tiles;
     const int grid = (int)(tiles < sms ? tiles : sms);
-    gemm_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmW, p);
+    fn<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmW, tmA_lo, tmW_lo, p);
     return l3ac_launch_status();
 }

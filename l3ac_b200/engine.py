@@ -8,8 +8,11 @@ is one-time, input-independent preprocessing done with torch on the parameters' 
 Precision modes
   ``fp32``  every GEMM on the fp32 SIMT path (parity mode, 1e-5 class).
   ``bf16``  decode side (en_decoder + decoder) GEMM operands in bf16 on the tcgen05 path with fp32
-            accumulation and fp32 residual stream; the encode side stays fp32 because token indices
-            flip under bf16 rounding (93.6 % agreement at bf16, 100 % at fp32 class).
+            accumulation and fp32 residual stream.  The encode side also runs on the tcgen05 path but with
+            split-bf16 operands (x = hi + lo, three MMAs per k-block: hi*hi + lo*hi + hi*lo, fp32 accumulate),
+            because token indices flip under plain bf16 rounding (93.6 % index agreement
+            at bf16, 100 % / 99.985 % with the 3-term split).  ``encoder_precision="fp32"`` keeps the encode
+            side on the SIMT path instead.
 """
 from __future__ import annotations
 
@@ -43,22 +46,31 @@ def _taps_major(w: torch.Tensor) -> torch.Tensor:
 
 
 class _Linear:
-    """A packed GEMM weight: fp32 master + optional bf16 copy for the tcgen05 path."""
+    """A packed GEMM weight: fp32 master + the copy the chosen path needs (bf16, or a split (hi, lo) bf16 pair)."""
 
-    def __init__(self, w: torch.Tensor, bias: Optional[torch.Tensor], bf16: bool):
+    def __init__(self, w: torch.Tensor, bias: Optional[torch.Tensor], kind):
         self.w32 = w.contiguous().float()
-        self.w16 = self.w32.to(torch.bfloat16).contiguous() if bf16 else None
+        self.w16 = self.w32.to(torch.bfloat16).contiguous() if kind == torch.bfloat16 else None
+        self.wsp = None
+        if kind == ops.SPLIT:
+            hi = self.w32.to(torch.bfloat16)
+            self.wsp = ops.Split(hi.contiguous(), (self.w32 - hi.float()).to(torch.bfloat16).contiguous())
         self.bias = None if bias is None else bias.contiguous().float()
 
-    def weight_for(self, a: torch.Tensor) -> torch.Tensor:
+    def weight_for(self, a):
+        if isinstance(a, ops.Split):
+            return self.wsp
         return self.w32 if a.dtype == torch.float32 else self.w16
 
 
 class Engine:
     def __init__(self, mc: ModelConfig, weights: Dict[str, Dict[str, torch.Tensor]], device, precision: str = "bf16",
-                 max_chunk_seconds: float = 160.0):
+                 max_chunk_seconds: float = 160.0, encoder_precision: Optional[str] = None):
         if precision not in ("fp32", "bf16"):
             raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
+        encoder_precision = encoder_precision or ("fp32" if precision == "fp32" else "split")
+        if encoder_precision not in ("fp32", "split"):
+            raise ValueError(f"encoder_precision must be 'fp32' or 'split', got {encoder_precision!r}")
         if not mc.en_coder_dynamic_pos:
             raise NotImplementedError("rotary position path (en_coder_dynamic_pos=false) is not built yet")
         if mc.decoder_last_layer != "legacy" or mc.base_unit != "normal" or not mc.use_norm or not mc.use_snake_act:
@@ -72,6 +84,7 @@ class Engine:
         self.precision = precision
         self.max_chunk_samples = int(max_chunk_seconds * 16000)
         self.dec_dtype = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.enc_dtype = ops.SPLIT if encoder_precision == "split" else torch.float32
         w = {m: {k: v.detach().to(self.device) for k, v in sd.items()} for m, sd in weights.items()}
         with torch.no_grad():
             self._pack_encoder(w["encoder"])
@@ -81,22 +94,23 @@ class Engine:
             self._pack_decoder(w["decoder"])
 
     # ------------------------------------------------------------------ packing
-    def _conv_unit(self, sd, p, bf16):
+    def _conv_unit(self, sd, p, kind):
         dw = fold_weight_norm(sd, f"{p}.dw_conv")                      # (C, 1, 7)
         gamma, beta = sd[f"{p}.grn.gamma"].float().flatten(), sd[f"{p}.grn.beta"].float().flatten()
         return dict(
             dw_w=dw[:, 0, :].t().contiguous(), dw_b=sd[f"{p}.dw_conv.bias"].float().contiguous(),
             ln_w=sd[f"{p}.norm.weight"].float().contiguous(), ln_b=sd[f"{p}.norm.bias"].float().contiguous(),
-            pw1=_Linear(fold_weight_norm(sd, f"{p}.pw_conv1"), sd[f"{p}.pw_conv1.bias"], bf16),
+            pw1=_Linear(fold_weight_norm(sd, f"{p}.pw_conv1"), sd[f"{p}.pw_conv1.bias"], kind),
             alpha=sd[f"{p}.act.alpha"].float().flatten().contiguous(),
             # GRN (l3ac/layers.py:112-115): n_x = g/(g+1e-8) == 1 to within 1e-8/g, so gamma*(x*n_x)+beta+x is the
             # per-channel affine (1+gamma) x + beta (absolute deviation <= 1e-8*|gamma|).
             scale=(1.0 + gamma).contiguous(), shift=beta.contiguous(),
-            pw2=_Linear(fold_weight_norm(sd, f"{p}.pw_conv2"), sd[f"{p}.pw_conv2.bias"], bf16),
+            pw2=_Linear(fold_weight_norm(sd, f"{p}.pw_conv2"), sd[f"{p}.pw_conv2.bias"], kind),
         )
 
     def _pack_encoder(self, sd):
         mc = self.mc
+        ek = self.enc_dtype
         bw = torch.stack([fold_weight_norm(sd, f"blocks.0.blocks.{i}.1")[:, 0, :] for i in range(5)])   # (5,4,7)
         bb = torch.cat([sd[f"blocks.0.blocks.{i}.1.bias"].float() for i in range(5)])
         self.stem = dict(
@@ -106,17 +120,17 @@ class Engine:
         self.enc_stages = []
         blk = 1
         for i, stride in enumerate(mc.compress_rates):
-            units = [self._conv_unit(sd, f"blocks.{blk}.{j}.module", False) for j in range(mc.encoder_depths[i])]
+            units = [self._conv_unit(sd, f"blocks.{blk}.{j}.module", ek) for j in range(mc.encoder_depths[i])]
             blk += 1
-            down = _Linear(_taps_major(fold_weight_norm(sd, f"blocks.{blk}.0")), sd[f"blocks.{blk}.0.bias"], False)
+            down = _Linear(_taps_major(fold_weight_norm(sd, f"blocks.{blk}.0")), sd[f"blocks.{blk}.0.bias"], ek)
             self.enc_stages.append(dict(units=units, stride=stride, down=down,
                                         cn_w=sd[f"blocks.{blk}.1.weight"].float().contiguous(),
                                         cn_b=sd[f"blocks.{blk}.1.bias"].float().contiguous()))
             blk += 1
-        self.enc_last = [self._conv_unit(sd, f"blocks.{blk}.{j}.module", False) for j in range(mc.encoder_depths[-1])]
-        self.enc_out = _Linear(_taps_major(fold_weight_norm(sd, f"blocks.{blk + 1}")), sd[f"blocks.{blk + 1}.bias"], False)
+        self.enc_last = [self._conv_unit(sd, f"blocks.{blk}.{j}.module", ek) for j in range(mc.encoder_depths[-1])]
+        self.enc_out = _Linear(_taps_major(fold_weight_norm(sd, f"blocks.{blk + 1}")), sd[f"blocks.{blk + 1}.bias"], ek)
 
-    def _local_trans(self, sd, p, depth, window, bf16):
+    def _local_trans(self, sd, p, depth, window, kind):
         """LocalTrans weights + the DynamicPositionBias table f[h][d], d = q_pos - k_pos in [0, 2w)
         (l3ac/local_trans.py:30,43; the MLP input is the integer distance, so the table is input-independent)."""
         q = f"{p}.dynamic_pos_bias.mlp"
@@ -137,23 +151,24 @@ class Engine:
             w2[:, :inner] = sd[f"{f}.4.weight"].float()
             layers.append(dict(
                 ln1_w=sd[f"{a}.norm.weight"].float().contiguous(), ln1_b=sd[f"{a}.norm.bias"].float().contiguous(),
-                qkv=_Linear(sd[f"{a}.to_qkv.weight"], None, bf16), out=_Linear(sd[f"{a}.to_out.weight"], None, bf16),
+                qkv=_Linear(sd[f"{a}.to_qkv.weight"], None, kind), out=_Linear(sd[f"{a}.to_out.weight"], None, kind),
                 ln2_w=sd[f"{f}.0.weight"].float().contiguous(), ln2_b=sd[f"{f}.0.bias"].float().contiguous(),
-                ff1=_Linear(w1i, None, bf16), ff2=_Linear(w2, None, bf16)))
+                ff1=_Linear(w1i, None, kind), ff2=_Linear(w2, None, kind)))
         return dict(layers=layers, window=window, table=table)
 
     def _pack_en_encoder(self, sd):
         mc = self.mc
         w, r = mc.en_coder_window_size, mc.en_coder_compress_rate
+        ek = self.enc_dtype
         if is_compressed(mc):
-            self.enc_trans_frame = self._local_trans(sd, "down_trans.trans", 3 // 2, w * r, False)
+            self.enc_trans_frame = self._local_trans(sd, "down_trans.trans", 3 // 2, w * r, ek)
             self.enc_trans_down = _Linear(_taps_major(fold_weight_norm(sd, "down_trans.down_layer")),
-                                          sd["down_trans.down_layer.bias"], False)
-            self.enc_trans_token = self._local_trans(sd, "local_trans", 3 - 3 // 2, w, False)
+                                          sd["down_trans.down_layer.bias"], ek)
+            self.enc_trans_token = self._local_trans(sd, "local_trans", 3 - 3 // 2, w, ek)
         else:
             self.enc_trans_frame = None
             self.enc_trans_down = None
-            self.enc_trans_token = self._local_trans(sd, "local_trans", 1, w, False)
+            self.enc_trans_token = self._local_trans(sd, "local_trans", 1, w, ek)
 
     def _pack_quantizer(self, sd):
         self.vq = dict(w_in=sd["project_in.weight"].float().contiguous(), b_in=sd["project_in.bias"].float().contiguous(),
@@ -162,7 +177,7 @@ class Engine:
 
     def _pack_en_decoder(self, sd):
         mc = self.mc
-        bf16 = self.precision == "bf16"
+        bf16 = self.dec_dtype
         w, r = mc.en_coder_window_size, mc.en_coder_compress_rate
         if is_compressed(mc):
             self.dec_trans_token = self._local_trans(sd, "local_trans", mc.en_coder_depth - 2, w, bf16)
@@ -173,7 +188,7 @@ class Engine:
 
     def _pack_decoder(self, sd):
         mc = self.mc
-        bf16 = self.precision == "bf16"
+        bf16 = self.dec_dtype
         self.dec_in = _Linear(_taps_major(fold_weight_norm(sd, "blocks.0")), sd["blocks.0.bias"], bf16)
         self.dec_stages = []
         blk = 1
@@ -212,6 +227,15 @@ class Engine:
     def _lin(a, lin: _Linear, B, T, K, **kw):
         return ops.gemm(a, lin.weight_for(a), B=B, T=T, K=K, bias=lin.bias, **kw)
 
+    @staticmethod
+    def _as_operand(x: torch.Tensor, kind):
+        """fp32 activation -> GEMM A operand of the requested kind."""
+        if kind == torch.float32:
+            return x
+        if kind == ops.SPLIT:
+            return ops.split_bf16(x)
+        return x.to(kind)
+
     def _run_conv_unit(self, x, u, act_dtype):
         """Residual(ConvUnit) -- l3ac/modules.py:32-44."""
         B, T, C = x.shape
@@ -227,9 +251,7 @@ class Engine:
             a = ops.layernorm(x, L["ln1_w"], L["ln1_b"], LN_EPS, out_dtype=act_dtype)
             qkv = self._lin(a, L["qkv"], B, T, D)                                   # fp32 (B,T,576)
             o = ops.local_attention(qkv, lt["table"], HEADS, lt["window"])
-            if act_dtype != torch.float32:
-                o = o.to(act_dtype)
-            x = self._lin(o, L["out"], B, T, o.shape[-1], residual=x)
+            x = self._lin(self._as_operand(o, act_dtype), L["out"], B, T, o.shape[-1], residual=x)
             a = ops.layernorm(x, L["ln2_w"], L["ln2_b"], LN_EPS, out_dtype=act_dtype)
             g = self._lin(a, L["ff1"], B, T, D, act=ops.ACT_GEGLU, out_dtype=act_dtype)   # (B,T,352)
             x = self._lin(g, L["ff2"], B, T, FF_PAD, residual=x)
@@ -239,7 +261,7 @@ class Engine:
     def encode_features(self, audio: torch.Tensor, taps: Optional[dict] = None) -> torch.Tensor:
         """preprocess + encoder + en_encoder (l3ac/__init__.py:109-111) -> trans_feature (B, T_tok, F)."""
         mc = self.mc
-        f32 = torch.float32
+        f32 = self.enc_dtype            # operand kind of the encode-side GEMMs (fp32 SIMT or split-bf16 tcgen05)
         B, T0 = audio.shape
         hop = mc.hop_length
         T = math.ceil(T0 / hop) * hop                      # Codec.preprocess, l3ac/codec.py:79-84
@@ -253,20 +275,20 @@ class Engine:
                 x = self._run_conv_unit(x, u, f32)
             B_, T_, C_ = x.shape
             s = st["stride"]
-            x = self._lin(x, st["down"], B_, T_ // s, s * C_)                       # Conv1d(k=s, stride=s) as a GEMM
+            x = self._lin(self._as_operand(x, f32), st["down"], B_, T_ // s, s * C_)   # Conv1d(k=s, stride=s) as a GEMM
             x = ops.layernorm(x, st["cn_w"], st["cn_b"], EPS)                       # channels-first ChannelNorm
             if taps is not None:
                 taps[f"enc_down{si}"] = x
         for u in self.enc_last:
             x = self._run_conv_unit(x, u, f32)
         B_, T_, C_ = x.shape
-        x = self._lin(x, self.enc_out, B_, T_, C_, taps=3, tap_shift0=-1)           # Conv1d(k3, pad 1)
+        x = self._lin(self._as_operand(x, f32), self.enc_out, B_, T_, C_, taps=3, tap_shift0=-1)   # Conv1d(k3, pad 1)
         if taps is not None:
             taps["enc_feature"] = x
         if self.enc_trans_frame is not None:                                        # l3ac/local_trans.py:138-142,161-165
             x = self._run_local_trans(x, self.enc_trans_frame, f32)
             r = mc.en_coder_compress_rate
-            x = self._lin(x, self.enc_trans_down, B_, T_ // r, r * x.shape[-1])
+            x = self._lin(self._as_operand(x, f32), self.enc_trans_down, B_, T_ // r, r * x.shape[-1])
         x = self._run_local_trans(x, self.enc_trans_token, f32)
         return x
 
@@ -315,8 +337,7 @@ class Engine:
         if taps is not None:
             taps["dec_feature"] = x
         B, T, F = x.shape
-        a = x if adt == torch.float32 else x.to(adt)
-        x = self._lin(a, self.dec_in, B, T, F, taps=3, tap_shift0=-1)               # Conv1d(k3, pad 1)
+        x = self._lin(self._as_operand(x, adt), self.dec_in, B, T, F, taps=3, tap_shift0=-1)   # Conv1d(k3, pad 1)
         for si, st in enumerate(self.dec_stages):
             for u in st["units"]:
                 x = self._run_conv_unit(x, u, adt)

@@ -55,10 +55,12 @@ class _Stage(ParamTree):
 
 
 class EnCodec(nn.Module):
-    def __init__(self, mc: ModelConfig, seed: Optional[int] = None, precision: str = "bf16"):
+    def __init__(self, mc: ModelConfig, seed: Optional[int] = None, precision: str = "bf16",
+                 encoder_precision: Optional[str] = None):
         super().__init__()
         self.mc = mc
         self.precision = precision
+        self.encoder_precision = encoder_precision
         network_spec(mc)                                   # validates the layer options early
         sds = init_state_dicts(mc, seed=0 if seed is None else seed)
         self.encoder = _Stage(sds["encoder"], self, "_call_encoder")
@@ -124,10 +126,11 @@ class EnCodec(nn.Module):
     @property
     def engine(self) -> Engine:
         dev = next(self.parameters()).device
-        key = (str(dev), self.precision)
+        key = (str(dev), self.precision, self.encoder_precision)
         if self._engine is None or self._engine_key != key:
             weights = {n: m.state_dict() for n, m in self.trainable_modules.items()}
-            self._engine = Engine(self.mc, weights, dev, precision=self.precision)
+            self._engine = Engine(self.mc, weights, dev, precision=self.precision,
+                                  encoder_precision=self.encoder_precision)
             self._engine_key = key
         return self._engine
 

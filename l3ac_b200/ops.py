@@ -12,9 +12,52 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import ACT_GEGLU, ACT_GELU, ACT_NONE, ACT_SNAKE, ACT_TANH, BF16, F32, GemmDesc, check  # noqa: F401
+from ._lib import ACT_GEGLU, ACT_GELU, ACT_NONE, ACT_SNAKE, ACT_TANH, BF16, BF16X2, F32, GemmDesc, check  # noqa: F401
 
-_DT = {torch.float32: F32, torch.bfloat16: BF16}
+SPLIT = "split_bf16"        # out_dtype marker: emit a (hi, lo) bf16 pair, the operand format of the 3-term GEMM
+_DT = {torch.float32: F32, torch.bfloat16: BF16, SPLIT: BF16X2}
+
+
+class Split:
+    """x ~= hi + lo with hi = bf16(x), lo = bf16(x - hi): two bf16 planes of identical shape."""
+    __slots__ = ("hi", "lo")
+
+    def __init__(self, hi: torch.Tensor, lo: torch.Tensor):
+        self.hi, self.lo = hi, lo
+
+    @property
+    def shape(self):
+        return self.hi.shape
+
+    @property
+    def device(self):
+        return self.hi.device
+
+    def float(self) -> torch.Tensor:
+        return self.hi.float() + self.lo.float()
+
+    def view(self, *shape) -> "Split":
+        return Split(self.hi.view(*shape), self.lo.view(*shape))
+
+
+def _empty_act(shape, device, out_dtype):
+    """Allocates an activation of the requested kind; returns (object, hi_ptr_tensor, lo_ptr_tensor_or_None)."""
+    if out_dtype == SPLIT:
+        hi = torch.empty(shape, device=device, dtype=torch.bfloat16)
+        lo = torch.empty(shape, device=device, dtype=torch.bfloat16)
+        return Split(hi, lo), hi, lo
+    t = torch.empty(shape, device=device, dtype=out_dtype)
+    return t, t, None
+
+# Instrumentation used by bench.py: number of kernels this library launched, and an optional hook that brackets
+# each GEMM launch with CUDA events (``GEMM_HOOK(kind, flops, bytes) -> context manager``).  Off by default.
+LAUNCHES = 0
+GEMM_HOOK = None
+
+
+def _count(n: int = 1):
+    global LAUNCHES
+    LAUNCHES += n
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -44,6 +87,7 @@ def stem(audio: torch.Tensor, branch_w, branch_b, w1, b1, w2, b2) -> torch.Tenso
     B, T = audio.shape
     Cout = w2.shape[0]
     out = torch.empty((B, T, Cout), device=audio.device, dtype=torch.float32)
+    _count()
     with torch.cuda.device(audio.device):
         check(_lib.load().l3ac_stem(_ptr(audio), B, T, _ptr(branch_w), _ptr(branch_b), _ptr(w1), _ptr(b1), _ptr(w2),
                                     _ptr(b2), Cout, _ptr(out), _stream(audio)), "l3ac_stem")
@@ -53,10 +97,11 @@ def stem(audio: torch.Tensor, branch_w, branch_b, w1, b1, w2, b2) -> torch.Tenso
 def dwconv7_ln(x, dw_w, dw_b, ln_w, ln_b, eps: float, out_dtype=torch.float32) -> torch.Tensor:
     _chk(x, name="x")
     B, T, Cc = x.shape
-    out = torch.empty((B, T, Cc), device=x.device, dtype=out_dtype)
+    out, hi, lo = _empty_act((B, T, Cc), x.device, out_dtype)
+    _count()
     with torch.cuda.device(x.device):
         check(_lib.load().l3ac_dwconv7_ln(_ptr(x), B, T, Cc, _ptr(dw_w), _ptr(dw_b), _ptr(ln_w), _ptr(ln_b), eps,
-                                          _ptr(out), _DT[out_dtype], _stream(x)), "l3ac_dwconv7_ln")
+                                          _ptr(hi), _ptr(lo), _DT[out_dtype], _stream(x)), "l3ac_dwconv7_ln")
     return out
 
 
@@ -64,10 +109,21 @@ def layernorm(x, w, b, eps: float, out_dtype=torch.float32) -> torch.Tensor:
     _chk(x, name="x")
     Cc = x.shape[-1]
     M = x.numel() // Cc
-    out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    out, hi, lo = _empty_act(x.shape, x.device, out_dtype)
+    _count()
     with torch.cuda.device(x.device):
-        check(_lib.load().l3ac_layernorm(_ptr(x), M, Cc, _ptr(w), _ptr(b), eps, _ptr(out), _DT[out_dtype], _stream(x)),
-              "l3ac_layernorm")
+        check(_lib.load().l3ac_layernorm(_ptr(x), M, Cc, _ptr(w), _ptr(b), eps, _ptr(hi), _ptr(lo), _DT[out_dtype],
+                                         _stream(x)), "l3ac_layernorm")
+    return out
+
+
+def split_bf16(x: torch.Tensor) -> Split:
+    """fp32 -> (hi, lo) bf16 pair."""
+    _chk(x, name="x")
+    out, hi, lo = _empty_act(x.shape, x.device, SPLIT)
+    _count()
+    with torch.cuda.device(x.device):
+        check(_lib.load().l3ac_split_bf16(_ptr(x), x.numel(), _ptr(hi), _ptr(lo), _stream(x)), "l3ac_split_bf16")
     return out
 
 
@@ -75,44 +131,61 @@ def snake(x, alpha, out_dtype=torch.float32) -> torch.Tensor:
     _chk(x, name="x")
     Cc = x.shape[-1]
     out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    _count()
     with torch.cuda.device(x.device):
         check(_lib.load().l3ac_snake(_ptr(x), x.numel() // Cc, Cc, _ptr(alpha), _ptr(out), _DT[out_dtype], _stream(x)),
               "l3ac_snake")
     return out
 
 
-def gemm(a: torch.Tensor, w: torch.Tensor, *, B: int, T: int, K: int, taps: int = 1, tap_shift0: int = 0,
-         tap_step: int = 1, bias=None, act: int = ACT_NONE, alpha=None, scale=None, shift=None, residual=None,
-         out_dtype=torch.float32, lda: Optional[int] = None) -> torch.Tensor:
+def gemm(a, w, *, B: int, T: int, K: int, taps: int = 1, tap_shift0: int = 0, tap_step: int = 1, bias=None,
+         act: int = ACT_NONE, alpha=None, scale=None, shift=None, residual=None, out_dtype=torch.float32,
+         lda: Optional[int] = None):
     """out[(b,t), n] = epi(bias[n] + sum_s sum_k a[b, t + shift_s, k] w[n, s*K + k])  (see the header).
 
-    ``a`` is any contiguous tensor whose memory is ``B*T`` rows of pitch ``lda`` (default ``K``); fp32 tensors take
-    the SIMT path, bf16 tensors the tcgen05 path.  Returns ``(B, T, N_out)``.
+    ``a`` is any contiguous tensor whose memory is ``B*T`` rows of pitch ``lda`` (default ``K``).  fp32 operands take
+    the SIMT path, bf16 operands the tcgen05 path, ``Split`` operands the 3-term split tcgen05 path.
+    ``out_dtype``: torch.float32 | torch.bfloat16 | ops.SPLIT.  Returns ``(B, T, N_out)``.
     """
-    if a.dtype not in _DT or a.dtype != w.dtype:
-        raise ValueError(f"gemm operands must both be fp32 or both bf16, got {a.dtype} / {w.dtype}")
-    _chk(a, a.dtype, "a")
-    _chk(w, w.dtype, "w")
+    split = isinstance(a, Split)
+    if split != isinstance(w, Split):
+        raise ValueError("gemm operands must both be Split pairs or both plain tensors")
+    a_hi, w_hi = (a.hi, w.hi) if split else (a, w)
+    if a_hi.dtype not in (torch.float32, torch.bfloat16) or a_hi.dtype != w_hi.dtype:
+        raise ValueError(f"gemm operands must both be fp32 or both bf16, got {a_hi.dtype} / {w_hi.dtype}")
+    for t, name in ((a_hi, "a"), (w_hi, "w")) + (((a.lo, "a.lo"), (w.lo, "w.lo")) if split else ()):
+        _chk(t, a_hi.dtype, name)
     lda = K if lda is None else lda
-    if a.numel() != B * T * lda:
-        raise ValueError(f"a has {a.numel()} elements, expected B*T*lda = {B * T * lda}")
-    N = w.shape[0]
-    if w.shape[1] != taps * K:
-        raise ValueError(f"w must be (N, taps*K) = (N, {taps * K}), got {tuple(w.shape)}")
+    if a_hi.numel() != B * T * lda:
+        raise ValueError(f"a has {a_hi.numel()} elements, expected B*T*lda = {B * T * lda}")
+    N = w_hi.shape[0]
+    if w_hi.shape[1] != taps * K:
+        raise ValueError(f"w must be (N, taps*K) = (N, {taps * K}), got {tuple(w_hi.shape)}")
     n_out = N // 2 if act == ACT_GEGLU else N
-    out = torch.empty((B, T, n_out), device=a.device, dtype=out_dtype)
+    out, o_hi, o_lo = _empty_act((B, T, n_out), a_hi.device, out_dtype)
     if residual is not None:
         _chk(residual, name="residual")
         if residual.numel() != B * T * n_out:
             raise ValueError("residual shape mismatch")
-    d = GemmDesc(A=_ptr(a), W=_ptr(w), bias=_ptr(bias), alpha=_ptr(alpha), scale=_ptr(scale), shift=_ptr(shift),
-                 residual=_ptr(residual), out=_ptr(out), lda=lda, ldr=n_out, ldo=n_out, B=B, T=T, K=K, N=N, taps=taps,
-                 tap_shift0=tap_shift0, tap_step=tap_step, act=act, out_dtype=_DT[out_dtype])
+    d = GemmDesc(A=_ptr(a_hi), W=_ptr(w_hi), bias=_ptr(bias), alpha=_ptr(alpha), scale=_ptr(scale), shift=_ptr(shift),
+                 residual=_ptr(residual), out=_ptr(o_hi), A_lo=_ptr(a.lo) if split else None,
+                 W_lo=_ptr(w.lo) if split else None, out_lo=_ptr(o_lo), lda=lda, ldr=n_out, ldo=n_out, B=B, T=T, K=K, N=N,
+                 taps=taps, tap_shift0=tap_shift0, tap_step=tap_step, act=act, out_dtype=_DT[out_dtype])
     lib = _lib.load()
-    fn, what = (lib.l3ac_gemm_f32, "l3ac_gemm_f32") if a.dtype == torch.float32 else (lib.l3ac_gemm_bf16_tc,
-                                                                                      "l3ac_gemm_bf16_tc")
-    with torch.cuda.device(a.device):
-        check(fn(C.byref(d), _stream(a)), what)
+    fn, what = (lib.l3ac_gemm_f32, "l3ac_gemm_f32") if a_hi.dtype == torch.float32 else (lib.l3ac_gemm_bf16_tc,
+                                                                                         "l3ac_gemm_bf16_tc")
+    _count()
+    with torch.cuda.device(a_hi.device):
+        if GEMM_HOOK is None:
+            check(fn(C.byref(d), _stream(a_hi)), what)
+        else:
+            flops = 2.0 * B * T * N * K * taps
+            esz = a_hi.element_size() * (2 if split else 1)
+            osz = {torch.float32: 4, torch.bfloat16: 2, SPLIT: 4}[out_dtype]
+            nbytes = esz * (B * T * K + N * K * taps) + osz * B * T * n_out + (0 if residual is None else 4 * residual.numel())
+            kind = "f32" if a_hi.dtype == torch.float32 else ("tc_split" if split else "tc")
+            with GEMM_HOOK(kind, flops, nbytes):
+                check(fn(C.byref(d), _stream(a_hi)), what)
     return out
 
 
@@ -124,6 +197,7 @@ def local_attention(qkv: torch.Tensor, bias_table: torch.Tensor, heads: int, win
     if tuple(bias_table.shape) != (heads, 2 * window):
         raise ValueError(f"bias_table must be (heads, 2*window), got {tuple(bias_table.shape)}")
     out = torch.empty((B, T, heads * D), device=qkv.device, dtype=torch.float32)
+    _count()
     with torch.cuda.device(qkv.device):
         check(_lib.load().l3ac_local_attention_f32(_ptr(qkv), _ptr(bias_table), B, T, heads, D, window, _ptr(out),
                                                    _stream(qkv)), "l3ac_local_attention_f32")
@@ -140,6 +214,7 @@ def fsq_quantize(x: torch.Tensor, w_in, b_in, w_out, b_out, levels: Sequence[int
     idx = torch.empty(lead, device=x.device, dtype=torch.int32)
     lvl = torch.empty((*lead, D), device=x.device, dtype=torch.float32)
     z = torch.empty((*lead, D), device=x.device, dtype=torch.float32) if want_z else None
+    _count()
     with torch.cuda.device(x.device):
         check(_lib.load().l3ac_fsq_quantize(_ptr(x), M, F, _ptr(w_in), _ptr(b_in), _ptr(w_out), _ptr(b_out),
                                             _levels(levels), D, _ptr(q), _ptr(idx), _ptr(lvl), _ptr(z), _stream(x)),
@@ -156,6 +231,7 @@ def fsq_quantize_latents(z: torch.Tensor, levels: Sequence[int]):
     q = torch.empty(z.shape, device=z.device, dtype=torch.float32)
     idx = torch.empty(lead, device=z.device, dtype=torch.int32)
     lvl = torch.empty(z.shape, device=z.device, dtype=torch.float32)
+    _count()
     with torch.cuda.device(z.device):
         check(_lib.load().l3ac_fsq_quantize_latents(_ptr(z), z.numel() // D, _levels(levels), D, _ptr(q), _ptr(idx),
                                                     _ptr(lvl), _stream(z)), "l3ac_fsq_quantize_latents")
@@ -168,6 +244,7 @@ def fsq_dequantize(indices: torch.Tensor, w_out, b_out, levels: Sequence[int]) -
     _chk(indices, indices.dtype, "indices")
     F = w_out.shape[0]
     out = torch.empty((*indices.shape, F), device=indices.device, dtype=torch.float32)
+    _count()
     with torch.cuda.device(indices.device):
         check(_lib.load().l3ac_fsq_dequantize(_ptr(indices), int(indices.dtype == torch.int64), indices.numel(), F,
                                               _ptr(w_out), _ptr(b_out), _levels(levels), len(levels), _ptr(out),
@@ -179,6 +256,7 @@ def upsample_linear_cn(x: torch.Tensor, scale: int, cn_w=None, cn_b=None, eps: f
     _chk(x, name="x")
     B, T, Cc = x.shape
     out = torch.empty((B, T * scale, Cc), device=x.device, dtype=torch.float32)
+    _count()
     with torch.cuda.device(x.device):
         check(_lib.load().l3ac_upsample_linear_cn(_ptr(x), B, T, Cc, scale, _ptr(cn_w), _ptr(cn_b), eps, _ptr(out),
                                                   _stream(x)), "l3ac_upsample_linear_cn")
@@ -191,6 +269,7 @@ def enhance(x: torch.Tensor, conv_w, conv_b, in_w, in_b, merge_w, merge_b, out_d
     lib = _lib.load()
     partials = torch.empty(lib.l3ac_enhance_partials_floats(B, T), device=x.device, dtype=torch.float32)
     out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    _count(2)
     with torch.cuda.device(x.device):
         st = _stream(x)
         check(lib.l3ac_enhance_stats(_ptr(x), B, T, Cc, _ptr(conv_w), _ptr(conv_b), _ptr(partials), st),
@@ -205,6 +284,7 @@ def tail_conv_tanh(x: torch.Tensor, alpha, w, bias: float) -> torch.Tensor:
     _chk(x, name="x")
     B, T, Cc = x.shape
     out = torch.empty((B, T), device=x.device, dtype=torch.float32)
+    _count()
     with torch.cuda.device(x.device):
         check(_lib.load().l3ac_tail_conv_tanh(_ptr(x), B, T, Cc, _ptr(alpha), _ptr(w), float(bias), _ptr(out),
                                               _stream(x)), "l3ac_tail_conv_tanh")

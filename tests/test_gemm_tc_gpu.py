@@ -82,3 +82,42 @@ def test_gemm_tc_linearity_at_full_size(cuda_lib):
     y2 = ops.gemm(a2, w, B=B, T=T, K=K)
     y12 = ops.gemm((a1.float() + a2.float()).to(torch.bfloat16), w, B=B, T=T, K=K)
     assert torch.equal(y12, y1 + y2)          # all products/sums are exact in fp32 for these dyadic operands
+
+
+def _split(x):
+    hi = x.to(torch.bfloat16)
+    return ops.Split(hi.to(DEV).contiguous(), (x - hi.float()).to(torch.bfloat16).to(DEV).contiguous())
+
+
+@pytest.mark.parametrize("B,T,K,N,taps,shift0,step", [
+    (2, 300, 24, 96, 1, 0, 1), (2, 300, 96, 24, 1, 0, 1), (1, 200, 144, 48, 1, 0, 1), (2, 150, 192, 128, 3, -1, 1),
+    (1, 500, 192, 768, 1, 0, 1), (1, 500, 768, 192, 1, 0, 1), (1, 260, 128, 576, 1, 0, 1)])
+def test_gemm_tc_split_is_fp32_class(cuda_lib, B, T, K, N, taps, shift0, step):
+    """3-term split-bf16 GEMM against fp64 on the *unrounded* fp32 operands: error at the 2^-16 level, not 2^-8."""
+    a, w, bias = rnd(B, T, K, seed=1), rnd(N, taps * K, seed=2, scale=0.1), rnd(N, seed=3)
+    want = _gemm_ref(a, w, bias, taps, shift0, step)
+    got = ops.gemm(_split(a), _split(w), B=B, T=T, K=K, taps=taps, tap_shift0=shift0, tap_step=step, bias=bias.to(DEV))
+    scale = max(1.0, float(want.abs().max()))
+    assert max_abs(got.cpu(), want) < 3e-5 * scale
+    plain = ops.gemm(bf(a).to(DEV), bf(w).to(DEV), B=B, T=T, K=K, taps=taps, tap_shift0=shift0, tap_step=step, bias=bias.to(DEV))
+    assert max_abs(got.cpu(), want) < 0.05 * max_abs(plain.cpu(), want) + 1e-6     # >= 20x closer than plain bf16
+
+
+def test_split_outputs_and_producers(cuda_lib):
+    x = rnd(3, 100, 96, seed=1)
+    sp = ops.split_bf16(x.to(DEV))
+    assert max_abs(sp.float().cpu(), x) < 2e-5 and torch.equal(sp.hi.cpu(), x.to(torch.bfloat16))
+    w, b = 1 + rnd(96, seed=2, scale=0.1), rnd(96, seed=3, scale=0.1)
+    ln32 = ops.layernorm(x.to(DEV), w.to(DEV), b.to(DEV), 1e-5)
+    lnsp = ops.layernorm(x.to(DEV), w.to(DEV), b.to(DEV), 1e-5, out_dtype=ops.SPLIT)
+    assert max_abs(lnsp.float(), ln32) < 3e-5
+    # GEMM epilogue emitting a split pair (snake + affine), then consumed by a second split GEMM
+    a, w1, w2 = rnd(2, 200, 48, seed=4), rnd(192, 48, seed=5, scale=0.2), rnd(48, 192, seed=6, scale=0.1)
+    alpha = 0.5 + torch.rand(192)
+    h = ops.gemm(_split(a), _split(w1), B=2, T=200, K=48, act=ops.ACT_SNAKE, alpha=alpha.to(DEV), out_dtype=ops.SPLIT)
+    lin = a.double() @ w1.double().t()
+    want_h = lin + (alpha.double() + 1e-8).reciprocal() * torch.sin(alpha.double() * lin).pow(2)
+    assert max_abs(h.float().cpu(), want_h) < 1e-4              # precise sinf; pair representation error |x| * 2^-17
+    y = ops.gemm(h, _split(w2), B=2, T=200, K=192, residual=a.to(DEV))
+    want_y = h.float().cpu().double() @ w2.double().t() + a.double()
+    assert max_abs(y.cpu(), want_y) < 3e-5 * max(1.0, float(want_y.abs().max()))

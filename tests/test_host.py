@@ -77,9 +77,9 @@ def test_header_symbols_are_bound_and_exported():
 
 
 def test_gemm_desc_layout_matches_header():
-    """The ctypes mirror of l3ac_gemm_desc has the C layout (8 pointers, 3 int64, 9 int32 -> 128 bytes)."""
-    assert ctypes.sizeof(_lib.GemmDesc) == 8 * 8 + 3 * 8 + 9 * 4 + 4
-    assert _lib.GemmDesc.lda.offset == 64 and _lib.GemmDesc.B.offset == 88 and _lib.GemmDesc.out_dtype.offset == 120
+    """The ctypes mirror of l3ac_gemm_desc has the C layout (11 pointers, 3 int64, 9 int32 -> 152 bytes)."""
+    assert ctypes.sizeof(_lib.GemmDesc) == 11 * 8 + 3 * 8 + 9 * 4 + 4
+    assert _lib.GemmDesc.lda.offset == 88 and _lib.GemmDesc.B.offset == 112 and _lib.GemmDesc.out_dtype.offset == 144
 
 
 def test_no_cpu_fallback():
