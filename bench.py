@@ -235,32 +235,55 @@ def main():
         e1.record()
         records.append((kind, flops, nbytes, e0, e1))
 
-    ops.GEMM_HOOK = hook
+    ops.OP_HOOK = hook
     with torch.inference_mode():
+        e_all0, e_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e_all0.record()
         step_resident(0)
+        e_all1.record()
     torch.cuda.synchronize()
-    ops.GEMM_HOOK = None
+    ops.OP_HOOK = None
+    inst_ms = e_all0.elapsed_time(e_all1)
+    by_op = {}
+    for k, f, b, a, c in records:
+        ms = a.elapsed_time(c)
+        o = by_op.setdefault(k, dict(launches=0, ms=0.0, gflop=0.0, mb=0.0))
+        o["launches"] += 1
+        o["ms"] += ms
+        o["gflop"] += f / 1e9
+        o["mb"] += b / 1e6
     if os.environ.get("L3AC_BENCH_DUMP"):
         with open(os.environ["L3AC_BENCH_DUMP"], "w") as fh:
             for k, f, b, a, c in records:
                 ms = a.elapsed_time(c)
                 fh.write(f"{k} gflop={f / 1e9:.2f} mb={b / 1e6:.1f} us={ms * 1e3:.1f} tflops={f / ms / 1e9:.1f} gbs={b / ms / 1e6:.0f}\n")
-    tc = [(f, b, a.elapsed_time(c)) for k, f, b, a, c in records if k == "tc"]
-    f32 = [(f, b, a.elapsed_time(c)) for k, f, b, a, c in records if k == "f32"]
+            fh.write(f"# instrumented step {inst_ms:.2f} ms, sum of ops {sum(o['ms'] for o in by_op.values()):.2f} ms\n")
+            for k, o in sorted(by_op.items(), key=lambda kv: -kv[1]["ms"]):
+                fh.write(f"# {k:22s} n={o['launches']:4d} {o['ms']:8.2f} ms  {o['gflop'] / max(o['ms'], 1e-9):8.1f} TF/s "
+                         f"{o['mb'] / max(o['ms'], 1e-9):8.0f} GB/s\n")
+    tc = [(f, b, a.elapsed_time(c)) for k, f, b, a, c in records if k in ("gemm_tc", "gemm_tc_split")]
+    f32 = [(f, b, a.elapsed_time(c)) for k, f, b, a, c in records if k == "gemm_f32"]
     tc_ms, tc_flops = sum(t for _, _, t in tc), sum(f for f, _, _ in tc)
     f32_ms, f32_flops = sum(t for _, _, t in f32), sum(f for f, _, _ in f32)
     roofline = None
     if tc:
         ach = tc_flops / (tc_ms * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM, all launches of one step)",
+        roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM incl. 3-term split launches, all launches of one step; "
+                                                   "split launches are counted at their algorithmic 2*M*N*K, not 3x)",
                     "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
                     "traffic": None, "peak_source": f"{pk['src']} (sustained bf16)", "launches": len(tc),
                     "share_of_step": tc_ms / ms_step, "flops_per_step": tc_flops}
+    hbm_ops = {k: o for k, o in by_op.items() if not k.startswith("gemm")}
+    hbm_ms, hbm_mb = sum(o["ms"] for o in hbm_ops.values()), sum(o["mb"] for o in hbm_ops.values())
     total_gflop = GFLOP_PER_10S.get(args.config, 0.0) * secs / 10.0 * B
     extras = {
         "step_algorithmic_tflops": total_gflop / ms_step, "step_tensor_frac": total_gflop / ms_step / pk["tf_sustained"],
         "fp32_simt_gemm": {"launches": len(f32), "ms": f32_ms, "tflops": (f32_flops / (f32_ms * 1e-3) / 1e12) if f32 else None,
                            "share_of_step": f32_ms / ms_step},
+        "roofline_hbm": {"bound": "hbm", "kernel": "all non-GEMM kernels of one step (stencil / norm / attention / fsq), algorithmic bytes",
+                         "achieved": (hbm_mb / hbm_ms) if hbm_ms else None, "peak": pk["hbm"], "unit": "GB/s",
+                         "frac": (hbm_mb / hbm_ms / pk["hbm"]) if hbm_ms else None, "share_of_step": hbm_ms / ms_step},
+        "op_ms": {k: round(o["ms"], 3) for k, o in sorted(by_op.items(), key=lambda kv: -kv[1]["ms"])},
     }
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -88,6 +88,80 @@ __global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* __restrict
     }
 }
 
+// Thin-channel variant (C <= 96): one warp handles R consecutive time steps of one sample per iteration and issues
+// all (R + 6) * CPL input loads up front.  With 96..384 B rows the one-row-per-warp kernel above is latency-bound
+// (one DRAM round trip per row and warp); this keeps ~8x more bytes in flight and reads every input row once per warp
+// instead of seven times.
+template <int CPL, int R, typename OutT>
+__global__ void __launch_bounds__(256) dwconv7_ln_rows_kernel(const float* __restrict__ x, int B, int T, int C,
+                                                              const float* __restrict__ dw_w,
+                                                              const float* __restrict__ dw_b,
+                                                              const float* __restrict__ ln_w,
+                                                              const float* __restrict__ ln_b, float eps,
+                                                              OutT* __restrict__ out, OutT* __restrict__ out_lo) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    float w[7][CPL], bias[CPL], lw[CPL], lb[CPL];
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+        const int c = lane + 32 * i;
+        const bool ok = c < C;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) w[j][i] = ok ? __ldg(dw_w + j * C + c) : 0.f;
+        bias[i] = ok ? __ldg(dw_b + c) : 0.f;
+        lw[i] = ok ? __ldg(ln_w + c) : 0.f;
+        lb[i] = ok ? __ldg(ln_b + c) : 0.f;
+    }
+    const int runs_per_sample = (T + R - 1) / R;
+    const long long total_runs = (long long)B * runs_per_sample;
+    const float inv_c = 1.0f / (float)C;
+    for (long long run = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); run < total_runs;
+         run += (long long)gridDim.x * warps_per_block) {
+        const int b = (int)(run / runs_per_sample);
+        const int t0 = (int)(run - (long long)b * runs_per_sample) * R;
+        const float* xb = x + (long long)b * T * C;
+        float xr[R + 6][CPL];
+#pragma unroll
+        for (int r = 0; r < R + 6; ++r) {
+            const int t = t0 + r - 3;
+            const bool row_ok = t >= 0 && t < T;      // warp-uniform
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+                const int c = lane + 32 * i;
+                xr[r][i] = (row_ok && c < C) ? __ldg(xb + (long long)t * C + c) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (t0 + r >= T) break;                   // warp-uniform
+            float acc[CPL];
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+                float a = bias[i];
+#pragma unroll
+                for (int j = 0; j < 7; ++j) a = fmaf(w[j][i], xr[r + j][i], a);
+                acc[i] = a;
+                s += (lane + 32 * i < C) ? a : 0.f;
+            }
+            const float mean = warp_sum(s) * inv_c;
+            float v = 0.f;
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+                const float dlt = acc[i] - mean;
+                v += (lane + 32 * i < C) ? dlt * dlt : 0.f;
+            }
+            const float rstd = 1.0f / sqrtf(warp_sum(v) * inv_c + eps);
+            const long long row = (long long)b * T + t0 + r;
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+                const int c = lane + 32 * i;
+                if (c < C) store_act<OutT>(out, out_lo, row * C + c, (acc[i] - mean) * rstd * lw[i] + lb[i]);
+            }
+        }
+    }
+}
+
 template <int CPL, typename OutT>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, long long M, int C,
                                                         const float* __restrict__ w,
@@ -445,6 +519,24 @@ extern "C" int l3ac_dwconv7_ln(const float* x, int B, int T, int C, const float*
     L3AC_CHECK_ARG((out_dtype == L3AC_BF16X2) == (out_lo != nullptr));
     cudaStream_t st = (cudaStream_t)stream;
     const long long rows = (long long)B * T;
+    if (C <= 96) {
+        constexpr int R = 8;
+        const int grid = grid_for_rows((rows + R - 1) / R + B, 8);
+#define L3AC_ROWS_LAUNCH(CPLV)                                                                                          \
+    do {                                                                                                               \
+        if (out_dtype == L3AC_F32)                                                                                     \
+            dwconv7_ln_rows_kernel<CPLV, R, float><<<grid, 256, 0, st>>>(x, B, T, C, dw_w, dw_b, ln_w, ln_b, eps,       \
+                                                                         (float*)out, nullptr);                        \
+        else                                                                                                           \
+            dwconv7_ln_rows_kernel<CPLV, R, __nv_bfloat16><<<grid, 256, 0, st>>>(                                      \
+                x, B, T, C, dw_w, dw_b, ln_w, ln_b, eps, (__nv_bfloat16*)out, (__nv_bfloat16*)out_lo);                 \
+    } while (0)
+        if (C <= 32) L3AC_ROWS_LAUNCH(1);
+        else if (C <= 64) L3AC_ROWS_LAUNCH(2);
+        else L3AC_ROWS_LAUNCH(3);
+#undef L3AC_ROWS_LAUNCH
+        return l3ac_launch_status();
+    }
     const int grid = grid_for_rows(rows, 8);
     const size_t smem = (size_t)10 * C * sizeof(float);
     DISPATCH_CPL(C, {

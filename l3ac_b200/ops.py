@@ -50,14 +50,41 @@ def _empty_act(shape, device, out_dtype):
     return t, t, None
 
 # Instrumentation used by bench.py: number of kernels this library launched, and an optional hook that brackets
-# each GEMM launch with CUDA events (``GEMM_HOOK(kind, flops, bytes) -> context manager``).  Off by default.
+# every launch with CUDA events (``OP_HOOK(name, flops, bytes) -> context manager``).  Off by default.
 LAUNCHES = 0
-GEMM_HOOK = None
+OP_HOOK = None
 
 
 def _count(n: int = 1):
     global LAUNCHES
     LAUNCHES += n
+
+
+class _NullCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+_NULL = _NullCtx()
+
+
+def _hook(name: str, nbytes: float = 0.0, flops: float = 0.0):
+    return _NULL if OP_HOOK is None else OP_HOOK(name, flops, nbytes)
+
+
+def _nbytes(*tensors) -> int:
+    n = 0
+    for t in tensors:
+        if t is None:
+            continue
+        if isinstance(t, Split):
+            n += 2 * t.hi.numel() * 2
+        else:
+            n += t.numel() * t.element_size()
+    return n
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -88,7 +115,7 @@ def stem(audio: torch.Tensor, branch_w, branch_b, w1, b1, w2, b2) -> torch.Tenso
     Cout = w2.shape[0]
     out = torch.empty((B, T, Cout), device=audio.device, dtype=torch.float32)
     _count()
-    with torch.cuda.device(audio.device):
+    with _hook("stem", _nbytes(audio, out), 2.0 * audio.numel() * 3700), torch.cuda.device(audio.device):
         check(_lib.load().l3ac_stem(_ptr(audio), B, T, _ptr(branch_w), _ptr(branch_b), _ptr(w1), _ptr(b1), _ptr(w2),
                                     _ptr(b2), Cout, _ptr(out), _stream(audio)), "l3ac_stem")
     return out
@@ -99,7 +126,7 @@ def dwconv7_ln(x, dw_w, dw_b, ln_w, ln_b, eps: float, out_dtype=torch.float32) -
     B, T, Cc = x.shape
     out, hi, lo = _empty_act((B, T, Cc), x.device, out_dtype)
     _count()
-    with torch.cuda.device(x.device):
+    with _hook("dwconv7_ln", _nbytes(x, out)), torch.cuda.device(x.device):
         check(_lib.load().l3ac_dwconv7_ln(_ptr(x), B, T, Cc, _ptr(dw_w), _ptr(dw_b), _ptr(ln_w), _ptr(ln_b), eps,
                                           _ptr(hi), _ptr(lo), _DT[out_dtype], _stream(x)), "l3ac_dwconv7_ln")
     return out
@@ -111,7 +138,7 @@ def layernorm(x, w, b, eps: float, out_dtype=torch.float32) -> torch.Tensor:
     M = x.numel() // Cc
     out, hi, lo = _empty_act(x.shape, x.device, out_dtype)
     _count()
-    with torch.cuda.device(x.device):
+    with _hook("layernorm", _nbytes(x, out)), torch.cuda.device(x.device):
         check(_lib.load().l3ac_layernorm(_ptr(x), M, Cc, _ptr(w), _ptr(b), eps, _ptr(hi), _ptr(lo), _DT[out_dtype],
                                          _stream(x)), "l3ac_layernorm")
     return out
@@ -122,7 +149,7 @@ def split_bf16(x: torch.Tensor) -> Split:
     _chk(x, name="x")
     out, hi, lo = _empty_act(x.shape, x.device, SPLIT)
     _count()
-    with torch.cuda.device(x.device):
+    with _hook("split_bf16", _nbytes(x, out)), torch.cuda.device(x.device):
         check(_lib.load().l3ac_split_bf16(_ptr(x), x.numel(), _ptr(hi), _ptr(lo), _stream(x)), "l3ac_split_bf16")
     return out
 
@@ -132,7 +159,7 @@ def snake(x, alpha, out_dtype=torch.float32) -> torch.Tensor:
     Cc = x.shape[-1]
     out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
     _count()
-    with torch.cuda.device(x.device):
+    with _hook("snake", _nbytes(x, out)), torch.cuda.device(x.device):
         check(_lib.load().l3ac_snake(_ptr(x), x.numel() // Cc, Cc, _ptr(alpha), _ptr(out), _DT[out_dtype], _stream(x)),
               "l3ac_snake")
     return out
@@ -176,15 +203,15 @@ def gemm(a, w, *, B: int, T: int, K: int, taps: int = 1, tap_shift0: int = 0, ta
                                                                                          "l3ac_gemm_bf16_tc")
     _count()
     with torch.cuda.device(a_hi.device):
-        if GEMM_HOOK is None:
+        if OP_HOOK is None:
             check(fn(C.byref(d), _stream(a_hi)), what)
         else:
             flops = 2.0 * B * T * N * K * taps
             esz = a_hi.element_size() * (2 if split else 1)
             osz = {torch.float32: 4, torch.bfloat16: 2, SPLIT: 4}[out_dtype]
             nbytes = esz * (B * T * K + N * K * taps) + osz * B * T * n_out + (0 if residual is None else 4 * residual.numel())
-            kind = "f32" if a_hi.dtype == torch.float32 else ("tc_split" if split else "tc")
-            with GEMM_HOOK(kind, flops, nbytes):
+            kind = "gemm_f32" if a_hi.dtype == torch.float32 else ("gemm_tc_split" if split else "gemm_tc")
+            with OP_HOOK(kind, flops, nbytes):
                 check(fn(C.byref(d), _stream(a_hi)), what)
     return out
 
@@ -198,7 +225,7 @@ def local_attention(qkv: torch.Tensor, bias_table: torch.Tensor, heads: int, win
         raise ValueError(f"bias_table must be (heads, 2*window), got {tuple(bias_table.shape)}")
     out = torch.empty((B, T, heads * D), device=qkv.device, dtype=torch.float32)
     _count()
-    with torch.cuda.device(qkv.device):
+    with _hook("local_attention", _nbytes(qkv, out)), torch.cuda.device(qkv.device):
         check(_lib.load().l3ac_local_attention_f32(_ptr(qkv), _ptr(bias_table), B, T, heads, D, window, _ptr(out),
                                                    _stream(qkv)), "l3ac_local_attention_f32")
     return out
@@ -215,7 +242,7 @@ def fsq_quantize(x: torch.Tensor, w_in, b_in, w_out, b_out, levels: Sequence[int
     lvl = torch.empty((*lead, D), device=x.device, dtype=torch.float32)
     z = torch.empty((*lead, D), device=x.device, dtype=torch.float32) if want_z else None
     _count()
-    with torch.cuda.device(x.device):
+    with _hook("fsq_quantize", _nbytes(x, q, idx, lvl)), torch.cuda.device(x.device):
         check(_lib.load().l3ac_fsq_quantize(_ptr(x), M, F, _ptr(w_in), _ptr(b_in), _ptr(w_out), _ptr(b_out),
                                             _levels(levels), D, _ptr(q), _ptr(idx), _ptr(lvl), _ptr(z), _stream(x)),
               "l3ac_fsq_quantize")
@@ -232,7 +259,7 @@ def fsq_quantize_latents(z: torch.Tensor, levels: Sequence[int]):
     idx = torch.empty(lead, device=z.device, dtype=torch.int32)
     lvl = torch.empty(z.shape, device=z.device, dtype=torch.float32)
     _count()
-    with torch.cuda.device(z.device):
+    with _hook("fsq_quantize_latents", _nbytes(z, q, idx, lvl)), torch.cuda.device(z.device):
         check(_lib.load().l3ac_fsq_quantize_latents(_ptr(z), z.numel() // D, _levels(levels), D, _ptr(q), _ptr(idx),
                                                     _ptr(lvl), _stream(z)), "l3ac_fsq_quantize_latents")
     return q, idx, lvl
@@ -245,7 +272,7 @@ def fsq_dequantize(indices: torch.Tensor, w_out, b_out, levels: Sequence[int]) -
     F = w_out.shape[0]
     out = torch.empty((*indices.shape, F), device=indices.device, dtype=torch.float32)
     _count()
-    with torch.cuda.device(indices.device):
+    with _hook("fsq_dequantize", _nbytes(indices, out)), torch.cuda.device(indices.device):
         check(_lib.load().l3ac_fsq_dequantize(_ptr(indices), int(indices.dtype == torch.int64), indices.numel(), F,
                                               _ptr(w_out), _ptr(b_out), _levels(levels), len(levels), _ptr(out),
                                               _stream(indices)), "l3ac_fsq_dequantize")
@@ -257,7 +284,7 @@ def upsample_linear_cn(x: torch.Tensor, scale: int, cn_w=None, cn_b=None, eps: f
     B, T, Cc = x.shape
     out = torch.empty((B, T * scale, Cc), device=x.device, dtype=torch.float32)
     _count()
-    with torch.cuda.device(x.device):
+    with _hook("upsample_linear_cn", _nbytes(x, out)), torch.cuda.device(x.device):
         check(_lib.load().l3ac_upsample_linear_cn(_ptr(x), B, T, Cc, scale, _ptr(cn_w), _ptr(cn_b), eps, _ptr(out),
                                                   _stream(x)), "l3ac_upsample_linear_cn")
     return out
@@ -270,7 +297,7 @@ def enhance(x: torch.Tensor, conv_w, conv_b, in_w, in_b, merge_w, merge_b, out_d
     partials = torch.empty(lib.l3ac_enhance_partials_floats(B, T), device=x.device, dtype=torch.float32)
     out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
     _count(2)
-    with torch.cuda.device(x.device):
+    with _hook("enhance", 2 * x.numel() // x.shape[-1] * 4 + _nbytes(x, out)), torch.cuda.device(x.device):
         st = _stream(x)
         check(lib.l3ac_enhance_stats(_ptr(x), B, T, Cc, _ptr(conv_w), _ptr(conv_b), _ptr(partials), st),
               "l3ac_enhance_stats")
@@ -285,7 +312,7 @@ def tail_conv_tanh(x: torch.Tensor, alpha, w, bias: float) -> torch.Tensor:
     B, T, Cc = x.shape
     out = torch.empty((B, T), device=x.device, dtype=torch.float32)
     _count()
-    with torch.cuda.device(x.device):
+    with _hook("tail_conv_tanh", _nbytes(x, out)), torch.cuda.device(x.device):
         check(_lib.load().l3ac_tail_conv_tanh(_ptr(x), B, T, Cc, _ptr(alpha), _ptr(w), float(bias), _ptr(out),
                                               _stream(x)), "l3ac_tail_conv_tanh")
     return out
