@@ -134,6 +134,12 @@ int l3ac_gemm_bf16_tc(const l3ac_gemm_desc* d, l3ac_stream_t stream);
 int l3ac_local_attention_f32(const float* qkv, const float* bias_table, int B, int T, int H, int D,
                              int window, float* out, l3ac_stream_t stream);
 
+/* Tensor-core variant of the same attention over bf16 q/k/v (the QKV GEMM writes them directly).  qkv_hi (and
+ * qkv_lo for the 3-term split product, else NULL) are (B,T,3*H*D) bf16 planes packed [q | k | v]; out (B,T,H*D) is
+ * fp32, bf16 or a bf16 (hi, lo) pair (out_lo) -- the A operand of the output projection.  D must be 32. */
+int l3ac_local_attention_tc(const void* qkv_hi, const void* qkv_lo, const float* bias_table, int B, int T, int H,
+                            int D, int window, void* out, void* out_lo, int out_dtype, l3ac_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * FSQ bottleneck.  Replaces VQEmbed.forward (l3ac/vq/__init__.py:25-30) = project_in ->
  * SuperFSQ.forward (l3ac/vq/fsq.py:30-68; tanh_act l3ac/vq/fsq_act.py:38-39) -> project_out, and
@@ -178,6 +184,21 @@ int l3ac_enhance_apply(const float* x, int B, int T, int C, const float* conv_w,
  * x (B,T,C) fp32 -> out (B,T) fp32.  w is [7][C] (tap-major). */
 int l3ac_tail_conv_tanh(const float* x, int B, int T, int C, const float* alpha, const float* w, float bias,
                         float* out, l3ac_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused full-rate decoder tail: 3 x Residual(LegacyUnit) (l3ac/modules.py:47-64,174-179; dilations 1,3,9)
+ * + Snake -> Conv1d(C->1,k7,pad 3) -> tanh (l3ac/modules.py:192-194) in one kernel.
+ * x (B,T,24) fp32 -> out (B,T) fp32.  The k7 and 1x1 conv weights are bf16, pre-packed in mma.m16n8k16
+ * B-fragment order with K padded 24 -> 32:
+ *   conv_frags [3 units][7 taps][2 ksteps][3 ntiles][32 lanes][4] bf16, pw_frags [3][2][3][32][4] bf16, where the
+ *   4 values of lane l are W[n][k0], W[n][k0+1], W[n][k0+8], W[n][k0+9], n = 8*ntile + l/4, k0 = 16*kstep + 2*(l%4)
+ *   (W[n][k] = 0 for k >= 24).  conv_bias/pw_bias/alpha0/alpha1 are [3][24]; dilations is a HOST array of 3 ints
+ *   whose receptive field 3*(d0+d1+d2)+3 must be <= 42.  alpha_f [24], w_f [7][24] (tap-major), bias_f: final conv.
+ * ------------------------------------------------------------------------------------------ */
+int l3ac_decoder_tail(const float* x, int B, int T, int C, const void* conv_frags, const float* conv_bias,
+                      const void* pw_frags, const float* pw_bias, const float* alpha0, const float* alpha1,
+                      const int* dilations, const float* alpha_f, const float* w_f, float bias_f, float* out,
+                      l3ac_stream_t stream);
 
 #ifdef __cplusplus
 }

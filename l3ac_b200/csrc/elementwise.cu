@@ -162,6 +162,77 @@ __global__ void __launch_bounds__(256) dwconv7_ln_rows_kernel(const float* __res
     }
 }
 
+// Wide-channel variant (C a multiple of 32, 128 <= C <= 512): one CTA = TT consecutive time steps x all channels,
+// one thread per channel.  Each input element is loaded once (38 coalesced loads in flight per thread), the conv
+// outputs stay in registers, and the per-time-step LayerNorm statistics are reduced warp -> shared memory -> CTA
+// (two passes: mean, then centred sum of squares, like F.layer_norm).
+template <int TT, typename OutT>
+__global__ void __launch_bounds__(512) dwconv7_ln_tile_kernel(const float* __restrict__ x, int B, int T, int C,
+                                                              const float* __restrict__ dw_w,
+                                                              const float* __restrict__ dw_b,
+                                                              const float* __restrict__ ln_w,
+                                                              const float* __restrict__ ln_b, float eps,
+                                                              OutT* __restrict__ out, OutT* __restrict__ out_lo) {
+    __shared__ float s_part[TT][16];     // [time][warp]
+    __shared__ float s_stat[TT];
+    const int c = threadIdx.x, lane = c & 31, warp = c >> 5, nwarps = blockDim.x >> 5;
+    const int b = blockIdx.y, t0 = blockIdx.x * TT;
+    const float* xb = x + (long long)b * T * C + c;
+    float w[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) w[j] = __ldg(dw_w + j * C + c);
+    const float bias = __ldg(dw_b + c), lw = __ldg(ln_w + c), lb = __ldg(ln_b + c);
+    float xr[TT + 6];
+#pragma unroll
+    for (int r = 0; r < TT + 6; ++r) {
+        const int t = t0 + r - 3;
+        xr[r] = (t >= 0 && t < T) ? __ldg(xb + (long long)t * C) : 0.f;
+    }
+    float y[TT];
+#pragma unroll
+    for (int i = 0; i < TT; ++i) {
+        float a = bias;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) a = fmaf(w[j], xr[i + j], a);
+        y[i] = a;
+    }
+    const float inv_c = 1.0f / (float)C;
+    // pass 1: mean over channels for every time step
+#pragma unroll
+    for (int i = 0; i < TT; ++i) {
+        const float s = warp_sum(y[i]);
+        if (lane == 0) s_part[i][warp] = s;
+    }
+    __syncthreads();
+    if (c < TT) {
+        float s = 0.f;
+        for (int q = 0; q < nwarps; ++q) s += s_part[c][q];
+        s_stat[c] = s * inv_c;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < TT; ++i) y[i] -= s_stat[i];
+    __syncthreads();
+    // pass 2: biased variance
+#pragma unroll
+    for (int i = 0; i < TT; ++i) {
+        const float s = warp_sum(y[i] * y[i]);
+        if (lane == 0) s_part[i][warp] = s;
+    }
+    __syncthreads();
+    if (c < TT) {
+        float s = 0.f;
+        for (int q = 0; q < nwarps; ++q) s += s_part[c][q];
+        s_stat[c] = 1.0f / sqrtf(s * inv_c + eps);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < TT; ++i) {
+        const int t = t0 + i;
+        if (t < T) store_act<OutT>(out, out_lo, ((long long)b * T + t) * C + c, y[i] * s_stat[i] * lw + lb);
+    }
+}
+
 template <int CPL, typename OutT>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, long long M, int C,
                                                         const float* __restrict__ w,
@@ -535,6 +606,16 @@ extern "C" int l3ac_dwconv7_ln(const float* x, int B, int T, int C, const float*
         else if (C <= 64) L3AC_ROWS_LAUNCH(2);
         else L3AC_ROWS_LAUNCH(3);
 #undef L3AC_ROWS_LAUNCH
+        return l3ac_launch_status();
+    }
+    if (C % 32 == 0 && C >= 128 && C <= 512 && B <= 65535) {
+        constexpr int TT = 32;
+        dim3 tgrid(l3ac_cdiv(T, TT), B);
+        if (out_dtype == L3AC_F32)
+            dwconv7_ln_tile_kernel<TT, float><<<tgrid, C, 0, st>>>(x, B, T, C, dw_w, dw_b, ln_w, ln_b, eps, (float*)out, nullptr);
+        else
+            dwconv7_ln_tile_kernel<TT, __nv_bfloat16><<<tgrid, C, 0, st>>>(x, B, T, C, dw_w, dw_b, ln_w, ln_b, eps,
+                                                                           (__nv_bfloat16*)out, (__nv_bfloat16*)out_lo);
         return l3ac_launch_status();
     }
     const int grid = grid_for_rows(rows, 8);

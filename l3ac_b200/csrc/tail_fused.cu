@@ -1,0 +1,281 @@
+// Fused full-rate decoder tail (l3ac/modules.py:174-194): three Residual(LegacyUnit) blocks with dilations d0,d1,d2
+//   x += Conv1x1( snake( Conv_k7,dil d( snake(x, a0) ) + b, a1 ) ) + b'          (l3ac/modules.py:47-64)
+// followed by Snake -> Conv1d(C -> 1, k7, pad 3) -> tanh, in ONE kernel: the (B, T, 24) fp32 stream is read once from
+// HBM and only the (B, T) waveform is written.  As separate launches these nine full-rate tensors are pure HBM
+// traffic ("thin full-rate layers are HBM-bound").
+//
+// One CTA owns kRows = 384 consecutive samples of one clip (300 outputs + 42-sample halo on each side = the receptive
+// field 3*(1+3+9)+3).  The fp32 residual stream, the bf16 snake(x) operand and the bf16 hidden operand live in shared
+// memory; the two convs run on the tensor cores as warp-level mma.m16n8k16 (bf16 in, fp32 accumulate) with
+// A = activations [time][channel] via ldmatrix (XOR-swizzled 16-byte chunks) and B = weights pre-packed on the host
+// in fragment order.  Channels are padded 24 -> 32 (K) with zeros.
+// (This kernel is HBM/latency-bound by construction -- 24 channels cannot feed a 128x256 tcgen05 tile -- so it uses
+// the register-level MMA path; the fat layers use tcgen05 in gemm_tc.cu.)
+#include "common.cuh"
+
+namespace l3ac {
+namespace tail {
+
+constexpr int kC = 24;
+constexpr int kCP = 32;                 // padded channels (bf16 row = 64 B = 4 chunks of 16 B)
+constexpr int kHalo = 42;
+constexpr int kRows = 384;
+constexpr int kOut = kRows - 2 * kHalo; // 300 outputs per CTA
+constexpr int kThreads = 256;
+constexpr int kConvFragWords = 7 * 2 * 3 * 32 * 2;   // uint32 per unit: [tap][kstep][ntile][lane][2]
+constexpr int kPwFragWords = 2 * 3 * 32 * 2;
+
+struct Params {
+    const float* x;
+    const uint32_t* conv_frags;   // [3][kConvFragWords]
+    const uint32_t* pw_frags;     // [3][kPwFragWords]
+    const float* conv_bias;       // [3][24]
+    const float* pw_bias;         // [3][24]
+    const float* alpha0;          // [3][24]
+    const float* alpha1;          // [3][24]
+    const float* alpha_f;         // [24]
+    const float* w_f;             // [7][24]
+    float bias_f;
+    int dil[3];
+    int B, T;
+    float* out;
+};
+
+__device__ __forceinline__ uint32_t swz(int row, int chunk) {      // byte offset of a 16-byte chunk in a [rows][64 B] buffer
+    return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
+}
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr));
+}
+
+__device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ int clamp_row(int r) { return r < 0 ? 0 : (r >= kRows ? kRows - 1 : r); }
+
+__global__ void __launch_bounds__(kThreads, 2) decoder_tail_kernel(const Params p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    float* xs = reinterpret_cast<float*>(smem);                             // [kRows][24] fp32 residual stream
+    uint8_t* a_buf = smem + kRows * kC * 4;                                  // [kRows][32] bf16, swizzled
+    uint8_t* h_buf = a_buf + kRows * 64;                                     // [kRows][32] bf16, swizzled
+    uint32_t* w_conv = reinterpret_cast<uint32_t*>(h_buf + kRows * 64);      // [kConvFragWords]
+    uint32_t* w_pw = w_conv + kConvFragWords;                                // [kPwFragWords]
+    float* s_par = reinterpret_cast<float*>(w_pw + kPwFragWords);            // conv_bias, pw_bias, alpha0, ialpha0, alpha1, ialpha1 [6][24]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y;
+    const int t_first = blockIdx.x * kOut - kHalo;       // global sample of smem row 0
+    const float* xb = p.x + (long long)b * p.T * kC;
+    const uint32_t a_addr = (uint32_t)__cvta_generic_to_shared(a_buf);
+    const uint32_t h_addr = (uint32_t)__cvta_generic_to_shared(h_buf);
+
+    // ---- load the fp32 tile (rows outside the clip are zero: every conv on the path zero-pads its input)
+    for (int i = tid; i < kRows * kC / 4; i += kThreads) {
+        const int row = (i * 4) / kC;
+        const int t = t_first + row;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t >= 0 && t < p.T) v = __ldg(reinterpret_cast<const float4*>(xb + (long long)t_first * kC) + i);
+        reinterpret_cast<float4*>(xs)[i] = v;
+    }
+    // zero the K padding (channels 24..31 = chunk 3) of both operand buffers once
+    for (int r = tid; r < kRows; r += kThreads) {
+        *reinterpret_cast<uint4*>(a_buf + swz(r, 3)) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(h_buf + swz(r, 3)) = make_uint4(0, 0, 0, 0);
+    }
+
+    for (int u = 0; u < 3; ++u) {
+        const int d = p.dil[u];
+        __syncthreads();     // xs complete (load or previous unit); previous unit's weights no longer in use
+        for (int i = tid; i < kConvFragWords; i += kThreads) w_conv[i] = __ldg(p.conv_frags + u * kConvFragWords + i);
+        for (int i = tid; i < kPwFragWords; i += kThreads) w_pw[i] = __ldg(p.pw_frags + u * kPwFragWords + i);
+        if (tid < kC) {
+            s_par[tid] = p.conv_bias[u * kC + tid];
+            s_par[kC + tid] = p.pw_bias[u * kC + tid];
+            const float a0 = p.alpha0[u * kC + tid], a1 = p.alpha1[u * kC + tid];
+            s_par[2 * kC + tid] = a0;
+            s_par[3 * kC + tid] = 1.0f / (a0 + kEps);
+            s_par[4 * kC + tid] = a1;
+            s_par[5 * kC + tid] = 1.0f / (a1 + kEps);
+        }
+        __syncthreads();
+        // ---- a = bf16(snake(x, alpha0)): one thread per (row, 8-channel chunk)
+        for (int i = tid; i < kRows * 3; i += kThreads) {
+            const int row = i / 3, ch = i - row * 3;
+            const float4 v0 = *reinterpret_cast<const float4*>(xs + row * kC + ch * 8);
+            const float4 v1 = *reinterpret_cast<const float4*>(xs + row * kC + ch * 8 + 4);
+            const float in[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int c0 = ch * 8 + 2 * e;
+                const float s0 = __sinf(s_par[2 * kC + c0] * in[2 * e]);
+                const float s1 = __sinf(s_par[2 * kC + c0 + 1] * in[2 * e + 1]);
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaf(s_par[3 * kC + c0], s0 * s0, in[2 * e]),
+                                                                fmaf(s_par[3 * kC + c0 + 1], s1 * s1, in[2 * e + 1]));
+                pk[e] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+            *reinterpret_cast<uint4*>(a_buf + swz(row, ch)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        __syncthreads();
+        // ---- h = bf16(snake(conv_k7_dil_d(a) + bias, alpha1)): M = time (16-row tiles), N = 24 (3 x 8), K = 7 taps x 32
+        for (int mt = warp; mt < kRows / 16; mt += kThreads / 32) {
+            const int r0 = mt * 16;
+            float acc[3][4];
+#pragma unroll
+            for (int n = 0; n < 3; ++n)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[n][e] = 0.f;
+            const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8;      // ldmatrix: lanes 0-15 rows 0-15 (k lo), 16-31 rows 0-15 (k hi)
+            const int lchunk = lane >> 4;
+#pragma unroll
+            for (int tap = 0; tap < 7; ++tap) {
+                const int row = clamp_row(r0 + lrow + (tap - 3) * d);
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    uint32_t a0, a1, a2, a3;
+                    ldmatrix_x4(a_addr + swz(row, 2 * ks + lchunk), a0, a1, a2, a3);
+#pragma unroll
+                    for (int n = 0; n < 3; ++n) {
+                        const uint2 bw = *reinterpret_cast<const uint2*>(w_conv + (((tap * 2 + ks) * 3 + n) * 32 + lane) * 2);
+                        mma_bf16(acc[n], a0, a1, a2, a3, bw.x, bw.y);
+                    }
+                }
+            }
+#pragma unroll
+            for (int n = 0; n < 3; ++n) {
+                const int col = n * 8 + (lane & 3) * 2;
+#pragma unroll
+                for (int hrow = 0; hrow < 2; ++hrow) {
+                    const int row = r0 + (lane >> 2) + hrow * 8;
+                    float v0 = acc[n][2 * hrow] + s_par[col], v1 = acc[n][2 * hrow + 1] + s_par[col + 1];
+                    const float s0 = __sinf(s_par[4 * kC + col] * v0), s1 = __sinf(s_par[4 * kC + col + 1] * v1);
+                    v0 = fmaf(s_par[5 * kC + col], s0 * s0, v0);
+                    v1 = fmaf(s_par[5 * kC + col + 1], s1 * s1, v1);
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+                    *reinterpret_cast<uint32_t*>(h_buf + swz(row, n) + (lane & 3) * 4) = *reinterpret_cast<const uint32_t*>(&h2);
+                }
+            }
+        }
+        __syncthreads();
+        // ---- x += conv1x1(h) + bias   (rows outside the clip stay zero)
+        for (int mt = warp; mt < kRows / 16; mt += kThreads / 32) {
+            const int r0 = mt * 16;
+            float acc[3][4];
+#pragma unroll
+            for (int n = 0; n < 3; ++n)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[n][e] = 0.f;
+            const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8;
+            const int lchunk = lane >> 4;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                uint32_t a0, a1, a2, a3;
+                ldmatrix_x4(h_addr + swz(r0 + lrow, 2 * ks + lchunk), a0, a1, a2, a3);
+#pragma unroll
+                for (int n = 0; n < 3; ++n) {
+                    const uint2 bw = *reinterpret_cast<const uint2*>(w_pw + ((ks * 3 + n) * 32 + lane) * 2);
+                    mma_bf16(acc[n], a0, a1, a2, a3, bw.x, bw.y);
+                }
+            }
+#pragma unroll
+            for (int n = 0; n < 3; ++n) {
+                const int col = n * 8 + (lane & 3) * 2;
+#pragma unroll
+                for (int hrow = 0; hrow < 2; ++hrow) {
+                    const int row = r0 + (lane >> 2) + hrow * 8;
+                    const int t = t_first + row;
+                    if (t >= 0 && t < p.T) {
+                        float2* px = reinterpret_cast<float2*>(xs + row * kC + col);
+                        float2 xv = *px;
+                        xv.x += acc[n][2 * hrow] + s_par[kC + col];
+                        xv.y += acc[n][2 * hrow + 1] + s_par[kC + col + 1];
+                        *px = xv;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- final: x <- snake(x, alpha_f) in place (fp32), then Conv1d(24 -> 1, k7, pad 3) + tanh
+    for (int i = tid; i < kRows * kC; i += kThreads) {
+        const int c = i % kC;
+        const float a = __ldg(p.alpha_f + c);
+        xs[i] = snake_f(xs[i], a, 1.0f / (a + kEps));
+    }
+    float* s_wf = s_par;     // reuse: 6 * 24 floats >= ... need 7 * 24 -> use w_conv area instead
+    float* wf = reinterpret_cast<float*>(w_conv);
+    __syncthreads();
+    for (int i = tid; i < 7 * kC; i += kThreads) wf[i] = __ldg(p.w_f + i);
+    (void)s_wf;
+    __syncthreads();
+    for (int i = tid; i < kOut; i += kThreads) {
+        const int t = blockIdx.x * kOut + i;
+        if (t >= p.T) break;
+        const int row = i + kHalo;
+        float acc = p.bias_f;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            const float* xr = xs + (row + j - 3) * kC;
+#pragma unroll
+            for (int c = 0; c < kC; c += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(xr + c);
+                const float4 w4 = *reinterpret_cast<const float4*>(wf + j * kC + c);
+                acc = fmaf(w4.x, v.x, acc);
+                acc = fmaf(w4.y, v.y, acc);
+                acc = fmaf(w4.z, v.z, acc);
+                acc = fmaf(w4.w, v.w, acc);
+            }
+        }
+        p.out[(long long)b * p.T + t] = tanhf(acc);
+    }
+}
+
+constexpr size_t kSmemBytes = (size_t)kRows * kC * 4 + 2 * kRows * 64 + (kConvFragWords + kPwFragWords) * 4 + 6 * kC * 4;
+
+}  // namespace tail
+}  // namespace l3ac
+
+extern "C" int l3ac_decoder_tail(const float* x, int B, int T, int C, const void* conv_frags, const float* conv_bias,
+                                 const void* pw_frags, const float* pw_bias, const float* alpha0, const float* alpha1,
+                                 const int* dilations, const float* alpha_f, const float* w_f, float bias_f, float* out,
+                                 l3ac_stream_t stream) {
+    using namespace l3ac::tail;
+    L3AC_CHECK_ARG(x && conv_frags && conv_bias && pw_frags && pw_bias && alpha0 && alpha1 && dilations && alpha_f && w_f && out);
+    L3AC_CHECK_ARG(B > 0 && B <= 65535 && T > 0);
+    if (C != kC) return L3AC_EUNSUPPORTED;
+    L3AC_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    Params p{};
+    p.x = x;
+    p.conv_frags = (const uint32_t*)conv_frags;
+    p.pw_frags = (const uint32_t*)pw_frags;
+    p.conv_bias = conv_bias;
+    p.pw_bias = pw_bias;
+    p.alpha0 = alpha0;
+    p.alpha1 = alpha1;
+    p.alpha_f = alpha_f;
+    p.w_f = w_f;
+    p.bias_f = bias_f;
+    int reach = 3;
+    for (int i = 0; i < 3; ++i) {
+        p.dil[i] = dilations[i];
+        L3AC_CHECK_ARG(dilations[i] >= 1);
+        reach += 3 * dilations[i];
+    }
+    if (reach > kHalo) return L3AC_EUNSUPPORTED;      // receptive field must fit the 42-sample halo (dilations 1,3,9)
+    p.B = B;
+    p.T = T;
+    p.out = out;
+    cudaError_t e = cudaFuncSetAttribute(decoder_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid(l3ac_cdiv(T, kOut), B);
+    decoder_tail_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(p);
+    return l3ac_launch_status();
+}

@@ -221,6 +221,23 @@ class Engine:
         self.dec_tail = dict(alpha=sd[f"{p}.1.alpha"].float().flatten().contiguous(),
                              w=fold_weight_norm(sd, f"{p}.2")[0].t().contiguous(),       # (7, C)
                              bias=float(sd[f"{p}.2.bias"].float().item()))
+        # fused tail (bf16 decode mode, 24 channels, dilations 1/3/9): weights in mma B-fragment order
+        self.dec_tail_fused = None
+        if bf16 == torch.bfloat16 and mc.decoder_dims[-1] == 24:
+            convs, pws = [], []
+            for j in range(3):
+                q = f"{p}.0.{j}.module.block"
+                wc = fold_weight_norm(sd, f"{q}.1")                                         # (24, 24, 7)
+                convs.append(torch.stack([ops.pack_mma_b_fragments(wc[:, :, t]) for t in range(7)]))
+                pws.append(ops.pack_mma_b_fragments(fold_weight_norm(sd, f"{q}.3")[:, :, 0]))
+            self.dec_tail_fused = dict(
+                conv_frags=torch.stack(convs).contiguous(), pw_frags=torch.stack(pws).contiguous(),
+                conv_bias=torch.stack([u["conv"].bias for u in self.dec_legacy]).contiguous(),
+                pw_bias=torch.stack([u["pw"].bias for u in self.dec_legacy]).contiguous(),
+                alpha0=torch.stack([u["alpha0"] for u in self.dec_legacy]).contiguous(),
+                alpha1=torch.stack([u["alpha1"] for u in self.dec_legacy]).contiguous(),
+                dilations=[u["dil"] for u in self.dec_legacy], alpha_f=self.dec_tail["alpha"], w_f=self.dec_tail["w"],
+                bias_f=self.dec_tail["bias"])
 
     # ------------------------------------------------------------------ building blocks
     @staticmethod
@@ -249,9 +266,13 @@ class Engine:
         B, T, D = x.shape
         for L in lt["layers"]:
             a = ops.layernorm(x, L["ln1_w"], L["ln1_b"], LN_EPS, out_dtype=act_dtype)
-            qkv = self._lin(a, L["qkv"], B, T, D)                                   # fp32 (B,T,576)
-            o = ops.local_attention(qkv, lt["table"], HEADS, lt["window"])
-            x = self._lin(self._as_operand(o, act_dtype), L["out"], B, T, o.shape[-1], residual=x)
+            if act_dtype == torch.float32:
+                qkv = self._lin(a, L["qkv"], B, T, D)                               # fp32 (B,T,576)
+                o = ops.local_attention(qkv, lt["table"], HEADS, lt["window"])
+            else:   # q/k/v stay in the GEMM operand format (bf16 or split pair) and feed the tensor-core attention
+                qkv = self._lin(a, L["qkv"], B, T, D, out_dtype=act_dtype)
+                o = ops.local_attention_tc(qkv, lt["table"], HEADS, lt["window"], out_dtype=act_dtype)
+            x = self._lin(o, L["out"], B, T, o.shape[-1], residual=x)
             a = ops.layernorm(x, L["ln2_w"], L["ln2_b"], LN_EPS, out_dtype=act_dtype)
             g = self._lin(a, L["ff1"], B, T, D, act=ops.ACT_GEGLU, out_dtype=act_dtype)   # (B,T,352)
             x = self._lin(g, L["ff2"], B, T, FF_PAD, residual=x)
@@ -348,6 +369,8 @@ class Engine:
             if taps is not None:
                 taps[f"dec_up{si}"] = x
         B, T, C = x.shape
+        if self.dec_tail_fused is not None:                                         # 3 LegacyUnits + tail conv in one kernel
+            return ops.decoder_tail(x, **self.dec_tail_fused)
         for u in self.dec_legacy:                                                   # Residual(LegacyUnit), modules.py:47-64
             d = u["dil"]
             a = ops.snake(x, u["alpha0"], out_dtype=adt)

@@ -231,6 +231,30 @@ def local_attention(qkv: torch.Tensor, bias_table: torch.Tensor, heads: int, win
     return out
 
 
+def local_attention_tc(qkv, bias_table: torch.Tensor, heads: int, window: int, out_dtype=torch.float32):
+    """Tensor-core attention over bf16 q/k/v: ``qkv`` is a bf16 tensor or a ``Split`` pair of shape (B, T, 3*heads*32)."""
+    split = isinstance(qkv, Split)
+    hi = qkv.hi if split else qkv
+    _chk(hi, torch.bfloat16, "qkv")
+    if split:
+        _chk(qkv.lo, torch.bfloat16, "qkv.lo")
+    _chk(bias_table, name="bias_table")
+    B, T, three_hd = hi.shape
+    D = three_hd // (3 * heads)
+    if tuple(bias_table.shape) != (heads, 2 * window):
+        raise ValueError(f"bias_table must be (heads, 2*window), got {tuple(bias_table.shape)}")
+    out, o_hi, o_lo = _empty_act((B, T, heads * D), hi.device, out_dtype)
+    _count()
+    # useful MACs: query p sees (w if p >= w else 0) + (p mod w) + 1 keys; two products of D MACs each
+    keys = sum((window if p >= window else 0) + (p % window) + 1 for p in range(T)) if OP_HOOK is not None else 0
+    with _hook("local_attention_tc_split" if split else "local_attention_tc", _nbytes(qkv, out),
+               2.0 * 2 * B * heads * keys * D * (1 if not split else 1)), torch.cuda.device(hi.device):
+        check(_lib.load().l3ac_local_attention_tc(_ptr(hi), _ptr(qkv.lo) if split else None, _ptr(bias_table), B, T, heads, D,
+                                                  window, _ptr(o_hi), _ptr(o_lo), _DT[out_dtype], _stream(hi)),
+              "l3ac_local_attention_tc")
+    return out
+
+
 def fsq_quantize(x: torch.Tensor, w_in, b_in, w_out, b_out, levels: Sequence[int], want_z: bool = False):
     _chk(x, name="x")
     F = x.shape[-1]
@@ -315,4 +339,34 @@ def tail_conv_tanh(x: torch.Tensor, alpha, w, bias: float) -> torch.Tensor:
     with _hook("tail_conv_tanh", _nbytes(x, out)), torch.cuda.device(x.device):
         check(_lib.load().l3ac_tail_conv_tanh(_ptr(x), B, T, Cc, _ptr(alpha), _ptr(w), float(bias), _ptr(out),
                                               _stream(x)), "l3ac_tail_conv_tanh")
+    return out
+
+
+def pack_mma_b_fragments(w: torch.Tensor, k_pad: int = 32) -> torch.Tensor:
+    """(N, K) fp32 weight -> bf16 mma.m16n8k16 B fragments [K_pad/16 ksteps][N/8 ntiles][32 lanes][4] (see the header)."""
+    N, K = w.shape
+    if N % 8 or k_pad % 16 or K > k_pad:
+        raise ValueError("pack_mma_b_fragments needs N % 8 == 0 and K <= k_pad, k_pad % 16 == 0")
+    wp = torch.zeros((N, k_pad), dtype=torch.float32, device=w.device)
+    wp[:, :K] = w
+    lane = torch.arange(32, device=w.device)
+    n = (torch.arange(N // 8, device=w.device)[:, None] * 8 + lane[None, :] // 4)              # (ntiles, 32)
+    k0 = (torch.arange(k_pad // 16, device=w.device)[:, None] * 16 + (lane[None, :] % 4) * 2)  # (ksteps, 32)
+    offs = torch.tensor([0, 1, 8, 9], device=w.device)
+    kk = k0[:, None, :, None] + offs                                                           # (ksteps, 1, 32, 4)
+    nn = n[None, :, :, None].expand(k_pad // 16, N // 8, 32, 4)
+    return wp[nn, kk.expand_as(nn)].to(torch.bfloat16).contiguous()
+
+
+def decoder_tail(x: torch.Tensor, conv_frags, conv_bias, pw_frags, pw_bias, alpha0, alpha1, dilations, alpha_f, w_f,
+                 bias_f: float) -> torch.Tensor:
+    _chk(x, name="x")
+    B, T, Cc = x.shape
+    out = torch.empty((B, T), device=x.device, dtype=torch.float32)
+    dil = (C.c_int * 3)(*[int(d) for d in dilations])
+    _count()
+    with _hook("decoder_tail", _nbytes(x, out), 2.0 * B * T * (3 * (7 * 24 * 24 + 24 * 24) + 7 * 24)), torch.cuda.device(x.device):
+        check(_lib.load().l3ac_decoder_tail(_ptr(x), B, T, Cc, _ptr(conv_frags), _ptr(conv_bias), _ptr(pw_frags), _ptr(pw_bias),
+                                            _ptr(alpha0), _ptr(alpha1), dil, _ptr(alpha_f), _ptr(w_f), float(bias_f), _ptr(out),
+                                            _stream(x)), "l3ac_decoder_tail")
     return out

@@ -206,3 +206,71 @@ def test_argument_validation(cuda_lib):
         ops.gemm(torch.zeros(8, 8, device=DEV), torch.zeros(4, 9, device=DEV), B=1, T=8, K=8)   # bad weight shape
     with pytest.raises(ValueError):
         ops.fsq_quantize_latents(torch.zeros(4, 6, device=DEV), (1, 7, 7, 7, 7, 7))       # level < 2
+
+
+@pytest.mark.parametrize("T", [50, 300, 1000, 2717])
+def test_fused_decoder_tail(cuda_lib, T):
+    """3 x Residual(LegacyUnit) + Snake + Conv(24->1,k7) + tanh in one kernel vs the oracle's decoder tail (bf16 operands)."""
+    C = 24
+    sd = {}
+    for j in range(3):
+        q = f"blocks.0.block.0.{j}.module.block"
+        sd[f"{q}.0.alpha"], sd[f"{q}.2.alpha"] = (0.5 + torch.rand(1, C, 1)), (0.5 + torch.rand(1, C, 1))
+        sd[f"{q}.1.weight"], sd[f"{q}.1.bias"] = rnd(C, C, 7, seed=10 + j, scale=0.08), rnd(C, seed=20 + j, scale=0.05)
+        sd[f"{q}.3.weight"], sd[f"{q}.3.bias"] = rnd(C, C, 1, seed=30 + j, scale=0.15), rnd(C, seed=40 + j, scale=0.05)
+    sd["blocks.0.block.1.alpha"] = 0.5 + torch.rand(1, C, 1)
+    sd["blocks.0.block.2.weight"], sd["blocks.0.block.2.bias"] = rnd(1, C, 7, seed=50, scale=0.1), rnd(1, seed=51, scale=0.05)
+    x = rnd(2, C, T, seed=1, scale=0.7)
+    bf = lambda t: t.to(torch.bfloat16).float()
+    h = x
+    for j, dil in enumerate((1, 3, 9)):                       # same operand rounding as the kernel: bf16 a, h and weights
+        q = f"blocks.0.block.0.{j}.module.block"
+        a = bf(O.snake(h, sd[f"{q}.0.alpha"]))
+        hid = F.conv1d(a, bf(sd[f"{q}.1.weight"]), sd[f"{q}.1.bias"], dilation=dil, padding=3 * dil)
+        hid = bf(O.snake(hid, sd[f"{q}.2.alpha"]))
+        h = h + F.conv1d(hid, bf(sd[f"{q}.3.weight"]), sd[f"{q}.3.bias"])
+    want = torch.tanh(F.conv1d(O.snake(h, sd["blocks.0.block.1.alpha"]), sd["blocks.0.block.2.weight"],
+                               sd["blocks.0.block.2.bias"], padding=3))[:, 0]
+    exact = x
+    for j, dil in enumerate((1, 3, 9)):
+        exact = O.legacy_unit(sd, f"blocks.0.block.0.{j}.module", exact, dil)
+    exact = torch.tanh(F.conv1d(O.snake(exact, sd["blocks.0.block.1.alpha"]), sd["blocks.0.block.2.weight"],
+                                sd["blocks.0.block.2.bias"], padding=3))[:, 0]
+    convs = torch.stack([torch.stack([ops.pack_mma_b_fragments(sd[f"blocks.0.block.0.{j}.module.block.1.weight"][:, :, t].to(DEV))
+                                      for t in range(7)]) for j in range(3)]).contiguous()
+    pws = torch.stack([ops.pack_mma_b_fragments(sd[f"blocks.0.block.0.{j}.module.block.3.weight"][:, :, 0].to(DEV))
+                       for j in range(3)]).contiguous()
+    st = lambda key: torch.stack([sd[f"blocks.0.block.0.{j}.module.block.{key}"].flatten() for j in range(3)]).contiguous().to(DEV)
+    got = ops.decoder_tail(cl(x), convs, st("1.bias"), pws, st("3.bias"), st("0.alpha"), st("2.alpha"), (1, 3, 9),
+                           sd["blocks.0.block.1.alpha"].flatten().to(DEV), sd["blocks.0.block.2.weight"][0].t().contiguous().to(DEV),
+                           float(sd["blocks.0.block.2.bias"]))
+    # The kernel and the CPU emulation round the same operands to bf16, but a 1-ulp fp32 difference upstream can flip a
+    # bf16 rounding, so the two agree only statistically: both must sit at the same distance from the exact oracle.
+    e_kernel, e_emul = max_abs(got.cpu(), exact), max_abs(want, exact)
+    rms = lambda a, b: float((a.double() - b.double()).pow(2).mean().sqrt())
+    r_kernel, r_emul, r_between = rms(got.cpu(), exact), rms(want, exact), rms(got.cpu(), want)
+    print(f"[tail T={T}] max-abs vs exact: kernel {e_kernel:.4f} emulation {e_emul:.4f}; rms {r_kernel:.5f} / {r_emul:.5f}; "
+          f"kernel-vs-emulation rms {r_between:.5f}")
+    assert e_kernel < 6e-2 and r_kernel < 1.5 * r_emul + 1e-4
+    assert r_between < 1.5 * r_emul + 1e-4
+
+
+@pytest.mark.parametrize("T,w", [(100, 40), (333, 100), (593, 250), (64, 200), (257, 64), (1779, 750)])
+@pytest.mark.parametrize("split", [False, True])
+def test_local_attention_tc(cuda_lib, T, w, split):
+    """Tensor-core attention vs the oracle on the bf16-rounded (or hi+lo) q/k/v it actually consumes."""
+    B, H, D = 2, 6, 32
+    qkv = rnd(B, T, 3 * H * D, seed=T)
+    table = rnd(H, 2 * w, seed=w, scale=0.5)
+    hi = qkv.to(torch.bfloat16)
+    lo = (qkv - hi.float()).to(torch.bfloat16)
+    seen = (hi.float() + lo.float()) if split else hi.float()
+    q, k, v = (t.reshape(B, T, H, D).transpose(1, 2).reshape(B * H, T, D) for t in seen.chunk(3, dim=-1))
+    idx = (torch.arange(w, 2 * w)[:, None] - torch.arange(2 * w)[None, :]).abs()
+    want = O.local_attention(q, k, v, table[:, idx], w).reshape(B, H, T, D).transpose(1, 2).reshape(B, T, H * D)
+    arg = ops.Split(hi.to(DEV), lo.to(DEV)) if split else hi.to(DEV)
+    got = ops.local_attention_tc(arg, table.to(DEV), H, w)
+    tol = 3e-5 if split else 2e-2          # split: fp32-class; plain: P is rounded to bf16 before the second product
+    assert max_abs(got.cpu(), want) < tol
+    got2 = ops.local_attention_tc(arg, table.to(DEV), H, w, out_dtype=ops.SPLIT)
+    assert max_abs(got2.float().cpu(), got.cpu()) < 3e-5
