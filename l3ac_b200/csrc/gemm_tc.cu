@@ -31,11 +31,17 @@ constexpr int kBK = 64;                       // 64 bf16 = 128 B = one SWIZZLE_1
 constexpr int kATileBytes = kBM * kBK * 2;    // 16 KB
 constexpr int kMaxBN = 256;
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 320;
-constexpr int kEpiThreads = 256;
-constexpr int kSmemBudget = 176 * 1024;
+#ifndef L3AC_EPI_GROUPS
+#define L3AC_EPI_GROUPS 4                                     // epilogue warp groups (4 warps each, one per TMEM lane quadrant)
+#endif
+constexpr int kGroups = L3AC_EPI_GROUPS;
+constexpr int kEpiWarps = 4 * kGroups;
+constexpr int kEpiThreads = 32 * kEpiWarps;
+constexpr int kThreads = 64 + kEpiThreads;
 constexpr int kStagePitch = 36;                               // floats per staged row (32 + 4 pad)
-constexpr int kStageBytes = 8 * 32 * kStagePitch * 4;        // one 32-row slab per epilogue warp
+constexpr int kStageBytes = kEpiWarps * 32 * kStagePitch * 4; // one 32-row slab per epilogue warp
+constexpr int kSmemBudget = 227 * 1024 - kStageBytes - 5 * 256 * 4 - 2048;   // what is left for the TMA/MMA stage ring
+constexpr int kMaxAcc = 4;                                    // accumulator stages in TMEM (thin mode uses all four)
 
 struct Params {
     const float* bias;
@@ -205,13 +211,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t bar_base = tail + 5 * kMaxBN * 4 + kStageBytes;
     const uint32_t full_bar = bar_base;                          // [kMaxStages]
     const uint32_t empty_bar = bar_base + 8 * kMaxStages;        // [kMaxStages]
-    const uint32_t tfull_bar = bar_base + 16 * kMaxStages;       // [2]
-    const uint32_t tempty_bar = tfull_bar + 16;                  // [2]
-    const uint32_t tmem_slot = tempty_bar + 16;
+    const uint32_t tfull_bar = bar_base + 16 * kMaxStages;       // [kMaxAcc]
+    const uint32_t tempty_bar = tfull_bar + 8 * kMaxAcc;         // [kMaxAcc]
+    const uint32_t tmem_slot = tempty_bar + 8 * kMaxAcc;
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tmem_cols = (2 * p.BN <= 32) ? 32 : (2 * p.BN <= 64) ? 64 : (2 * p.BN <= 128) ? 128 : (2 * p.BN <= 256) ? 256 : 512;
+    const int n_acc = p.thin ? kGroups : 2;       // accumulator stages
+    const int acc_cols = n_acc * p.BN;
+    const int tmem_cols = (acc_cols <= 32) ? 32 : (acc_cols <= 64) ? 64 : (acc_cols <= 128) ? 128 : (acc_cols <= 256) ? 256 : 512;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -220,9 +228,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(full_bar + 8 * s, 1);
             mbar_init(empty_bar + 8 * s, 1);
         }
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < kMaxAcc; ++a) {
             mbar_init(tfull_bar + 8 * a, 1);
-            mbar_init(tempty_bar + 8 * a, p.thin ? kEpiThreads / 64 : kEpiThreads / 32);
+            mbar_init(tempty_bar + 8 * a, p.thin ? 4 : kEpiWarps);      // thin: one group of 4 warps owns a stage
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -307,8 +315,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
                 tc_commit(tfull_bar + 8 * acc);
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
+                if (++acc == n_acc) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
             }
         }
     } else {
@@ -320,7 +330,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         using OutElem = typename std::conditional<OUT == L3AC_F32, float, __nv_bfloat16>::type;
         const int ep_tid = threadIdx.x - 64;
         const int quad = warp & 3;            // TMEM lane quadrant this warp may access
-        const int half = (warp - 2) >> 2;     // which half of the column chunks
+        const int half = (warp - 2) >> 2;     // epilogue group: owns column chunks c = half (mod kGroups)
         const int n_chunks = p.BN / 32;
         float* s_bias = s_par;
         float* s_alpha = s_par + kMaxBN;
@@ -334,12 +344,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int n_out_total = GEGLU ? (p.N >> 1) : p.N;
         const bool vec_ok = ((p.ldo & 3) == 0) && (!RES || (p.ldr & 3) == 0) && ((n_out_total & 3) == 0);
         const long long out_step = (long long)RPI * p.ldo, res_step = (long long)RPI * p.ldr;
-        // Normal mode: all 8 warps work on one tile (two column halves).  Thin mode (one 32-column chunk, one N tile):
-        // the two groups of 4 warps take alternate tiles -- group h owns accumulator stage h -- which doubles the
-        // number of tiles whose (latency-bound) epilogue is in flight.
+        // Normal mode: all groups work on one tile, group g on column chunks g, g + kGroups, ...  Thin mode (one
+        // 32-column chunk, one N tile): the groups take alternate tiles -- group g owns accumulator stage g -- which
+        // multiplies the number of tiles whose (latency-bound) epilogue is in flight.
         int acc = p.thin ? half : 0;
         uint32_t acc_phase = 0;
-        const int tile_step = p.thin ? 2 * gridDim.x : gridDim.x;
+        const int tile_step = p.thin ? kGroups * gridDim.x : gridDim.x;
         const int chunk0 = p.thin ? 0 : half;
         bool params_loaded = false;
         for (int tile = blockIdx.x + (p.thin ? half * gridDim.x : 0); tile < num_tiles; tile += tile_step) {
@@ -350,7 +360,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 // thin mode: every tile has n0 == 0, so the per-column parameters are staged once, by each group
                 // into identical values (benign duplicate writes), guarded by a per-group named barrier
                 if (p.thin) asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
-                else asm volatile("bar.sync 1, 256;" ::: "memory");     // previous tile's parameter reads are done
+                else asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");     // previous tile's parameter reads are done
                 const int tid0 = p.thin ? (ep_tid & 127) : ep_tid;
                 const int nthr = p.thin ? 128 : kEpiThreads;
                 for (int i = tid0; i < p.BN; i += nthr) {
@@ -366,7 +376,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
                 if (p.thin) asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
-                else asm volatile("bar.sync 1, 256;" ::: "memory");
+                else asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
                 params_loaded = true;
             }
             long long row_base;
@@ -380,7 +390,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
             mbar_wait(tfull_bar + 8 * acc, acc_phase);
             tc_fence_after();
-            for (int c = chunk0; c < n_chunks; c += 2) {
+            for (int c = chunk0; c < n_chunks; c += kGroups) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.BN + c * 32), v);
                 const int cb = c * 32;              // column offset inside the tile
@@ -475,9 +485,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
             if (p.thin) {
                 acc_phase ^= 1;          // this group revisits its own accumulator stage every time
-            } else {
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
+            } else if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
             }
         }
     }
@@ -546,7 +556,15 @@ static KernelFn pick_kernel(int act, int out_dtype, bool res, bool split) {
         case L3AC_ACT_NONE: return pick_out<L3AC_ACT_NONE, false>(out_dtype, res);
         case L3AC_ACT_GEGLU: return pick_out<L3AC_ACT_GEGLU, false>(out_dtype, res);
         case L3AC_ACT_SNAKE:
+            // The split (encode-side) GEMMs may use the precise sinf (L3AC_SPLIT_PRECISE_SIN=1 at build time); measured
+            // on the golden vectors the MUFU __sinf (abs error ~5e-7 on the O(1) arguments seen here, i.e. below the
+            // 2^-17 error of the split operands) leaves index agreement unchanged, and costs 4x fewer instructions.
+#if defined(L3AC_SPLIT_PRECISE_SIN) && L3AC_SPLIT_PRECISE_SIN
             return split ? pick_out<L3AC_ACT_SNAKE, true>(out_dtype, res) : pick_out<L3AC_ACT_SNAKE, false>(out_dtype, res);
+#else
+            (void)split;
+            return pick_out<L3AC_ACT_SNAKE, false>(out_dtype, res);
+#endif
     }
     return nullptr;
 }
@@ -628,7 +646,7 @@ extern "C" int l3ac_gemm_bf16_tc(const l3ac_gemm_desc* d, l3ac_stream_t stream) 
         tmW_lo = tmW;
     }
 
-    const size_t smem = 1024 /* alignment slack */ + (size_t)p.stages * stage_bytes + 5 * kMaxBN * 4 + kStageBytes + 16 * kMaxStages + 64;
+    const size_t smem = 1024 /* alignment slack */ + (size_t)p.stages * stage_bytes + 5 * kMaxBN * 4 + kStageBytes + 16 * kMaxStages + 16 * kMaxAcc + 64;
     KernelFn fn = pick_kernel(d->act, d->out_dtype, d->residual != nullptr, split);
     if (!fn) return L3AC_EUNSUPPORTED;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

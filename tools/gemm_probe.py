@@ -10,9 +10,11 @@ from l3ac_b200 import ops  # noqa: E402
 DEV = "cuda:0"
 
 
-def run(M, K, N, out_dtype=torch.float32, residual=False, act=ops.ACT_NONE, taps=1, iters=5, flush=True, tag=""):
+def run(M, K, N, out_dtype=torch.float32, residual=False, act=ops.ACT_NONE, taps=1, iters=5, flush=True, tag="", split=False):
     a = torch.randn(M, K, device=DEV).to(torch.bfloat16)
     w = (torch.randn(N, taps * K, device=DEV) * 0.05).to(torch.bfloat16)
+    if split:
+        a, w = ops.Split(a, a.clone()), ops.Split(w, w.clone())
     n_out = N // 2 if act == ops.ACT_GEGLU else N
     res = torch.randn(M, n_out, device=DEV) if residual else None
     alpha = torch.ones(N, device=DEV) if act == ops.ACT_SNAKE else None
@@ -31,7 +33,7 @@ def run(M, K, N, out_dtype=torch.float32, residual=False, act=ops.ACT_NONE, taps
             times.append(e0.elapsed_time(e1) * 1e3)
     t = sorted(times)[len(times) // 2]
     flops = 2.0 * M * K * N * taps
-    osz = 4 if out_dtype == torch.float32 else 2
+    osz = 2 if out_dtype == torch.bfloat16 else 4
     nbytes = 2 * (M * K + N * K * taps) + osz * M * n_out + (4 * M * n_out if residual else 0)
     print(f"{tag:28s} M={M:8d} K={K:5d} N={N:5d} taps={taps} out={'f32' if osz == 4 else 'bf16'} res={int(residual)} act={act} "
           f"{t:8.1f} us  {flops / t / 1e6:7.1f} TF/s  {nbytes / t / 1e3:7.0f} GB/s", flush=True)
@@ -39,6 +41,26 @@ def run(M, K, N, out_dtype=torch.float32, residual=False, act=ops.ACT_NONE, taps
 
 if __name__ == "__main__":
     only = sys.argv[1] if len(sys.argv) > 1 else None
+    thin = {
+        "t_k96_n24": dict(M=2401650, K=96, N=24),
+        "t_k96_n24_res": dict(M=2401650, K=96, N=24, residual=True),
+        "t_k96_n24_split": dict(M=2401650, K=96, N=24, split=True),
+        "t_k96_n24_split_res": dict(M=2401650, K=96, N=24, split=True, residual=True),
+        "t_k64_n24": dict(M=2401650, K=64, N=24),
+        "t_k128_n24": dict(M=2401650, K=128, N=24),
+        "t_k192_n24": dict(M=2401650, K=192, N=24),
+        "t_k96_n32": dict(M=2401650, K=96, N=32),
+        "t_k96_n64": dict(M=2401650, K=96, N=64),
+        "t_k96_n96": dict(M=2401650, K=96, N=96),
+        "t_k24_n96_split": dict(M=2401650, K=24, N=96, split=True, out_dtype=torch.bfloat16),
+        "t_k192_n48_res": dict(M=400275, K=192, N=48, residual=True),
+        "t_k192_n48_split_res": dict(M=400275, K=192, N=48, residual=True, split=True),
+        "t_k32_n24_k7": dict(M=2401650, K=32, N=24, taps=7, out_dtype=torch.bfloat16),
+    }
+    if only == "thin":
+        for name, kw in thin.items():
+            run(tag=name, **kw)
+        sys.exit(0)
     cases = {
         "c256_pw2": dict(M=142320, K=1024, N=256, residual=True),
         "c256_pw2_nores": dict(M=142320, K=1024, N=256),
@@ -51,6 +73,7 @@ if __name__ == "__main__":
         "c96_pw1": dict(M=426960, K=96, N=384, out_dtype=torch.bfloat16, act=ops.ACT_SNAKE),
         "c96_pw2": dict(M=426960, K=384, N=96, residual=True),
         "c48_pw1": dict(M=1280880, K=48, N=192, out_dtype=torch.bfloat16, act=ops.ACT_SNAKE),
+        "c24_pw1_split": dict(M=2561760, K=24, N=96, split=True, out_dtype=ops.SPLIT, act=ops.ACT_SNAKE),
         "c24_1x1": dict(M=2561760, K=24, N=24, residual=True),
         "c24_k7": dict(M=2561760, K=24, N=24, taps=7, out_dtype=torch.bfloat16, act=ops.ACT_SNAKE),
         "square_4k": dict(M=4096, K=4096, N=4096, out_dtype=torch.bfloat16),
