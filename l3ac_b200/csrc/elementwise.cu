@@ -21,6 +21,27 @@ __device__ __forceinline__ void store_act<__nv_bfloat16>(__nv_bfloat16* hi, __nv
     if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
+// Four consecutive values (16-byte aligned destination for fp32, 8-byte for bf16).
+template <typename OutT>
+__device__ __forceinline__ void store_act4(OutT* hi, OutT* lo, long long i, float4 v) {
+    *reinterpret_cast<float4*>(hi + i) = v;
+}
+template <>
+__device__ __forceinline__ void store_act4<__nv_bfloat16>(__nv_bfloat16* hi, __nv_bfloat16* lo, long long i, float4 v) {
+    const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<const uint32_t*>(&h01);
+    pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+    *reinterpret_cast<uint2*>(hi + i) = pk;
+    if (lo) {
+        const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+        const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
+        pk.x = *reinterpret_cast<const uint32_t*>(&l01);
+        pk.y = *reinterpret_cast<const uint32_t*>(&l23);
+        *reinterpret_cast<uint2*>(lo + i) = pk;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // depthwise conv k7 (pad 3) + LayerNorm over C.  One warp per (b, t) row; lane owns channels
 // lane, lane+32, ...  Weights are staged in shared memory ([7][C] taps, bias, ln w/b).
@@ -520,6 +541,248 @@ __global__ void __launch_bounds__(256) enhance_apply_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------
+// Vectorised row kernels.  A row of C channels is handled by a group of GS lanes (GS = 8, 16 or 32), each lane
+// owning VPL float4 (chunk index g + GS*v); a warp therefore processes 32/GS rows at once and U such row sets per
+// iteration, with every load issued before the first use.  Row statistics are xor-shuffle reductions inside the group.
+// ------------------------------------------------------------------------------------------
+template <int GS>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = GS / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int GS, int VPL, int U>
+__global__ void __launch_bounds__(256) upsample_cn_vec_kernel(const float* __restrict__ x, int B, int T, int C, int scale,
+                                                              const float* __restrict__ cn_w, const float* __restrict__ cn_b,
+                                                              float eps, float* __restrict__ out) {
+    constexpr int RW = 32 / GS;                 // rows per warp
+    const int lane = threadIdx.x & 31, g = lane % GS, sub = lane / GS;
+    const int C4 = C >> 2;
+    const int To = T * scale;
+    const long long rows = (long long)B * To;
+    const float rscale = (float)(1.0 / (double)scale);
+    const float inv_c = 1.0f / (float)C;
+    float4 w4[VPL], b4[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        const int c4 = g + GS * v;
+        w4[v] = (cn_w && c4 < C4) ? __ldg(reinterpret_cast<const float4*>(cn_w) + c4) : make_float4(1.f, 1.f, 1.f, 1.f);
+        b4[v] = (cn_b && c4 < C4) ? __ldg(reinterpret_cast<const float4*>(cn_b) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long base = warp_global * (RW * U); base < rows; base += nwarps * (RW * U)) {
+        float4 a0[U][VPL], a1[U][VPL];
+        float l1[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long row = base + u * RW + sub;
+            ok[u] = row < rows;
+            const long long rr = ok[u] ? row : rows - 1;
+            const int b = (int)(rr / To), j = (int)(rr - (long long)b * To);
+            float src = fmaf(rscale, (float)j + 0.5f, -0.5f);   // ATen contracts this to one fma
+            src = src < 0.f ? 0.f : src;
+            int i0 = (int)src;
+            if (i0 > T - 1) i0 = T - 1;
+            const int i1 = i0 + (i0 < T - 1 ? 1 : 0);
+            l1[u] = src - (float)i0;
+            const float4* p0 = reinterpret_cast<const float4*>(x + ((long long)b * T + i0) * C);
+            const float4* p1 = reinterpret_cast<const float4*>(x + ((long long)b * T + i1) * C);
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                const int c4 = g + GS * v;
+                a0[u][v] = (c4 < C4) ? __ldg(p0 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                a1[u][v] = (c4 < C4) ? __ldg(p1 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float w1 = l1[u], w0 = 1.0f - l1[u];
+            float4 val[VPL];
+            float s = 0.f;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                val[v].x = __fmaf_rn(w1, a1[u][v].x, __fmul_rn(w0, a0[u][v].x));
+                val[v].y = __fmaf_rn(w1, a1[u][v].y, __fmul_rn(w0, a0[u][v].y));
+                val[v].z = __fmaf_rn(w1, a1[u][v].z, __fmul_rn(w0, a0[u][v].z));
+                val[v].w = __fmaf_rn(w1, a1[u][v].w, __fmul_rn(w0, a0[u][v].w));
+                s += (val[v].x + val[v].y) + (val[v].z + val[v].w);      // lanes beyond C4 hold zeros
+            }
+            float mean = 0.f, rstd = 1.f;
+            if (cn_w) {
+                mean = group_sum<GS>(s) * inv_c;
+                float q = 0.f;
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) {
+                    if (g + GS * v < C4) {
+                        const float dx = val[v].x - mean, dy = val[v].y - mean, dz = val[v].z - mean, dw = val[v].w - mean;
+                        q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+                    }
+                }
+                rstd = 1.0f / sqrtf(group_sum<GS>(q) * inv_c + eps);
+            }
+            if (!ok[u]) continue;
+            float4* orow = reinterpret_cast<float4*>(out + (base + u * RW + sub) * C);
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                const int c4 = g + GS * v;
+                if (c4 < C4) {
+                    float4 o;
+                    o.x = (val[v].x - mean) * rstd * w4[v].x + b4[v].x;
+                    o.y = (val[v].y - mean) * rstd * w4[v].y + b4[v].y;
+                    o.z = (val[v].z - mean) * rstd * w4[v].z + b4[v].z;
+                    o.w = (val[v].w - mean) * rstd * w4[v].w + b4[v].w;
+                    orow[c4] = o;
+                }
+            }
+        }
+    }
+}
+
+template <int GS, int VPL, int U, typename OutT>
+__global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restrict__ x, long long M, int C,
+                                                            const float* __restrict__ w, const float* __restrict__ b,
+                                                            float eps, OutT* __restrict__ out, OutT* __restrict__ out_lo) {
+    constexpr int RW = 32 / GS;
+    const int lane = threadIdx.x & 31, g = lane % GS, sub = lane / GS;
+    const int C4 = C >> 2;
+    const float inv_c = 1.0f / (float)C;
+    float4 w4[VPL], b4[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        const int c4 = g + GS * v;
+        w4[v] = (c4 < C4) ? __ldg(reinterpret_cast<const float4*>(w) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        b4[v] = (c4 < C4) ? __ldg(reinterpret_cast<const float4*>(b) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long base = warp_global * (RW * U); base < M; base += nwarps * (RW * U)) {
+        float4 val[U][VPL];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long row = base + u * RW + sub;
+            const float4* p = reinterpret_cast<const float4*>(x + (row < M ? row : M - 1) * C);
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                const int c4 = g + GS * v;
+                val[u][v] = (c4 < C4) ? __ldg(p + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            float s = 0.f;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) s += (val[u][v].x + val[u][v].y) + (val[u][v].z + val[u][v].w);
+            const float mean = group_sum<GS>(s) * inv_c;
+            float q = 0.f;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                if (g + GS * v < C4) {
+                    const float dx = val[u][v].x - mean, dy = val[u][v].y - mean, dz = val[u][v].z - mean, dw = val[u][v].w - mean;
+                    q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+                }
+            }
+            const float rstd = 1.0f / sqrtf(group_sum<GS>(q) * inv_c + eps);
+            const long long row = base + u * RW + sub;
+            if (row >= M) continue;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                const int c4 = g + GS * v;
+                if (c4 < C4) {
+                    const long long i = row * C + 4 * c4;
+                    store_act4<OutT>(out, out_lo, i,
+                                     make_float4((val[u][v].x - mean) * rstd * w4[v].x + b4[v].x,
+                                                 (val[u][v].y - mean) * rstd * w4[v].y + b4[v].y,
+                                                 (val[u][v].z - mean) * rstd * w4[v].z + b4[v].z,
+                                                 (val[u][v].w - mean) * rstd * w4[v].w + b4[v].w));
+                }
+            }
+        }
+    }
+}
+
+// EnhanceBlock gating, vectorised: a thread owns one float4 of channels (its merge weights stay in registers) and walks
+// the rows of the tile with a stride, four rows in flight.
+template <typename OutT>
+__global__ void __launch_bounds__(256) enhance_apply_vec_kernel(const float* __restrict__ x, int B, int T, int C,
+                                                                const float* __restrict__ conv_w,
+                                                                const float* __restrict__ conv_b,
+                                                                const float* __restrict__ in_w, const float* __restrict__ in_b,
+                                                                const float* __restrict__ merge_w,
+                                                                const float* __restrict__ merge_b,
+                                                                const float* __restrict__ partials, int nchunk,
+                                                                OutT* __restrict__ out) {
+    constexpr int CH = kEnhTile;
+    __shared__ float xs[CH + 2 * kEnhReach], ms[CH + 2 * kEnhReach], ps[CH + 2 * kEnhReach];
+    __shared__ float ys[4 * CH];
+    __shared__ float s_scale[4], s_shift[4];
+    const int b = blockIdx.y, t0 = blockIdx.x * CH;
+    if (threadIdx.x < 4) {
+        const int j = threadIdx.x;
+        double s = 0.0, q = 0.0;
+        for (int c = 0; c < nchunk; ++c) {
+            s += (double)partials[((long long)b * nchunk + c) * 8 + 2 * j];
+            q += (double)partials[((long long)b * nchunk + c) * 8 + 2 * j + 1];
+        }
+        const double mean = s / (double)T;
+        double var = q / (double)T - mean * mean;   // biased variance (InstanceNorm1d)
+        if (var < 0.0) var = 0.0;
+        const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+        const float gg = in_w[j] * rstd;
+        s_scale[j] = gg;
+        s_shift[j] = in_b[j] - (float)mean * gg;
+    }
+    enhance_branches<CH>(x + (long long)b * T * C, T, C, t0, conv_w, conv_b, xs, ms, ps, ys);
+    for (int i = threadIdx.x; i < 4 * CH; i += blockDim.x) {
+        const int j = i / CH;
+        ys[i] = fmaf(ys[i], s_scale[j], s_shift[j]);
+    }
+    __syncthreads();
+    const int nt = min(CH, T - t0);
+    const int C4 = C >> 2;
+    const int rpp = blockDim.x / C4;                  // rows per pass
+    const int c4 = threadIdx.x % C4, r0 = threadIdx.x / C4;
+    if (r0 >= rpp) return;
+    float4 mw[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) mw[q] = __ldg(reinterpret_cast<const float4*>(merge_w) + 4 * c4 + q);   // merge_w[c][0..3]
+    const float4 mb = __ldg(reinterpret_cast<const float4*>(merge_b) + c4);
+    const float4* xrow = reinterpret_cast<const float4*>(x + ((long long)b * T + t0) * C) + c4;
+    OutT* obase = out + ((long long)b * T + t0) * C + 4 * c4;
+    for (int i0 = r0; i0 < nt; i0 += 4 * rpp) {
+        float4 xv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * rpp;
+            xv[u] = (i < nt) ? __ldg(xrow + (long long)i * C4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * rpp;
+            if (i >= nt) break;
+            const float y0 = ys[i], y1 = ys[CH + i], y2 = ys[2 * CH + i], y3 = ys[3 * CH + i];
+            float4 r;
+            r.x = fmaf(fmaf(mw[0].w, y3, fmaf(mw[0].z, y2, fmaf(mw[0].y, y1, fmaf(mw[0].x, y0, mb.x)))), xv[u].x, xv[u].x);
+            r.y = fmaf(fmaf(mw[1].w, y3, fmaf(mw[1].z, y2, fmaf(mw[1].y, y1, fmaf(mw[1].x, y0, mb.y)))), xv[u].y, xv[u].y);
+            r.z = fmaf(fmaf(mw[2].w, y3, fmaf(mw[2].z, y2, fmaf(mw[2].y, y1, fmaf(mw[2].x, y0, mb.z)))), xv[u].z, xv[u].z);
+            r.w = fmaf(fmaf(mw[3].w, y3, fmaf(mw[3].z, y2, fmaf(mw[3].y, y1, fmaf(mw[3].x, y0, mb.w)))), xv[u].w, xv[u].w);
+            OutT* o = obase + (long long)i * C;
+            if (sizeof(OutT) == 4) {
+                *reinterpret_cast<float4*>(o) = r;
+            } else {
+                const __nv_bfloat162 h01 = __floats2bfloat162_rn(r.x, r.y), h23 = __floats2bfloat162_rn(r.z, r.w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<const uint32_t*>(&h01);
+                pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+                *reinterpret_cast<uint2*>(o) = pk;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // decoder tail: snake -> conv(C->1, k7, pad 3) -> tanh.  Block = 256 output samples.
 // ------------------------------------------------------------------------------------------
 constexpr int kTailTile = 256;
@@ -638,6 +901,26 @@ extern "C" int l3ac_layernorm(const float* x, long long M, int C, const float* w
     L3AC_CHECK_ARG(out_dtype == L3AC_F32 || out_dtype == L3AC_BF16 || out_dtype == L3AC_BF16X2);
     L3AC_CHECK_ARG((out_dtype == L3AC_BF16X2) == (out_lo != nullptr));
     cudaStream_t st = (cudaStream_t)stream;
+    if (C % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+        ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(b)) & 15) == 0) {
+        const int C4 = C / 4;
+#define L3AC_LN(GS, VPL, U)                                                                                        \
+    do {                                                                                                           \
+        const int g_ = grid_for_rows(M, 8 * (32 / GS) * U);                                                        \
+        if (out_dtype == L3AC_F32)                                                                                 \
+            layernorm_vec_kernel<GS, VPL, U, float><<<g_, 256, 0, st>>>(x, M, C, w, b, eps, (float*)out, nullptr);   \
+        else                                                                                                       \
+            layernorm_vec_kernel<GS, VPL, U, __nv_bfloat16><<<g_, 256, 0, st>>>(x, M, C, w, b, eps, (__nv_bfloat16*)out, \
+                                                                                (__nv_bfloat16*)out_lo);             \
+    } while (0)
+        if (C4 <= 8) L3AC_LN(8, 1, 4);
+        else if (C4 <= 16) L3AC_LN(16, 1, 4);
+        else if (C4 <= 32) L3AC_LN(32, 1, 4);
+        else if (C4 <= 64) L3AC_LN(32, 2, 2);
+        else L3AC_LN(32, 4, 1);
+#undef L3AC_LN
+        return l3ac_launch_status();
+    }
     const int grid = grid_for_rows(M, 8);
     DISPATCH_CPL(C, {
         if (out_dtype == L3AC_F32)
@@ -678,6 +961,20 @@ extern "C" int l3ac_upsample_linear_cn(const float* x, int B, int T, int C, int 
     L3AC_CHECK_ARG((cn_w == nullptr) == (cn_b == nullptr));
     cudaStream_t st = (cudaStream_t)stream;
     const long long rows = (long long)B * T * scale;
+    if (C % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+        (!cn_w || ((reinterpret_cast<uintptr_t>(cn_w) | reinterpret_cast<uintptr_t>(cn_b)) & 15) == 0)) {
+        const int C4 = C / 4;
+#define L3AC_UPS(GS, VPL, U)                                                                                      \
+    upsample_cn_vec_kernel<GS, VPL, U><<<grid_for_rows(rows, 8 * (32 / GS) * U), 256, 0, st>>>(x, B, T, C, scale, cn_w, \
+                                                                                                cn_b, eps, out)
+        if (C4 <= 8) L3AC_UPS(8, 1, 4);
+        else if (C4 <= 16) L3AC_UPS(16, 1, 4);
+        else if (C4 <= 32) L3AC_UPS(32, 1, 4);
+        else if (C4 <= 64) L3AC_UPS(32, 2, 2);
+        else L3AC_UPS(32, 4, 1);
+#undef L3AC_UPS
+        return l3ac_launch_status();
+    }
     const int grid = grid_for_rows(rows, 8);
     DISPATCH_CPL(C, { upsample_cn_kernel<CPL><<<grid, 256, 0, st>>>(x, B, T, C, scale, cn_w, cn_b, eps, out); });
     return l3ac_launch_status();
@@ -706,6 +1003,16 @@ extern "C" int l3ac_enhance_apply(const float* x, int B, int T, int C, const flo
     dim3 grid(l3ac_cdiv(T, kEnhTile), B);
     const int nchunk = l3ac_cdiv(T, kEnhChunk);
     cudaStream_t st = (cudaStream_t)stream;
+    if (C % 4 == 0 && C / 4 <= 256 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(merge_b) & 15) == 0) {
+        if (out_dtype == L3AC_F32)
+            enhance_apply_vec_kernel<float><<<grid, 256, 0, st>>>(x, B, T, C, conv_w, conv_b, in_w, in_b, merge_w, merge_b,
+                                                                  partials, nchunk, (float*)out);
+        else
+            enhance_apply_vec_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, B, T, C, conv_w, conv_b, in_w, in_b, merge_w,
+                                                                          merge_b, partials, nchunk, (__nv_bfloat16*)out);
+        return l3ac_launch_status();
+    }
     if (out_dtype == L3AC_F32)
         enhance_apply_kernel<float><<<grid, 256, 0, st>>>(x, B, T, C, conv_w, conv_b, in_w, in_b, merge_w, merge_b,
                                                           partials, nchunk, (float*)out);

@@ -83,6 +83,7 @@ class Engine:
             raise RuntimeError("l3ac_b200 runs on CUDA devices only; move the network with .cuda() first")
         self.precision = precision
         self.max_chunk_samples = int(max_chunk_seconds * 16000)
+        self.hidden_block_bytes = 0              # >0: L2-blocked ConvUnit MLP (measured slower, see _run_conv_unit)
         self.dec_dtype = torch.bfloat16 if precision == "bf16" else torch.float32
         self.enc_dtype = ops.SPLIT if encoder_precision == "split" else torch.float32
         w = {m: {k: v.detach().to(self.device) for k, v in sd.items()} for m, sd in weights.items()}
@@ -254,12 +255,35 @@ class Engine:
         return x.to(kind)
 
     def _run_conv_unit(self, x, u, act_dtype):
-        """Residual(ConvUnit) -- l3ac/modules.py:32-44."""
+        """Residual(ConvUnit) -- l3ac/modules.py:32-44.
+
+        The 4C-wide hidden tensor is the largest activation of the path.  Optionally (``hidden_block_bytes`` > 0) the
+        two point-wise GEMMs run back to back over row blocks sized so that one block of the hidden tensor stays in the
+        126 MB L2.  Measured on B200 (profiles/r01_bench_history.md) this LOSES: blocks of ~20 k rows are only ~4 tiles
+        per CTA, and the fill/drain of the persistent GEMM costs more than the saved HBM traffic (C=256 pw_conv2: 636
+        -> 331 TFLOP/s), so it is off by default; keeping the hidden tensor on chip needs the fused MLP kernel."""
         B, T, C = x.shape
         a = ops.dwconv7_ln(x, u["dw_w"], u["dw_b"], u["ln_w"], u["ln_b"], EPS, out_dtype=act_dtype)
-        h = self._lin(a, u["pw1"], B, T, C, act=ops.ACT_SNAKE, alpha=u["alpha"], scale=u["scale"], shift=u["shift"],
-                      out_dtype=act_dtype)
-        return self._lin(h, u["pw2"], B, T, 4 * C, residual=x)
+        M = B * T
+        esz = {torch.float32: 4, torch.bfloat16: 2, ops.SPLIT: 4}[act_dtype]
+        rows_blk = max(128 * 148, (self.hidden_block_bytes // (4 * C * esz)) // 128 * 128)
+        if self.hidden_block_bytes <= 0 or act_dtype == torch.float32 or M <= rows_blk + rows_blk // 2:
+            h = self._lin(a, u["pw1"], B, T, C, act=ops.ACT_SNAKE, alpha=u["alpha"], scale=u["scale"], shift=u["shift"],
+                          out_dtype=act_dtype)
+            return self._lin(h, u["pw2"], B, T, 4 * C, residual=x)
+        out = torch.empty_like(x)
+        a2, x2, o2 = a.view(M, C), x.view(M, C), out.view(M, C)
+        split = act_dtype == ops.SPLIT
+        hbuf = ops._empty_act((rows_blk, 4 * C), x.device, act_dtype)[0]          # reused by every block
+        for m0 in range(0, M, rows_blk):
+            m1 = min(M, m0 + rows_blk)
+            n = m1 - m0
+            ab = ops.Split(a2.hi[m0:m1], a2.lo[m0:m1]) if split else a2[m0:m1]
+            hb = ops.Split(hbuf.hi[:n], hbuf.lo[:n]) if split else hbuf[:n]
+            self._lin(ab, u["pw1"], 1, n, C, act=ops.ACT_SNAKE, alpha=u["alpha"], scale=u["scale"], shift=u["shift"],
+                      out_dtype=act_dtype, out=hb)
+            self._lin(hb, u["pw2"], 1, n, 4 * C, residual=x2[m0:m1], out=o2[m0:m1])
+        return out
 
     def _run_local_trans(self, x, lt, act_dtype):
         """LocalTrans.forward -- l3ac/local_trans.py:42-48 (LocalMHA prenorm + GEGLU FeedForward)."""

@@ -167,7 +167,7 @@ def snake(x, alpha, out_dtype=torch.float32) -> torch.Tensor:
 
 def gemm(a, w, *, B: int, T: int, K: int, taps: int = 1, tap_shift0: int = 0, tap_step: int = 1, bias=None,
          act: int = ACT_NONE, alpha=None, scale=None, shift=None, residual=None, out_dtype=torch.float32,
-         lda: Optional[int] = None):
+         lda: Optional[int] = None, out=None):
     """out[(b,t), n] = epi(bias[n] + sum_s sum_k a[b, t + shift_s, k] w[n, s*K + k])  (see the header).
 
     ``a`` is any contiguous tensor whose memory is ``B*T`` rows of pitch ``lda`` (default ``K``).  fp32 operands take
@@ -189,7 +189,14 @@ def gemm(a, w, *, B: int, T: int, K: int, taps: int = 1, tap_shift0: int = 0, ta
     if w_hi.shape[1] != taps * K:
         raise ValueError(f"w must be (N, taps*K) = (N, {taps * K}), got {tuple(w_hi.shape)}")
     n_out = N // 2 if act == ACT_GEGLU else N
-    out, o_hi, o_lo = _empty_act((B, T, n_out), a_hi.device, out_dtype)
+    if out is None:
+        out, o_hi, o_lo = _empty_act((B, T, n_out), a_hi.device, out_dtype)
+    else:       # caller-provided destination (a contiguous row range of a larger activation)
+        o_hi, o_lo = (out.hi, out.lo) if isinstance(out, Split) else (out, None)
+        want = torch.bfloat16 if out_dtype == SPLIT else out_dtype
+        if (out_dtype == SPLIT) != isinstance(out, Split) or o_hi.dtype != want or o_hi.numel() != B * T * n_out or \
+                not o_hi.is_contiguous():
+            raise ValueError("out does not match the requested output kind / shape")
     if residual is not None:
         _chk(residual, name="residual")
         if residual.numel() != B * T * n_out:
