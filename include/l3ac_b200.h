@@ -124,6 +124,18 @@ int l3ac_gemm_f32(const l3ac_gemm_desc* d, l3ac_stream_t stream);
 int l3ac_gemm_bf16_tc(const l3ac_gemm_desc* d, l3ac_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Fused ConvUnit MLP (pw_conv1 -> Snake -> GRN -> pw_conv2 -> Residual; l3ac/modules.py:36-44, layers.py:29-33,112-115,
+ * xtract/nn/layers.py:59-62) in one tcgen05 kernel: the 4C-wide hidden activation stays in TMEM / shared memory.
+ *   out[m,:] = residual[m,:] + b2 + W2 . ( scale * snake(W1 . a[m,:] + b1; alpha) + shift )
+ * a (M,C) bf16, w1 (4C,C) bf16, w2 (C,4C) bf16, b1/alpha/ialpha/scale/shift [4C] with ialpha = 1/(alpha + 1e-8),
+ * b2 [C], residual/out (M,C) fp32.
+ * 16 <= C <= 256, C % 8 == 0 (C = 512 does not fit one SM's shared memory: use the two GEMM calls).
+ * ------------------------------------------------------------------------------------------ */
+int l3ac_convunit_mlp_tc(const void* a, const void* w1, const float* b1, const float* alpha, const float* ialpha,
+                         const float* scale, const float* shift, const void* w2, const float* b2, const float* residual,
+                         float* out, long long M, int C, l3ac_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Block-local causal attention.  Replaces LocalAttention.forward of local-attention==1.11.2 as
  * configured at l3ac/local_trans.py:34-38 (causal, look_backward=1, exact_windowsize=False, autopad)
  * plus the DynamicPositionBias gather (local_trans.py:43):

@@ -83,6 +83,10 @@ class Engine:
             raise RuntimeError("l3ac_b200 runs on CUDA devices only; move the network with .cuda() first")
         self.precision = precision
         self.max_chunk_samples = int(max_chunk_seconds * 16000)
+        # Fused tcgen05 MLP kernel (mlp_fused.cu) for decode-side ConvUnits with C <= 256.  Bit-identical to the two-GEMM
+        # path but not yet faster on B200 (C=256: 386 vs 278 us, C=96: 362 vs 316, C=48: 501 vs 490 per 16-clip block; the
+        # per-tile latency chain A-load -> GEMM1 -> snake -> GEMM2 -> output epilogue is not overlapped across tiles), so off.
+        self.fused_mlp = False
         self.hidden_block_bytes = 0              # >0: L2-blocked ConvUnit MLP (measured slower, see _run_conv_unit)
         self.dec_dtype = torch.bfloat16 if precision == "bf16" else torch.float32
         self.enc_dtype = ops.SPLIT if encoder_precision == "split" else torch.float32
@@ -103,6 +107,7 @@ class Engine:
             ln_w=sd[f"{p}.norm.weight"].float().contiguous(), ln_b=sd[f"{p}.norm.bias"].float().contiguous(),
             pw1=_Linear(fold_weight_norm(sd, f"{p}.pw_conv1"), sd[f"{p}.pw_conv1.bias"], kind),
             alpha=sd[f"{p}.act.alpha"].float().flatten().contiguous(),
+            ialpha=(1.0 / (sd[f"{p}.act.alpha"].float().flatten() + 1e-8)).contiguous(),
             # GRN (l3ac/layers.py:112-115): n_x = g/(g+1e-8) == 1 to within 1e-8/g, so gamma*(x*n_x)+beta+x is the
             # per-channel affine (1+gamma) x + beta (absolute deviation <= 1e-8*|gamma|).
             scale=(1.0 + gamma).contiguous(), shift=beta.contiguous(),
@@ -267,6 +272,9 @@ class Engine:
         M = B * T
         esz = {torch.float32: 4, torch.bfloat16: 2, ops.SPLIT: 4}[act_dtype]
         rows_blk = max(128 * 148, (self.hidden_block_bytes // (4 * C * esz)) // 128 * 128)
+        if act_dtype == torch.bfloat16 and self.fused_mlp and 16 <= C <= 256 and C % 16 == 0:
+            return ops.convunit_mlp(a, u["pw1"].w16, u["pw1"].bias, u["alpha"], u["scale"], u["shift"], u["pw2"].w16,
+                                    u["pw2"].bias, x, ialpha=u["ialpha"])
         if self.hidden_block_bytes <= 0 or act_dtype == torch.float32 or M <= rows_blk + rows_blk // 2:
             h = self._lin(a, u["pw1"], B, T, C, act=ops.ACT_SNAKE, alpha=u["alpha"], scale=u["scale"], shift=u["shift"],
                           out_dtype=act_dtype)

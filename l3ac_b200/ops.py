@@ -223,6 +223,24 @@ def gemm(a, w, *, B: int, T: int, K: int, taps: int = 1, tap_shift0: int = 0, ta
     return out
 
 
+def convunit_mlp(a: torch.Tensor, w1, b1, alpha, scale, shift, w2, b2, residual: torch.Tensor, ialpha=None) -> torch.Tensor:
+    """Fused pw_conv1 -> snake/GRN -> pw_conv2 -> +residual (tcgen05, hidden activation on chip).  a (…, C) bf16."""
+    _chk(a, torch.bfloat16, "a")
+    _chk(residual, name="residual")
+    Cc = a.shape[-1]
+    M = a.numel() // Cc
+    if tuple(w1.shape) != (4 * Cc, Cc) or tuple(w2.shape) != (Cc, 4 * Cc) or residual.numel() != a.numel():
+        raise ValueError("convunit_mlp shape mismatch")
+    out = torch.empty(residual.shape, device=a.device, dtype=torch.float32)
+    if ialpha is None:
+        ialpha = 1.0 / (alpha + 1e-8)
+    _count()
+    with _hook("convunit_mlp_tc", _nbytes(a, residual, out, w1, w2), 2.0 * M * 2 * 4 * Cc * Cc), torch.cuda.device(a.device):
+        check(_lib.load().l3ac_convunit_mlp_tc(_ptr(a), _ptr(w1), _ptr(b1), _ptr(alpha), _ptr(ialpha), _ptr(scale), _ptr(shift), _ptr(w2),
+                                               _ptr(b2), _ptr(residual), _ptr(out), M, Cc, _stream(a)), "l3ac_convunit_mlp_tc")
+    return out
+
+
 def local_attention(qkv: torch.Tensor, bias_table: torch.Tensor, heads: int, window: int) -> torch.Tensor:
     _chk(qkv, name="qkv")
     _chk(bias_table, name="bias_table")

@@ -121,3 +121,24 @@ def test_split_outputs_and_producers(cuda_lib):
     y = ops.gemm(h, _split(w2), B=2, T=200, K=192, residual=a.to(DEV))
     want_y = h.float().cpu().double() @ w2.double().t() + a.double()
     assert max_abs(y.cpu(), want_y) < 3e-5 * max(1.0, float(want_y.abs().max()))
+
+
+@pytest.mark.parametrize("M,C", [(128, 256), (1000, 256), (333, 96), (2000, 48), (5000, 96), (40000, 256), (300, 192), (130, 64)])
+def test_fused_convunit_mlp(cuda_lib, M, C):
+    """Fused MLP kernel vs (a) the two-GEMM tcgen05 path it replaces and (b) fp64 on the same bf16 operands."""
+    a = bf(rnd(1, M, C, seed=1))
+    w1, w2 = bf(rnd(4 * C, C, seed=2, scale=C ** -0.5)), bf(rnd(C, 4 * C, seed=3, scale=(4 * C) ** -0.5))
+    b1, b2 = rnd(4 * C, seed=4, scale=0.1), rnd(C, seed=5, scale=0.1)
+    alpha, gamma, beta = 0.5 + torch.rand(4 * C), rnd(4 * C, seed=6, scale=0.1), rnd(4 * C, seed=7, scale=0.1)
+    x = rnd(1, M, C, seed=8)
+    dev = lambda t: t.to(DEV)
+    got = ops.convunit_mlp(dev(a), dev(w1), dev(b1), dev(alpha), dev(1 + gamma), dev(beta), dev(w2), dev(b2), dev(x))
+    h = ops.gemm(dev(a), dev(w1), B=1, T=M, K=C, bias=dev(b1), act=ops.ACT_SNAKE, alpha=dev(alpha), scale=dev(1 + gamma),
+                 shift=dev(beta), out_dtype=torch.bfloat16)
+    two = ops.gemm(h, dev(w2), B=1, T=M, K=4 * C, bias=dev(b2), residual=dev(x))
+    lin = a.double() @ w1.double().t() + b1.double()
+    hid = (lin + (alpha.double() + 1e-8).reciprocal() * torch.sin(alpha.double() * lin).pow(2)) * (1 + gamma.double()) + beta.double()
+    want = hid.to(torch.bfloat16).double() @ w2.double().t() + b2.double() + x.double()
+    e_two, e_fused = max_abs(two.cpu(), want), max_abs(got.cpu(), want)
+    print(f"[mlp M={M} C={C}] max-abs vs fp64(bf16 hidden): fused {e_fused:.2e}  two-GEMM {e_two:.2e}; fused-vs-two {max_abs(got, two):.2e}")
+    assert e_fused < 2e-2 * max(1.0, float(want.abs().max())) and e_fused < 3 * e_two + 1e-3

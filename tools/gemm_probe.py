@@ -39,8 +39,43 @@ def run(M, K, N, out_dtype=torch.float32, residual=False, act=ops.ACT_NONE, taps
           f"{t:8.1f} us  {flops / t / 1e6:7.1f} TF/s  {nbytes / t / 1e3:7.0f} GB/s", flush=True)
 
 
+def run_mlp(M, C, iters=5):
+    a = torch.randn(M, C, device=DEV).to(torch.bfloat16)
+    w1 = (torch.randn(4 * C, C, device=DEV) * C ** -0.5).to(torch.bfloat16)
+    w2 = (torch.randn(C, 4 * C, device=DEV) * (4 * C) ** -0.5).to(torch.bfloat16)
+    b1, b2 = torch.randn(4 * C, device=DEV) * 0.1, torch.randn(C, device=DEV) * 0.1
+    alpha, scale, shift = torch.ones(4 * C, device=DEV), torch.ones(4 * C, device=DEV), torch.zeros(4 * C, device=DEV)
+    x = torch.randn(M, C, device=DEV)
+    junk = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+    res = {}
+    for name in ("fused", "two_gemm"):
+        times = []
+        for i in range(iters + 2):
+            junk.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            if name == "fused":
+                ops.convunit_mlp(a, w1, b1, alpha, scale, shift, w2, b2, x)
+            else:
+                h = ops.gemm(a, w1, B=1, T=M, K=C, bias=b1, act=ops.ACT_SNAKE, alpha=alpha, scale=scale, shift=shift,
+                             out_dtype=torch.bfloat16)
+                ops.gemm(h, w2, B=1, T=M, K=4 * C, bias=b2, residual=x)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                times.append(e0.elapsed_time(e1) * 1e3)
+        res[name] = sorted(times)[len(times) // 2]
+    flops = 2.0 * M * 2 * 4 * C * C
+    print(f"mlp M={M:8d} C={C:4d}  fused {res['fused']:8.1f} us ({flops / res['fused'] / 1e6:6.1f} TF/s)   two-GEMM {res['two_gemm']:8.1f} us "
+          f"({flops / res['two_gemm'] / 1e6:6.1f} TF/s)", flush=True)
+
+
 if __name__ == "__main__":
     only = sys.argv[1] if len(sys.argv) > 1 else None
+    if only == "mlp":
+        for M, C in ((142320, 256), (426960, 96), (1280880, 48), (28464, 256), (2561760, 48)):
+            run_mlp(M, C)
+        sys.exit(0)
     thin = {
         "t_k96_n24": dict(M=2401650, K=96, N=24),
         "t_k96_n24_res": dict(M=2401650, K=96, N=24, residual=True),
