@@ -32,7 +32,7 @@ constexpr int kATileBytes = kBM * kBK * 2;    // 16 KB
 constexpr int kMaxBN = 256;
 constexpr int kMaxStages = 8;
 #ifndef L3AC_EPI_GROUPS
-#define L3AC_EPI_GROUPS 4                                     // epilogue warp groups (4 warps each, one per TMEM lane quadrant)
+#define L3AC_EPI_GROUPS 2                                     // epilogue warp groups (4 warps each, one per TMEM lane quadrant)
 #endif
 constexpr int kGroups = L3AC_EPI_GROUPS;
 constexpr int kEpiWarps = 4 * kGroups;
@@ -193,8 +193,11 @@ __device__ __noinline__ void store_scalar_tail(const Params& p, const float* stg
     }
 }
 
+// __launch_bounds__(.., 2): thin / short-K GEMMs are latency-bound per tile (TMA round trip -> MMA -> epilogue with its
+// own HBM round trip for the residual), so the host launches them with a small stage ring and two CTAs per SM; fat
+// GEMMs use the whole shared memory and run one CTA per SM.
 template <int ACT, int OUT, bool RES, bool PRECISE>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmA_lo, const __grid_constant__ CUtensorMap tmW_lo, const Params p) {
     extern __shared__ uint8_t smem_raw[];
@@ -597,6 +600,13 @@ extern "C" int l3ac_gemm_bf16_tc(const l3ac_gemm_desc* d, l3ac_stream_t stream) 
     const int stage_bytes = kATileBytes + p.BN * kBK * 2;
     p.stages = kSmemBudget / stage_bytes;
     if (p.stages > kMaxStages) p.stages = kMaxStages;
+    // two co-resident CTAs per SM for latency-bound shapes: accumulators of both must fit TMEM (<= 256 columns each) and
+    // each CTA gets half the shared memory
+    const int k_iters = d->taps * ((d->K + kBK - 1) / kBK) * (split ? 3 : 1);
+    const int tail_bytes = 5 * kMaxBN * 4 + kStageBytes + 16 * kMaxStages + 16 * kMaxAcc + 64 + 1024;
+    const int occ2_stages = (113 * 1024 - tail_bytes) / stage_bytes;
+    const bool occ2 = p.BN <= 128 && k_iters <= 12 && occ2_stages >= 2;
+    if (occ2) p.stages = occ2_stages > kMaxStages ? kMaxStages : occ2_stages;
     p.flat = (d->taps == 1 && d->tap_shift0 == 0) ? 1 : 0;
     p.k_blocks = (d->K + kBK - 1) / kBK;
     const long long M = (long long)d->B * d->T;
@@ -658,7 +668,8 @@ extern "C" int l3ac_gemm_bf16_tc(const l3ac_gemm_desc* d, l3ac_stream_t stream) 
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
     const long long tiles = (long long)p.num_m_tiles * p.num_n_tiles;
-    const int grid = (int)(tiles < sms ? tiles : sms);
+    const long long max_ctas = occ2 ? 2LL * sms : sms;
+    const int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
     fn<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmW, tmA_lo, tmW_lo, p);
     return l3ac_launch_status();
 }
