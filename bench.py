@@ -291,7 +291,7 @@ def main():
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": f"{args.config}, batch {B} x {secs:g} s clips per GPU, encode_audio + decode_audio(indices=)",
                        "bitrate": args.config, "batch_per_gpu": B, "clip_seconds": secs, "parallelism": f"dp{world}",
-                       "precision": "encode side fp32 SIMT, decode side bf16 tcgen05 (fp32 accumulate)" if args.precision == "bf16" else "fp32",
+                       "precision": "encode side split-bf16 (3-term) tcgen05, decode side bf16 tcgen05, fp32 accumulate and residual stream" if args.precision == "bf16" else "fp32 SIMT",
                        "l2": f"{n_rot} rotating input batches ({n_rot * B * secs * 64e3 / 1e6:.0f} MB) and a multi-GB "
                              "activation working set per step, both larger than the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,

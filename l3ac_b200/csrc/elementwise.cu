@@ -21,6 +21,13 @@ __device__ __forceinline__ void store_act<__nv_bfloat16>(__nv_bfloat16* hi, __nv
     if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
+template <int GS>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = GS / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
 // Four consecutive values (16-byte aligned destination for fp32, 8-byte for bf16).
 template <typename OutT>
 __device__ __forceinline__ void store_act4(OutT* hi, OutT* lo, long long i, float4 v) {
@@ -178,6 +185,68 @@ __global__ void __launch_bounds__(256) dwconv7_ln_rows_kernel(const float* __res
             for (int i = 0; i < CPL; ++i) {
                 const int c = lane + 32 * i;
                 if (c < C) store_act<OutT>(out, out_lo, row * C + c, (acc[i] - mean) * rstd * lw[i] + lb[i]);
+            }
+        }
+    }
+}
+
+// Thin-channel vector variant (C % 4 == 0, C <= 128): a row is owned by a group of GS lanes (one float4 of channels
+// per lane), a warp handles 32/GS independent runs of R consecutive time steps, every lane issues its R+6 128-bit
+// loads up front, and the LayerNorm statistics are log2(GS)-step shuffle reductions.  ~14 instructions per output
+// element instead of ~42 for the scalar one-channel-per-lane kernel (which is instruction-bound at C = 24).
+template <int GS, int R, typename OutT>
+__global__ void __launch_bounds__(256) dwconv7_ln_vec_kernel(const float* __restrict__ x, int B, int T, int C,
+                                                             const float* __restrict__ dw_w, const float* __restrict__ dw_b,
+                                                             const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                                                             float eps, OutT* __restrict__ out, OutT* __restrict__ out_lo) {
+    constexpr int RW = 32 / GS;
+    const int lane = threadIdx.x & 31, g = lane % GS, sub = lane / GS;
+    const int C4 = C >> 2;
+    const bool act = g < C4;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 w[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) w[j] = act ? __ldg(reinterpret_cast<const float4*>(dw_w + j * C) + g) : z4;
+    const float4 bias = act ? __ldg(reinterpret_cast<const float4*>(dw_b) + g) : z4;
+    const float4 lw = act ? __ldg(reinterpret_cast<const float4*>(ln_w) + g) : z4;
+    const float4 lb = act ? __ldg(reinterpret_cast<const float4*>(ln_b) + g) : z4;
+    const int runs_per_sample = (T + R - 1) / R;
+    const long long total_runs = (long long)B * runs_per_sample;
+    const float inv_c = 1.0f / (float)C;
+    const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long base = warp_global * RW; base < total_runs; base += nwarps * RW) {
+        const long long run = base + sub;
+        const bool run_ok = run < total_runs;
+        const long long rr = run_ok ? run : total_runs - 1;
+        const int b = (int)(rr / runs_per_sample);
+        const int t0 = (int)(rr - (long long)b * runs_per_sample) * R;
+        const float4* xb = reinterpret_cast<const float4*>(x + (long long)b * T * C) + g;
+        float4 xr[R + 6];
+#pragma unroll
+        for (int r = 0; r < R + 6; ++r) {
+            const int t = t0 + r - 3;
+            xr[r] = (act && t >= 0 && t < T) ? __ldg(xb + (long long)t * C4) : z4;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float4 a = bias;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                a.x = fmaf(w[j].x, xr[r + j].x, a.x);
+                a.y = fmaf(w[j].y, xr[r + j].y, a.y);
+                a.z = fmaf(w[j].z, xr[r + j].z, a.z);
+                a.w = fmaf(w[j].w, xr[r + j].w, a.w);
+            }
+            const float mean = group_sum<GS>((a.x + a.y) + (a.z + a.w)) * inv_c;     // inactive lanes hold zeros
+            const float dx = a.x - mean, dy = a.y - mean, dz = a.z - mean, dw = a.w - mean;
+            const float q = act ? (dx * dx + dy * dy) + (dz * dz + dw * dw) : 0.f;
+            const float rstd = 1.0f / sqrtf(group_sum<GS>(q) * inv_c + eps);
+            if (act && run_ok && t0 + r < T) {
+                const long long i = ((long long)b * T + t0 + r) * C + 4 * g;
+                store_act4<OutT>(out, out_lo, i,
+                                 make_float4(dx * rstd * lw.x + lb.x, dy * rstd * lw.y + lb.y, dz * rstd * lw.z + lb.z,
+                                             dw * rstd * lw.w + lb.w));
             }
         }
     }
@@ -545,12 +614,6 @@ __global__ void __launch_bounds__(256) enhance_apply_kernel(const float* __restr
 // owning VPL float4 (chunk index g + GS*v); a warp therefore processes 32/GS rows at once and U such row sets per
 // iteration, with every load issued before the first use.  Row statistics are xor-shuffle reductions inside the group.
 // ------------------------------------------------------------------------------------------
-template <int GS>
-__device__ __forceinline__ float group_sum(float v) {
-#pragma unroll
-    for (int o = GS / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
 
 template <int GS, int VPL, int U>
 __global__ void __launch_bounds__(256) upsample_cn_vec_kernel(const float* __restrict__ x, int B, int T, int C, int scale,
@@ -853,6 +916,27 @@ extern "C" int l3ac_dwconv7_ln(const float* x, int B, int T, int C, const float*
     L3AC_CHECK_ARG((out_dtype == L3AC_BF16X2) == (out_lo != nullptr));
     cudaStream_t st = (cudaStream_t)stream;
     const long long rows = (long long)B * T;
+    if (C % 4 == 0 && C <= 128 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+        ((reinterpret_cast<uintptr_t>(dw_w) | reinterpret_cast<uintptr_t>(dw_b) | reinterpret_cast<uintptr_t>(ln_w) |
+          reinterpret_cast<uintptr_t>(ln_b) | reinterpret_cast<uintptr_t>(out_lo)) & 15) == 0) {
+        constexpr int R = 8;
+        const long long runs = (long long)B * ((T + R - 1) / R);
+#define L3AC_DWV(GS)                                                                                                   \
+    do {                                                                                                               \
+        const int g_ = grid_for_rows(runs, 8 * (32 / GS));                                                             \
+        if (out_dtype == L3AC_F32)                                                                                     \
+            dwconv7_ln_vec_kernel<GS, R, float><<<g_, 256, 0, st>>>(x, B, T, C, dw_w, dw_b, ln_w, ln_b, eps, (float*)out, \
+                                                                    nullptr);                                          \
+        else                                                                                                           \
+            dwconv7_ln_vec_kernel<GS, R, __nv_bfloat16><<<g_, 256, 0, st>>>(x, B, T, C, dw_w, dw_b, ln_w, ln_b, eps,     \
+                                                                            (__nv_bfloat16*)out, (__nv_bfloat16*)out_lo); \
+    } while (0)
+        if (C <= 32) L3AC_DWV(8);
+        else if (C <= 64) L3AC_DWV(16);
+        else L3AC_DWV(32);
+#undef L3AC_DWV
+        return l3ac_launch_status();
+    }
     if (C <= 96) {
         constexpr int R = 8;
         const int grid = grid_for_rows((rows + R - 1) / R + B, 8);

@@ -125,42 +125,56 @@ __global__ void __launch_bounds__(kThreads, 2) decoder_tail_kernel(const Params 
             *reinterpret_cast<uint4*>(a_buf + swz(row, ch)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
         __syncthreads();
-        // ---- h = bf16(snake(conv_k7_dil_d(a) + bias, alpha1)): M = time (16-row tiles), N = 24 (3 x 8), K = 7 taps x 32
-        for (int mt = warp; mt < kRows / 16; mt += kThreads / 32) {
-            const int r0 = mt * 16;
-            float acc[3][4];
+        // ---- h = bf16(snake(conv_k7_dil_d(a) + bias, alpha1)): M = time (16-row tiles), N = 24 (3 x 8), K = 7 taps x 32.
+        // Each warp owns kMT = 3 m-tiles; the weight fragments of one (tap, k-step) are loaded once and reused for all
+        // three, so the inner loop is 1 ldmatrix + 3 MMAs per m-tile.
+        {
+            constexpr int kMT = kRows / 16 / (kThreads / 32);
+            static_assert(kMT * (kThreads / 32) * 16 == kRows, "m-tiles must divide evenly over the warps");
+            float acc[kMT][3][4];
 #pragma unroll
-            for (int n = 0; n < 3; ++n)
+            for (int i = 0; i < kMT; ++i)
 #pragma unroll
-                for (int e = 0; e < 4; ++e) acc[n][e] = 0.f;
+                for (int n = 0; n < 3; ++n)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc[i][n][e] = 0.f;
             const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8;      // ldmatrix: lanes 0-15 rows 0-15 (k lo), 16-31 rows 0-15 (k hi)
             const int lchunk = lane >> 4;
 #pragma unroll
             for (int tap = 0; tap < 7; ++tap) {
-                const int row = clamp_row(r0 + lrow + (tap - 3) * d);
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks) {
-                    uint32_t a0, a1, a2, a3;
-                    ldmatrix_x4(a_addr + swz(row, 2 * ks + lchunk), a0, a1, a2, a3);
+                    uint2 bw[3];
 #pragma unroll
-                    for (int n = 0; n < 3; ++n) {
-                        const uint2 bw = *reinterpret_cast<const uint2*>(w_conv + (((tap * 2 + ks) * 3 + n) * 32 + lane) * 2);
-                        mma_bf16(acc[n], a0, a1, a2, a3, bw.x, bw.y);
+                    for (int n = 0; n < 3; ++n)
+                        bw[n] = *reinterpret_cast<const uint2*>(w_conv + (((tap * 2 + ks) * 3 + n) * 32 + lane) * 2);
+#pragma unroll
+                    for (int i = 0; i < kMT; ++i) {
+                        const int r0 = (warp + i * (kThreads / 32)) * 16;
+                        const int row = clamp_row(r0 + lrow + (tap - 3) * d);
+                        uint32_t a0, a1, a2, a3;
+                        ldmatrix_x4(a_addr + swz(row, 2 * ks + lchunk), a0, a1, a2, a3);
+#pragma unroll
+                        for (int n = 0; n < 3; ++n) mma_bf16(acc[i][n], a0, a1, a2, a3, bw[n].x, bw[n].y);
                     }
                 }
             }
 #pragma unroll
-            for (int n = 0; n < 3; ++n) {
-                const int col = n * 8 + (lane & 3) * 2;
+            for (int i = 0; i < kMT; ++i) {
+                const int r0 = (warp + i * (kThreads / 32)) * 16;
 #pragma unroll
-                for (int hrow = 0; hrow < 2; ++hrow) {
-                    const int row = r0 + (lane >> 2) + hrow * 8;
-                    float v0 = acc[n][2 * hrow] + s_par[col], v1 = acc[n][2 * hrow + 1] + s_par[col + 1];
-                    const float s0 = __sinf(s_par[4 * kC + col] * v0), s1 = __sinf(s_par[4 * kC + col + 1] * v1);
-                    v0 = fmaf(s_par[5 * kC + col], s0 * s0, v0);
-                    v1 = fmaf(s_par[5 * kC + col + 1], s1 * s1, v1);
-                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
-                    *reinterpret_cast<uint32_t*>(h_buf + swz(row, n) + (lane & 3) * 4) = *reinterpret_cast<const uint32_t*>(&h2);
+                for (int n = 0; n < 3; ++n) {
+                    const int col = n * 8 + (lane & 3) * 2;
+#pragma unroll
+                    for (int hrow = 0; hrow < 2; ++hrow) {
+                        const int row = r0 + (lane >> 2) + hrow * 8;
+                        float v0 = acc[i][n][2 * hrow] + s_par[col], v1 = acc[i][n][2 * hrow + 1] + s_par[col + 1];
+                        const float s0 = __sinf(s_par[4 * kC + col] * v0), s1 = __sinf(s_par[4 * kC + col + 1] * v1);
+                        v0 = fmaf(s_par[5 * kC + col], s0 * s0, v0);
+                        v1 = fmaf(s_par[5 * kC + col + 1], s1 * s1, v1);
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+                        *reinterpret_cast<uint32_t*>(h_buf + swz(row, n) + (lane & 3) * 4) = *reinterpret_cast<const uint32_t*>(&h2);
+                    }
                 }
             }
         }
