@@ -354,12 +354,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t acc_phase = 0;
         const int tile_step = p.thin ? kGroups * gridDim.x : gridDim.x;
         const int chunk0 = p.thin ? 0 : half;
-        bool params_loaded = false;
+        int staged_n0 = -1;      // N tile whose per-column parameters are currently staged in shared memory
         for (int tile = blockIdx.x + (p.thin ? half * gridDim.x : 0); tile < num_tiles; tile += tile_step) {
             int m_tile, n_tile;
             tile_coords(p, tile, m_tile, n_tile);
             const int n0 = n_tile * p.BN;
-            if (!p.thin || !params_loaded) {
+            // The tile order keeps a CTA on the same N tile whenever gridDim.x is a multiple of num_n_tiles (always for 1, 2
+            // and 4 N tiles on 148 SMs), so the parameters are normally staged once per kernel.  n0 is CTA-uniform, hence so
+            // is this branch and the barriers inside it.
+            if (n0 != staged_n0) {
                 // thin mode: every tile has n0 == 0, so the per-column parameters are staged once, by each group
                 // into identical values (benign duplicate writes), guarded by a per-group named barrier
                 if (p.thin) asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
@@ -380,7 +383,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 if (p.thin) asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
                 else asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-                params_loaded = true;
+                staged_n0 = n0;
             }
             long long row_base;
             int rows_valid;

@@ -1,19 +1,21 @@
 // Encoder stem = V3FirstBlock (l3ac/tconv/__init__.py:8-27) fused into one kernel:
 //   5 x [TrendPool(k) -> Conv1d(1->4,k7,pad 3)]  (k = 1,5,11,21,45; l3ac/tconv/base.py:8-45)
 //   -> Conv1d 1x1 20->80 -> exact GELU -> cat raw x -> Conv1d 1x1 81->C
-// audio (B,T) -> out (B,T,C) channels-last.  One block = 128 consecutive samples of one clip,
+// audio (B,T) -> out (B,T,C) channels-last.  One block = 256 consecutive samples of one clip (2 per thread),
 // halo 47 = 44 (max+avg pool of 45) + 3 (conv k7).
 #include "common.cuh"
 
 namespace l3ac {
 
-constexpr int kStemTile = 128;
+constexpr int kStemThreads = 128;
+constexpr int kStemSPT = 1;                       // samples per thread (2 halves the weight LDS traffic but 201 registers cut occupancy: measured 3.65 vs 3.29 ms)
+constexpr int kStemTile = kStemThreads * kStemSPT;
 constexpr int kStemReach = 47;
 constexpr int kStemW = kStemTile + 2 * kStemReach;
 constexpr int kStemH = 80;
 
 template <int CO>
-__global__ void __launch_bounds__(kStemTile) stem_kernel(const float* __restrict__ audio, int B, int T,
+__global__ void __launch_bounds__(kStemThreads) stem_kernel(const float* __restrict__ audio, int B, int T,
                                                          const float* __restrict__ branch_w,
                                                          const float* __restrict__ branch_b,
                                                          const float* __restrict__ w1, const float* __restrict__ b1,
@@ -41,8 +43,7 @@ __global__ void __launch_bounds__(kStemTile) stem_kernel(const float* __restrict
     for (int i = threadIdx.x; i < 20; i += blockDim.x) s_bb[i] = branch_b[i];
     __syncthreads();
 
-    float h[20];
-    const int li = threadIdx.x + kStemReach;   // this thread's sample inside xs/ps
+    float h[kStemSPT][20];
     const int pool_k[5] = {1, 5, 11, 21, 45};
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
@@ -71,46 +72,67 @@ __global__ void __launch_bounds__(kStemTile) stem_kernel(const float* __restrict
             src = ps;
         }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            float acc = s_bb[j * 4 + c];
+        for (int sp = 0; sp < kStemSPT; ++sp) {
+            const int li = threadIdx.x + sp * kStemThreads + kStemReach;   // this thread's sample inside xs/ps
 #pragma unroll
-            for (int q = 0; q < 7; ++q) acc = fmaf(s_bw[(j * 4 + c) * 7 + q], src[li + q - 3], acc);
-            h[j * 4 + c] = acc;
+            for (int c = 0; c < 4; ++c) {
+                float acc = s_bb[j * 4 + c];
+#pragma unroll
+                for (int q = 0; q < 7; ++q) acc = fmaf(s_bw[(j * 4 + c) * 7 + q], src[li + q - 3], acc);
+                h[sp][j * 4 + c] = acc;
+            }
         }
         __syncthreads();   // ms/ps are rewritten by the next branch
     }
 
-    const int t = t0 + threadIdx.x;
-    if (t >= T) return;
-    float acc[CO];
-    const float xv = xs[li];
+    float acc[kStemSPT][CO];
 #pragma unroll
-    for (int c = 0; c < CO; ++c) acc[c] = fmaf(s_w2t[kStemH * CO + c], xv, s_b2[c]);
+    for (int sp = 0; sp < kStemSPT; ++sp) {
+        const float xv = xs[threadIdx.x + sp * kStemThreads + kStemReach];
+#pragma unroll
+        for (int c = 0; c < CO; ++c) acc[sp][c] = fmaf(s_w2t[kStemH * CO + c], xv, s_b2[c]);
+    }
     for (int u = 0; u < kStemH; ++u) {
-        float a = s_b1[u];
+        float a[kStemSPT];
+#pragma unroll
+        for (int sp = 0; sp < kStemSPT; ++sp) a[sp] = s_b1[u];
         const float4* wr = reinterpret_cast<const float4*>(s_w1 + u * 20);
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
             const float4 w4 = wr[i];
-            a = fmaf(w4.x, h[4 * i], a);
-            a = fmaf(w4.y, h[4 * i + 1], a);
-            a = fmaf(w4.z, h[4 * i + 2], a);
-            a = fmaf(w4.w, h[4 * i + 3], a);
+#pragma unroll
+            for (int sp = 0; sp < kStemSPT; ++sp) {
+                a[sp] = fmaf(w4.x, h[sp][4 * i], a[sp]);
+                a[sp] = fmaf(w4.y, h[sp][4 * i + 1], a[sp]);
+                a[sp] = fmaf(w4.z, h[sp][4 * i + 2], a[sp]);
+                a[sp] = fmaf(w4.w, h[sp][4 * i + 3], a[sp]);
+            }
         }
-        const float g = gelu_erf(a);
+        float g[kStemSPT];
+#pragma unroll
+        for (int sp = 0; sp < kStemSPT; ++sp) g[sp] = gelu_erf(a[sp]);
         const float4* w2r = reinterpret_cast<const float4*>(s_w2t + u * CO);
 #pragma unroll
         for (int i = 0; i < CO / 4; ++i) {
             const float4 w4 = w2r[i];
-            acc[4 * i] = fmaf(w4.x, g, acc[4 * i]);
-            acc[4 * i + 1] = fmaf(w4.y, g, acc[4 * i + 1]);
-            acc[4 * i + 2] = fmaf(w4.z, g, acc[4 * i + 2]);
-            acc[4 * i + 3] = fmaf(w4.w, g, acc[4 * i + 3]);
+#pragma unroll
+            for (int sp = 0; sp < kStemSPT; ++sp) {
+                acc[sp][4 * i] = fmaf(w4.x, g[sp], acc[sp][4 * i]);
+                acc[sp][4 * i + 1] = fmaf(w4.y, g[sp], acc[sp][4 * i + 1]);
+                acc[sp][4 * i + 2] = fmaf(w4.z, g[sp], acc[sp][4 * i + 2]);
+                acc[sp][4 * i + 3] = fmaf(w4.w, g[sp], acc[sp][4 * i + 3]);
+            }
         }
     }
-    float4* o = reinterpret_cast<float4*>(out + ((long long)b * T + t) * CO);
 #pragma unroll
-    for (int i = 0; i < CO / 4; ++i) o[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+    for (int sp = 0; sp < kStemSPT; ++sp) {
+        const int t = t0 + threadIdx.x + sp * kStemThreads;
+        if (t >= T) continue;
+        float4* o = reinterpret_cast<float4*>(out + ((long long)b * T + t) * CO);
+#pragma unroll
+        for (int i = 0; i < CO / 4; ++i)
+            o[i] = make_float4(acc[sp][4 * i], acc[sp][4 * i + 1], acc[sp][4 * i + 2], acc[sp][4 * i + 3]);
+    }
 }
 
 }  // namespace l3ac
@@ -122,7 +144,7 @@ extern "C" int l3ac_stem(const float* audio, int B, int T, const float* branch_w
     L3AC_CHECK_ARG(B > 0 && B <= 65535 && T > 0);
     if (C != 24) return L3AC_EUNSUPPORTED;
     dim3 grid(l3ac_cdiv(T, l3ac::kStemTile), B);
-    l3ac::stem_kernel<24><<<grid, l3ac::kStemTile, 0, (cudaStream_t)stream>>>(audio, B, T, branch_w, branch_b, w1, b1,
+    l3ac::stem_kernel<24><<<grid, l3ac::kStemThreads, 0, (cudaStream_t)stream>>>(audio, B, T, branch_w, branch_b, w1, b1,
                                                                               w2, b2, out);
     return l3ac_launch_status();
 }
