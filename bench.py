@@ -209,6 +209,19 @@ def main():
             ms = float(t.item())
         return ms / steps
 
+    if os.environ.get("L3AC_BENCH_NCU"):
+        # profiling aid: `ncu --profile-from-start off ...` captures exactly one warm step (numbers printed under a
+        # profiler are never bench values, so nothing is printed)
+        with torch.inference_mode():
+            for i in range(max(1, args.warmup)):
+                step_resident(i)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
+            step_resident(0)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
+        return
+
     sampler = ClockSampler(local)
     launches0 = ops.LAUNCHES
     with torch.inference_mode():

@@ -114,3 +114,19 @@ def test_round_trip_at_bench_size(cuda_lib):
     lv = idx["level_indices"].long()
     basis = torch.tensor([1, 7, 49, 343, 2401, 16807], device=DEV)
     assert torch.equal((lv * basis).sum(-1).int(), idx["indices"])   # mixed-radix checksum of the level digits
+
+
+def test_micro_batching_is_transparent(cuda_lib):
+    """Batches larger than one 160 s micro-batch are processed in chunks; results must equal per-clip processing."""
+    codec = l3ac_b200.get_model("3kbps", pretrained=False)
+    codec.network.cuda()
+    codec.network.engine.max_chunk_samples = 16000 * 12          # force 3 chunks for 7 clips of 5 s
+    audio = make_audio(7, 5.0, seed=21).to(DEV)
+    with torch.inference_mode():
+        q, idx = codec.encode_audio(audio)
+        wav = codec.decode_audio(indices=idx["indices"])
+        q1, idx1 = codec.encode_audio(audio[5:6])
+        wav1 = codec.decode_audio(indices=idx1["indices"])
+    assert idx["indices"].shape[0] == 7 and wav.shape[0] == 7
+    assert torch.equal(idx["indices"][5:6], idx1["indices"]) and torch.equal(q[5:6], q1)
+    assert torch.equal(wav[5:6], wav1)
