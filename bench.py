@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--seconds", type=float, default=10.0)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="encdec", choices=["encdec", "decode"],
+                    help="encdec = BASELINE headline; decode = decode_audio(indices=) only (BASELINE config #5 sweep)")
     return ap.parse_args()
 
 
@@ -170,7 +172,14 @@ def main():
     T_tok = -(-dev_inputs[0].shape[1] // mc.hop_length)
     gathered = torch.empty((world * B, T_tok), dtype=torch.int32, device=dev) if world > 1 else None
 
+    dec_indices = None
+    if args.mode == "decode":
+        with torch.inference_mode():
+            dec_indices = [codec.encode_audio(x)[1]["indices"] for x in dev_inputs]
+
     def step_resident(i):
+        if dec_indices is not None:
+            return codec.decode_audio(indices=dec_indices[i % n_rot])
         q, idx = codec.encode_audio(dev_inputs[i % n_rot])
         if world > 1:       # the only exchange step on the path: gather token indices (B*T_tok*4 bytes per rank)
             dist.all_gather_into_tensor(gathered, idx["indices"])
@@ -179,7 +188,13 @@ def main():
     host_wav = torch.empty((B, T_tok * mc.hop_length), dtype=torch.float32).pin_memory()
     host_idx = torch.empty((B, T_tok), dtype=torch.int32).pin_memory()
 
+    host_dec_idx = [t.cpu().pin_memory() for t in dec_indices] if dec_indices is not None else None
+
     def step_e2e(i):
+        if host_dec_idx is not None:
+            wav = codec.decode_audio(indices=host_dec_idx[i % n_rot].to(dev, non_blocking=True))
+            host_wav.copy_(wav, non_blocking=True)
+            return
         audio = host_inputs[i % n_rot].to(dev, non_blocking=True)
         q, idx = codec.encode_audio(audio)
         wav = codec.decode_audio(indices=idx["indices"])
@@ -302,14 +317,16 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": f"{args.config}, batch {B} x {secs:g} s clips per GPU, encode_audio + decode_audio(indices=)",
+            "config": {"workload": f"{args.config}, batch {B} x {secs:g} s clips per GPU, " +
+                                   ("encode_audio + decode_audio(indices=)" if args.mode == "encdec" else "decode_audio(indices=) only"),
+                       "mode": args.mode,
                        "bitrate": args.config, "batch_per_gpu": B, "clip_seconds": secs, "parallelism": f"dp{world}",
                        "precision": "encode side split-bf16 (3-term) tcgen05, decode side bf16 tcgen05, fp32 accumulate and residual stream" if args.precision == "bf16" else "fp32 SIMT",
                        "l2": f"{n_rot} rotating input batches ({n_rot * B * secs * 64e3 / 1e6:.0f} MB) and a multi-GB "
                              "activation working set per step, both larger than the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": int(host_inputs[0].numel() * 4),
-                    "d2h_bytes_per_step": int(host_wav.numel() * 4 + host_idx.numel() * 4)},
+                    "h2d_bytes_per_step": int(host_inputs[0].numel() * 4) if args.mode == "encdec" else int(host_idx.numel() * 4),
+                    "d2h_bytes_per_step": int(host_wav.numel() * 4 + (host_idx.numel() * 4 if args.mode == "encdec" else 0))},
             "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks, "roofline": roofline, **extras}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

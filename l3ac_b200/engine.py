@@ -83,6 +83,11 @@ class Engine:
             raise RuntimeError("l3ac_b200 runs on CUDA devices only; move the network with .cuda() first")
         self.precision = precision
         self.max_chunk_samples = int(max_chunk_seconds * 16000)
+        # Small batches are launch-bound (~220 kernels per encode+decode step, ~1 ms of GPU work for one 10 s clip):
+        # the kernel sequence of a given (batch, length) is captured once into a CUDA graph and replayed.
+        self.graph_max_samples = int(40.0 * 16000)
+        self.graph_cache_size = 8
+        self._graphs = {}
         # Fused tcgen05 MLP kernel (mlp_fused.cu) for decode-side ConvUnits with C <= 256.  Bit-identical to the two-GEMM
         # path but not yet faster on B200 (C=256: 386 vs 278 us, C=96: 362 vs 316, C=48: 501 vs 490 per 16-clip block; the
         # per-tile latency chain A-load -> GEMM1 -> snake -> GEMM2 -> output epilogue is not overlapped across tiles), so off.
@@ -358,11 +363,43 @@ class Engine:
         per = max(1, self.max_chunk_samples // max(T, 1))
         return [(i, min(B, i + per)) for i in range(0, B, per)]
 
+    # ------------------------------------------------------------------ CUDA graphs (small, launch-bound batches)
+    def _graphed(self, key, fn, inp: torch.Tensor):
+        """Runs ``fn(static copy of inp)`` through a cached CUDA graph; returns fresh clones of its outputs."""
+        slot = self._graphs.get(key)
+        if slot is None:
+            if len(self._graphs) >= self.graph_cache_size:
+                self._graphs.pop(next(iter(self._graphs)))          # drop the oldest capture (and its memory pool)
+            static_in = inp.clone()
+            cur = torch.cuda.current_stream(self.device)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):                            # warm-up outside capture (lazy init, attribute calls)
+                fn(static_in)
+            cur.wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                outs = fn(static_in)
+            slot = (graph, static_in, outs)
+            self._graphs[key] = slot
+        graph, static_in, outs = slot
+        static_in.copy_(inp)
+        graph.replay()
+        return tuple(o.clone() for o in outs)
+
+    def _encode_one_chunk(self, audio: torch.Tensor):
+        q, idx, lvl, _ = self.quantize(self.encode_features(audio))
+        return q, idx, lvl
+
     def encode(self, audio: torch.Tensor, taps: Optional[dict] = None):
         """L3AC.encode_audio -- l3ac/__init__.py:108-114."""
         if audio.dim() != 2:
             raise RuntimeError(f"encode_audio expects a (batch, samples) tensor, got shape {tuple(audio.shape)}")
         audio = audio.to(device=self.device, dtype=torch.float32)
+        if taps is None and 0 < audio.numel() <= self.graph_max_samples and not torch.cuda.is_current_stream_capturing():
+            with torch.cuda.device(self.device):
+                q, idx, lvl = self._graphed(("enc",) + tuple(audio.shape), self._encode_one_chunk, audio.contiguous())
+            return q, {"indices": idx, "level_indices": lvl}
         outs = []
         for lo, hi in self._chunks(*audio.shape):
             t = self.encode_features(audio[lo:hi], taps if (lo == 0 and hi == audio.shape[0]) else None)
@@ -421,6 +458,10 @@ class Engine:
             audio_feature = self.dequantize(indices.to(self.device))
         feat = audio_feature.to(device=self.device, dtype=torch.float32).contiguous()
         B, T_tok, _ = feat.shape
+        if taps is None and 0 < B * T_tok * self.mc.hop_length <= self.graph_max_samples and \
+                not torch.cuda.is_current_stream_capturing():
+            with torch.cuda.device(self.device):
+                return self._graphed(("dec", B, T_tok), lambda f: (self.decode_features(f),), feat)[0]
         outs = [self.decode_features(feat[lo:hi].contiguous(), taps if (lo == 0 and hi == B) else None)
                 for lo, hi in self._chunks(B, T_tok * self.mc.hop_length)]
         return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)

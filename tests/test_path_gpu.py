@@ -130,3 +130,26 @@ def test_micro_batching_is_transparent(cuda_lib):
     assert idx["indices"].shape[0] == 7 and wav.shape[0] == 7
     assert torch.equal(idx["indices"][5:6], idx1["indices"]) and torch.equal(q[5:6], q1)
     assert torch.equal(wav[5:6], wav1)
+
+
+def test_cuda_graph_path_matches_eager(cuda_lib):
+    """Small batches replay a captured CUDA graph; results must be bit-identical to the eager launch sequence."""
+    codec = l3ac_b200.get_model("1kbps", pretrained=False)
+    codec.network.cuda()
+    eng = codec.network.engine
+    audio = make_audio(2, 3.0, seed=31).to(DEV)
+    with torch.inference_mode():
+        eng.graph_max_samples = 0                       # eager
+        q0, idx0 = codec.encode_audio(audio)
+        w0 = codec.decode_audio(indices=idx0["indices"])
+        eng.graph_max_samples = 16000 * 40              # graphed: first call captures, second replays
+        for _ in range(2):
+            q1, idx1 = codec.encode_audio(audio)
+            w1 = codec.decode_audio(indices=idx1["indices"])
+        other = make_audio(2, 3.0, seed=32).to(DEV)     # same shape, different data -> same graph, new results
+        q2, idx2 = codec.encode_audio(other)
+        eng.graph_max_samples = 0
+        q3, idx3 = codec.encode_audio(other)
+    assert torch.equal(idx0["indices"], idx1["indices"]) and torch.equal(q0, q1) and torch.equal(w0, w1)
+    assert torch.equal(idx2["indices"], idx3["indices"]) and torch.equal(q2, q3)
+    assert len(eng._graphs) == 2
