@@ -65,7 +65,7 @@ class _Linear:
 
 class Engine:
     def __init__(self, mc: ModelConfig, weights: Dict[str, Dict[str, torch.Tensor]], device, precision: str = "bf16",
-                 max_chunk_seconds: float = 160.0, encoder_precision: Optional[str] = None):
+                 max_chunk_seconds: float = 240.0, encoder_precision: Optional[str] = None):
         if precision not in ("fp32", "bf16"):
             raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
         encoder_precision = encoder_precision or ("fp32" if precision == "fp32" else "split")
@@ -82,12 +82,18 @@ class Engine:
         if self.device.type != "cuda":
             raise RuntimeError("l3ac_b200 runs on CUDA devices only; move the network with .cuda() first")
         self.precision = precision
+        import os
+        max_chunk_seconds = float(os.environ.get("L3AC_CHUNK_SECONDS", max_chunk_seconds))     # tuning knobs (bench sweeps)
         self.max_chunk_samples = int(max_chunk_seconds * 16000)
         # Small batches are launch-bound (~220 kernels per encode+decode step, ~1 ms of GPU work for one 10 s clip):
         # the kernel sequence of a given (batch, length) is captured once into a CUDA graph and replayed.
         self.graph_max_samples = int(40.0 * 16000)
         self.graph_cache_size = 8
         self._graphs = {}
+        # Micro-batches are independent, so they are issued round-robin on a few streams: the HBM-bound stencil kernels of
+        # one micro-batch then overlap the tensor-core GEMMs (one persistent, shared-memory-heavy CTA per SM) of another.
+        self.num_streams = int(os.environ.get("L3AC_STREAMS", 4))    # measured: 2 -> +11 %, 4 -> +14 % at 64 x 10 s
+        self._streams = None
         # Fused tcgen05 MLP kernel (mlp_fused.cu) for decode-side ConvUnits with C <= 256.  Bit-identical to the two-GEMM
         # path but not yet faster on B200 (C=256: 386 vs 278 us, C=96: 362 vs 316, C=48: 501 vs 490 per 16-clip block; the
         # per-tile latency chain A-load -> GEMM1 -> snake -> GEMM2 -> output epilogue is not overlapped across tiles), so off.
@@ -387,6 +393,28 @@ class Engine:
         graph.replay()
         return tuple(o.clone() for o in outs)
 
+    def _run_chunks(self, fn, chunks):
+        """Runs ``fn(lo, hi)`` for every micro-batch, round-robin over ``num_streams`` side streams; returns the results
+        in order.  All side streams are joined back into the caller's stream before returning."""
+        if len(chunks) <= 1 or self.num_streams <= 1 or torch.cuda.is_current_stream_capturing():
+            return [fn(lo, hi) for lo, hi in chunks]
+        if self._streams is None or len(self._streams) != self.num_streams:
+            self._streams = [torch.cuda.Stream(device=self.device) for _ in range(self.num_streams)]
+        cur = torch.cuda.current_stream(self.device)
+        for st in self._streams:
+            st.wait_stream(cur)
+        results = []
+        for i, (lo, hi) in enumerate(chunks):
+            with torch.cuda.stream(self._streams[i % self.num_streams]):
+                results.append(fn(lo, hi))
+        for st in self._streams:
+            cur.wait_stream(st)
+        for r in results:                                    # outputs were allocated on a side stream, are consumed on `cur`
+            for t in (r if isinstance(r, (tuple, list)) else (r,)):
+                if isinstance(t, torch.Tensor):
+                    t.record_stream(cur)
+        return results
+
     def _encode_one_chunk(self, audio: torch.Tensor):
         q, idx, lvl, _ = self.quantize(self.encode_features(audio))
         return q, idx, lvl
@@ -400,15 +428,18 @@ class Engine:
             with torch.cuda.device(self.device):
                 q, idx, lvl = self._graphed(("enc",) + tuple(audio.shape), self._encode_one_chunk, audio.contiguous())
             return q, {"indices": idx, "level_indices": lvl}
-        outs = []
-        for lo, hi in self._chunks(*audio.shape):
-            t = self.encode_features(audio[lo:hi], taps if (lo == 0 and hi == audio.shape[0]) else None)
+        n_all = audio.shape[0]
+
+        def run(lo, hi):
+            t = self.encode_features(audio[lo:hi], taps if (lo == 0 and hi == n_all) else None)
             if taps is not None:
                 taps["trans_feature"] = t
             q, idx, lvl, z = self.quantize(t, want_z=taps is not None)
             if taps is not None:
                 taps["z"] = z
-            outs.append((q, idx, lvl))
+            return q, idx, lvl
+
+        outs = self._run_chunks(run, self._chunks(*audio.shape))
         if len(outs) == 1:
             q, idx, lvl = outs[0]
         else:
@@ -462,6 +493,6 @@ class Engine:
                 not torch.cuda.is_current_stream_capturing():
             with torch.cuda.device(self.device):
                 return self._graphed(("dec", B, T_tok), lambda f: (self.decode_features(f),), feat)[0]
-        outs = [self.decode_features(feat[lo:hi].contiguous(), taps if (lo == 0 and hi == B) else None)
-                for lo, hi in self._chunks(B, T_tok * self.mc.hop_length)]
+        outs = self._run_chunks(lambda lo, hi: self.decode_features(feat[lo:hi].contiguous(), taps if (lo == 0 and hi == B) else None),
+                                self._chunks(B, T_tok * self.mc.hop_length))
         return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)

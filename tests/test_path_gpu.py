@@ -120,7 +120,8 @@ def test_micro_batching_is_transparent(cuda_lib):
     """Batches larger than one 160 s micro-batch are processed in chunks; results must equal per-clip processing."""
     codec = l3ac_b200.get_model("3kbps", pretrained=False)
     codec.network.cuda()
-    codec.network.engine.max_chunk_samples = 16000 * 12          # force 3 chunks for 7 clips of 5 s
+    codec.network.engine.max_chunk_samples = 16000 * 12          # force 3 chunks for 7 clips of 5 s (issued on side streams)
+    codec.network.engine.graph_max_samples = 0
     audio = make_audio(7, 5.0, seed=21).to(DEV)
     with torch.inference_mode():
         q, idx = codec.encode_audio(audio)
