@@ -33,6 +33,54 @@ def get_model(config_name, pretrained: bool = True, precision: str = "bf16") -> 
     return codec
 
 
+def get_model_info(model: "EnCodec", eval_flops_seconds=10, sample_rate: int = 16000) -> dict:
+    """l3ac/__init__.py:28-51 without the ``ptflops`` dependency: the same dictionary keys, with MACs counted
+    analytically (conv / linear layers and the useful, unmasked attention products) for ``eval_flops_seconds`` of audio."""
+    import math
+    from .spec import HEADS, is_compressed, network_spec
+    mc = model.mc
+    T = math.ceil(eval_flops_seconds * sample_rate / mc.hop_length) * mc.hop_length
+    macs = 0
+    # encoder
+    t = T
+    macs += t * (5 * 4 * 7 + 20 * 80 + 81 * mc.encoder_dims[0])
+    unit = lambda c, n: n * (7 * c + 8 * c * c)
+    for i, s in enumerate(mc.compress_rates):
+        macs += mc.encoder_depths[i] * unit(mc.encoder_dims[i], t)
+        t //= s
+        macs += t * mc.encoder_dims[i] * s * mc.encoder_dims[i + 1]
+    macs += mc.encoder_depths[-1] * unit(mc.encoder_dims[-1], t) + t * 3 * mc.encoder_dims[-1] * mc.feature_dim
+    t_f, d, inner, ff = t, mc.feature_dim, HEADS * (mc.feature_dim // 4), int(mc.feature_dim * 4 * 2 / 3)
+
+    def trans(n, w, depth):
+        keys = sum((w if p >= w else 0) + (p % w) + 1 for p in range(n))
+        return depth * (n * (3 * inner * d + inner * d + 3 * ff * d) + 2 * HEADS * keys * (d // 4))
+
+    w, r = mc.en_coder_window_size, mc.en_coder_compress_rate
+    t_tok = t_f // r
+    if is_compressed(mc):
+        macs += trans(t_f, w * r, 1) + t_tok * r * d * d + trans(t_tok, w, 2)
+        macs += trans(t_tok, w, mc.en_coder_depth - 2) + trans(t_f, w * r, 2)
+    else:
+        macs += trans(t_f, w, 1) + trans(t_f, w, mc.en_coder_depth)
+    macs += 2 * t_tok * d * len(mc.levels)
+    # decoder
+    t = t_f
+    macs += t * 3 * d * mc.decoder_dims[0]
+    for i, s in enumerate(mc.decode_rates):
+        c = mc.decoder_dims[i]
+        macs += mc.decoder_depths[i] * unit(c, t) + t * (4 * 7 + 4 * c) + t * c * mc.decoder_dims[i + 1]
+        t *= s
+    c = mc.decoder_dims[-1]
+    macs += t * (3 * (7 * c * c + c * c) + 7 * c)
+    params = sum(int(math.prod(shape)) for spec in network_spec(mc).values() for shape, _, _ in spec.values())
+    codebook_size = math.prod(mc.levels)
+    frame_rate = sample_rate / mc.hop_length
+    return {"macs": f"{macs / 1e9:.2f} GMac", "params": f"{params / 1e6:.2f} M", "codebook_size": codebook_size,
+            "frame_rate": frame_rate, "bps": frame_rate * math.log2(codebook_size),
+            "receptive_field": mc.en_coder_window_size / frame_rate}
+
+
 class L3AC:
     """l3ac/__init__.py:84-121."""
 

@@ -93,3 +93,16 @@ def test_no_cpu_fallback():
             net.engine
     src = "".join(p.read_text() for p in (ROOT / "l3ac_b200").glob("*.py"))
     assert "oracle" not in src.replace("# oracle", ""), "product code must not reference the oracle"
+
+
+@pytest.mark.parametrize("name,tokens,codes,bps", [("0k75bps", 44.44, 117649, 748.6), ("1kbps", 59.26, 117649, 998.2),
+                                                  ("1k5bps", 88.89, 117649, 1497.3), ("3kbps", 166.67, 250047, 2988.6)])
+def test_get_model_info_matches_readme_table(name, tokens, codes, bps):
+    """The model table of the reference README.md:71-76 (tokens/s, codebook size, bitrate) and SURVEY's MAC counts."""
+    net = l3ac_b200.EnCodec(model_config(name))
+    info = l3ac_b200.get_model_info(net)
+    assert info["codebook_size"] == codes
+    assert abs(info["frame_rate"] - tokens) < 0.01 and abs(info["bps"] - bps) < 0.1
+    gmac = float(info["macs"].split()[0])
+    want = {"0k75bps": 67.29, "1kbps": 83.39, "1k5bps": 84.30, "3kbps": 72.82}[name] / 2      # SURVEY section 8d, GFLOP = 2 * GMAC
+    assert abs(gmac - want) / want < 0.03, (gmac, want)
