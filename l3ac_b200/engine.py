@@ -424,6 +424,13 @@ class Engine:
         if audio.dim() != 2:
             raise RuntimeError(f"encode_audio expects a (batch, samples) tensor, got shape {tuple(audio.shape)}")
         audio = audio.to(device=self.device, dtype=torch.float32)
+        if audio.shape[0] == 0 or audio.shape[1] == 0:            # empty batch: empty results of the right shapes
+            if audio.shape[1] == 0:
+                raise RuntimeError("encode_audio got clips of length 0")
+            t_tok = math.ceil(audio.shape[1] / self.mc.hop_length)
+            z = lambda *sh, dt=torch.float32: torch.zeros(sh, device=self.device, dtype=dt)
+            return z(0, t_tok, self.mc.feature_dim), {"indices": z(0, t_tok, dt=torch.int32),
+                                                      "level_indices": z(0, t_tok, len(self.mc.levels))}
         if taps is None and 0 < audio.numel() <= self.graph_max_samples and not torch.cuda.is_current_stream_capturing():
             with torch.cuda.device(self.device):
                 q, idx, lvl = self._graphed(("enc",) + tuple(audio.shape), self._encode_one_chunk, audio.contiguous())
@@ -486,9 +493,13 @@ class Engine:
             if indices is None:
                 # the reference fails inside quantizer.to_features(None) with AttributeError
                 raise AttributeError("decode_audio needs audio_feature or indices ('NoneType' has no attribute 'unsqueeze')")
+            if indices.shape[0] == 0:
+                return torch.zeros((0, indices.shape[1] * self.mc.hop_length), device=self.device, dtype=torch.float32)
             audio_feature = self.dequantize(indices.to(self.device))
         feat = audio_feature.to(device=self.device, dtype=torch.float32).contiguous()
         B, T_tok, _ = feat.shape
+        if B == 0:
+            return torch.zeros((0, T_tok * self.mc.hop_length), device=self.device, dtype=torch.float32)
         if taps is None and 0 < B * T_tok * self.mc.hop_length <= self.graph_max_samples and \
                 not torch.cuda.is_current_stream_capturing():
             with torch.cuda.device(self.device):

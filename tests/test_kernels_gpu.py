@@ -40,7 +40,7 @@ def test_stem(cuda_lib):
     assert max_abs(cf(got), want) < 2e-5
 
 
-@pytest.mark.parametrize("C,T", [(24, 300), (96, 77), (192, 50), (512, 40)])
+@pytest.mark.parametrize("C,T", [(24, 300), (48, 1001), (96, 77), (128, 9), (192, 50), (256, 133), (384, 20), (512, 40)])
 def test_dwconv7_ln(cuda_lib, C, T):
     x = rnd(2, C, T, seed=1)
     w, b = rnd(C, 1, 7, seed=2, scale=0.3), rnd(C, seed=3, scale=0.1)
@@ -49,7 +49,7 @@ def test_dwconv7_ln(cuda_lib, C, T):
     got = ops.dwconv7_ln(cl(x), w[:, 0].t().contiguous().to(DEV), b.to(DEV), lw.to(DEV), lb.to(DEV), 1e-8)
     assert max_abs(got.cpu(), want) < 2e-5
     got16 = ops.dwconv7_ln(cl(x), w[:, 0].t().contiguous().to(DEV), b.to(DEV), lw.to(DEV), lb.to(DEV), 1e-8, torch.bfloat16)
-    assert max_abs(got16.float().cpu(), want) < 3e-2
+    assert max_abs(got16.float().cpu(), want) < 2 ** -8 * max(1.0, float(want.abs().max()))      # bf16 rounding
 
 
 @pytest.mark.parametrize("C", [48, 128, 192])

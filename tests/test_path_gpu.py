@@ -91,6 +91,10 @@ def test_api_surface_and_invariants(cuda_lib):
     oq, oidx = orc.encode_audio(audio.cpu())
     assert (oidx["indices"] == idx["indices"].cpu()).float().mean() >= 0.999
     assert max_abs(orc.decode_audio(indices=idx["indices"].cpu()), b.cpu()) < 1e-4
+    with torch.inference_mode():                        # empty batch: empty outputs with the right trailing shapes
+        qe, ide = codec.encode_audio(audio[:0])
+        we = codec.decode_audio(indices=ide["indices"])
+    assert qe.shape == (0, q.shape[1], 128) and ide["indices"].shape == (0, q.shape[1]) and we.shape == (0, b.shape[1])
     short = make_audio(1, 0.01, seed=2).to(DEV)       # 160 samples -> one hop
     with torch.inference_mode():
         qs, ids = codec.encode_audio(short)
