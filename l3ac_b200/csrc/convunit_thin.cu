@@ -1,0 +1,151 @@
+// Fused thin-channel Residual(ConvUnit) in fp32 (l3ac/modules.py:10-44 for C = 24, the full-rate encoder stage):
+//   out = x + pw_conv2( GRN( snake( pw_conv1( LayerNorm( dwconv7(x) ) ) ) ) )
+// With 24 channels the two point-wise GEMMs are 2 x 2304 MAC per time step: as tensor-core launches they are bound by
+// the TMA row rate (48-byte rows) and by a 4C-wide hidden tensor (1.8 GB per 24 clips as a split-bf16 pair) that has to
+// round-trip through HBM.  Here one thread owns one time step: depthwise conv and LayerNorm are in-thread (no
+// shuffles), the hidden activation lives one value at a time in a register, the weights are warp-broadcast float4
+// reads from shared memory, and HBM sees only x in and x out (192 B per time step).  Exact fp32 arithmetic, so the
+// encode side needs no operand splitting here.
+#include "common.cuh"
+
+namespace l3ac {
+namespace thin {
+
+constexpr int kC = 24;
+constexpr int kH = 96;
+constexpr int kTile = 128;              // time steps (= threads) per CTA
+constexpr int kPitch = 28;              // floats per staged x row: float4 reads by consecutive threads are conflict-free
+
+__global__ void __launch_bounds__(kTile) convunit_thin_kernel(const float* __restrict__ x, int B, int T,
+                                                              const float* __restrict__ dw_w, const float* __restrict__ dw_b,
+                                                              const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                                                              float eps, const float* __restrict__ w1,
+                                                              const float* __restrict__ b1, const float* __restrict__ alpha,
+                                                              const float* __restrict__ scale, const float* __restrict__ shift,
+                                                              const float* __restrict__ w2, const float* __restrict__ b2,
+                                                              float* __restrict__ out) {
+    __shared__ __align__(16) float xs[(kTile + 6) * kPitch];
+    __shared__ __align__(16) float s_w1[kH * kC];       // [u][c]
+    __shared__ __align__(16) float s_w2t[kH * kC];      // [u][c] = w2[c][u]
+    __shared__ __align__(16) float s_dw[7 * kC];
+    __shared__ __align__(16) float s_par[5 * kH];       // b1, alpha, 1/(alpha+eps), scale, shift
+    __shared__ __align__(16) float s_c[4 * kC];         // dw_b, ln_w, ln_b, b2
+
+    const int b = blockIdx.y, t0 = blockIdx.x * kTile, tid = threadIdx.x;
+    const float* xb = x + (long long)b * T * kC;
+    for (int i = tid; i < (kTile + 6) * (kC / 4); i += kTile) {
+        const int r = i / (kC / 4), c4 = i - r * (kC / 4);
+        const int t = t0 + r - 3;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t >= 0 && t < T) v = __ldg(reinterpret_cast<const float4*>(xb + (long long)t * kC) + c4);
+        *reinterpret_cast<float4*>(xs + r * kPitch + 4 * c4) = v;
+    }
+    for (int i = tid; i < kH * kC; i += kTile) {
+        s_w1[i] = __ldg(w1 + i);
+        const int u = i / kC, c = i - u * kC;
+        s_w2t[i] = __ldg(w2 + c * kH + u);
+    }
+    for (int i = tid; i < 7 * kC; i += kTile) s_dw[i] = __ldg(dw_w + i);
+    for (int i = tid; i < kH; i += kTile) {
+        const float a = __ldg(alpha + i);
+        s_par[i] = __ldg(b1 + i);
+        s_par[kH + i] = a;
+        s_par[2 * kH + i] = 1.0f / (a + kEps);
+        s_par[3 * kH + i] = __ldg(scale + i);
+        s_par[4 * kH + i] = __ldg(shift + i);
+    }
+    if (tid < kC) {
+        s_c[tid] = __ldg(dw_b + tid);
+        s_c[kC + tid] = __ldg(ln_w + tid);
+        s_c[2 * kC + tid] = __ldg(ln_b + tid);
+        s_c[3 * kC + tid] = __ldg(b2 + tid);
+    }
+    __syncthreads();
+    const int t = t0 + tid;
+    if (t >= T) return;
+
+    // depthwise conv k7 (zero padded) + LayerNorm over the 24 channels, all in registers
+    float a[kC];
+#pragma unroll
+    for (int c = 0; c < kC; ++c) a[c] = s_c[c];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+        const float* xr = xs + (tid + j) * kPitch;
+#pragma unroll
+        for (int c4 = 0; c4 < kC / 4; ++c4) {
+            const float4 xv = *reinterpret_cast<const float4*>(xr + 4 * c4);
+            const float4 wv = *reinterpret_cast<const float4*>(s_dw + j * kC + 4 * c4);
+            a[4 * c4] = fmaf(wv.x, xv.x, a[4 * c4]);
+            a[4 * c4 + 1] = fmaf(wv.y, xv.y, a[4 * c4 + 1]);
+            a[4 * c4 + 2] = fmaf(wv.z, xv.z, a[4 * c4 + 2]);
+            a[4 * c4 + 3] = fmaf(wv.w, xv.w, a[4 * c4 + 3]);
+        }
+    }
+    float mean = 0.f;
+#pragma unroll
+    for (int c = 0; c < kC; ++c) mean += a[c];
+    mean *= (1.0f / kC);
+    float var = 0.f;
+#pragma unroll
+    for (int c = 0; c < kC; ++c) {
+        a[c] -= mean;
+        var = fmaf(a[c], a[c], var);
+    }
+    const float rstd = 1.0f / sqrtf(var * (1.0f / kC) + eps);
+#pragma unroll
+    for (int c = 0; c < kC; ++c) a[c] = fmaf(a[c] * rstd, s_c[kC + c], s_c[2 * kC + c]);
+
+    // MLP: for every hidden unit  h = affine(snake(w1[u] . a + b1[u]))  and  acc += w2[:, u] * h
+    float acc[kC];
+    {
+        const float* xr = xs + (tid + 3) * kPitch;
+#pragma unroll
+        for (int c = 0; c < kC; ++c) acc[c] = xr[c] + s_c[3 * kC + c];      // residual + b2
+    }
+#pragma unroll 4
+    for (int u = 0; u < kH; ++u) {
+        float h = s_par[u];
+        const float4* wr = reinterpret_cast<const float4*>(s_w1 + u * kC);
+#pragma unroll
+        for (int c4 = 0; c4 < kC / 4; ++c4) {
+            const float4 wv = wr[c4];
+            h = fmaf(wv.x, a[4 * c4], h);
+            h = fmaf(wv.y, a[4 * c4 + 1], h);
+            h = fmaf(wv.z, a[4 * c4 + 2], h);
+            h = fmaf(wv.w, a[4 * c4 + 3], h);
+        }
+        const float sn = __sinf(s_par[kH + u] * h);
+        h = fmaf(s_par[2 * kH + u], sn * sn, h);
+        h = fmaf(h, s_par[3 * kH + u], s_par[4 * kH + u]);
+        const float4* w2r = reinterpret_cast<const float4*>(s_w2t + u * kC);
+#pragma unroll
+        for (int c4 = 0; c4 < kC / 4; ++c4) {
+            const float4 wv = w2r[c4];
+            acc[4 * c4] = fmaf(wv.x, h, acc[4 * c4]);
+            acc[4 * c4 + 1] = fmaf(wv.y, h, acc[4 * c4 + 1]);
+            acc[4 * c4 + 2] = fmaf(wv.z, h, acc[4 * c4 + 2]);
+            acc[4 * c4 + 3] = fmaf(wv.w, h, acc[4 * c4 + 3]);
+        }
+    }
+    float4* o = reinterpret_cast<float4*>(out + ((long long)b * T + t) * kC);
+#pragma unroll
+    for (int c4 = 0; c4 < kC / 4; ++c4) o[c4] = make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
+}
+
+}  // namespace thin
+}  // namespace l3ac
+
+extern "C" int l3ac_convunit_thin_f32(const float* x, int B, int T, int C, const float* dw_w, const float* dw_b,
+                                      const float* ln_w, const float* ln_b, float eps, const float* w1, const float* b1,
+                                      const float* alpha, const float* scale, const float* shift, const float* w2,
+                                      const float* b2, float* out, l3ac_stream_t stream) {
+    using namespace l3ac::thin;
+    L3AC_CHECK_ARG(x && dw_w && dw_b && ln_w && ln_b && w1 && b1 && alpha && scale && shift && w2 && b2 && out);
+    L3AC_CHECK_ARG(B > 0 && B <= 65535 && T > 0);
+    if (C != kC) return L3AC_EUNSUPPORTED;
+    L3AC_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0);
+    dim3 grid(l3ac_cdiv(T, kTile), B);
+    convunit_thin_kernel<<<grid, kTile, 0, (cudaStream_t)stream>>>(x, B, T, dw_w, dw_b, ln_w, ln_b, eps, w1, b1, alpha, scale,
+                                                                 shift, w2, b2, out);
+    return l3ac_launch_status();
+}

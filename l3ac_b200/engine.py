@@ -279,6 +279,9 @@ class Engine:
         per CTA, and the fill/drain of the persistent GEMM costs more than the saved HBM traffic (C=256 pw_conv2: 636
         -> 331 TFLOP/s), so it is off by default; keeping the hidden tensor on chip needs the fused MLP kernel."""
         B, T, C = x.shape
+        if C == 24 and act_dtype != torch.bfloat16:      # thin full-rate encoder stage: one fused fp32 kernel
+            return ops.convunit_thin(x, u["dw_w"], u["dw_b"], u["ln_w"], u["ln_b"], EPS, u["pw1"].w32, u["pw1"].bias,
+                                     u["alpha"], u["scale"], u["shift"], u["pw2"].w32, u["pw2"].bias)
         a = ops.dwconv7_ln(x, u["dw_w"], u["dw_b"], u["ln_w"], u["ln_b"], EPS, out_dtype=act_dtype)
         M = B * T
         esz = {torch.float32: 4, torch.bfloat16: 2, ops.SPLIT: 4}[act_dtype]

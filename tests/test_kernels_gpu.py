@@ -274,3 +274,23 @@ def test_local_attention_tc(cuda_lib, T, w, split):
     assert max_abs(got.cpu(), want) < tol
     got2 = ops.local_attention_tc(arg, table.to(DEV), H, w, out_dtype=ops.SPLIT)
     assert max_abs(got2.float().cpu(), got.cpu()) < 3e-5
+
+
+@pytest.mark.parametrize("T", [1, 100, 129, 1000])
+def test_fused_thin_convunit(cuda_lib, T):
+    """Fused fp32 Residual(ConvUnit) for C = 24 against the oracle's conv_unit (weight-normed layers passed folded)."""
+    C = 24
+    sd = {"u.dw_conv.weight": rnd(C, 1, 7, seed=1, scale=0.3), "u.dw_conv.bias": rnd(C, seed=2, scale=0.1),
+          "u.norm.weight": 1 + rnd(C, seed=3, scale=0.1), "u.norm.bias": rnd(C, seed=4, scale=0.1),
+          "u.pw_conv1.weight": rnd(4 * C, C, seed=5, scale=0.2), "u.pw_conv1.bias": rnd(4 * C, seed=6, scale=0.1),
+          "u.act.alpha": 0.5 + torch.rand(1, 1, 4 * C), "u.grn.gamma": rnd(1, 4 * C, seed=7, scale=0.1),
+          "u.grn.beta": rnd(1, 4 * C, seed=8, scale=0.1),
+          "u.pw_conv2.weight": rnd(C, 4 * C, seed=9, scale=0.1), "u.pw_conv2.bias": rnd(C, seed=10, scale=0.1)}
+    x = rnd(2, C, T, seed=11)
+    want = O.conv_unit(sd, "u", x)
+    d = lambda t: t.contiguous().to(DEV)
+    got = ops.convunit_thin(cl(x), d(sd["u.dw_conv.weight"][:, 0].t()), d(sd["u.dw_conv.bias"]), d(sd["u.norm.weight"]),
+                            d(sd["u.norm.bias"]), 1e-8, d(sd["u.pw_conv1.weight"]), d(sd["u.pw_conv1.bias"]),
+                            d(sd["u.act.alpha"].flatten()), d(1 + sd["u.grn.gamma"].flatten()), d(sd["u.grn.beta"].flatten()),
+                            d(sd["u.pw_conv2.weight"]), d(sd["u.pw_conv2.bias"]))
+    assert max_abs(cf(got), want) < 3e-5
