@@ -64,10 +64,11 @@ __global__ void __launch_bounds__(kTile) convunit_thin_kernel(const float* __res
     const int t = t0 + tid;
     if (t >= T) return;
 
-    // depthwise conv k7 (zero padded) + LayerNorm over the 24 channels, all in registers
-    float a[kC];
+    // depthwise conv k7 (zero padded) + LayerNorm over the 24 channels, all in registers.  Channel pairs are kept as
+    // float2 so that every multiply-add below is one packed FFMA2.
+    float2 a2[kC / 2];
 #pragma unroll
-    for (int c = 0; c < kC; ++c) a[c] = s_c[c];
+    for (int c = 0; c < kC / 2; ++c) a2[c] = make_float2(s_c[2 * c], s_c[2 * c + 1]);
 #pragma unroll
     for (int j = 0; j < 7; ++j) {
         const float* xr = xs + (tid + j) * kPitch;
@@ -75,57 +76,65 @@ __global__ void __launch_bounds__(kTile) convunit_thin_kernel(const float* __res
         for (int c4 = 0; c4 < kC / 4; ++c4) {
             const float4 xv = *reinterpret_cast<const float4*>(xr + 4 * c4);
             const float4 wv = *reinterpret_cast<const float4*>(s_dw + j * kC + 4 * c4);
-            a[4 * c4] = fmaf(wv.x, xv.x, a[4 * c4]);
-            a[4 * c4 + 1] = fmaf(wv.y, xv.y, a[4 * c4 + 1]);
-            a[4 * c4 + 2] = fmaf(wv.z, xv.z, a[4 * c4 + 2]);
-            a[4 * c4 + 3] = fmaf(wv.w, xv.w, a[4 * c4 + 3]);
+            a2[2 * c4] = ffma2(make_float2(wv.x, wv.y), make_float2(xv.x, xv.y), a2[2 * c4]);
+            a2[2 * c4 + 1] = ffma2(make_float2(wv.z, wv.w), make_float2(xv.z, xv.w), a2[2 * c4 + 1]);
         }
     }
     float mean = 0.f;
 #pragma unroll
-    for (int c = 0; c < kC; ++c) mean += a[c];
+    for (int c = 0; c < kC / 2; ++c) mean += a2[c].x + a2[c].y;
     mean *= (1.0f / kC);
     float var = 0.f;
 #pragma unroll
-    for (int c = 0; c < kC; ++c) {
-        a[c] -= mean;
-        var = fmaf(a[c], a[c], var);
+    for (int c = 0; c < kC / 2; ++c) {
+        a2[c].x -= mean;
+        a2[c].y -= mean;
+        var = fmaf(a2[c].x, a2[c].x, var);
+        var = fmaf(a2[c].y, a2[c].y, var);
     }
     const float rstd = 1.0f / sqrtf(var * (1.0f / kC) + eps);
 #pragma unroll
-    for (int c = 0; c < kC; ++c) a[c] = fmaf(a[c] * rstd, s_c[kC + c], s_c[2 * kC + c]);
+    for (int c = 0; c < kC / 2; ++c) {
+        a2[c].x = fmaf(a2[c].x * rstd, s_c[kC + 2 * c], s_c[2 * kC + 2 * c]);
+        a2[c].y = fmaf(a2[c].y * rstd, s_c[kC + 2 * c + 1], s_c[2 * kC + 2 * c + 1]);
+    }
 
     // MLP: for every hidden unit  h = affine(snake(w1[u] . a + b1[u]))  and  acc += w2[:, u] * h
-    float acc[kC];
+    float2 acc2[kC / 2];
     {
         const float* xr = xs + (tid + 3) * kPitch;
 #pragma unroll
-        for (int c = 0; c < kC; ++c) acc[c] = xr[c] + s_c[3 * kC + c];      // residual + b2
+        for (int c = 0; c < kC / 2; ++c)
+            acc2[c] = make_float2(xr[2 * c] + s_c[3 * kC + 2 * c], xr[2 * c + 1] + s_c[3 * kC + 2 * c + 1]);      // residual + b2
     }
 #pragma unroll 4
     for (int u = 0; u < kH; ++u) {
-        float h = s_par[u];
+        float2 hp = make_float2(s_par[u], 0.f);               // two partial dot products (even / odd channel pairs)
         const float4* wr = reinterpret_cast<const float4*>(s_w1 + u * kC);
 #pragma unroll
         for (int c4 = 0; c4 < kC / 4; ++c4) {
             const float4 wv = wr[c4];
-            h = fmaf(wv.x, a[4 * c4], h);
-            h = fmaf(wv.y, a[4 * c4 + 1], h);
-            h = fmaf(wv.z, a[4 * c4 + 2], h);
-            h = fmaf(wv.w, a[4 * c4 + 3], h);
+            hp = ffma2(make_float2(wv.x, wv.y), a2[2 * c4], hp);
+            hp = ffma2(make_float2(wv.z, wv.w), a2[2 * c4 + 1], hp);
         }
+        float h = hp.x + hp.y;
         const float sn = __sinf(s_par[kH + u] * h);
         h = fmaf(s_par[2 * kH + u], sn * sn, h);
         h = fmaf(h, s_par[3 * kH + u], s_par[4 * kH + u]);
+        const float2 hh = make_float2(h, h);
         const float4* w2r = reinterpret_cast<const float4*>(s_w2t + u * kC);
 #pragma unroll
         for (int c4 = 0; c4 < kC / 4; ++c4) {
             const float4 wv = w2r[c4];
-            acc[4 * c4] = fmaf(wv.x, h, acc[4 * c4]);
-            acc[4 * c4 + 1] = fmaf(wv.y, h, acc[4 * c4 + 1]);
-            acc[4 * c4 + 2] = fmaf(wv.z, h, acc[4 * c4 + 2]);
-            acc[4 * c4 + 3] = fmaf(wv.w, h, acc[4 * c4 + 3]);
+            acc2[2 * c4] = ffma2(make_float2(wv.x, wv.y), hh, acc2[2 * c4]);
+            acc2[2 * c4 + 1] = ffma2(make_float2(wv.z, wv.w), hh, acc2[2 * c4 + 1]);
         }
+    }
+    float acc[kC];
+#pragma unroll
+    for (int c = 0; c < kC / 2; ++c) {
+        acc[2 * c] = acc2[c].x;
+        acc[2 * c + 1] = acc2[c].y;
     }
     float4* o = reinterpret_cast<float4*>(out + ((long long)b * T + t) * kC);
 #pragma unroll

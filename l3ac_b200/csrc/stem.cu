@@ -85,45 +85,55 @@ __global__ void __launch_bounds__(kStemThreads) stem_kernel(const float* __restr
         __syncthreads();   // ms/ps are rewritten by the next branch
     }
 
-    float acc[kStemSPT][CO];
+    // The two 1x1 convs (20 -> 80 -> GELU -> 24) as packed FFMA2: inputs and accumulators are float2 pairs.
+    float2 acc2[kStemSPT][CO / 2];
 #pragma unroll
     for (int sp = 0; sp < kStemSPT; ++sp) {
         const float xv = xs[threadIdx.x + sp * kStemThreads + kStemReach];
 #pragma unroll
-        for (int c = 0; c < CO; ++c) acc[sp][c] = fmaf(s_w2t[kStemH * CO + c], xv, s_b2[c]);
+        for (int c = 0; c < CO / 2; ++c)
+            acc2[sp][c] = make_float2(fmaf(s_w2t[kStemH * CO + 2 * c], xv, s_b2[2 * c]),
+                                      fmaf(s_w2t[kStemH * CO + 2 * c + 1], xv, s_b2[2 * c + 1]));
     }
     for (int u = 0; u < kStemH; ++u) {
-        float a[kStemSPT];
+        float2 ap[kStemSPT];
 #pragma unroll
-        for (int sp = 0; sp < kStemSPT; ++sp) a[sp] = s_b1[u];
+        for (int sp = 0; sp < kStemSPT; ++sp) ap[sp] = make_float2(s_b1[u], 0.f);
         const float4* wr = reinterpret_cast<const float4*>(s_w1 + u * 20);
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
             const float4 w4 = wr[i];
 #pragma unroll
             for (int sp = 0; sp < kStemSPT; ++sp) {
-                a[sp] = fmaf(w4.x, h[sp][4 * i], a[sp]);
-                a[sp] = fmaf(w4.y, h[sp][4 * i + 1], a[sp]);
-                a[sp] = fmaf(w4.z, h[sp][4 * i + 2], a[sp]);
-                a[sp] = fmaf(w4.w, h[sp][4 * i + 3], a[sp]);
+                ap[sp] = ffma2(make_float2(w4.x, w4.y), make_float2(h[sp][4 * i], h[sp][4 * i + 1]), ap[sp]);
+                ap[sp] = ffma2(make_float2(w4.z, w4.w), make_float2(h[sp][4 * i + 2], h[sp][4 * i + 3]), ap[sp]);
             }
         }
-        float g[kStemSPT];
+        float2 g[kStemSPT];
 #pragma unroll
-        for (int sp = 0; sp < kStemSPT; ++sp) g[sp] = gelu_erf(a[sp]);
+        for (int sp = 0; sp < kStemSPT; ++sp) {
+            const float gv = gelu_erf(ap[sp].x + ap[sp].y);
+            g[sp] = make_float2(gv, gv);
+        }
         const float4* w2r = reinterpret_cast<const float4*>(s_w2t + u * CO);
 #pragma unroll
         for (int i = 0; i < CO / 4; ++i) {
             const float4 w4 = w2r[i];
 #pragma unroll
             for (int sp = 0; sp < kStemSPT; ++sp) {
-                acc[sp][4 * i] = fmaf(w4.x, g[sp], acc[sp][4 * i]);
-                acc[sp][4 * i + 1] = fmaf(w4.y, g[sp], acc[sp][4 * i + 1]);
-                acc[sp][4 * i + 2] = fmaf(w4.z, g[sp], acc[sp][4 * i + 2]);
-                acc[sp][4 * i + 3] = fmaf(w4.w, g[sp], acc[sp][4 * i + 3]);
+                acc2[sp][2 * i] = ffma2(make_float2(w4.x, w4.y), g[sp], acc2[sp][2 * i]);
+                acc2[sp][2 * i + 1] = ffma2(make_float2(w4.z, w4.w), g[sp], acc2[sp][2 * i + 1]);
             }
         }
     }
+    float acc[kStemSPT][CO];
+#pragma unroll
+    for (int sp = 0; sp < kStemSPT; ++sp)
+#pragma unroll
+        for (int c = 0; c < CO / 2; ++c) {
+            acc[sp][2 * c] = acc2[sp][c].x;
+            acc[sp][2 * c + 1] = acc2[sp][c].y;
+        }
 #pragma unroll
     for (int sp = 0; sp < kStemSPT; ++sp) {
         const int t = t0 + threadIdx.x + sp * kStemThreads;
