@@ -8,13 +8,16 @@
 // SWIZZLE_128B K-major shared-memory layout the tensor core reads, and consumed by the second GEMM whose C-wide
 // accumulator stays in TMEM for the whole tile.
 //
-// One persistent CTA per SM, 10 warps:
-//   warp 0     TMA producer: the 128 x C activation tile (resident for the tile) and a ring of 16 KB weight boxes
-//              (W1: 64 hidden rows x 64 k, W2: <=128 output rows x 64 k) in exactly the order the MMA warp consumes them
-//   warp 1     MMA issuer (one thread): GEMM1(j+1) is issued before GEMM2(j), so the snake epilogue of chunk j overlaps
-//              tensor-core work; D1 is double-buffered (2 x 64 TMEM columns), D2 owns C columns
-//   warps 2-9  epilogue: tcgen05.ld D1 -> bias/snake/affine -> bf16 -> swizzled smem A2 (fence.proxy.async) ; at the end
-//              of the tile D2 -> + b2 + residual -> coalesced fp32 stores
+// One persistent CTA per SM, 18 warps:
+//   warp 0      TMA producer: the 128 x C activation tile (resident for the tile) and a ring of 16 KB weight slots
+//               (GEMM1: two [64 hidden x 64 k] W1 boxes per slot, GEMM2: one [<=128 out x 64 k] W2 box per slot) in
+//               exactly the order the MMA warp consumes them
+//   warp 1      MMA issuer (one thread).  D1 has FOUR 64-column TMEM buffers and the hidden operand A2 four 16 KB
+//               shared-memory buffers, so GEMM1 runs three chunks ahead of GEMM2 and the latency of the snake epilogue
+//               (TMEM -> registers -> MUFU -> smem -> fence) is hidden behind tensor-core work.  D2 owns C columns.
+//   warps 2-17  epilogue, four groups of four warps (one per TMEM lane quadrant); group g owns D1[g] / A2[g], i.e.
+//               the chunks whose sequence number is g (mod 4).  At the end of the tile all sixteen warps drain D2: + b2 + residual -> coalesced
+//               fp32 stores through 16-column staging slabs that alias the group's own A2 buffer.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -24,16 +27,34 @@ namespace mlp {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kTileBytes = kBM * kBK * 2;      // 16 KB: one [128 x 64] bf16 SW128 tile (A k-block, A2 buffer, ring stage)
-constexpr int kMaxAKb = 4;                     // C <= 256
-constexpr int kMaxRing = 12;
-constexpr int kEpiWarps = 8;
+constexpr int kTileBytes = kBM * kBK * 2;      // 16 KB: one [128 x 64] bf16 SW128 tile (A k-block, A2 buffer, ring slot)
+constexpr int kNB = 4;                         // D1 / A2 buffers = epilogue groups
+constexpr int kMaxRing = 8;
+constexpr int kEpiWarps = 4 * kNB;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
-constexpr int kStagePitch = 36;
-constexpr int kStageBytes = kEpiWarps * 32 * kStagePitch * 4;   // output staging, aliased onto the A2 buffers
-constexpr int kD1Cols = 256;                   // two D1 buffers of up to 128 columns
-constexpr int kNumBars = 2 * kMaxRing + 2 + 4 + 4 + 2;
+constexpr int kSlabPitch = 20;                 // floats per staged row: 16 columns + 4 pad (conflict-free float4 access)
+constexpr int kSlabBytes = 32 * kSlabPitch * 4;   // 2560 B per warp, four warps per group < one 16 KB A2 buffer
+constexpr int kD1Stride = 64;                  // TMEM columns per D1 buffer
+constexpr int kD2Col = kNB * kD1Stride;        // D2 starts after the D1 buffers (256 + C <= 512)
+constexpr int kNumBars = 2 * kMaxRing + 2 + 4 * kNB + 2;
 constexpr int kSmemLimit = 227 * 1024;
+
+#ifdef L3AC_MLP_TRACE
+// Debug build only: CTA 0 stamps clock64() at pipeline hand-overs of two steady-state tiles (tools/mlp_trace.py).  Every
+// tracing thread owns a 512-entry region and a private index, so a stamp is one fire-and-forget store.
+__device__ unsigned long long g_trace_buf[8 * 512];
+#define MLP_TRACE_DECL(role) unsigned int trace_n = 0; const unsigned int trace_role = (role);
+#define MLP_TRACE(ev, j)                                                                          \
+    do {                                                                                          \
+        if (blockIdx.x == 0 && it >= 2 && it <= 3 && trace_n < 511) {                             \
+            g_trace_buf[trace_role * 512 + 1 + trace_n++] = ((unsigned long long)clock64() << 20) | ((unsigned long long)(it) << 16) | ((unsigned long long)(ev) << 8) | (unsigned long long)(j); \
+            g_trace_buf[trace_role * 512] = trace_n;                                              \
+        }                                                                                         \
+    } while (0)
+#else
+#define MLP_TRACE_DECL(role)
+#define MLP_TRACE(ev, j) do {} while (0)
+#endif
 
 struct Params {
     const float* b1;
@@ -45,12 +66,12 @@ struct Params {
     const float* residual;
     float* out;
     long long M;
-    int C, H4, HN, NC;        // channels, hidden = 4C, hidden chunk width, number of chunks
+    int C, H4, HN, NC;        // channels, hidden = 4C, hidden chunk width (64 or 32), number of chunks
     int a_kb;                 // k-blocks of the activation tile = ceil(C / 64)
-    int n_halves;             // GEMM2 N splits of <= 128 output columns
-    int hn_kb;                // k-blocks of one hidden chunk = ceil(HN / 64)
-    int ring;                 // weight ring depth (16 KB slots)
-    int resident;             // ring == boxes per tile: every weight box is loaded once per CTA and stays in shared memory
+    int g1_slots;             // ring slots per GEMM1 = ceil(a_kb / 2)
+    int n_halves;             // GEMM2 N splits of <= 128 output columns (one ring slot each)
+    int ring;                 // ring depth (16 KB slots)
+    int resident;             // ring == slots per tile: every weight slot is loaded once per CTA and stays in shared memory
     int num_m_tiles;
 };
 
@@ -98,6 +119,17 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uin
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.b32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -125,40 +157,37 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
 }
 
-__host__ __device__ inline int a2_stride_bytes(int hn_kb) {
-    const int need = hn_kb * kTileBytes, slabs = 20 * 1024;      // 4 slabs of 32 x 36 floats = 18 432 B, rounded to 1 KB
-    return need > slabs ? need : slabs;
-}
-
 __global__ void __launch_bounds__(kThreads, 1)
 convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
                     const __grid_constant__ CUtensorMap tmW2, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-    // layout (all 1024-aligned): A tile [a_kb], A2 [2][hn_kb] (the output staging slabs alias it), ring [ring], barriers
+    // layout (all 1024-aligned): A tile [a_kb], A2 [kNB] (the output staging slabs alias it), ring [ring], barriers
     const uint32_t a_base = smem_base;
     const uint32_t a2_base = a_base + p.a_kb * kTileBytes;
-    // each epilogue group owns one A2 buffer; its four output-staging slabs (4 x 4608 B) alias that same buffer, so a
-    // group never touches shared memory the other group may be writing for the next tile
-    const uint32_t a2_buf_bytes = (uint32_t)a2_stride_bytes(p.hn_kb);
-    const uint32_t ring_base = a2_base + 2 * a2_buf_bytes;
-    float* s_stage = reinterpret_cast<float*>(smem_gen + (a2_base - smem_base));
-    const uint32_t bar_base = ring_base + p.ring * kTileBytes;
+    const uint32_t ring_base = a2_base + kNB * kTileBytes;
+    uint8_t* a2_gen = smem_gen + (a2_base - smem_base);
+    // per-column epilogue parameters [5][H4] (b1, alpha, 1/(alpha+eps), scale, shift): staged once -- with ~220 KB of
+    // shared memory carved out there is next to no L1 left, and a global load per use is an exposed L2 round trip
+    const uint32_t par_base = ring_base + p.ring * kTileBytes;
+    float* s_par = reinterpret_cast<float*>(smem_gen + (par_base - smem_base));
+    const uint32_t bar_base = par_base + 5 * p.H4 * 4;
     const uint32_t ring_full = bar_base;                       // [kMaxRing]
     const uint32_t ring_empty = ring_full + 8 * kMaxRing;      // [kMaxRing]
     const uint32_t a_full = ring_empty + 8 * kMaxRing;         // [1]
     const uint32_t a_empty = a_full + 8;                       // [1]
-    const uint32_t d1_full = a_empty + 8;                      // [2]
-    const uint32_t d1_empty = d1_full + 16;                    // [2]
-    const uint32_t a2_full = d1_empty + 16;                    // [2]
-    const uint32_t a2_empty = a2_full + 16;                    // [2]
-    const uint32_t d2_full = a2_empty + 16;                    // [1]
+    const uint32_t d1_full = a_empty + 8;                      // [kNB]
+    const uint32_t d1_empty = d1_full + 8 * kNB;               // [kNB]
+    const uint32_t a2_full = d1_empty + 8 * kNB;               // [kNB]
+    const uint32_t a2_empty = a2_full + 8 * kNB;               // [kNB]
+    const uint32_t d2_full = a2_empty + 8 * kNB;               // [1]
     const uint32_t d2_empty = d2_full + 8;                     // [1]
     const uint32_t tmem_slot = d2_empty + 8;
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // broadcast from lane 0: lets the compiler treat the role branches below as warp-uniform
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -170,15 +199,22 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kNB; ++i) {
             mbar_init(d1_full + 8 * i, 1);
-            mbar_init(d1_empty + 8 * i, kEpiWarps / 2);      // each D1 / A2 buffer belongs to one group of four warps
-            mbar_init(a2_full + 8 * i, kEpiWarps / 2);
+            mbar_init(d1_empty + 8 * i, 4);       // each D1 / A2 buffer belongs to one group of four warps
+            mbar_init(a2_full + 8 * i, 4);
             mbar_init(a2_empty + 8 * i, 1);
         }
         mbar_init(d2_full, 1);
         mbar_init(d2_empty, kEpiWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < p.H4; i += kThreads) {
+        s_par[i] = p.b1[i];
+        s_par[p.H4 + i] = p.alpha[i];
+        s_par[2 * p.H4 + i] = p.ialpha[i];
+        s_par[3 * p.H4 + i] = p.scale[i];
+        s_par[4 * p.H4 + i] = p.shift[i];
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
@@ -188,156 +224,205 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
-    const uint32_t d2_tmem = tmem_base + kD1Cols;
+    const uint32_t d2_tmem = tmem_base + kD2Col;
 
     const int n_my_tiles = (p.num_m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int lookahead = kNB - 1;      // GEMM1 chunks issued ahead of GEMM2
+    // GEMM2 sums over hidden chunks in any order: every CTA starts at a different chunk so that the 148 CTAs do not all
+    // pull the same 16 KB weight box out of the same L2 lines at the same moment.
+    const int rot = p.resident ? 0 : (int)(blockIdx.x % (unsigned)p.NC);
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ------------------------------------------------------------------ TMA producer
-            int rs = 0;
-            uint32_t rphase = 0;
-            bool first_tile = true;
-            auto ring_load = [&](const CUtensorMap* map, int c0, int c1, uint32_t bytes) {
-                if (p.resident && !first_tile) return;            // weights already resident in their slots
-                mbar_wait(ring_empty + 8 * rs, rphase ^ 1);
-                mbar_arrive_expect_tx(ring_full + 8 * rs, bytes);
-                tma_load_2d(ring_base + rs * kTileBytes, map, c0, c1, ring_full + 8 * rs);
-                if (++rs == p.ring) {
-                    rs = 0;
-                    rphase ^= 1;
-                }
-            };
-            const uint32_t w1_bytes = p.HN * kBK * 2, w2_bytes = kBM * kBK * 2;     // HN <= 128 rows per W1 box
-            auto gemm1_boxes = [&](int j) {
-                for (int kb = 0; kb < p.a_kb; ++kb) ring_load(&tmW1, kb * kBK, j * p.HN, w1_bytes);
-            };
-            for (int it = 0; it < n_my_tiles; ++it) {
-                const int m_tile = blockIdx.x + it * gridDim.x;
-                mbar_wait(a_empty, (it & 1) ^ 1);                // previous tile's GEMM1s have finished reading A
+        // ------------------------------------------------------------------ TMA producer
+        // The whole warp runs the loop (warp-uniform control flow keeps coordinates and addresses in uniform registers);
+        // one elected lane issues the copies.
+        MLP_TRACE_DECL(0)
+        const bool leader = elect_one();
+        int rs = 0;
+        uint32_t rphase = 0;
+        const uint32_t w1_box = p.HN * kBK * 2, w2_box = kBM * kBK * 2;
+        for (int it = 0; it < n_my_tiles; ++it) {
+            const int m_tile = blockIdx.x + it * gridDim.x;
+            const bool load_w = !(p.resident && it > 0);      // resident weights are loaded once per CTA
+            mbar_wait(a_empty, (it & 1) ^ 1);                 // previous tile's GEMM1s have finished reading A
+            if (leader) MLP_TRACE(1, 0);
+            if (leader) {
                 mbar_arrive_expect_tx(a_full, p.a_kb * kTileBytes);
                 for (int kb = 0; kb < p.a_kb; ++kb) tma_load_2d(a_base + kb * kTileBytes, &tmA, kb * kBK, m_tile * kBM, a_full);
-                gemm1_boxes(0);
-                for (int j = 0; j < p.NC; ++j) {
-                    if (j + 1 < p.NC) gemm1_boxes(j + 1);
-                    for (int kb = 0; kb < p.hn_kb; ++kb)
-                        for (int h = 0; h < p.n_halves; ++h) ring_load(&tmW2, j * p.HN + kb * kBK, h * 128, w2_bytes);
+            }
+            if (!load_w) continue;
+            // same order as the MMA warp: step s issues GEMM1(s) and GEMM2(s - lookahead)
+            for (int s = 0; s < p.NC + lookahead; ++s) {
+                if (s < p.NC) {
+                    int j = s + rot;
+                    if (j >= p.NC) j -= p.NC;
+                    for (int q = 0; q < p.g1_slots; ++q) {    // two consecutive W1 k-blocks share a slot (8 KB halves)
+                        const int kb0 = 2 * q, nkb = (kb0 + 1 < p.a_kb) ? 2 : 1;
+                        mbar_wait(ring_empty + 8 * rs, rphase ^ 1);
+                        if (leader) {
+                            mbar_arrive_expect_tx(ring_full + 8 * rs, nkb * w1_box);
+                            for (int e = 0; e < nkb; ++e)
+                                tma_load_2d(ring_base + rs * kTileBytes + e * (kTileBytes / 2), &tmW1, (kb0 + e) * kBK, j * p.HN,
+                                            ring_full + 8 * rs);
+                        }
+                        if (++rs == p.ring) {
+                            rs = 0;
+                            rphase ^= 1;
+                        }
+                    }
                 }
-                first_tile = false;
+                if (s >= lookahead) {
+                    int j = s - lookahead + rot;
+                    if (j >= p.NC) j -= p.NC;
+                    for (int h = 0; h < p.n_halves; ++h) {
+                        mbar_wait(ring_empty + 8 * rs, rphase ^ 1);
+                        if (leader) {
+                            mbar_arrive_expect_tx(ring_full + 8 * rs, w2_box);
+                            tma_load_2d(ring_base + rs * kTileBytes, &tmW2, j * p.HN, h * 128, ring_full + 8 * rs);
+                        }
+                        if (++rs == p.ring) {
+                            rs = 0;
+                            rphase ^= 1;
+                        }
+                    }
+                }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ------------------------------------------------------------------ MMA issuer
-            int rs = 0;
-            uint32_t rphase = 0;
-            uint32_t d1_use[2] = {0, 0}, a2_use[2] = {0, 0};      // how many times each buffer has been handed over
-            bool ring_sync = true;                                // resident mode: only the first tile waits for the weight boxes
-            const uint32_t idesc1 = make_idesc(p.HN);
-            auto gemm1 = [&](int j) {
-                const int buf = j & 1;
-                mbar_wait(d1_empty + 8 * buf, (d1_use[buf] & 1) ^ 1);     // epilogue has drained this D1 buffer
-                tc_fence_after();
-                const uint32_t d1 = tmem_base + buf * 128;
-                for (int kb = 0; kb < p.a_kb; ++kb) {
-                    if (ring_sync) {
-                        mbar_wait(ring_full + 8 * rs, rphase);
-                        tc_fence_after();
-                    }
-                    const uint64_t a_desc = make_sw128_desc(a_base + kb * kTileBytes);
-                    const uint64_t b_desc = make_sw128_desc(ring_base + rs * kTileBytes);
-                    const int k_left = p.C - kb * kBK;
-                    const int k16 = k_left >= kBK ? kBK / 16 : (k_left + 15) / 16;
-                    for (int k = 0; k < k16; ++k) tc_mma_f16(d1, a_desc + 2 * k, b_desc + 2 * k, idesc1, (kb > 0 || k > 0) ? 1u : 0u);
-                    if (!p.resident) tc_commit(ring_empty + 8 * rs);
-                    if (++rs == p.ring) {
-                        rs = 0;
-                        rphase ^= 1;
-                    }
-                }
-                tc_commit(d1_full + 8 * buf);
-                ++d1_use[buf];
-            };
-            for (int it = 0; it < n_my_tiles; ++it) {
-                mbar_wait(a_full, it & 1);
-                tc_fence_after();
-                gemm1(0);
-                for (int j = 0; j < p.NC; ++j) {
-                    if (j + 1 < p.NC) gemm1(j + 1);
-                    if (j + 1 == p.NC) tc_commit(a_empty);        // all GEMM1s of this tile issued: A is free once they complete
-                    const int buf = j & 1;
-                    mbar_wait(a2_full + 8 * buf, a2_use[buf] & 1);       // epilogue wrote the bf16 hidden chunk
+        // ------------------------------------------------------------------ MMA issuer
+        // All 32 lanes walk the schedule and wait on the barriers; one elected lane issues tcgen05.mma / commit.  Keeping
+        // the control flow warp-uniform matters: under a divergent `if (lane == 0)` the compiler cannot prove the shared
+        // memory descriptors uniform and wraps every MMA in an ELECT / R2UR.BROADCAST waterfall (~200 cycles per MMA).
+        MLP_TRACE_DECL(1)
+        const bool leader = elect_one();
+        int rs = 0;
+        uint32_t rphase = 0;
+        uint32_t d1_uses = 0, a2_uses = 0;         // GEMM1s / GEMM2s issued so far: buffer = count % kNB, phase from count / kNB
+        const uint32_t idesc1 = make_idesc(p.HN);
+        for (int it = 0; it < n_my_tiles; ++it) {
+            const bool ring_sync = !(p.resident && it > 0);    // resident mode: only the first tile waits for weight slots
+            mbar_wait(a_full, it & 1);
+            tc_fence_after();
+            if (leader) MLP_TRACE(10, 0);
+            for (int s = 0; s < p.NC + lookahead; ++s) {
+                if (s < p.NC) {
+                    // ---- GEMM1(s): D1[s % kNB] = A . W1[chunk]^T
+                    const int buf = d1_uses % kNB;      // buffers rotate over the global chunk sequence, across tiles
+                    if (leader) MLP_TRACE(14, s);
+                    mbar_wait(d1_empty + 8 * buf, ((d1_uses / kNB) & 1) ^ 1);      // the group has drained this D1 buffer
                     tc_fence_after();
-                    if (j == 0) {
-                        mbar_wait(d2_empty, (it & 1) ^ 1);               // previous tile's output epilogue has drained D2
-                        tc_fence_after();
-                    }
-                    for (int kb = 0; kb < p.hn_kb; ++kb) {
-                        const uint64_t a_desc = make_sw128_desc(a2_base + buf * a2_buf_bytes + kb * kTileBytes);
-                        const int k_left = p.HN - kb * kBK;
-                        const int k16 = k_left >= kBK ? kBK / 16 : k_left / 16;
-                        for (int h = 0; h < p.n_halves; ++h) {
-                            if (ring_sync) {
-                                mbar_wait(ring_full + 8 * rs, rphase);
-                                tc_fence_after();
-                            }
-                            const uint64_t b_desc = make_sw128_desc(ring_base + rs * kTileBytes);
-                            const int n = min(128, (p.C - h * 128 + 15) & ~15);    // UMMA N is a multiple of 16; extra W2 rows are TMA zero fill
-                            const uint32_t idesc2 = make_idesc(n);
-                            for (int k = 0; k < k16; ++k)
-                                tc_mma_f16(d2_tmem + h * 128, a_desc + 2 * k, b_desc + 2 * k, idesc2, (j > 0 || kb > 0 || k > 0) ? 1u : 0u);
-                            if (!p.resident) tc_commit(ring_empty + 8 * rs);
-                            if (++rs == p.ring) {
-                                rs = 0;
-                                rphase ^= 1;
-                            }
+                    if (leader) MLP_TRACE(15, s);
+                    const uint32_t d1 = tmem_base + buf * kD1Stride;
+                    for (int q = 0; q < p.g1_slots; ++q) {
+                        if (ring_sync) {
+                            mbar_wait(ring_full + 8 * rs, rphase);
+                            tc_fence_after();
+                        }
+                        for (int e = 0; e < 2 && 2 * q + e < p.a_kb; ++e) {
+                            const int kb = 2 * q + e;
+                            const uint64_t a_desc = make_sw128_desc(a_base + kb * kTileBytes);
+                            const uint64_t b_desc = make_sw128_desc(ring_base + rs * kTileBytes + e * (kTileBytes / 2));
+                            const int k_left = p.C - kb * kBK;
+                            const int k16 = k_left >= kBK ? kBK / 16 : (k_left + 15) / 16;
+                            if (leader)
+                                for (int k = 0; k < k16; ++k) tc_mma_f16(d1, a_desc + 2 * k, b_desc + 2 * k, idesc1, (kb > 0 || k > 0) ? 1u : 0u);
+                        }
+                        if (leader && !p.resident) tc_commit(ring_empty + 8 * rs);
+                        if (++rs == p.ring) {
+                            rs = 0;
+                            rphase ^= 1;
                         }
                     }
-                    tc_commit(a2_empty + 8 * buf);
-                    ++a2_use[buf];
+                    if (leader) {
+                        tc_commit(d1_full + 8 * buf);
+                        if (s == p.NC - 1) tc_commit(a_empty);       // last GEMM1 of the tile: A is free once it completes
+                    }
+                    if (leader) MLP_TRACE(16, s);
+                    ++d1_uses;
                 }
-                tc_commit(d2_full);
-                if (p.resident) ring_sync = false;
+                if (s >= lookahead) {
+                    // ---- GEMM2(j): D2 += A2[j % kNB] . W2[:, chunk]^T
+                    const int j = s - lookahead;
+                    const int buf = a2_uses % kNB;
+                    if (leader) MLP_TRACE(11, j);
+                    mbar_wait(a2_full + 8 * buf, (a2_uses / kNB) & 1);             // the group wrote the bf16 hidden chunk
+                    if (j == 0) mbar_wait(d2_empty, (it & 1) ^ 1);                 // previous tile's output epilogue drained D2
+                    tc_fence_after();
+                    if (leader) MLP_TRACE(12, j);
+                    const uint64_t a_desc = make_sw128_desc(a2_base + buf * kTileBytes);
+                    for (int h = 0; h < p.n_halves; ++h) {
+                        if (ring_sync) {
+                            mbar_wait(ring_full + 8 * rs, rphase);
+                            tc_fence_after();
+                        }
+                        const uint64_t b_desc = make_sw128_desc(ring_base + rs * kTileBytes);
+                        const int n = min(128, (p.C - h * 128 + 15) & ~15);    // UMMA N is a multiple of 16; extra W2 rows are TMA zero fill
+                        const uint32_t idesc2 = make_idesc(n);
+                        if (leader) {
+                            for (int k = 0; k < p.HN / 16; ++k)
+                                tc_mma_f16(d2_tmem + h * 128, a_desc + 2 * k, b_desc + 2 * k, idesc2, (j > 0 || k > 0) ? 1u : 0u);
+                            if (!p.resident) tc_commit(ring_empty + 8 * rs);
+                        }
+                        if (++rs == p.ring) {
+                            rs = 0;
+                            rphase ^= 1;
+                        }
+                    }
+                    if (leader) tc_commit(a2_empty + 8 * buf);
+                    if (leader) MLP_TRACE(13, j);
+                    ++a2_uses;
+                }
             }
+            if (leader) tc_commit(d2_full);
+            __syncwarp();
         }
     } else {
         // ---------------------------------------------------------------------- epilogue warps
         const int quad = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int grp = (warp - 2) >> 2;                          // group index = buffer index
+        MLP_TRACE_DECL(2 + grp)
         const int row = quad * 32 + lane;                         // accumulator row of this thread
-        float* stg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s_stage) + half * a2_buf_bytes) + quad * 32 * kStagePitch;
-        const int lane_r = lane >> 3, ci = lane & 7;              // coalesced output phase: 4 rows x 8 float4 per pass
-        const float* stg_rd = stg + lane_r * kStagePitch + 4 * ci;
-        float* stg_wr = stg + lane * kStagePitch;
-        uint32_t my_use = 0;                                      // chunks this group has processed (its buffer index == half)
+        float* stg = reinterpret_cast<float*>(a2_gen + grp * kTileBytes + quad * kSlabBytes);
+        const int lane_r = lane >> 2, ci = lane & 3;              // coalesced output phase: 8 rows x 4 float4 (16 columns) per pass
+        const float* stg_rd = stg + lane_r * kSlabPitch + 4 * ci;
+        float* stg_wr = stg + lane * kSlabPitch;
+        uint32_t my_use = 0;                                      // chunks this group has processed
         const int n_passes = p.HN / 32;                           // 32-column passes per chunk
-        // A2 write address: SW128 K-major tiles of 64 columns; row = accumulator row
-        const uint32_t a2_row = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
+        const uint32_t a2_row = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);   // SW128 K-major tile, row = accumulator row
         for (int it = 0; it < n_my_tiles; ++it) {
             const int m_tile = blockIdx.x + it * gridDim.x;
-            for (int j = half; j < p.NC; j += 2) {                // group `half` owns D1[half] / A2[half] = chunks j == half (mod 2)
-                const int buf = half;
-                mbar_wait(d1_full + 8 * buf, my_use & 1);
+            {   // pull this warp's share of the residual tile towards L2 now; the output epilogue reads it ~10 us later
+                const long long rb = (long long)m_tile * kBM + quad * 32 + lane_r;
+                for (int c = grp; c * 32 < p.C; c += kNB)
+                    for (int q = 0; q < 4; ++q)
+                        if (rb + 8 * q < p.M && ci < 2 && c * 32 + 16 * ci < p.C)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual + (rb + 8 * q) * p.C + c * 32 + 16 * ci));
+            }
+            // chunk j of tile `it` is number it * NC + j of this CTA's chunk sequence and lives in buffer (it * NC + j) % kNB
+            for (int j = (grp - (it * p.NC) % kNB + kNB) % kNB; j < p.NC; j += kNB) {
+                if (quad == 0 && lane == 0) MLP_TRACE(20 + grp, j);
+                mbar_wait(d1_full + 8 * grp, my_use & 1);
                 tc_fence_after();
-                mbar_wait(a2_empty + 8 * buf, (my_use & 1) ^ 1);         // GEMM2(j-2) has finished reading this A2 buffer
+                if (quad == 0 && lane == 0) MLP_TRACE(30 + grp, j);
+                mbar_wait(a2_empty + 8 * grp, (my_use & 1) ^ 1);         // GEMM2(j - kNB) has finished reading this A2 buffer
                 ++my_use;
                 for (int cc = 0; cc < n_passes; ++cc) {
                     uint32_t v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 128 + cc * 32), v);
-                    if (cc + 1 == n_passes) {                            // last read of D1[buf]: GEMM1(j+2) may overwrite it
+                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(grp * kD1Stride + cc * 32), v);
+                    if (cc + 1 == n_passes) {                            // last read of D1[grp]: GEMM1(j + kNB) may overwrite it
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(d1_empty + 8 * buf);
+                        if (lane == 0) mbar_arrive(d1_empty + 8 * grp);
                     }
-                    const int n0 = j * p.HN + cc * 32;                   // first hidden column of this pass
+                    const int n0 = ((j + rot) % p.NC) * p.HN + cc * 32;  // first hidden column of this pass
                     uint32_t pk[16];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.b1 + n0) + i);
-                        const float4 a4 = __ldg(reinterpret_cast<const float4*>(p.alpha + n0) + i);
-                        const float4 i4 = __ldg(reinterpret_cast<const float4*>(p.ialpha + n0) + i);
-                        const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.scale + n0) + i);
-                        const float4 h4 = __ldg(reinterpret_cast<const float4*>(p.shift + n0) + i);
+                        const float4 b4 = reinterpret_cast<const float4*>(s_par + n0)[i];
+                        const float4 a4 = reinterpret_cast<const float4*>(s_par + p.H4 + n0)[i];
+                        const float4 i4 = reinterpret_cast<const float4*>(s_par + 2 * p.H4 + n0)[i];
+                        const float4 c4 = reinterpret_cast<const float4*>(s_par + 3 * p.H4 + n0)[i];
+                        const float4 h4 = reinterpret_cast<const float4*>(s_par + 4 * p.H4 + n0)[i];
                         float r[4];
                         const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, aa[4] = {a4.x, a4.y, a4.z, a4.w};
                         const float ii[4] = {i4.x, i4.y, i4.z, i4.w};
@@ -353,10 +438,10 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         pk[2 * i] = *reinterpret_cast<const uint32_t*>(&h01);
                         pk[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&h23);
                     }
-                    const uint32_t dst = a2_base + buf * a2_buf_bytes + (cc >> 1) * kTileBytes + a2_row;
+                    const uint32_t dst = a2_base + grp * kTileBytes + a2_row;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const uint32_t chunk = (uint32_t)((4 * (cc & 1) + q) ^ (row & 7));
+                        const uint32_t chunk = (uint32_t)((4 * cc + q) ^ (row & 7));
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + chunk * 16), "r"(pk[4 * q]),
                                      "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
                                      : "memory");
@@ -364,53 +449,62 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
                 __syncwarp();
-                if (lane == 0) mbar_arrive(a2_full + 8 * buf);
+                if (lane == 0) mbar_arrive(a2_full + 8 * grp);
+                if (quad == 0 && lane == 0) MLP_TRACE(40 + grp, j);
             }
-            // ---- output epilogue: D2 (+ b2 + residual) -> fp32, 32-column chunks, coalesced through the staging slab
+            // ---- output epilogue: D2 (+ b2 + residual) -> fp32.  32-column TMEM chunks, staged 16 columns at a time.
+            if (quad == 0 && lane == 0) MLP_TRACE(50 + grp, 0);
             mbar_wait(d2_full, it & 1);
             tc_fence_after();
+            if (quad == 0 && lane == 0) MLP_TRACE(60 + grp, 0);
             const long long row_base = (long long)m_tile * kBM;
             const int rows_valid = (int)((p.M - row_base) < kBM ? (p.M - row_base) : kBM);
             const int slab_rows = rows_valid - quad * 32;
             const long long row_lane = row_base + quad * 32 + lane_r;
             const int n_chunks = (p.C + 31) / 32;
-            for (int c = half; c < n_chunks; c += 2) {
+            for (int c = grp; c < n_chunks; c += kNB) {
+                // residual loads of both 16-column halves go out first, the TMEM read and the staging overlap them
+                float4 res[2][4];
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        res[hf][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (lane_r + 8 * q < slab_rows && c * 32 + 16 * hf < p.C)
+                            res[hf][q] = __ldg(reinterpret_cast<const float4*>(p.residual + (row_lane + 8 * q) * p.C + c * 32 + 16 * hf + 4 * ci));
+                    }
                 uint32_t v[32];
                 tmem_ld32(d2_tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32), v);
-                __syncwarp();
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int n = c * 32 + 4 * i;
-                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (n < p.C) b4 = __ldg(reinterpret_cast<const float4*>(p.b2 + n));
-                    *reinterpret_cast<float4*>(stg_wr + 4 * i) =
-                        make_float4(__uint_as_float(v[4 * i]) + b4.x, __uint_as_float(v[4 * i + 1]) + b4.y,
-                                    __uint_as_float(v[4 * i + 2]) + b4.z, __uint_as_float(v[4 * i + 3]) + b4.w);
-                }
-                __syncwarp();
-                const int col = c * 32 + 4 * ci;
-                const bool col_ok = col < p.C;
-                float4 res[8];
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int nb = c * 32 + 16 * hf;
+                    if (nb >= p.C) break;                      // warp-uniform
+                    __syncwarp();
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    res[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (col_ok && lane_r + 4 * q < slab_rows)
-                        res[q] = __ldg(reinterpret_cast<const float4*>(p.residual + (row_lane + 4 * q) * p.C + col));
-                }
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.b2 + nb) + i);
+                        *reinterpret_cast<float4*>(stg_wr + 4 * i) =
+                            make_float4(__uint_as_float(v[16 * hf + 4 * i]) + b4.x, __uint_as_float(v[16 * hf + 4 * i + 1]) + b4.y,
+                                        __uint_as_float(v[16 * hf + 4 * i + 2]) + b4.z, __uint_as_float(v[16 * hf + 4 * i + 3]) + b4.w);
+                    }
+                    __syncwarp();
+                    const int col = nb + 4 * ci;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    if (!(col_ok && lane_r + 4 * q < slab_rows)) continue;
-                    float4 val = *reinterpret_cast<const float4*>(stg_rd + 4 * q * kStagePitch);
-                    val.x += res[q].x; val.y += res[q].y; val.z += res[q].z; val.w += res[q].w;
-                    *reinterpret_cast<float4*>(p.out + (row_lane + 4 * q) * p.C + col) = val;
+                    for (int q = 0; q < 4; ++q) {
+                        if (!(lane_r + 8 * q < slab_rows)) continue;
+                        float4 val = *reinterpret_cast<const float4*>(stg_rd + 8 * q * kSlabPitch);
+                        val.x += res[hf][q].x; val.y += res[hf][q].y; val.z += res[hf][q].z; val.w += res[hf][q].w;
+                        *reinterpret_cast<float4*>(p.out + (row_lane + 8 * q) * p.C + col) = val;
+                    }
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(d2_empty);
+            if (quad == 0 && lane == 0) MLP_TRACE(70 + grp, 0);
             // The staging slabs alias this group's A2 buffer: no warp of the group may start writing the next tile's
             // hidden chunk into it before every warp of the group has finished reading its slab.
-            asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
+            asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
         }
     }
 
@@ -455,20 +549,30 @@ static bool encode_2d(EncodeTiledFn enc, CUtensorMap* tm, const void* ptr, long 
 }  // namespace mlp
 }  // namespace l3ac
 
+#ifdef L3AC_MLP_TRACE
+extern "C" int l3ac_debug_mlp_trace(unsigned long long* host_buf) {      // host_buf: 8 * 512 entries
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(host_buf, l3ac::mlp::g_trace_buf, 8 * 512 * sizeof(unsigned long long));
+    static unsigned long long zeros[8 * 512];
+    cudaMemcpyToSymbol(l3ac::mlp::g_trace_buf, zeros, sizeof(zeros));
+    return 0;
+}
+#endif
+
 extern "C" int l3ac_convunit_mlp_tc(const void* a, const void* w1, const float* b1, const float* alpha, const float* ialpha,
                                     const float* scale, const float* shift, const void* w2, const float* b2,
                                     const float* residual, float* out, long long M, int C, l3ac_stream_t stream) {
     using namespace l3ac::mlp;
     L3AC_CHECK_ARG(a && w1 && b1 && alpha && ialpha && scale && shift && w2 && b2 && residual && out && M > 0);
-    if (C < 16 || C > 256 || C % 8 != 0) return L3AC_EUNSUPPORTED;       // C = 512 does not fit shared memory: use the two-GEMM path
+    // C = 512 does not fit shared memory / TMEM (two-GEMM path); the 16-column output staging wants whole 16-column groups
+    if (C < 16 || C > 256 || C % 16 != 0) return L3AC_EUNSUPPORTED;
     const int H4 = 4 * C;
-    const int HN = (H4 % 128 == 0) ? 128 : (H4 % 64 == 0) ? 64 : 32;
+    const int HN = (H4 % 64 == 0) ? 64 : 32;
     if (H4 % HN != 0) return L3AC_EUNSUPPORTED;
     L3AC_CHECK_ARG(((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(w1) | reinterpret_cast<uintptr_t>(w2) |
                      reinterpret_cast<uintptr_t>(residual) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(b1) |
                      reinterpret_cast<uintptr_t>(alpha) | reinterpret_cast<uintptr_t>(ialpha) | reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(shift) |
                      reinterpret_cast<uintptr_t>(b2)) & 15) == 0);
-    L3AC_CHECK_ARG(C % 4 == 0);
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return L3AC_EDRIVER;
     Params p{};
@@ -476,15 +580,14 @@ extern "C" int l3ac_convunit_mlp_tc(const void* a, const void* w1, const float* 
     p.M = M; p.C = C; p.H4 = H4; p.HN = HN; p.NC = H4 / HN;
     p.a_kb = (C + kBK - 1) / kBK;
     p.n_halves = (C + 127) / 128;
-    p.hn_kb = (HN + kBK - 1) / kBK;
-    const int a2_region = 2 * a2_stride_bytes(p.hn_kb);
-    const int fixed = 1024 + p.a_kb * kTileBytes + a2_region + 8 * kNumBars + 64;
+    p.g1_slots = (p.a_kb + 1) / 2;
+    const int fixed = 1024 + p.a_kb * kTileBytes + kNB * kTileBytes + 5 * H4 * 4 + 8 * kNumBars + 64;
     p.ring = (kSmemLimit - fixed) / kTileBytes;
     if (p.ring > kMaxRing) p.ring = kMaxRing;
     if (p.ring < 2) return L3AC_EUNSUPPORTED;
-    const int boxes_per_tile = p.NC * (p.a_kb + p.hn_kb * p.n_halves);
-    p.resident = boxes_per_tile <= p.ring ? 1 : 0;
-    if (p.resident) p.ring = boxes_per_tile;
+    const int slots_per_tile = p.NC * (p.g1_slots + p.n_halves);
+    p.resident = slots_per_tile <= p.ring ? 1 : 0;
+    if (p.resident) p.ring = slots_per_tile;
     const size_t smem_bytes = (size_t)fixed + (size_t)p.ring * kTileBytes;
     const long long mt = (M + kBM - 1) / kBM;
     L3AC_CHECK_ARG(mt < (1LL << 30));

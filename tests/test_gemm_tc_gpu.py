@@ -123,7 +123,8 @@ def test_split_outputs_and_producers(cuda_lib):
     assert max_abs(y.cpu(), want_y) < 3e-5 * max(1.0, float(want_y.abs().max()))
 
 
-@pytest.mark.parametrize("M,C", [(128, 256), (1000, 256), (333, 96), (2000, 48), (5000, 96), (40000, 256), (300, 192), (130, 64)])
+@pytest.mark.parametrize("M,C", [(128, 256), (1000, 256), (333, 96), (2000, 48), (5000, 96), (40000, 256), (300, 192), (130, 64),
+                                  (128 * 148 * 5 + 77, 48), (128 * 148 * 3 + 5, 96), (128 * 148 * 2 + 1, 128)])
 def test_fused_convunit_mlp(cuda_lib, M, C):
     """Fused MLP kernel vs (a) the two-GEMM tcgen05 path it replaces and (b) fp64 on the same bf16 operands."""
     a = bf(rnd(1, M, C, seed=1))

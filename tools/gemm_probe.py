@@ -72,6 +72,9 @@ def run_mlp(M, C, iters=5):
 
 if __name__ == "__main__":
     only = sys.argv[1] if len(sys.argv) > 1 else None
+    if only == "mlp1":      # one shape, for ncu: python tools/gemm_probe.py mlp1 M C
+        run_mlp(int(sys.argv[2]), int(sys.argv[3]), iters=1)
+        sys.exit(0)
     if only == "mlp":
         for M, C in ((142320, 256), (426960, 96), (1280880, 48), (28464, 256), (2561760, 48)):
             run_mlp(M, C)
