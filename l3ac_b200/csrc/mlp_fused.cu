@@ -228,9 +228,6 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     const int n_my_tiles = (p.num_m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int lookahead = kNB - 1;      // GEMM1 chunks issued ahead of GEMM2
-    // GEMM2 sums over hidden chunks in any order: every CTA starts at a different chunk so that the 148 CTAs do not all
-    // pull the same 16 KB weight box out of the same L2 lines at the same moment.
-    const int rot = p.resident ? 0 : (int)(blockIdx.x % (unsigned)p.NC);
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -254,8 +251,7 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // same order as the MMA warp: step s issues GEMM1(s) and GEMM2(s - lookahead)
             for (int s = 0; s < p.NC + lookahead; ++s) {
                 if (s < p.NC) {
-                    int j = s + rot;
-                    if (j >= p.NC) j -= p.NC;
+                    const int j = s;
                     for (int q = 0; q < p.g1_slots; ++q) {    // two consecutive W1 k-blocks share a slot (8 KB halves)
                         const int kb0 = 2 * q, nkb = (kb0 + 1 < p.a_kb) ? 2 : 1;
                         mbar_wait(ring_empty + 8 * rs, rphase ^ 1);
@@ -272,8 +268,7 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
                 }
                 if (s >= lookahead) {
-                    int j = s - lookahead + rot;
-                    if (j >= p.NC) j -= p.NC;
+                    const int j = s - lookahead;
                     for (int h = 0; h < p.n_halves; ++h) {
                         mbar_wait(ring_empty + 8 * rs, rphase ^ 1);
                         if (leader) {
@@ -414,7 +409,7 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         __syncwarp();
                         if (lane == 0) mbar_arrive(d1_empty + 8 * grp);
                     }
-                    const int n0 = ((j + rot) % p.NC) * p.HN + cc * 32;  // first hidden column of this pass
+                    const int n0 = j * p.HN + cc * 32;                   // first hidden column of this pass
                     uint32_t pk[16];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {

@@ -94,10 +94,12 @@ class Engine:
         # one micro-batch then overlap the tensor-core GEMMs (one persistent, shared-memory-heavy CTA per SM) of another.
         self.num_streams = int(os.environ.get("L3AC_STREAMS", 4))    # measured: 2 -> +11 %, 4 -> +14 % at 64 x 10 s
         self._streams = None
-        # Fused tcgen05 MLP kernel (mlp_fused.cu) for decode-side ConvUnits with C <= 256.  Bit-identical to the two-GEMM
-        # path but not yet faster on B200 (C=256: 386 vs 278 us, C=96: 362 vs 316, C=48: 501 vs 490 per 16-clip block; the
-        # per-tile latency chain A-load -> GEMM1 -> snake -> GEMM2 -> output epilogue is not overlapped across tiles), so off.
-        self.fused_mlp = False
+        # Fused tcgen05 MLP kernel (mlp_fused.cu) for the bf16 (decode-side) ConvUnits: the 4C hidden activation stays in
+        # TMEM / shared memory.  Bit-identical to the two-GEMM path.  Per 24-clip chunk on B200: C=48 288 vs 429 us, C=96
+        # 222 vs 298 us; at C=256 the fused kernel re-streams 1 MB of weights per 128-row tile and is L2-bound at parity
+        # (282 vs 280 us), so the two-GEMM path keeps that width.
+        self.fused_mlp = True
+        self.fused_mlp_max_c = 128
         self.hidden_block_bytes = 0              # >0: L2-blocked ConvUnit MLP (measured slower, see _run_conv_unit)
         self.dec_dtype = torch.bfloat16 if precision == "bf16" else torch.float32
         self.enc_dtype = ops.SPLIT if encoder_precision == "split" else torch.float32
@@ -286,7 +288,7 @@ class Engine:
         M = B * T
         esz = {torch.float32: 4, torch.bfloat16: 2, ops.SPLIT: 4}[act_dtype]
         rows_blk = max(128 * 148, (self.hidden_block_bytes // (4 * C * esz)) // 128 * 128)
-        if act_dtype == torch.bfloat16 and self.fused_mlp and 16 <= C <= 256 and C % 16 == 0:
+        if act_dtype == torch.bfloat16 and self.fused_mlp and 16 <= C <= self.fused_mlp_max_c and C % 16 == 0:
             return ops.convunit_mlp(a, u["pw1"].w16, u["pw1"].bias, u["alpha"], u["scale"], u["shift"], u["pw2"].w16,
                                     u["pw2"].bias, x, ialpha=u["ialpha"])
         if self.hidden_block_bytes <= 0 or act_dtype == torch.float32 or M <= rows_blk + rows_blk // 2:
