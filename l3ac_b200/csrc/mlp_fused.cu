@@ -8,16 +8,24 @@
 // SWIZZLE_128B K-major shared-memory layout the tensor core reads, and consumed by the second GEMM whose C-wide
 // accumulator stays in TMEM for the whole tile.
 //
-// One persistent CTA per SM, 18 warps:
-//   warp 0      TMA producer: the 128 x C activation tile (resident for the tile) and a ring of 16 KB weight slots
-//               (GEMM1: two [64 hidden x 64 k] W1 boxes per slot, GEMM2: one [<=128 out x 64 k] W2 box per slot) in
-//               exactly the order the MMA warp consumes them
-//   warp 1      MMA issuer (one thread).  D1 has FOUR 64-column TMEM buffers and the hidden operand A2 four 16 KB
-//               shared-memory buffers, so GEMM1 runs three chunks ahead of GEMM2 and the latency of the snake epilogue
-//               (TMEM -> registers -> MUFU -> smem -> fence) is hidden behind tensor-core work.  D2 owns C columns.
-//   warps 2-17  epilogue, four groups of four warps (one per TMEM lane quadrant); group g owns D1[g] / A2[g], i.e.
-//               the chunks whose sequence number is g (mod 4).  At the end of the tile all sixteen warps drain D2: + b2 + residual -> coalesced
-//               fp32 stores through 16-column staging slabs that alias the group's own A2 buffer.
+// One persistent CTA per SM, 20 warps.  The two GEMMs are issued by different warps from different weight rings, so the
+// only coupling between them is the data flow D1 -> snake -> A2:
+//   warp 0      TMA producer 1: the 128 x C activation tile and the W1 ring (two [64 hidden x 64 k] boxes per 16 KB slot)
+//   warp 1      GEMM1 issuer: D1[b] = A . W1[chunk]^T into one of FOUR 64-column TMEM buffers, as soon as the buffer has
+//               been drained and the slot has landed -- up to four chunks ahead of the snake epilogue
+//   warp 2      TMA producer 2: the W2 ring (one [<=128 out x 64 k] box per 16 KB slot)
+//   warp 3      GEMM2 issuer: D2 += A2[b] . W2[:, chunk]^T as soon as a hidden chunk has been written
+//   warps 4-19  epilogue, four groups of four warps (one per TMEM lane quadrant).  Group g owns D1[g] / A2[g], i.e. the
+//               chunks whose sequence number is g (mod 4).  All sixteen warps also drain D2 (+ b2 + residual -> fp32)
+//               through 16-column staging slabs.
+// C <= 128 ("pipelined"): D2 is double-buffered and the staging slabs have their own shared memory, so the epilogue warps
+// run the snake chunks of tile t+1 BEFORE the output of tile t -- the residual loads and the stores of a tile are off the
+// critical path and the tensor core never waits for them.  C > 128: one D2, the slabs alias the group's A2 buffer and the
+// output of tile t comes before the chunks of tile t+1.
+//
+// All issuing warps run warp-uniform loops and issue through one elected lane: under a divergent `if (lane == 0)` the
+// compiler cannot prove the shared-memory descriptors uniform and wraps every tcgen05.mma in an ELECT / R2UR.BROADCAST
+// waterfall (~200 cycles per MMA, measured with tools/mlp_trace.py).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -29,15 +37,37 @@ constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kTileBytes = kBM * kBK * 2;      // 16 KB: one [128 x 64] bf16 SW128 tile (A k-block, A2 buffer, ring slot)
 constexpr int kNB = 4;                         // D1 / A2 buffers = epilogue groups
-constexpr int kMaxRing = 8;
+constexpr int kMaxRing = 8;                    // per ring
+constexpr int kEpiWarp0 = 4;                   // first epilogue warp (a multiple of 4: warp & 3 is the TMEM lane quadrant)
 constexpr int kEpiWarps = 4 * kNB;
-constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kThreads = 32 * (kEpiWarp0 + kEpiWarps);
 constexpr int kSlabPitch = 20;                 // floats per staged row: 16 columns + 4 pad (conflict-free float4 access)
-constexpr int kSlabBytes = 32 * kSlabPitch * 4;   // 2560 B per warp, four warps per group < one 16 KB A2 buffer
+constexpr int kSlabBytes = 32 * kSlabPitch * 4;   // 2560 B per warp
+constexpr int kStageBytes = kEpiWarps * kSlabBytes;   // 40 KB of dedicated staging in pipelined mode
 constexpr int kD1Stride = 64;                  // TMEM columns per D1 buffer
-constexpr int kD2Col = kNB * kD1Stride;        // D2 starts after the D1 buffers (256 + C <= 512)
-constexpr int kNumBars = 2 * kMaxRing + 2 + 4 * kNB + 2;
+constexpr int kD2Col = kNB * kD1Stride;        // D2 starts after the D1 buffers: 256 + C (or 2 x 128) <= 512
+constexpr int kNumBars = 4 * kMaxRing + 2 + 4 * kNB + 4;
 constexpr int kSmemLimit = 227 * 1024;
+
+struct Params {
+    const float* b1;
+    const float* alpha;
+    const float* ialpha;
+    const float* scale;
+    const float* shift;
+    const float* b2;
+    const float* residual;
+    float* out;
+    long long M;
+    int C, H4, HN, NC;        // channels, hidden = 4C, hidden chunk width (64), number of chunks
+    int a_kb;                 // k-blocks of the activation tile = ceil(C / 64)
+    int g1_slots;             // W1 ring slots per GEMM1 = ceil(a_kb / 2)
+    int n_halves;             // GEMM2 N splits of <= 128 output columns (one W2 ring slot each)
+    int ring1, ring2;         // ring depths (16 KB slots)
+    int resident;             // each ring holds a whole tile's slots: weights are loaded once per CTA and stay
+    int pipelined;            // C <= 128: two D2 buffers, dedicated staging, output(t) after chunks(t+1)
+    int num_m_tiles;
+};
 
 #ifdef L3AC_MLP_TRACE
 // Debug build only: CTA 0 stamps clock64() at pipeline hand-overs of two steady-state tiles (tools/mlp_trace.py).  Every
@@ -55,25 +85,6 @@ __device__ unsigned long long g_trace_buf[8 * 512];
 #define MLP_TRACE_DECL(role)
 #define MLP_TRACE(ev, j) do {} while (0)
 #endif
-
-struct Params {
-    const float* b1;
-    const float* alpha;
-    const float* ialpha;
-    const float* scale;
-    const float* shift;
-    const float* b2;
-    const float* residual;
-    float* out;
-    long long M;
-    int C, H4, HN, NC;        // channels, hidden = 4C, hidden chunk width (64 or 32), number of chunks
-    int a_kb;                 // k-blocks of the activation tile = ceil(C / 64)
-    int g1_slots;             // ring slots per GEMM1 = ceil(a_kb / 2)
-    int n_halves;             // GEMM2 N splits of <= 128 output columns (one ring slot each)
-    int ring;                 // ring depth (16 KB slots)
-    int resident;             // ring == slots per tile: every weight slot is loaded once per CTA and stays in shared memory
-    int num_m_tiles;
-};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -163,27 +174,30 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-    // layout (all 1024-aligned): A tile [a_kb], A2 [kNB] (the output staging slabs alias it), ring [ring], barriers
+    // layout (1024-aligned tiles first): A [a_kb], A2 [kNB], W1 ring, W2 ring, staging (pipelined), parameters, barriers
     const uint32_t a_base = smem_base;
     const uint32_t a2_base = a_base + p.a_kb * kTileBytes;
-    const uint32_t ring_base = a2_base + kNB * kTileBytes;
-    uint8_t* a2_gen = smem_gen + (a2_base - smem_base);
+    const uint32_t ring1_base = a2_base + kNB * kTileBytes;
+    const uint32_t ring2_base = ring1_base + p.ring1 * kTileBytes;
+    const uint32_t stage_base = ring2_base + p.ring2 * kTileBytes;
     // per-column epilogue parameters [5][H4] (b1, alpha, 1/(alpha+eps), scale, shift): staged once -- with ~220 KB of
     // shared memory carved out there is next to no L1 left, and a global load per use is an exposed L2 round trip
-    const uint32_t par_base = ring_base + p.ring * kTileBytes;
+    const uint32_t par_base = stage_base + (p.pipelined ? kStageBytes : 0);
     float* s_par = reinterpret_cast<float*>(smem_gen + (par_base - smem_base));
     const uint32_t bar_base = par_base + 5 * p.H4 * 4;
-    const uint32_t ring_full = bar_base;                       // [kMaxRing]
-    const uint32_t ring_empty = ring_full + 8 * kMaxRing;      // [kMaxRing]
-    const uint32_t a_full = ring_empty + 8 * kMaxRing;         // [1]
+    const uint32_t r1_full = bar_base;                         // [kMaxRing]
+    const uint32_t r1_empty = r1_full + 8 * kMaxRing;          // [kMaxRing]
+    const uint32_t r2_full = r1_empty + 8 * kMaxRing;          // [kMaxRing]
+    const uint32_t r2_empty = r2_full + 8 * kMaxRing;          // [kMaxRing]
+    const uint32_t a_full = r2_empty + 8 * kMaxRing;           // [1]
     const uint32_t a_empty = a_full + 8;                       // [1]
     const uint32_t d1_full = a_empty + 8;                      // [kNB]
     const uint32_t d1_empty = d1_full + 8 * kNB;               // [kNB]
     const uint32_t a2_full = d1_empty + 8 * kNB;               // [kNB]
     const uint32_t a2_empty = a2_full + 8 * kNB;               // [kNB]
-    const uint32_t d2_full = a2_empty + 8 * kNB;               // [1]
-    const uint32_t d2_empty = d2_full + 8;                     // [1]
-    const uint32_t tmem_slot = d2_empty + 8;
+    const uint32_t d2_full = a2_empty + 8 * kNB;               // [2]
+    const uint32_t d2_empty = d2_full + 16;                    // [2]
+    const uint32_t tmem_slot = d2_empty + 16;
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
     // broadcast from lane 0: lets the compiler treat the role branches below as warp-uniform
@@ -193,9 +207,11 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW1) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW2) : "memory");
-        for (int s = 0; s < p.ring; ++s) {
-            mbar_init(ring_full + 8 * s, 1);
-            mbar_init(ring_empty + 8 * s, 1);
+        for (int s = 0; s < kMaxRing; ++s) {
+            mbar_init(r1_full + 8 * s, 1);
+            mbar_init(r1_empty + 8 * s, 1);
+            mbar_init(r2_full + 8 * s, 1);
+            mbar_init(r2_empty + 8 * s, 1);
         }
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
@@ -205,8 +221,10 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_init(a2_full + 8 * i, 4);
             mbar_init(a2_empty + 8 * i, 1);
         }
-        mbar_init(d2_full, 1);
-        mbar_init(d2_empty, kEpiWarps);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(d2_full + 8 * i, 1);
+            mbar_init(d2_empty + 8 * i, kEpiWarps);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = threadIdx.x; i < p.H4; i += kThreads) {
@@ -224,170 +242,224 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
-    const uint32_t d2_tmem = tmem_base + kD2Col;
 
     const int n_my_tiles = (p.num_m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int lookahead = kNB - 1;      // GEMM1 chunks issued ahead of GEMM2
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer
-        // The whole warp runs the loop (warp-uniform control flow keeps coordinates and addresses in uniform registers);
-        // one elected lane issues the copies.
+        // ------------------------------------------------------------------ TMA producer 1: activation tile + W1 ring
         MLP_TRACE_DECL(0)
         const bool leader = elect_one();
         int rs = 0;
         uint32_t rphase = 0;
-        const uint32_t w1_box = p.HN * kBK * 2, w2_box = kBM * kBK * 2;
+        const uint32_t w1_box = p.HN * kBK * 2;
         for (int it = 0; it < n_my_tiles; ++it) {
             const int m_tile = blockIdx.x + it * gridDim.x;
-            const bool load_w = !(p.resident && it > 0);      // resident weights are loaded once per CTA
-            mbar_wait(a_empty, (it & 1) ^ 1);                 // previous tile's GEMM1s have finished reading A
+            mbar_wait(a_empty, (it & 1) ^ 1);                 // the previous tile's GEMM1s have finished reading A
             if (leader) MLP_TRACE(1, 0);
             if (leader) {
                 mbar_arrive_expect_tx(a_full, p.a_kb * kTileBytes);
                 for (int kb = 0; kb < p.a_kb; ++kb) tma_load_2d(a_base + kb * kTileBytes, &tmA, kb * kBK, m_tile * kBM, a_full);
             }
-            if (!load_w) continue;
-            // same order as the MMA warp: step s issues GEMM1(s) and GEMM2(s - lookahead)
-            for (int s = 0; s < p.NC + lookahead; ++s) {
-                if (s < p.NC) {
-                    const int j = s;
-                    for (int q = 0; q < p.g1_slots; ++q) {    // two consecutive W1 k-blocks share a slot (8 KB halves)
-                        const int kb0 = 2 * q, nkb = (kb0 + 1 < p.a_kb) ? 2 : 1;
-                        mbar_wait(ring_empty + 8 * rs, rphase ^ 1);
-                        if (leader) {
-                            mbar_arrive_expect_tx(ring_full + 8 * rs, nkb * w1_box);
-                            for (int e = 0; e < nkb; ++e)
-                                tma_load_2d(ring_base + rs * kTileBytes + e * (kTileBytes / 2), &tmW1, (kb0 + e) * kBK, j * p.HN,
-                                            ring_full + 8 * rs);
-                        }
-                        if (++rs == p.ring) {
-                            rs = 0;
-                            rphase ^= 1;
-                        }
+            if (p.resident && it > 0) continue;               // resident weights are loaded once per CTA
+            for (int j = 0; j < p.NC; ++j)
+                for (int q = 0; q < p.g1_slots; ++q) {        // two consecutive W1 k-blocks share a slot (8 KB halves)
+                    const int kb0 = 2 * q, nkb = (kb0 + 1 < p.a_kb) ? 2 : 1;
+                    mbar_wait(r1_empty + 8 * rs, rphase ^ 1);
+                    if (leader) {
+                        mbar_arrive_expect_tx(r1_full + 8 * rs, nkb * w1_box);
+                        for (int e = 0; e < nkb; ++e)
+                            tma_load_2d(ring1_base + rs * kTileBytes + e * (kTileBytes / 2), &tmW1, (kb0 + e) * kBK, j * p.HN,
+                                        r1_full + 8 * rs);
+                    }
+                    if (++rs == p.ring1) {
+                        rs = 0;
+                        rphase ^= 1;
                     }
                 }
-                if (s >= lookahead) {
-                    const int j = s - lookahead;
-                    for (int h = 0; h < p.n_halves; ++h) {
-                        mbar_wait(ring_empty + 8 * rs, rphase ^ 1);
-                        if (leader) {
-                            mbar_arrive_expect_tx(ring_full + 8 * rs, w2_box);
-                            tma_load_2d(ring_base + rs * kTileBytes, &tmW2, j * p.HN, h * 128, ring_full + 8 * rs);
-                        }
-                        if (++rs == p.ring) {
-                            rs = 0;
-                            rphase ^= 1;
-                        }
-                    }
-                }
-            }
         }
+    } else if (warp == 2) {
+        // ------------------------------------------------------------------ TMA producer 2: W2 ring
+        const bool leader = elect_one();
+        int rs = 0;
+        uint32_t rphase = 0;
+        const uint32_t w2_box = kBM * kBK * 2;
+        for (int it = 0; it < (p.resident ? 1 : n_my_tiles); ++it)
+            for (int j = 0; j < p.NC; ++j)
+                for (int h = 0; h < p.n_halves; ++h) {
+                    mbar_wait(r2_empty + 8 * rs, rphase ^ 1);
+                    if (leader) {
+                        mbar_arrive_expect_tx(r2_full + 8 * rs, w2_box);
+                        tma_load_2d(ring2_base + rs * kTileBytes, &tmW2, j * p.HN, h * 128, r2_full + 8 * rs);
+                    }
+                    if (++rs == p.ring2) {
+                        rs = 0;
+                        rphase ^= 1;
+                    }
+                }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        // All 32 lanes walk the schedule and wait on the barriers; one elected lane issues tcgen05.mma / commit.  Keeping
-        // the control flow warp-uniform matters: under a divergent `if (lane == 0)` the compiler cannot prove the shared
-        // memory descriptors uniform and wraps every MMA in an ELECT / R2UR.BROADCAST waterfall (~200 cycles per MMA).
+        // ------------------------------------------------------------------ GEMM1 issuer: D1[seq % kNB] = A . W1[chunk]^T
         MLP_TRACE_DECL(1)
         const bool leader = elect_one();
         int rs = 0;
         uint32_t rphase = 0;
-        uint32_t d1_uses = 0, a2_uses = 0;         // GEMM1s / GEMM2s issued so far: buffer = count % kNB, phase from count / kNB
+        uint32_t seq = 0;                          // chunk sequence number of this CTA, across tiles
         const uint32_t idesc1 = make_idesc(p.HN);
         for (int it = 0; it < n_my_tiles; ++it) {
             const bool ring_sync = !(p.resident && it > 0);    // resident mode: only the first tile waits for weight slots
             mbar_wait(a_full, it & 1);
             tc_fence_after();
             if (leader) MLP_TRACE(10, 0);
-            for (int s = 0; s < p.NC + lookahead; ++s) {
-                if (s < p.NC) {
-                    // ---- GEMM1(s): D1[s % kNB] = A . W1[chunk]^T
-                    const int buf = d1_uses % kNB;      // buffers rotate over the global chunk sequence, across tiles
-                    if (leader) MLP_TRACE(14, s);
-                    mbar_wait(d1_empty + 8 * buf, ((d1_uses / kNB) & 1) ^ 1);      // the group has drained this D1 buffer
-                    tc_fence_after();
-                    if (leader) MLP_TRACE(15, s);
-                    const uint32_t d1 = tmem_base + buf * kD1Stride;
-                    for (int q = 0; q < p.g1_slots; ++q) {
-                        if (ring_sync) {
-                            mbar_wait(ring_full + 8 * rs, rphase);
-                            tc_fence_after();
-                        }
-                        for (int e = 0; e < 2 && 2 * q + e < p.a_kb; ++e) {
-                            const int kb = 2 * q + e;
-                            const uint64_t a_desc = make_sw128_desc(a_base + kb * kTileBytes);
-                            const uint64_t b_desc = make_sw128_desc(ring_base + rs * kTileBytes + e * (kTileBytes / 2));
-                            const int k_left = p.C - kb * kBK;
-                            const int k16 = k_left >= kBK ? kBK / 16 : (k_left + 15) / 16;
-                            if (leader)
-                                for (int k = 0; k < k16; ++k) tc_mma_f16(d1, a_desc + 2 * k, b_desc + 2 * k, idesc1, (kb > 0 || k > 0) ? 1u : 0u);
-                        }
-                        if (leader && !p.resident) tc_commit(ring_empty + 8 * rs);
-                        if (++rs == p.ring) {
-                            rs = 0;
-                            rphase ^= 1;
-                        }
+            for (int j = 0; j < p.NC; ++j, ++seq) {
+                const int buf = seq % kNB;
+                mbar_wait(d1_empty + 8 * buf, ((seq / kNB) & 1) ^ 1);       // the group has drained this D1 buffer
+                tc_fence_after();
+                if (leader) MLP_TRACE(15, j);
+                const uint32_t d1 = tmem_base + buf * kD1Stride;
+                for (int q = 0; q < p.g1_slots; ++q) {
+                    if (ring_sync) {
+                        mbar_wait(r1_full + 8 * rs, rphase);
+                        tc_fence_after();
                     }
-                    if (leader) {
-                        tc_commit(d1_full + 8 * buf);
-                        if (s == p.NC - 1) tc_commit(a_empty);       // last GEMM1 of the tile: A is free once it completes
+                    for (int e = 0; e < 2 && 2 * q + e < p.a_kb; ++e) {
+                        const int kb = 2 * q + e;
+                        const uint64_t a_desc = make_sw128_desc(a_base + kb * kTileBytes);
+                        const uint64_t b_desc = make_sw128_desc(ring1_base + rs * kTileBytes + e * (kTileBytes / 2));
+                        const int k_left = p.C - kb * kBK;
+                        const int k16 = k_left >= kBK ? kBK / 16 : (k_left + 15) / 16;
+                        if (leader)
+                            for (int k = 0; k < k16; ++k) tc_mma_f16(d1, a_desc + 2 * k, b_desc + 2 * k, idesc1, (kb > 0 || k > 0) ? 1u : 0u);
                     }
-                    if (leader) MLP_TRACE(16, s);
-                    ++d1_uses;
+                    if (leader && !p.resident) tc_commit(r1_empty + 8 * rs);
+                    if (++rs == p.ring1) {
+                        rs = 0;
+                        rphase ^= 1;
+                    }
                 }
-                if (s >= lookahead) {
-                    // ---- GEMM2(j): D2 += A2[j % kNB] . W2[:, chunk]^T
-                    const int j = s - lookahead;
-                    const int buf = a2_uses % kNB;
-                    if (leader) MLP_TRACE(11, j);
-                    mbar_wait(a2_full + 8 * buf, (a2_uses / kNB) & 1);             // the group wrote the bf16 hidden chunk
-                    if (j == 0) mbar_wait(d2_empty, (it & 1) ^ 1);                 // previous tile's output epilogue drained D2
-                    tc_fence_after();
-                    if (leader) MLP_TRACE(12, j);
-                    const uint64_t a_desc = make_sw128_desc(a2_base + buf * kTileBytes);
-                    for (int h = 0; h < p.n_halves; ++h) {
-                        if (ring_sync) {
-                            mbar_wait(ring_full + 8 * rs, rphase);
-                            tc_fence_after();
-                        }
-                        const uint64_t b_desc = make_sw128_desc(ring_base + rs * kTileBytes);
-                        const int n = min(128, (p.C - h * 128 + 15) & ~15);    // UMMA N is a multiple of 16; extra W2 rows are TMA zero fill
-                        const uint32_t idesc2 = make_idesc(n);
-                        if (leader) {
-                            for (int k = 0; k < p.HN / 16; ++k)
-                                tc_mma_f16(d2_tmem + h * 128, a_desc + 2 * k, b_desc + 2 * k, idesc2, (j > 0 || k > 0) ? 1u : 0u);
-                            if (!p.resident) tc_commit(ring_empty + 8 * rs);
-                        }
-                        if (++rs == p.ring) {
-                            rs = 0;
-                            rphase ^= 1;
-                        }
-                    }
-                    if (leader) tc_commit(a2_empty + 8 * buf);
-                    if (leader) MLP_TRACE(13, j);
-                    ++a2_uses;
+                if (leader) {
+                    tc_commit(d1_full + 8 * buf);
+                    if (j == p.NC - 1) tc_commit(a_empty);           // last GEMM1 of the tile: A is free once it completes
                 }
+                if (leader) MLP_TRACE(16, j);
             }
-            if (leader) tc_commit(d2_full);
+            __syncwarp();
+        }
+    } else if (warp == 3) {
+        // ------------------------------------------------------------------ GEMM2 issuer: D2 += A2[seq % kNB] . W2[:, chunk]^T
+        MLP_TRACE_DECL(6)
+        const bool leader = elect_one();
+        int rs = 0;
+        uint32_t rphase = 0;
+        uint32_t seq = 0;
+        for (int it = 0; it < n_my_tiles; ++it) {
+            const bool ring_sync = !(p.resident && it > 0);
+            const int d2b = p.pipelined ? (it & 1) : 0;
+            const uint32_t d2_tmem = tmem_base + kD2Col + d2b * 128;
+            for (int j = 0; j < p.NC; ++j, ++seq) {
+                const int buf = seq % kNB;
+                mbar_wait(a2_full + 8 * buf, (seq / kNB) & 1);               // the group wrote the bf16 hidden chunk
+                if (j == 0)                                                  // the output epilogue has drained this D2 buffer
+                    mbar_wait(d2_empty + 8 * d2b, ((p.pipelined ? (it >> 1) : it) & 1) ^ 1);
+                tc_fence_after();
+                if (leader) MLP_TRACE(12, j);
+                const uint64_t a_desc = make_sw128_desc(a2_base + buf * kTileBytes);
+                for (int h = 0; h < p.n_halves; ++h) {
+                    if (ring_sync) {
+                        mbar_wait(r2_full + 8 * rs, rphase);
+                        tc_fence_after();
+                    }
+                    const uint64_t b_desc = make_sw128_desc(ring2_base + rs * kTileBytes);
+                    const int n = min(128, (p.C - h * 128 + 15) & ~15);    // UMMA N is a multiple of 16; extra W2 rows are TMA zero fill
+                    const uint32_t idesc2 = make_idesc(n);
+                    if (leader) {
+                        for (int k = 0; k < p.HN / 16; ++k)
+                            tc_mma_f16(d2_tmem + h * 128, a_desc + 2 * k, b_desc + 2 * k, idesc2, (j > 0 || k > 0) ? 1u : 0u);
+                        if (!p.resident) tc_commit(r2_empty + 8 * rs);
+                    }
+                    if (++rs == p.ring2) {
+                        rs = 0;
+                        rphase ^= 1;
+                    }
+                }
+                if (leader) tc_commit(a2_empty + 8 * buf);
+                if (leader) MLP_TRACE(13, j);
+            }
+            if (leader) tc_commit(d2_full + 8 * d2b);
             __syncwarp();
         }
     } else {
         // ---------------------------------------------------------------------- epilogue warps
         const int quad = warp & 3;
-        const int grp = (warp - 2) >> 2;                          // group index = buffer index
+        const int grp = (warp - kEpiWarp0) >> 2;                  // group index = D1 / A2 buffer index
         MLP_TRACE_DECL(2 + grp)
         const int row = quad * 32 + lane;                         // accumulator row of this thread
-        float* stg = reinterpret_cast<float*>(a2_gen + grp * kTileBytes + quad * kSlabBytes);
+        float* stg = p.pipelined ? reinterpret_cast<float*>(smem_gen + (stage_base - smem_base) + (warp - kEpiWarp0) * kSlabBytes)
+                                 : reinterpret_cast<float*>(smem_gen + (a2_base - smem_base) + grp * kTileBytes + quad * kSlabBytes);
         const int lane_r = lane >> 2, ci = lane & 3;              // coalesced output phase: 8 rows x 4 float4 (16 columns) per pass
         const float* stg_rd = stg + lane_r * kSlabPitch + 4 * ci;
         float* stg_wr = stg + lane * kSlabPitch;
         uint32_t my_use = 0;                                      // chunks this group has processed
         const int n_passes = p.HN / 32;                           // 32-column passes per chunk
         const uint32_t a2_row = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);   // SW128 K-major tile, row = accumulator row
+        const int n_out_chunks = (p.C + 31) / 32;
+
+        // D2 of tile `ot` (+ b2 + residual) -> fp32.  32-column TMEM chunks, staged 16 columns at a time.
+        auto output_tile = [&](int ot) {
+            const int it = ot;                                    // (trace macro)
+            const int d2b = p.pipelined ? (ot & 1) : 0;
+            if (quad == 0 && lane == 0) MLP_TRACE(50 + grp, 0);
+            mbar_wait(d2_full + 8 * d2b, (p.pipelined ? (ot >> 1) : ot) & 1);
+            tc_fence_after();
+            if (quad == 0 && lane == 0) MLP_TRACE(60 + grp, 0);
+            const uint32_t d2_tmem = tmem_base + kD2Col + d2b * 128;
+            const long long row_base = (long long)(blockIdx.x + ot * gridDim.x) * kBM;
+            const int rows_valid = (int)((p.M - row_base) < kBM ? (p.M - row_base) : kBM);
+            const int slab_rows = rows_valid - quad * 32;
+            const long long row_lane = row_base + quad * 32 + lane_r;
+            for (int c = grp; c < n_out_chunks; c += kNB) {
+                // residual loads of both 16-column halves go out first, the TMEM read and the staging overlap them
+                float4 res[2][4];
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        res[hf][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (lane_r + 8 * q < slab_rows && c * 32 + 16 * hf < p.C)
+                            res[hf][q] = __ldg(reinterpret_cast<const float4*>(p.residual + (row_lane + 8 * q) * p.C + c * 32 + 16 * hf + 4 * ci));
+                    }
+                uint32_t v[32];
+                tmem_ld32(d2_tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32), v);
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int nb = c * 32 + 16 * hf;
+                    if (nb >= p.C) break;                      // warp-uniform
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.b2 + nb) + i);
+                        *reinterpret_cast<float4*>(stg_wr + 4 * i) =
+                            make_float4(__uint_as_float(v[16 * hf + 4 * i]) + b4.x, __uint_as_float(v[16 * hf + 4 * i + 1]) + b4.y,
+                                        __uint_as_float(v[16 * hf + 4 * i + 2]) + b4.z, __uint_as_float(v[16 * hf + 4 * i + 3]) + b4.w);
+                    }
+                    __syncwarp();
+                    const int col = nb + 4 * ci;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (!(lane_r + 8 * q < slab_rows)) continue;
+                        float4 val = *reinterpret_cast<const float4*>(stg_rd + 8 * q * kSlabPitch);
+                        val.x += res[hf][q].x; val.y += res[hf][q].y; val.z += res[hf][q].z; val.w += res[hf][q].w;
+                        *reinterpret_cast<float4*>(p.out + (row_lane + 8 * q) * p.C + col) = val;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(d2_empty + 8 * d2b);
+            if (quad == 0 && lane == 0) MLP_TRACE(70 + grp, 0);
+        };
+
         for (int it = 0; it < n_my_tiles; ++it) {
-            const int m_tile = blockIdx.x + it * gridDim.x;
-            {   // pull this warp's share of the residual tile towards L2 now; the output epilogue reads it ~10 us later
-                const long long rb = (long long)m_tile * kBM + quad * 32 + lane_r;
+            {   // pull this warp's share of the residual tile towards L2 now; the output epilogue reads it microseconds later
+                const long long rb = (long long)(blockIdx.x + it * gridDim.x) * kBM + quad * 32 + lane_r;
                 for (int c = grp; c * 32 < p.C; c += kNB)
                     for (int q = 0; q < 4; ++q)
                         if (rb + 8 * q < p.M && ci < 2 && c * 32 + 16 * ci < p.C)
@@ -399,12 +471,12 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 mbar_wait(d1_full + 8 * grp, my_use & 1);
                 tc_fence_after();
                 if (quad == 0 && lane == 0) MLP_TRACE(30 + grp, j);
-                mbar_wait(a2_empty + 8 * grp, (my_use & 1) ^ 1);         // GEMM2(j - kNB) has finished reading this A2 buffer
+                mbar_wait(a2_empty + 8 * grp, (my_use & 1) ^ 1);         // GEMM2 of the chunk kNB earlier has finished reading this A2 buffer
                 ++my_use;
                 for (int cc = 0; cc < n_passes; ++cc) {
                     uint32_t v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(grp * kD1Stride + cc * 32), v);
-                    if (cc + 1 == n_passes) {                            // last read of D1[grp]: GEMM1(j + kNB) may overwrite it
+                    if (cc + 1 == n_passes) {                            // last read of D1[grp]: the GEMM1 kNB chunks later may overwrite it
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(d1_empty + 8 * grp);
@@ -447,60 +519,16 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (lane == 0) mbar_arrive(a2_full + 8 * grp);
                 if (quad == 0 && lane == 0) MLP_TRACE(40 + grp, j);
             }
-            // ---- output epilogue: D2 (+ b2 + residual) -> fp32.  32-column TMEM chunks, staged 16 columns at a time.
-            if (quad == 0 && lane == 0) MLP_TRACE(50 + grp, 0);
-            mbar_wait(d2_full, it & 1);
-            tc_fence_after();
-            if (quad == 0 && lane == 0) MLP_TRACE(60 + grp, 0);
-            const long long row_base = (long long)m_tile * kBM;
-            const int rows_valid = (int)((p.M - row_base) < kBM ? (p.M - row_base) : kBM);
-            const int slab_rows = rows_valid - quad * 32;
-            const long long row_lane = row_base + quad * 32 + lane_r;
-            const int n_chunks = (p.C + 31) / 32;
-            for (int c = grp; c < n_chunks; c += kNB) {
-                // residual loads of both 16-column halves go out first, the TMEM read and the staging overlap them
-                float4 res[2][4];
-#pragma unroll
-                for (int hf = 0; hf < 2; ++hf)
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        res[hf][q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (lane_r + 8 * q < slab_rows && c * 32 + 16 * hf < p.C)
-                            res[hf][q] = __ldg(reinterpret_cast<const float4*>(p.residual + (row_lane + 8 * q) * p.C + c * 32 + 16 * hf + 4 * ci));
-                    }
-                uint32_t v[32];
-                tmem_ld32(d2_tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32), v);
-#pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-                    const int nb = c * 32 + 16 * hf;
-                    if (nb >= p.C) break;                      // warp-uniform
-                    __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.b2 + nb) + i);
-                        *reinterpret_cast<float4*>(stg_wr + 4 * i) =
-                            make_float4(__uint_as_float(v[16 * hf + 4 * i]) + b4.x, __uint_as_float(v[16 * hf + 4 * i + 1]) + b4.y,
-                                        __uint_as_float(v[16 * hf + 4 * i + 2]) + b4.z, __uint_as_float(v[16 * hf + 4 * i + 3]) + b4.w);
-                    }
-                    __syncwarp();
-                    const int col = nb + 4 * ci;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        if (!(lane_r + 8 * q < slab_rows)) continue;
-                        float4 val = *reinterpret_cast<const float4*>(stg_rd + 8 * q * kSlabPitch);
-                        val.x += res[hf][q].x; val.y += res[hf][q].y; val.z += res[hf][q].z; val.w += res[hf][q].w;
-                        *reinterpret_cast<float4*>(p.out + (row_lane + 8 * q) * p.C + col) = val;
-                    }
-                }
+            if (p.pipelined) {
+                if (it > 0) output_tile(it - 1);      // tile it-1 is certainly through GEMM2 by now: no wait, off the critical path
+            } else {
+                output_tile(it);
+                // The staging slabs alias this group's A2 buffer: no warp of the group may start writing the next tile's
+                // hidden chunk into it before every warp of the group has finished reading its slab.
+                asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(d2_empty);
-            if (quad == 0 && lane == 0) MLP_TRACE(70 + grp, 0);
-            // The staging slabs alias this group's A2 buffer: no warp of the group may start writing the next tile's
-            // hidden chunk into it before every warp of the group has finished reading its slab.
-            asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
         }
+        if (p.pipelined && n_my_tiles > 0) output_tile(n_my_tiles - 1);
     }
 
     tc_fence_before();
@@ -576,14 +604,25 @@ extern "C" int l3ac_convunit_mlp_tc(const void* a, const void* w1, const float* 
     p.a_kb = (C + kBK - 1) / kBK;
     p.n_halves = (C + 127) / 128;
     p.g1_slots = (p.a_kb + 1) / 2;
-    const int fixed = 1024 + p.a_kb * kTileBytes + kNB * kTileBytes + 5 * H4 * 4 + 8 * kNumBars + 64;
-    p.ring = (kSmemLimit - fixed) / kTileBytes;
-    if (p.ring > kMaxRing) p.ring = kMaxRing;
-    if (p.ring < 2) return L3AC_EUNSUPPORTED;
-    const int slots_per_tile = p.NC * (p.g1_slots + p.n_halves);
-    p.resident = slots_per_tile <= p.ring ? 1 : 0;
-    if (p.resident) p.ring = slots_per_tile;
-    const size_t smem_bytes = (size_t)fixed + (size_t)p.ring * kTileBytes;
+    p.pipelined = C <= 128 ? 1 : 0;
+    const int fixed = 1024 + p.a_kb * kTileBytes + kNB * kTileBytes + (p.pipelined ? kStageBytes : 0) + 5 * H4 * 4 + 8 * kNumBars + 64;
+    const int slots = (kSmemLimit - fixed) / kTileBytes;          // 16 KB slots left for the two weight rings
+    const int need1 = p.NC * p.g1_slots, need2 = p.NC * p.n_halves;
+    if (slots < 4) return L3AC_EUNSUPPORTED;
+    if (need1 + need2 <= slots && need1 <= kMaxRing && need2 <= kMaxRing) {
+        p.resident = 1;
+        p.ring1 = need1;
+        p.ring2 = need2;
+    } else {      // split the slots in proportion to the slots each GEMM consumes per chunk
+        p.resident = 0;
+        p.ring1 = slots * p.g1_slots / (p.g1_slots + p.n_halves);
+        if (p.ring1 < 2) p.ring1 = 2;
+        if (p.ring1 > kMaxRing) p.ring1 = kMaxRing;
+        p.ring2 = slots - p.ring1;
+        if (p.ring2 > kMaxRing) p.ring2 = kMaxRing;
+        if (p.ring2 < 2) return L3AC_EUNSUPPORTED;
+    }
+    const size_t smem_bytes = (size_t)fixed + (size_t)(p.ring1 + p.ring2) * kTileBytes;
     const long long mt = (M + kBM - 1) / kBM;
     L3AC_CHECK_ARG(mt < (1LL << 30));
     p.num_m_tiles = (int)mt;

@@ -17,14 +17,12 @@ CSRC = ROOT / "l3ac_b200" / "csrc"
 OUT = ROOT / "gpurun_out"
 
 EVENTS = {
-    1: "prod  a_empty acquired (A load issued)",
-    10: "mma   a_full acquired",
-    11: "mma   wait a2_full ...",
-    12: "mma   a2_full acquired",
-    13: "mma   GEMM2 issued + commit",
-    14: "mma   wait d1_empty ...",
-    15: "mma   d1_empty acquired",
-    16: "mma   GEMM1 issued + commit",
+    1: "prod1 a_empty acquired (A load issued)",
+    10: "mma1  a_full acquired",
+    12: "mma2  a2_full (+ d2_empty) acquired",
+    13: "mma2  GEMM2 issued + commit",
+    15: "mma1  d1_empty acquired",
+    16: "mma1  GEMM1 issued + commit",
 }
 for g in range(4):
     EVENTS[20 + g] = f"epi{g}  wait d1_full ..."
