@@ -61,6 +61,33 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     return d;
 }
 
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    unsigned long long ra, rb, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    unsigned long long ra, rb, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+// Two lanes of  f(v) = (v + sin^2(alpha v) / (alpha + eps)) * scale + shift  (snake + folded GRN affine) with the MUFU
+// sine; the packed ops round exactly like their scalar counterparts, so this is bit-identical to the scalar formula.
+__device__ __forceinline__ float2 snake_affine2(float2 v, float2 alpha, float2 inv_alpha, float2 scale, float2 shift) {
+    const float2 t = fmul2(alpha, v);
+    const float2 s = make_float2(__sinf(t.x), __sinf(t.y));
+    v = ffma2(inv_alpha, fmul2(s, s), v);
+    return ffma2(v, scale, shift);
+}
+
 // Output-type adapters used by kernels that can emit fp32 or bf16 activations.
 template <typename T> __device__ __forceinline__ T cvt_out(float v);
 template <> __device__ __forceinline__ float cvt_out<float>(float v) { return v; }

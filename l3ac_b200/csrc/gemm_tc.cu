@@ -428,10 +428,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             const float4 i4 = *reinterpret_cast<const float4*>(s_ialpha + cb + 4 * i);
                             const float4 c4 = *reinterpret_cast<const float4*>(s_scale + cb + 4 * i);
                             const float4 h4 = *reinterpret_cast<const float4*>(s_shift + cb + 4 * i);
-                            r.x = snake_affine<PRECISE>(r.x, a4.x, i4.x, c4.x, h4.x);
-                            r.y = snake_affine<PRECISE>(r.y, a4.y, i4.y, c4.y, h4.y);
-                            r.z = snake_affine<PRECISE>(r.z, a4.z, i4.z, c4.z, h4.z);
-                            r.w = snake_affine<PRECISE>(r.w, a4.w, i4.w, c4.w, h4.w);
+                            if (PRECISE) {
+                                r.x = snake_affine<PRECISE>(r.x, a4.x, i4.x, c4.x, h4.x);
+                                r.y = snake_affine<PRECISE>(r.y, a4.y, i4.y, c4.y, h4.y);
+                                r.z = snake_affine<PRECISE>(r.z, a4.z, i4.z, c4.z, h4.z);
+                                r.w = snake_affine<PRECISE>(r.w, a4.w, i4.w, c4.w, h4.w);
+                            } else {      // packed fp32 pairs (same rounding, ~30 % fewer issued instructions)
+                                const float2 r01 = snake_affine2(make_float2(r.x, r.y), make_float2(a4.x, a4.y), make_float2(i4.x, i4.y),
+                                                                 make_float2(c4.x, c4.y), make_float2(h4.x, h4.y));
+                                const float2 r23 = snake_affine2(make_float2(r.z, r.w), make_float2(a4.z, a4.w), make_float2(i4.z, i4.w),
+                                                                 make_float2(c4.z, c4.w), make_float2(h4.z, h4.w));
+                                r = make_float4(r01.x, r01.y, r23.x, r23.y);
+                            }
                         }
                         *reinterpret_cast<float4*>(stg_wr + 4 * i) = r;
                     }

@@ -490,17 +490,13 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         const float4 i4 = reinterpret_cast<const float4*>(s_par + 2 * p.H4 + n0)[i];
                         const float4 c4 = reinterpret_cast<const float4*>(s_par + 3 * p.H4 + n0)[i];
                         const float4 h4 = reinterpret_cast<const float4*>(s_par + 4 * p.H4 + n0)[i];
-                        float r[4];
-                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, aa[4] = {a4.x, a4.y, a4.z, a4.w};
-                        const float ii[4] = {i4.x, i4.y, i4.z, i4.w};
-                        const float cc4[4] = {c4.x, c4.y, c4.z, c4.w}, hh[4] = {h4.x, h4.y, h4.z, h4.w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            float x = __uint_as_float(v[4 * i + e]) + bb[e];
-                            const float sn = __sinf(aa[e] * x);
-                            x = fmaf(ii[e], sn * sn, x);
-                            r[e] = fmaf(x, cc4[e], hh[e]);
-                        }
+                        // packed fp32 (FADD2 / FMUL2 / FFMA2): the epilogue warps are issue-bound, and the packed ops round
+                        // exactly like the scalar ones
+                        const float2 x01 = fadd2(make_float2(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])), make_float2(b4.x, b4.y));
+                        const float2 x23 = fadd2(make_float2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])), make_float2(b4.z, b4.w));
+                        const float2 r01 = snake_affine2(x01, make_float2(a4.x, a4.y), make_float2(i4.x, i4.y), make_float2(c4.x, c4.y), make_float2(h4.x, h4.y));
+                        const float2 r23 = snake_affine2(x23, make_float2(a4.z, a4.w), make_float2(i4.z, i4.w), make_float2(c4.z, c4.w), make_float2(h4.z, h4.w));
+                        const float r[4] = {r01.x, r01.y, r23.x, r23.y};
                         const __nv_bfloat162 h01 = __floats2bfloat162_rn(r[0], r[1]), h23 = __floats2bfloat162_rn(r[2], r[3]);
                         pk[2 * i] = *reinterpret_cast<const uint32_t*>(&h01);
                         pk[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&h23);
