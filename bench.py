@@ -294,21 +294,30 @@ def main():
             for k, o in sorted(by_op.items(), key=lambda kv: -kv[1]["ms"]):
                 fh.write(f"# {k:22s} n={o['launches']:4d} {o['ms']:8.2f} ms  {o['gflop'] / max(o['ms'], 1e-9):8.1f} TF/s "
                          f"{o['mb'] / max(o['ms'], 1e-9):8.0f} GB/s\n")
-    tc = [(f, b, a.elapsed_time(c)) for k, f, b, a, c in records if k in ("gemm_tc", "gemm_tc_split")]
+    TC_KINDS = ("convunit_mlp_tc", "gemm_tc", "gemm_tc_split")       # the tcgen05 kernels of the path
+    tc = [(k, f, b, a.elapsed_time(c)) for k, f, b, a, c in records if k in TC_KINDS]
     f32 = [(f, b, a.elapsed_time(c)) for k, f, b, a, c in records if k == "gemm_f32"]
-    tc_ms, tc_flops = sum(t for _, _, t in tc), sum(f for f, _, _ in tc)
+    tc_ms, tc_flops = sum(t for _, _, _, t in tc), sum(f for _, f, _, _ in tc)
     f32_ms, f32_flops = sum(t for _, _, t in f32), sum(f for f, _, _ in f32)
     roofline = None
     if tc:
         ach = tc_flops / (tc_ms * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM incl. 3-term split launches, all launches of one step; "
-                                                   "split launches are counted at their algorithmic 2*M*N*K, not 3x)",
+        per_kernel = {}
+        for kind in TC_KINDS:
+            sel = [(f, t) for k, f, _, t in tc if k == kind]
+            if sel:
+                kf, kt = sum(f for f, _ in sel), sum(t for _, t in sel)
+                per_kernel[kind] = {"launches": len(sel), "ms": round(kt, 3), "achieved": kf / (kt * 1e-3) / 1e12,
+                                    "frac": kf / (kt * 1e-3) / 1e12 / pk["tf_sustained"], "share_of_step": kt / inst_ms}
+        roofline = {"bound": "tensor", "kernel": "tcgen05 kernels of one step: convunit_mlp_kernel (fused ConvUnit MLP, hidden activation in "
+                                                   "TMEM/smem) + gemm_tc_kernel (bf16 GEMM incl. 3-term split launches, counted at their "
+                                                   "algorithmic 2*M*N*K, not 3x)",
                     "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
                     "traffic": None, "peak_source": f"{pk['src']} (sustained bf16)", "launches": len(tc),
-                    "share_of_step": tc_ms / inst_ms, "flops_per_step": tc_flops,
+                    "share_of_step": tc_ms / inst_ms, "flops_per_step": tc_flops, "per_kernel": per_kernel,
                     "note": "durations from one single-stream instrumented step (%.2f ms); the timed steps overlap "
                             "micro-batches on %d streams" % (inst_ms, saved_streams)}
-    hbm_ops = {k: o for k, o in by_op.items() if not k.startswith("gemm")}
+    hbm_ops = {k: o for k, o in by_op.items() if not k.startswith("gemm") and k != "convunit_mlp_tc"}
     hbm_ms, hbm_mb = sum(o["ms"] for o in hbm_ops.values()), sum(o["mb"] for o in hbm_ops.values())
     total_gflop = GFLOP_PER_10S.get(args.config, 0.0) * secs / 10.0 * B
     extras = {

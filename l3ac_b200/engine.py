@@ -99,7 +99,7 @@ class Engine:
         # 222 vs 298 us; at C=256 the fused kernel re-streams 1 MB of weights per 128-row tile and is L2-bound at parity
         # (282 vs 280 us), so the two-GEMM path keeps that width.
         self.fused_mlp = True
-        self.fused_mlp_max_c = 128
+        self.fused_mlp_max_c = 256
         self.hidden_block_bytes = 0              # >0: L2-blocked ConvUnit MLP (measured slower, see _run_conv_unit)
         self.dec_dtype = torch.bfloat16 if precision == "bf16" else torch.float32
         self.enc_dtype = ops.SPLIT if encoder_precision == "split" else torch.float32
