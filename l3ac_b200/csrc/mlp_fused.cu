@@ -28,6 +28,8 @@
 // waterfall (~200 cycles per MMA, measured with tools/mlp_trace.py).
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace l3ac {
@@ -43,10 +45,9 @@ constexpr int kEpiWarps = 4 * kNB;
 constexpr int kThreads = 32 * (kEpiWarp0 + kEpiWarps);
 constexpr int kSlabPitch = 20;                 // floats per staged row: 16 columns + 4 pad (conflict-free float4 access)
 constexpr int kSlabBytes = 32 * kSlabPitch * 4;   // 2560 B per warp
-constexpr int kStageBytes = kEpiWarps * kSlabBytes;   // 40 KB of dedicated staging in pipelined mode
 constexpr int kD1Stride = 64;                  // TMEM columns per D1 buffer
 constexpr int kD2Col = kNB * kD1Stride;        // D2 starts after the D1 buffers: 256 + C (or 2 x 128) <= 512
-constexpr int kNumBars = 4 * kMaxRing + 2 + 4 * kNB + 4;
+constexpr int kNumBars = 4 * kMaxRing + 4 + 4 * kNB + 4;
 constexpr int kSmemLimit = 227 * 1024;
 
 struct Params {
@@ -63,7 +64,11 @@ struct Params {
     int a_kb;                 // k-blocks of the activation tile = ceil(C / 64)
     int g1_slots;             // W1 ring slots per GEMM1 = ceil(a_kb / 2)
     int n_halves;             // GEMM2 N splits of <= 128 output columns (one W2 ring slot each)
-    int ring1, ring2;         // ring depths (16 KB slots)
+    int ring1, ring2;         // ring depths
+    int slot1_bytes;          // W1 ring slot: one or two [64 x 64] boxes (8 / 16 KB)
+    int slot2_bytes;          // W2 ring slot: one [w2_rows x 64] box
+    int w2_rows;              // rows of a W2 box = min(C, 128) rounded up to 16
+    int a_bufs;               // activation tile buffers (2: the next tile's load overlaps this tile's GEMM1s)
     int resident;             // each ring holds a whole tile's slots: weights are loaded once per CTA and stay
     int pipelined;            // C <= 128: two D2 buffers, dedicated staging, output(t) after chunks(t+1)
     int num_m_tiles;
@@ -141,6 +146,15 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(pred));
     return pred != 0;
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -174,24 +188,24 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-    // layout (1024-aligned tiles first): A [a_kb], A2 [kNB], W1 ring, W2 ring, staging (pipelined), parameters, barriers
+    // layout (1024-aligned tiles first): A [a_bufs][a_kb], A2 [kNB], W1 ring, W2 ring, staging (pipelined), parameters, barriers
     const uint32_t a_base = smem_base;
-    const uint32_t a2_base = a_base + p.a_kb * kTileBytes;
+    const uint32_t a2_base = a_base + p.a_bufs * p.a_kb * kTileBytes;
     const uint32_t ring1_base = a2_base + kNB * kTileBytes;
-    const uint32_t ring2_base = ring1_base + p.ring1 * kTileBytes;
-    const uint32_t stage_base = ring2_base + p.ring2 * kTileBytes;
-    // per-column epilogue parameters [5][H4] (b1, alpha, 1/(alpha+eps), scale, shift): staged once -- with ~220 KB of
+    const uint32_t ring2_base = ring1_base + p.ring1 * p.slot1_bytes;
+    const uint32_t stage_base = ring2_base + p.ring2 * p.slot2_bytes;
+    // per-column epilogue parameters [5][H4] (b1, alpha, 1/(alpha+eps), scale, shift) and b2 [C]: staged once -- with ~220 KB of
     // shared memory carved out there is next to no L1 left, and a global load per use is an exposed L2 round trip
-    const uint32_t par_base = stage_base + (p.pipelined ? kStageBytes : 0);
+    const uint32_t par_base = stage_base + (p.pipelined ? kEpiWarps * kSlabBytes : 0);
     float* s_par = reinterpret_cast<float*>(smem_gen + (par_base - smem_base));
-    const uint32_t bar_base = par_base + 5 * p.H4 * 4;
+    const uint32_t bar_base = par_base + (5 * p.H4 + p.C) * 4;
     const uint32_t r1_full = bar_base;                         // [kMaxRing]
     const uint32_t r1_empty = r1_full + 8 * kMaxRing;          // [kMaxRing]
     const uint32_t r2_full = r1_empty + 8 * kMaxRing;          // [kMaxRing]
     const uint32_t r2_empty = r2_full + 8 * kMaxRing;          // [kMaxRing]
-    const uint32_t a_full = r2_empty + 8 * kMaxRing;           // [1]
-    const uint32_t a_empty = a_full + 8;                       // [1]
-    const uint32_t d1_full = a_empty + 8;                      // [kNB]
+    const uint32_t a_full = r2_empty + 8 * kMaxRing;           // [2]
+    const uint32_t a_empty = a_full + 16;                      // [2]
+    const uint32_t d1_full = a_empty + 16;                     // [kNB]
     const uint32_t d1_empty = d1_full + 8 * kNB;               // [kNB]
     const uint32_t a2_full = d1_empty + 8 * kNB;               // [kNB]
     const uint32_t a2_empty = a2_full + 8 * kNB;               // [kNB]
@@ -213,8 +227,10 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_init(r2_full + 8 * s, 1);
             mbar_init(r2_empty + 8 * s, 1);
         }
-        mbar_init(a_full, 1);
-        mbar_init(a_empty, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(a_full + 8 * i, 1);
+            mbar_init(a_empty + 8 * i, 1);
+        }
         for (int i = 0; i < kNB; ++i) {
             mbar_init(d1_full + 8 * i, 1);
             mbar_init(d1_empty + 8 * i, 4);       // each D1 / A2 buffer belongs to one group of four warps
@@ -233,6 +249,7 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         s_par[2 * p.H4 + i] = p.ialpha[i];
         s_par[3 * p.H4 + i] = p.scale[i];
         s_par[4 * p.H4 + i] = p.shift[i];
+        if (i < p.C) s_par[5 * p.H4 + i] = p.b2[i];
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
@@ -254,11 +271,13 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint32_t w1_box = p.HN * kBK * 2;
         for (int it = 0; it < n_my_tiles; ++it) {
             const int m_tile = blockIdx.x + it * gridDim.x;
-            mbar_wait(a_empty, (it & 1) ^ 1);                 // the previous tile's GEMM1s have finished reading A
+            const int ab = it % p.a_bufs;
+            mbar_wait(a_empty + 8 * ab, ((it / p.a_bufs) & 1) ^ 1);      // the GEMM1s that read this buffer have finished
             if (leader) MLP_TRACE(1, 0);
             if (leader) {
-                mbar_arrive_expect_tx(a_full, p.a_kb * kTileBytes);
-                for (int kb = 0; kb < p.a_kb; ++kb) tma_load_2d(a_base + kb * kTileBytes, &tmA, kb * kBK, m_tile * kBM, a_full);
+                mbar_arrive_expect_tx(a_full + 8 * ab, p.a_kb * kTileBytes);
+                for (int kb = 0; kb < p.a_kb; ++kb)
+                    tma_load_2d(a_base + (ab * p.a_kb + kb) * kTileBytes, &tmA, kb * kBK, m_tile * kBM, a_full + 8 * ab);
             }
             if (p.resident && it > 0) continue;               // resident weights are loaded once per CTA
             for (int j = 0; j < p.NC; ++j)
@@ -268,7 +287,7 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (leader) {
                         mbar_arrive_expect_tx(r1_full + 8 * rs, nkb * w1_box);
                         for (int e = 0; e < nkb; ++e)
-                            tma_load_2d(ring1_base + rs * kTileBytes + e * (kTileBytes / 2), &tmW1, (kb0 + e) * kBK, j * p.HN,
+                            tma_load_2d(ring1_base + rs * p.slot1_bytes + e * (kTileBytes / 2), &tmW1, (kb0 + e) * kBK, j * p.HN,
                                         r1_full + 8 * rs);
                     }
                     if (++rs == p.ring1) {
@@ -282,14 +301,14 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const bool leader = elect_one();
         int rs = 0;
         uint32_t rphase = 0;
-        const uint32_t w2_box = kBM * kBK * 2;
+        const uint32_t w2_box = p.w2_rows * kBK * 2;
         for (int it = 0; it < (p.resident ? 1 : n_my_tiles); ++it)
             for (int j = 0; j < p.NC; ++j)
                 for (int h = 0; h < p.n_halves; ++h) {
                     mbar_wait(r2_empty + 8 * rs, rphase ^ 1);
                     if (leader) {
                         mbar_arrive_expect_tx(r2_full + 8 * rs, w2_box);
-                        tma_load_2d(ring2_base + rs * kTileBytes, &tmW2, j * p.HN, h * 128, r2_full + 8 * rs);
+                        tma_load_2d(ring2_base + rs * p.slot2_bytes, &tmW2, j * p.HN, h * 128, r2_full + 8 * rs);
                     }
                     if (++rs == p.ring2) {
                         rs = 0;
@@ -304,11 +323,17 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint32_t rphase = 0;
         uint32_t seq = 0;                          // chunk sequence number of this CTA, across tiles
         const uint32_t idesc1 = make_idesc(p.HN);
+        // descriptors differ only in the 14-bit (address >> 4) field: keep the bases and add offsets in the issue loop
+        const uint64_t a_desc0 = make_sw128_desc(a_base), w_desc0 = make_sw128_desc(ring1_base);
+        const int k16_last = (p.C - (p.a_kb - 1) * kBK + 15) / 16;      // K16 steps of the last k-block
+        const uint32_t slot1_q = (uint32_t)p.slot1_bytes >> 4;
         for (int it = 0; it < n_my_tiles; ++it) {
             const bool ring_sync = !(p.resident && it > 0);    // resident mode: only the first tile waits for weight slots
-            mbar_wait(a_full, it & 1);
+            const int ab = it % p.a_bufs;
+            mbar_wait(a_full + 8 * ab, (it / p.a_bufs) & 1);
             tc_fence_after();
             if (leader) MLP_TRACE(10, 0);
+            const uint64_t a_tile = a_desc0 + (uint64_t)((uint32_t)(ab * p.a_kb) * (kTileBytes >> 4));
             for (int j = 0; j < p.NC; ++j, ++seq) {
                 const int buf = seq % kNB;
                 mbar_wait(d1_empty + 8 * buf, ((seq / kNB) & 1) ^ 1);       // the group has drained this D1 buffer
@@ -320,16 +345,17 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         mbar_wait(r1_full + 8 * rs, rphase);
                         tc_fence_after();
                     }
-                    for (int e = 0; e < 2 && 2 * q + e < p.a_kb; ++e) {
-                        const int kb = 2 * q + e;
-                        const uint64_t a_desc = make_sw128_desc(a_base + kb * kTileBytes);
-                        const uint64_t b_desc = make_sw128_desc(ring1_base + rs * kTileBytes + e * (kTileBytes / 2));
-                        const int k_left = p.C - kb * kBK;
-                        const int k16 = k_left >= kBK ? kBK / 16 : (k_left + 15) / 16;
-                        if (leader)
+                    if (leader) {
+                        const uint64_t b0 = w_desc0 + (uint64_t)((uint32_t)rs * slot1_q);
+                        for (int e = 0; e < 2 && 2 * q + e < p.a_kb; ++e) {
+                            const int kb = 2 * q + e;
+                            const uint64_t a_desc = a_tile + (uint64_t)((uint32_t)kb * (kTileBytes >> 4));
+                            const uint64_t b_desc = b0 + (uint64_t)((uint32_t)e * (kTileBytes >> 5));
+                            const int k16 = kb == p.a_kb - 1 ? k16_last : kBK / 16;
                             for (int k = 0; k < k16; ++k) tc_mma_f16(d1, a_desc + 2 * k, b_desc + 2 * k, idesc1, (kb > 0 || k > 0) ? 1u : 0u);
+                        }
+                        if (!p.resident) tc_commit(r1_empty + 8 * rs);
                     }
-                    if (leader && !p.resident) tc_commit(r1_empty + 8 * rs);
                     if (++rs == p.ring1) {
                         rs = 0;
                         rphase ^= 1;
@@ -337,7 +363,7 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
                 if (leader) {
                     tc_commit(d1_full + 8 * buf);
-                    if (j == p.NC - 1) tc_commit(a_empty);           // last GEMM1 of the tile: A is free once it completes
+                    if (j == p.NC - 1) tc_commit(a_empty + 8 * ab);      // last GEMM1 on this A buffer: free once it completes
                 }
                 if (leader) MLP_TRACE(16, j);
             }
@@ -350,6 +376,10 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         int rs = 0;
         uint32_t rphase = 0;
         uint32_t seq = 0;
+        const uint64_t a2_desc0 = make_sw128_desc(a2_base), w_desc0 = make_sw128_desc(ring2_base);
+        const uint32_t slot2_q = (uint32_t)p.slot2_bytes >> 4;
+        const uint32_t idesc_full = make_idesc(p.w2_rows);                                  // every half but possibly the last
+        const uint32_t idesc_last = make_idesc((p.C - (p.n_halves - 1) * 128 + 15) & ~15);  // UMMA N is a multiple of 16; extra W2 rows are TMA zero fill
         for (int it = 0; it < n_my_tiles; ++it) {
             const bool ring_sync = !(p.resident && it > 0);
             const int d2b = p.pipelined ? (it & 1) : 0;
@@ -361,17 +391,17 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     mbar_wait(d2_empty + 8 * d2b, ((p.pipelined ? (it >> 1) : it) & 1) ^ 1);
                 tc_fence_after();
                 if (leader) MLP_TRACE(12, j);
-                const uint64_t a_desc = make_sw128_desc(a2_base + buf * kTileBytes);
+                const uint64_t a_desc = a2_desc0 + (uint64_t)((uint32_t)buf * (kTileBytes >> 4));
                 for (int h = 0; h < p.n_halves; ++h) {
                     if (ring_sync) {
                         mbar_wait(r2_full + 8 * rs, rphase);
                         tc_fence_after();
                     }
-                    const uint64_t b_desc = make_sw128_desc(ring2_base + rs * kTileBytes);
-                    const int n = min(128, (p.C - h * 128 + 15) & ~15);    // UMMA N is a multiple of 16; extra W2 rows are TMA zero fill
-                    const uint32_t idesc2 = make_idesc(n);
                     if (leader) {
-                        for (int k = 0; k < p.HN / 16; ++k)
+                        const uint64_t b_desc = w_desc0 + (uint64_t)((uint32_t)rs * slot2_q);
+                        const uint32_t idesc2 = h == p.n_halves - 1 ? idesc_last : idesc_full;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)      // HN = 64: four K16 steps
                             tc_mma_f16(d2_tmem + h * 128, a_desc + 2 * k, b_desc + 2 * k, idesc2, (j > 0 || k > 0) ? 1u : 0u);
                         if (!p.resident) tc_commit(r2_empty + 8 * rs);
                     }
@@ -392,7 +422,7 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int grp = (warp - kEpiWarp0) >> 2;                  // group index = D1 / A2 buffer index
         MLP_TRACE_DECL(2 + grp)
         const int row = quad * 32 + lane;                         // accumulator row of this thread
-        float* stg = p.pipelined ? reinterpret_cast<float*>(smem_gen + (stage_base - smem_base) + (warp - kEpiWarp0) * kSlabBytes)
+        float* stg = p.pipelined ? reinterpret_cast<float*>(smem_gen + (stage_base - smem_base) + (grp * 4 + quad) * kSlabBytes)
                                  : reinterpret_cast<float*>(smem_gen + (a2_base - smem_base) + grp * kTileBytes + quad * kSlabBytes);
         const int lane_r = lane >> 2, ci = lane & 3;              // coalesced output phase: 8 rows x 4 float4 (16 columns) per pass
         const float* stg_rd = stg + lane_r * kSlabPitch + 4 * ci;
@@ -400,7 +430,7 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint32_t my_use = 0;                                      // chunks this group has processed
         const int n_passes = p.HN / 32;                           // 32-column passes per chunk
         const uint32_t a2_row = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);   // SW128 K-major tile, row = accumulator row
-        const int n_out_chunks = (p.C + 31) / 32;
+        const int n_out_tasks = p.C / 16;                         // 16-column output slices per tile (C % 16 == 0)
 
         // D2 of tile `ot` (+ b2 + residual) -> fp32.  32-column TMEM chunks, staged 16 columns at a time.
         auto output_tile = [&](int ot) {
@@ -415,40 +445,34 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int rows_valid = (int)((p.M - row_base) < kBM ? (p.M - row_base) : kBM);
             const int slab_rows = rows_valid - quad * 32;
             const long long row_lane = row_base + quad * 32 + lane_r;
-            for (int c = grp; c < n_out_chunks; c += kNB) {
-                // residual loads of both 16-column halves go out first, the TMEM read and the staging overlap them
-                float4 res[2][4];
+            // task = one 16-column slice of the tile; the slices rotate over the four groups from tile to tile so that
+            // narrow layers (C = 48: three slices) do not pin the whole output phase on the same groups
+            for (int t = (grp - ot % kNB + kNB) % kNB; t < n_out_tasks; t += kNB) {
+                const int nb = 16 * t;
+                float4 res[4];
 #pragma unroll
-                for (int hf = 0; hf < 2; ++hf)
+                for (int q = 0; q < 4; ++q) {
+                    res[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (lane_r + 8 * q < slab_rows) res[q] = __ldg(reinterpret_cast<const float4*>(p.residual + (row_lane + 8 * q) * p.C + nb + 4 * ci));
+                }
+                uint32_t v[16];
+                tmem_ld16(d2_tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)nb, v);
+                __syncwarp();                          // the previous slice's staged rows have been read
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        res[hf][q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (lane_r + 8 * q < slab_rows && c * 32 + 16 * hf < p.C)
-                            res[hf][q] = __ldg(reinterpret_cast<const float4*>(p.residual + (row_lane + 8 * q) * p.C + c * 32 + 16 * hf + 4 * ci));
-                    }
-                uint32_t v[32];
-                tmem_ld32(d2_tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32), v);
+                for (int i = 0; i < 4; ++i) {
+                    const float4 b4 = reinterpret_cast<const float4*>(s_par + 5 * p.H4 + nb)[i];
+                    *reinterpret_cast<float4*>(stg_wr + 4 * i) =
+                        make_float4(__uint_as_float(v[4 * i]) + b4.x, __uint_as_float(v[4 * i + 1]) + b4.y,
+                                    __uint_as_float(v[4 * i + 2]) + b4.z, __uint_as_float(v[4 * i + 3]) + b4.w);
+                }
+                __syncwarp();
+                const int col = nb + 4 * ci;
 #pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-                    const int nb = c * 32 + 16 * hf;
-                    if (nb >= p.C) break;                      // warp-uniform
-                    __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.b2 + nb) + i);
-                        *reinterpret_cast<float4*>(stg_wr + 4 * i) =
-                            make_float4(__uint_as_float(v[16 * hf + 4 * i]) + b4.x, __uint_as_float(v[16 * hf + 4 * i + 1]) + b4.y,
-                                        __uint_as_float(v[16 * hf + 4 * i + 2]) + b4.z, __uint_as_float(v[16 * hf + 4 * i + 3]) + b4.w);
-                    }
-                    __syncwarp();
-                    const int col = nb + 4 * ci;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        if (!(lane_r + 8 * q < slab_rows)) continue;
-                        float4 val = *reinterpret_cast<const float4*>(stg_rd + 8 * q * kSlabPitch);
-                        val.x += res[hf][q].x; val.y += res[hf][q].y; val.z += res[hf][q].z; val.w += res[hf][q].w;
-                        *reinterpret_cast<float4*>(p.out + (row_lane + 8 * q) * p.C + col) = val;
-                    }
+                for (int q = 0; q < 4; ++q) {
+                    if (!(lane_r + 8 * q < slab_rows)) continue;
+                    float4 val = *reinterpret_cast<const float4*>(stg_rd + 8 * q * kSlabPitch);
+                    val.x += res[q].x; val.y += res[q].y; val.z += res[q].z; val.w += res[q].w;
+                    *reinterpret_cast<float4*>(p.out + (row_lane + 8 * q) * p.C + col) = val;
                 }
             }
             tc_fence_before();
@@ -460,10 +484,10 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int it = 0; it < n_my_tiles; ++it) {
             {   // pull this warp's share of the residual tile towards L2 now; the output epilogue reads it microseconds later
                 const long long rb = (long long)(blockIdx.x + it * gridDim.x) * kBM + quad * 32 + lane_r;
-                for (int c = grp; c * 32 < p.C; c += kNB)
-                    for (int q = 0; q < 4; ++q)
-                        if (rb + 8 * q < p.M && ci < 2 && c * 32 + 16 * ci < p.C)
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual + (rb + 8 * q) * p.C + c * 32 + 16 * ci));
+                for (int t = (grp - it % kNB + kNB) % kNB; t < n_out_tasks; t += kNB)
+                    if (ci == 0)
+                        for (int q = 0; q < 4; ++q)
+                            if (rb + 8 * q < p.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual + (rb + 8 * q) * p.C + 16 * t));
             }
             // chunk j of tile `it` is number it * NC + j of this CTA's chunk sequence and lives in buffer (it * NC + j) % kNB
             for (int j = (grp - (it * p.NC) % kNB + kNB) % kNB; j < p.NC; j += kNB) {
@@ -476,6 +500,7 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 for (int cc = 0; cc < n_passes; ++cc) {
                     uint32_t v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(grp * kD1Stride + cc * 32), v);
+                    if (quad == 0 && lane == 0) MLP_TRACE(80 + grp, cc);
                     if (cc + 1 == n_passes) {                            // last read of D1[grp]: the GEMM1 kNB chunks later may overwrite it
                         tc_fence_before();
                         __syncwarp();
@@ -510,6 +535,7 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                      : "memory");
                     }
                 }
+                if (quad == 0 && lane == 0) MLP_TRACE(90 + grp, 0);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(a2_full + 8 * grp);
@@ -594,36 +620,58 @@ extern "C" int l3ac_convunit_mlp_tc(const void* a, const void* w1, const float* 
                      reinterpret_cast<uintptr_t>(b2)) & 15) == 0);
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return L3AC_EDRIVER;
+    static int a_bufs_override = -1;
+    if (a_bufs_override < 0) {
+        const char* e = getenv("L3AC_MLP_A_BUFS");       // tuning knob: force 1 or 2 activation buffers
+        a_bufs_override = e ? atoi(e) : 0;
+    }
     Params p{};
     p.b1 = b1; p.alpha = alpha; p.ialpha = ialpha; p.scale = scale; p.shift = shift; p.b2 = b2; p.residual = residual; p.out = out;
     p.M = M; p.C = C; p.H4 = H4; p.HN = HN; p.NC = H4 / HN;
     p.a_kb = (C + kBK - 1) / kBK;
     p.n_halves = (C + 127) / 128;
     p.g1_slots = (p.a_kb + 1) / 2;
+    if (HN != 64) return L3AC_EUNSUPPORTED;
     p.pipelined = C <= 128 ? 1 : 0;
-    const int fixed = 1024 + p.a_kb * kTileBytes + kNB * kTileBytes + (p.pipelined ? kStageBytes : 0) + 5 * H4 * 4 + 8 * kNumBars + 64;
-    const int slots = (kSmemLimit - fixed) / kTileBytes;          // 16 KB slots left for the two weight rings
+    p.w2_rows = ((C < 128 ? C : 128) + 15) & ~15;
+    p.slot1_bytes = p.a_kb >= 2 ? kTileBytes : kTileBytes / 2;
+    p.slot2_bytes = p.w2_rows * kBK * 2;
     const int need1 = p.NC * p.g1_slots, need2 = p.NC * p.n_halves;
-    if (slots < 4) return L3AC_EUNSUPPORTED;
-    if (need1 + need2 <= slots && need1 <= kMaxRing && need2 <= kMaxRing) {
-        p.resident = 1;
-        p.ring1 = need1;
-        p.ring2 = need2;
-    } else {      // split the slots in proportion to the slots each GEMM consumes per chunk
-        p.resident = 0;
-        p.ring1 = slots * p.g1_slots / (p.g1_slots + p.n_halves);
-        if (p.ring1 < 2) p.ring1 = 2;
-        if (p.ring1 > kMaxRing) p.ring1 = kMaxRing;
-        p.ring2 = slots - p.ring1;
-        if (p.ring2 > kMaxRing) p.ring2 = kMaxRing;
-        if (p.ring2 < 2) return L3AC_EUNSUPPORTED;
+    // Try two activation buffers first (the next tile's load then overlaps this tile's GEMM1s), fall back to one.
+    bool placed = false;
+    size_t smem_bytes = 0;
+    for (p.a_bufs = (a_bufs_override > 0 ? a_bufs_override : 2); p.a_bufs >= 1 && !placed; --p.a_bufs) {
+        const int fixed = 1024 + p.a_bufs * p.a_kb * kTileBytes + kNB * kTileBytes + (p.pipelined ? kEpiWarps * kSlabBytes : 0) +
+                          (5 * H4 + C) * 4 + 8 * kNumBars + 64;
+        const int left = kSmemLimit - fixed;
+        if (need1 <= kMaxRing && need2 <= kMaxRing && need1 * p.slot1_bytes + need2 * p.slot2_bytes <= left) {
+            p.resident = 1;
+            p.ring1 = need1;
+            p.ring2 = need2;
+        } else {
+            // at least three chunks of weights in flight per ring when two A buffers are used, two otherwise
+            p.resident = 0;
+            const int min_chunks = p.a_bufs == 2 ? 3 : 2;
+            int c = left / (p.g1_slots * p.slot1_bytes + p.n_halves * p.slot2_bytes);       // whole chunks per ring
+            if (c < min_chunks && (p.a_bufs > 1 || c < 1)) continue;
+            p.ring1 = c * p.g1_slots;
+            p.ring2 = c * p.n_halves;
+            if (p.ring1 > kMaxRing) p.ring1 = kMaxRing;
+            if (p.ring2 > kMaxRing) p.ring2 = kMaxRing;
+            // hand leftover space to the rings one slot at a time
+            while (p.ring1 < kMaxRing && fixed + (p.ring1 + 1) * p.slot1_bytes + p.ring2 * p.slot2_bytes <= kSmemLimit) ++p.ring1;
+            while (p.ring2 < kMaxRing && fixed + p.ring1 * p.slot1_bytes + (p.ring2 + 1) * p.slot2_bytes <= kSmemLimit) ++p.ring2;
+        }
+        smem_bytes = (size_t)fixed + (size_t)p.ring1 * p.slot1_bytes + (size_t)p.ring2 * p.slot2_bytes;
+        placed = true;
+        break;
     }
-    const size_t smem_bytes = (size_t)fixed + (size_t)(p.ring1 + p.ring2) * kTileBytes;
+    if (!placed) return L3AC_EUNSUPPORTED;
     const long long mt = (M + kBM - 1) / kBM;
     L3AC_CHECK_ARG(mt < (1LL << 30));
     p.num_m_tiles = (int)mt;
     CUtensorMap tmA, tmW1, tmW2;
-    if (!encode_2d(enc, &tmA, a, C, M, kBM) || !encode_2d(enc, &tmW1, w1, C, H4, HN) || !encode_2d(enc, &tmW2, w2, H4, C, 128))
+    if (!encode_2d(enc, &tmA, a, C, M, kBM) || !encode_2d(enc, &tmW1, w1, C, H4, HN) || !encode_2d(enc, &tmW2, w2, H4, C, p.w2_rows))
         return L3AC_EINVAL;
     cudaError_t e = cudaFuncSetAttribute(convunit_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e != cudaSuccess) return (int)e;

@@ -31,6 +31,8 @@ for g in range(4):
     EVENTS[50 + g] = f"epi{g}  wait d2_full ..."
     EVENTS[60 + g] = f"epi{g}  d2_full acquired"
     EVENTS[70 + g] = f"epi{g}  output done (d2_empty arrive)"
+    EVENTS[80 + g] = f"epi{g}    tmem_ld done, pass j"
+    EVENTS[90 + g] = f"epi{g}    math + st.shared done"
 
 
 def build():
