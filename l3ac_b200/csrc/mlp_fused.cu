@@ -10,13 +10,14 @@
 //
 // One persistent CTA per SM, 20 warps.  The two GEMMs are issued by different warps from different weight rings, so the
 // only coupling between them is the data flow D1 -> snake -> A2:
-//   warp 0      TMA producer 1: the 128 x C activation tile and the W1 ring (two [64 hidden x 64 k] boxes per 16 KB slot)
-//   warp 1      GEMM1 issuer: D1[b] = A . W1[chunk]^T into one of FOUR 64-column TMEM buffers, as soon as the buffer has
-//               been drained and the slot has landed -- up to four chunks ahead of the snake epilogue
+//   warp 0      TMA producer 1: the 128 x C activation tile and the W1 ring (one [128 hidden x 64 k] box per 16 KB slot)
+//   warp 1      GEMM1 issuer: D1[b] = A . W1[super-chunk]^T, N = 128 (two 64-column chunks per MMA: every tcgen05
+//               instruction costs the issuing thread ~100 cycles here, so fewer and wider is better), into one of TWO
+//               128-column TMEM buffers, as soon as the buffer has been drained and the slots have landed
 //   warp 2      TMA producer 2: the W2 ring (one [<=128 out x 64 k] box per 16 KB slot)
 //   warp 3      GEMM2 issuer: D2 += A2[b] . W2[:, chunk]^T as soon as a hidden chunk has been written
-//   warps 4-19  epilogue, four groups of four warps (one per TMEM lane quadrant).  Group g owns D1[g] / A2[g], i.e. the
-//               chunks whose sequence number is g (mod 4).  All sixteen warps also drain D2 (+ b2 + residual -> fp32)
+//   warps 4-19  epilogue, four groups of four warps (one per TMEM lane quadrant).  Groups 2b and 2b+1 share D1[b] (one
+//               64-column half each); group g owns A2[g].  All sixteen warps also drain D2 (+ b2 + residual -> fp32)
 //               through 16-column staging slabs.
 // C <= 128 ("pipelined"): D2 is double-buffered and the staging slabs have their own shared memory, so the epilogue warps
 // run the snake chunks of tile t+1 BEFORE the output of tile t -- the residual loads and the stores of a tile are off the
@@ -62,10 +63,9 @@ struct Params {
     long long M;
     int C, H4, HN, NC;        // channels, hidden = 4C, hidden chunk width (64), number of chunks
     int a_kb;                 // k-blocks of the activation tile = ceil(C / 64)
-    int g1_slots;             // W1 ring slots per GEMM1 = ceil(a_kb / 2)
+    int NS;                   // super-chunks (128 hidden columns = two chunks) per tile = ceil(NC / 2)
     int n_halves;             // GEMM2 N splits of <= 128 output columns (one W2 ring slot each)
     int ring1, ring2;         // ring depths
-    int slot1_bytes;          // W1 ring slot: one or two [64 x 64] boxes (8 / 16 KB)
     int slot2_bytes;          // W2 ring slot: one [w2_rows x 64] box
     int w2_rows;              // rows of a W2 box = min(C, 128) rounded up to 16
     int a_bufs;               // activation tile buffers (2: the next tile's load overlaps this tile's GEMM1s)
@@ -192,7 +192,7 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t a_base = smem_base;
     const uint32_t a2_base = a_base + p.a_bufs * p.a_kb * kTileBytes;
     const uint32_t ring1_base = a2_base + kNB * kTileBytes;
-    const uint32_t ring2_base = ring1_base + p.ring1 * p.slot1_bytes;
+    const uint32_t ring2_base = ring1_base + p.ring1 * kTileBytes;
     const uint32_t stage_base = ring2_base + p.ring2 * p.slot2_bytes;
     // per-column epilogue parameters [5][H4] (b1, alpha, 1/(alpha+eps), scale, shift) and b2 [C]: staged once -- with ~220 KB of
     // shared memory carved out there is next to no L1 left, and a global load per use is an exposed L2 round trip
@@ -232,9 +232,9 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_init(a_empty + 8 * i, 1);
         }
         for (int i = 0; i < kNB; ++i) {
-            mbar_init(d1_full + 8 * i, 1);
-            mbar_init(d1_empty + 8 * i, 4);       // each D1 / A2 buffer belongs to one group of four warps
-            mbar_init(a2_full + 8 * i, 4);
+            mbar_init(d1_full + 8 * i, 1);        // (only [0..1] are used: two 128-column D1 buffers)
+            mbar_init(d1_empty + 8 * i, 8);       // a D1 buffer is shared by a pair of groups (eight warps)
+            mbar_init(a2_full + 8 * i, 4);        // an A2 buffer belongs to one group of four warps
             mbar_init(a2_empty + 8 * i, 1);
         }
         for (int i = 0; i < 2; ++i) {
@@ -268,7 +268,6 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const bool leader = elect_one();
         int rs = 0;
         uint32_t rphase = 0;
-        const uint32_t w1_box = p.HN * kBK * 2;
         for (int it = 0; it < n_my_tiles; ++it) {
             const int m_tile = blockIdx.x + it * gridDim.x;
             const int ab = it % p.a_bufs;
@@ -280,15 +279,12 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     tma_load_2d(a_base + (ab * p.a_kb + kb) * kTileBytes, &tmA, kb * kBK, m_tile * kBM, a_full + 8 * ab);
             }
             if (p.resident && it > 0) continue;               // resident weights are loaded once per CTA
-            for (int j = 0; j < p.NC; ++j)
-                for (int q = 0; q < p.g1_slots; ++q) {        // two consecutive W1 k-blocks share a slot (8 KB halves)
-                    const int kb0 = 2 * q, nkb = (kb0 + 1 < p.a_kb) ? 2 : 1;
+            for (int sc = 0; sc < p.NS; ++sc)
+                for (int kb = 0; kb < p.a_kb; ++kb) {         // one [128 hidden x 64 k] box per slot (rows past 4C are zero fill)
                     mbar_wait(r1_empty + 8 * rs, rphase ^ 1);
                     if (leader) {
-                        mbar_arrive_expect_tx(r1_full + 8 * rs, nkb * w1_box);
-                        for (int e = 0; e < nkb; ++e)
-                            tma_load_2d(ring1_base + rs * p.slot1_bytes + e * (kTileBytes / 2), &tmW1, (kb0 + e) * kBK, j * p.HN,
-                                        r1_full + 8 * rs);
+                        mbar_arrive_expect_tx(r1_full + 8 * rs, kTileBytes);
+                        tma_load_2d(ring1_base + rs * kTileBytes, &tmW1, kb * kBK, sc * 128, r1_full + 8 * rs);
                     }
                     if (++rs == p.ring1) {
                         rs = 0;
@@ -316,17 +312,16 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
                 }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ GEMM1 issuer: D1[seq % kNB] = A . W1[chunk]^T
+        // ------------------------------------------------------------------ GEMM1 issuer: D1[sseq % 2] = A . W1[super-chunk]^T
         MLP_TRACE_DECL(1)
         const bool leader = elect_one();
         int rs = 0;
         uint32_t rphase = 0;
-        uint32_t seq = 0;                          // chunk sequence number of this CTA, across tiles
-        const uint32_t idesc1 = make_idesc(p.HN);
+        uint32_t sseq = 0;                         // super-chunk sequence number of this CTA, across tiles
+        const uint32_t idesc1 = make_idesc(128);
         // descriptors differ only in the 14-bit (address >> 4) field: keep the bases and add offsets in the issue loop
         const uint64_t a_desc0 = make_sw128_desc(a_base), w_desc0 = make_sw128_desc(ring1_base);
         const int k16_last = (p.C - (p.a_kb - 1) * kBK + 15) / 16;      // K16 steps of the last k-block
-        const uint32_t slot1_q = (uint32_t)p.slot1_bytes >> 4;
         for (int it = 0; it < n_my_tiles; ++it) {
             const bool ring_sync = !(p.resident && it > 0);    // resident mode: only the first tile waits for weight slots
             const int ab = it % p.a_bufs;
@@ -334,26 +329,22 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tc_fence_after();
             if (leader) MLP_TRACE(10, 0);
             const uint64_t a_tile = a_desc0 + (uint64_t)((uint32_t)(ab * p.a_kb) * (kTileBytes >> 4));
-            for (int j = 0; j < p.NC; ++j, ++seq) {
-                const int buf = seq % kNB;
-                mbar_wait(d1_empty + 8 * buf, ((seq / kNB) & 1) ^ 1);       // the group has drained this D1 buffer
+            for (int sc = 0; sc < p.NS; ++sc, ++sseq) {
+                const int sb = sseq & 1;
+                mbar_wait(d1_empty + 8 * sb, ((sseq >> 1) & 1) ^ 1);        // both groups of the pair have drained this D1 buffer
                 tc_fence_after();
-                if (leader) MLP_TRACE(15, j);
-                const uint32_t d1 = tmem_base + buf * kD1Stride;
-                for (int q = 0; q < p.g1_slots; ++q) {
+                if (leader) MLP_TRACE(15, sc);
+                const uint32_t d1 = tmem_base + sb * 128;
+                for (int kb = 0; kb < p.a_kb; ++kb) {
                     if (ring_sync) {
                         mbar_wait(r1_full + 8 * rs, rphase);
                         tc_fence_after();
                     }
                     if (leader) {
-                        const uint64_t b0 = w_desc0 + (uint64_t)((uint32_t)rs * slot1_q);
-                        for (int e = 0; e < 2 && 2 * q + e < p.a_kb; ++e) {
-                            const int kb = 2 * q + e;
-                            const uint64_t a_desc = a_tile + (uint64_t)((uint32_t)kb * (kTileBytes >> 4));
-                            const uint64_t b_desc = b0 + (uint64_t)((uint32_t)e * (kTileBytes >> 5));
-                            const int k16 = kb == p.a_kb - 1 ? k16_last : kBK / 16;
-                            for (int k = 0; k < k16; ++k) tc_mma_f16(d1, a_desc + 2 * k, b_desc + 2 * k, idesc1, (kb > 0 || k > 0) ? 1u : 0u);
-                        }
+                        const uint64_t a_desc = a_tile + (uint64_t)((uint32_t)kb * (kTileBytes >> 4));
+                        const uint64_t b_desc = w_desc0 + (uint64_t)((uint32_t)rs * (kTileBytes >> 4));
+                        const int k16 = kb == p.a_kb - 1 ? k16_last : kBK / 16;
+                        for (int k = 0; k < k16; ++k) tc_mma_f16(d1, a_desc + 2 * k, b_desc + 2 * k, idesc1, (kb > 0 || k > 0) ? 1u : 0u);
                         if (!p.resident) tc_commit(r1_empty + 8 * rs);
                     }
                     if (++rs == p.ring1) {
@@ -362,20 +353,20 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
                 }
                 if (leader) {
-                    tc_commit(d1_full + 8 * buf);
-                    if (j == p.NC - 1) tc_commit(a_empty + 8 * ab);      // last GEMM1 on this A buffer: free once it completes
+                    tc_commit(d1_full + 8 * sb);
+                    if (sc == p.NS - 1) tc_commit(a_empty + 8 * ab);     // last GEMM1 on this A buffer: free once it completes
                 }
-                if (leader) MLP_TRACE(16, j);
+                if (leader) MLP_TRACE(16, sc);
             }
             __syncwarp();
         }
     } else if (warp == 3) {
-        // ------------------------------------------------------------------ GEMM2 issuer: D2 += A2[seq % kNB] . W2[:, chunk]^T
+        // ------------------------------------------------------------------ GEMM2 issuer: D2 += A2[group] . W2[:, chunk]^T
         MLP_TRACE_DECL(6)
         const bool leader = elect_one();
         int rs = 0;
         uint32_t rphase = 0;
-        uint32_t seq = 0;
+        uint32_t sseq = 0, a2_par = 0;             // super-chunk sequence number; phase parity bit per A2 buffer
         const uint64_t a2_desc0 = make_sw128_desc(a2_base), w_desc0 = make_sw128_desc(ring2_base);
         const uint32_t slot2_q = (uint32_t)p.slot2_bytes >> 4;
         const uint32_t idesc_full = make_idesc(p.w2_rows);                                  // every half but possibly the last
@@ -384,9 +375,11 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const bool ring_sync = !(p.resident && it > 0);
             const int d2b = p.pipelined ? (it & 1) : 0;
             const uint32_t d2_tmem = tmem_base + kD2Col + d2b * 128;
-            for (int j = 0; j < p.NC; ++j, ++seq) {
-                const int buf = seq % kNB;
-                mbar_wait(a2_full + 8 * buf, (seq / kNB) & 1);               // the group wrote the bf16 hidden chunk
+            for (int j = 0; j < p.NC; ++j) {
+                // chunk j is half (j & 1) of super-chunk sseq: it was written by group 2 * (sseq & 1) + (j & 1) into its A2 buffer
+                const int buf = 2 * (int)(sseq & 1) + (j & 1);
+                mbar_wait(a2_full + 8 * buf, (a2_par >> buf) & 1);           // the group wrote the bf16 hidden chunk
+                a2_par ^= 1u << buf;
                 if (j == 0)                                                  // the output epilogue has drained this D2 buffer
                     mbar_wait(d2_empty + 8 * d2b, ((p.pipelined ? (it >> 1) : it) & 1) ^ 1);
                 tc_fence_after();
@@ -412,7 +405,9 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
                 if (leader) tc_commit(a2_empty + 8 * buf);
                 if (leader) MLP_TRACE(13, j);
+                if (j & 1) ++sseq;
             }
+            if (p.NC & 1) ++sseq;                 // a tile with an odd chunk count ends on a half-filled super-chunk
             if (leader) tc_commit(d2_full + 8 * d2b);
             __syncwarp();
         }
@@ -427,7 +422,7 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int lane_r = lane >> 2, ci = lane & 3;              // coalesced output phase: 8 rows x 4 float4 (16 columns) per pass
         const float* stg_rd = stg + lane_r * kSlabPitch + 4 * ci;
         float* stg_wr = stg + lane * kSlabPitch;
-        uint32_t my_use = 0;                                      // chunks this group has processed
+        uint32_t my_use = 0, sb_use = 0;                          // chunks this group has processed; super-chunks seen on its D1 buffer
         const int n_passes = p.HN / 32;                           // 32-column passes per chunk
         const uint32_t a2_row = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);   // SW128 K-major tile, row = accumulator row
         const int n_out_tasks = p.C / 16;                         // 16-column output slices per tile (C % 16 == 0)
@@ -489,22 +484,31 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         for (int q = 0; q < 4; ++q)
                             if (rb + 8 * q < p.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual + (rb + 8 * q) * p.C + 16 * t));
             }
-            // chunk j of tile `it` is number it * NC + j of this CTA's chunk sequence and lives in buffer (it * NC + j) % kNB
-            for (int j = (grp - (it * p.NC) % kNB + kNB) % kNB; j < p.NC; j += kNB) {
+            // super-chunk sc of tile `it` is number it * NS + sc of this CTA's sequence and lives in D1[(it * NS + sc) & 1];
+            // this group reads half (grp & 1) of the buffers with index grp >> 1
+            for (int sc = ((grp >> 1) + it * p.NS) & 1; sc < p.NS; sc += 2) {
+                const int j = 2 * sc + (grp & 1);
                 if (quad == 0 && lane == 0) MLP_TRACE(20 + grp, j);
-                mbar_wait(d1_full + 8 * grp, my_use & 1);
+                mbar_wait(d1_full + 8 * (grp >> 1), sb_use & 1);
+                ++sb_use;
                 tc_fence_after();
+                if (j >= p.NC) {                                         // half-filled super-chunk: nothing to read, hand the buffer back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(d1_empty + 8 * (grp >> 1));
+                    continue;
+                }
                 if (quad == 0 && lane == 0) MLP_TRACE(30 + grp, j);
-                mbar_wait(a2_empty + 8 * grp, (my_use & 1) ^ 1);         // GEMM2 of the chunk kNB earlier has finished reading this A2 buffer
+                mbar_wait(a2_empty + 8 * grp, (my_use & 1) ^ 1);         // GEMM2 of this group's previous chunk has finished reading the A2 buffer
                 ++my_use;
                 for (int cc = 0; cc < n_passes; ++cc) {
                     uint32_t v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(grp * kD1Stride + cc * 32), v);
+                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(grp * kD1Stride + cc * 32), v);   // D1[grp >> 1], half grp & 1
                     if (quad == 0 && lane == 0) MLP_TRACE(80 + grp, cc);
                     if (cc + 1 == n_passes) {                            // last read of D1[grp]: the GEMM1 kNB chunks later may overwrite it
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(d1_empty + 8 * grp);
+                        if (lane == 0) mbar_arrive(d1_empty + 8 * (grp >> 1));
                     }
                     const int n0 = j * p.HN + cc * 32;                   // first hidden column of this pass
                     uint32_t pk[16];
@@ -630,13 +634,12 @@ extern "C" int l3ac_convunit_mlp_tc(const void* a, const void* w1, const float* 
     p.M = M; p.C = C; p.H4 = H4; p.HN = HN; p.NC = H4 / HN;
     p.a_kb = (C + kBK - 1) / kBK;
     p.n_halves = (C + 127) / 128;
-    p.g1_slots = (p.a_kb + 1) / 2;
+    p.NS = (p.NC + 1) / 2;
     if (HN != 64) return L3AC_EUNSUPPORTED;
     p.pipelined = C <= 128 ? 1 : 0;
     p.w2_rows = ((C < 128 ? C : 128) + 15) & ~15;
-    p.slot1_bytes = p.a_kb >= 2 ? kTileBytes : kTileBytes / 2;
     p.slot2_bytes = p.w2_rows * kBK * 2;
-    const int need1 = p.NC * p.g1_slots, need2 = p.NC * p.n_halves;
+    const int need1 = p.NS * p.a_kb, need2 = p.NC * p.n_halves;
     // Try two activation buffers first (the next tile's load then overlaps this tile's GEMM1s), fall back to one.
     bool placed = false;
     size_t smem_bytes = 0;
@@ -644,25 +647,25 @@ extern "C" int l3ac_convunit_mlp_tc(const void* a, const void* w1, const float* 
         const int fixed = 1024 + p.a_bufs * p.a_kb * kTileBytes + kNB * kTileBytes + (p.pipelined ? kEpiWarps * kSlabBytes : 0) +
                           (5 * H4 + C) * 4 + 8 * kNumBars + 64;
         const int left = kSmemLimit - fixed;
-        if (need1 <= kMaxRing && need2 <= kMaxRing && need1 * p.slot1_bytes + need2 * p.slot2_bytes <= left) {
+        if (need1 <= kMaxRing && need2 <= kMaxRing && need1 * kTileBytes + need2 * p.slot2_bytes <= left) {
             p.resident = 1;
             p.ring1 = need1;
             p.ring2 = need2;
         } else {
-            // at least three chunks of weights in flight per ring when two A buffers are used, two otherwise
+            // Split what is left between the rings in proportion to the bytes each streams per pair of chunks (W1: a_kb
+            // slots of 16 KB, W2: 2 * n_halves slots).  Two A buffers are only worth it if both rings stay >= 3 deep.
             p.resident = 0;
-            const int min_chunks = p.a_bufs == 2 ? 3 : 2;
-            int c = left / (p.g1_slots * p.slot1_bytes + p.n_halves * p.slot2_bytes);       // whole chunks per ring
-            if (c < min_chunks && (p.a_bufs > 1 || c < 1)) continue;
-            p.ring1 = c * p.g1_slots;
-            p.ring2 = c * p.n_halves;
+            const double w1 = (double)p.a_kb * kTileBytes, w2 = 2.0 * p.n_halves * p.slot2_bytes;
+            p.ring1 = (int)(left * (w1 / (w1 + w2))) / kTileBytes;
+            if (p.ring1 < 2) p.ring1 = 2;
             if (p.ring1 > kMaxRing) p.ring1 = kMaxRing;
+            p.ring2 = (left - p.ring1 * kTileBytes) / p.slot2_bytes;
             if (p.ring2 > kMaxRing) p.ring2 = kMaxRing;
-            // hand leftover space to the rings one slot at a time
-            while (p.ring1 < kMaxRing && fixed + (p.ring1 + 1) * p.slot1_bytes + p.ring2 * p.slot2_bytes <= kSmemLimit) ++p.ring1;
-            while (p.ring2 < kMaxRing && fixed + p.ring1 * p.slot1_bytes + (p.ring2 + 1) * p.slot2_bytes <= kSmemLimit) ++p.ring2;
+            const int min_depth = p.a_bufs == 2 ? 3 : 2;
+            if (left < 0 || p.ring1 < min_depth || p.ring2 < min_depth) continue;
+            while (p.ring1 < kMaxRing && fixed + (p.ring1 + 1) * kTileBytes + p.ring2 * p.slot2_bytes <= kSmemLimit) ++p.ring1;
         }
-        smem_bytes = (size_t)fixed + (size_t)p.ring1 * p.slot1_bytes + (size_t)p.ring2 * p.slot2_bytes;
+        smem_bytes = (size_t)fixed + (size_t)p.ring1 * kTileBytes + (size_t)p.ring2 * p.slot2_bytes;
         placed = true;
         break;
     }
@@ -671,7 +674,7 @@ extern "C" int l3ac_convunit_mlp_tc(const void* a, const void* w1, const float* 
     L3AC_CHECK_ARG(mt < (1LL << 30));
     p.num_m_tiles = (int)mt;
     CUtensorMap tmA, tmW1, tmW2;
-    if (!encode_2d(enc, &tmA, a, C, M, kBM) || !encode_2d(enc, &tmW1, w1, C, H4, HN) || !encode_2d(enc, &tmW2, w2, H4, C, p.w2_rows))
+    if (!encode_2d(enc, &tmA, a, C, M, kBM) || !encode_2d(enc, &tmW1, w1, C, H4, 128) || !encode_2d(enc, &tmW2, w2, H4, C, p.w2_rows))
         return L3AC_EINVAL;
     cudaError_t e = cudaFuncSetAttribute(convunit_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e != cudaSuccess) return (int)e;

@@ -23,6 +23,8 @@ EVENTS = {
     13: "mma2  GEMM2 issued + commit",
     15: "mma1  d1_empty acquired",
     16: "mma1  GEMM1 issued + commit",
+    17: "mma1    slot acquired, before MMAs",
+    18: "mma1    MMAs issued, before commits",
 }
 for g in range(4):
     EVENTS[20 + g] = f"epi{g}  wait d1_full ..."
