@@ -49,6 +49,15 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
+// 1/sqrt(v) for v >= 1e-8 (variance + eps): MUFU.RSQ and one Newton-Raphson step (<= 1 ulp, like sqrt followed by a divide)
+// in 5 instructions instead of the ~20 of the IEEE `1.0f / sqrtf(v)` sequence with its slow-path branches.
+__device__ __forceinline__ float rsqrt_nr(float v) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(v));
+    const float h = 0.5f * v * y;
+    return fmaf(y, fmaf(-h, y, 0.5f), y);        // y * (1.5 - 0.5 v y^2)
+}
+
 // Packed fp32 FMA (sm_100 `fma.rn.f32x2`, SASS FFMA2): two independent IEEE fp32 FMAs per issued instruction.
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     unsigned long long ra, rb, rc, rd;

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(kTile) convunit_thin_kernel(const float* __res
         var = fmaf(a2[c].x, a2[c].x, var);
         var = fmaf(a2[c].y, a2[c].y, var);
     }
-    const float rstd = 1.0f / sqrtf(var * (1.0f / kC) + eps);
+    const float rstd = rsqrt_nr(var * (1.0f / kC) + eps);
 #pragma unroll
     for (int c = 0; c < kC / 2; ++c) {
         a2[c].x = fmaf(a2[c].x * rstd, s_c[kC + 2 * c], s_c[2 * kC + 2 * c]);

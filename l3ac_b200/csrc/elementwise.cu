@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* __restrict
             const float dlt = acc[i] - mean;
             v += (lane + 32 * i < C) ? dlt * dlt : 0.f;
         }
-        const float rstd = 1.0f / sqrtf(warp_sum(v) / (float)C + eps);
+        const float rstd = rsqrt_nr(warp_sum(v) / (float)C + eps);
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
             const int c = lane + 32 * i;
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(256) dwconv7_ln_rows_kernel(const float* __res
                 const float dlt = acc[i] - mean;
                 v += (lane + 32 * i < C) ? dlt * dlt : 0.f;
             }
-            const float rstd = 1.0f / sqrtf(warp_sum(v) * inv_c + eps);
+            const float rstd = rsqrt_nr(warp_sum(v) * inv_c + eps);
             const long long row = (long long)b * T + t0 + r;
 #pragma unroll
             for (int i = 0; i < CPL; ++i) {
@@ -233,15 +233,14 @@ __global__ void __launch_bounds__(256) dwconv7_ln_vec_kernel(const float* __rest
             float4 a = bias;
 #pragma unroll
             for (int j = 0; j < 7; ++j) {
-                a.x = fmaf(w[j].x, xr[r + j].x, a.x);
-                a.y = fmaf(w[j].y, xr[r + j].y, a.y);
-                a.z = fmaf(w[j].z, xr[r + j].z, a.z);
-                a.w = fmaf(w[j].w, xr[r + j].w, a.w);
+                const float2 lo = ffma2(make_float2(w[j].x, w[j].y), make_float2(xr[r + j].x, xr[r + j].y), make_float2(a.x, a.y));
+                const float2 hi = ffma2(make_float2(w[j].z, w[j].w), make_float2(xr[r + j].z, xr[r + j].w), make_float2(a.z, a.w));
+                a = make_float4(lo.x, lo.y, hi.x, hi.y);
             }
             const float mean = group_sum<GS>((a.x + a.y) + (a.z + a.w)) * inv_c;     // inactive lanes hold zeros
             const float dx = a.x - mean, dy = a.y - mean, dz = a.z - mean, dw = a.w - mean;
             const float q = act ? (dx * dx + dy * dy) + (dz * dz + dw * dw) : 0.f;
-            const float rstd = 1.0f / sqrtf(group_sum<GS>(q) * inv_c + eps);
+            const float rstd = rsqrt_nr(group_sum<GS>(q) * inv_c + eps);
             if (act && run_ok && t0 + r < T) {
                 const long long i = ((long long)b * T + t0 + r) * C + 4 * g;
                 store_act4<OutT>(out, out_lo, i,
@@ -282,10 +281,9 @@ __global__ void __launch_bounds__(128) dwconv7_ln_wide_kernel(const float* __res
         float4 a = bias;
 #pragma unroll
         for (int j = 0; j < 7; ++j) {
-            a.x = fmaf(w[j].x, xr[r + j].x, a.x);
-            a.y = fmaf(w[j].y, xr[r + j].y, a.y);
-            a.z = fmaf(w[j].z, xr[r + j].z, a.z);
-            a.w = fmaf(w[j].w, xr[r + j].w, a.w);
+            const float2 lo = ffma2(make_float2(w[j].x, w[j].y), make_float2(xr[r + j].x, xr[r + j].y), make_float2(a.x, a.y));
+            const float2 hi = ffma2(make_float2(w[j].z, w[j].w), make_float2(xr[r + j].z, xr[r + j].w), make_float2(a.z, a.w));
+            a = make_float4(lo.x, lo.y, hi.x, hi.y);
         }
         y[r] = a;
         const float s = warp_sum((a.x + a.y) + (a.z + a.w));
@@ -309,7 +307,7 @@ __global__ void __launch_bounds__(128) dwconv7_ln_wide_kernel(const float* __res
         if (t0 + r >= T) break;
         float q = 0.f;
         for (int k = 0; k < nwarps; ++k) q += s_part[1][r][k];
-        const float rstd = 1.0f / sqrtf(q * inv_c + eps);
+        const float rstd = rsqrt_nr(q * inv_c + eps);
         store_act4<OutT>(out, out_lo, ((long long)b * T + t0 + r) * C + 4 * g,
                          make_float4(y[r].x * rstd * lw.x + lb.x, y[r].y * rstd * lw.y + lb.y, y[r].z * rstd * lw.z + lb.z,
                                      y[r].w * rstd * lw.w + lb.w));
@@ -377,7 +375,7 @@ __global__ void __launch_bounds__(512) dwconv7_ln_tile_kernel(const float* __res
     if (c < TT) {
         float s = 0.f;
         for (int q = 0; q < nwarps; ++q) s += s_part[c][q];
-        s_stat[c] = 1.0f / sqrtf(s * inv_c + eps);
+        s_stat[c] = rsqrt_nr(s * inv_c + eps);
     }
     __syncthreads();
 #pragma unroll
@@ -412,7 +410,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
             const float dlt = v[i] - mean;
             q += (lane + 32 * i < C) ? dlt * dlt : 0.f;
         }
-        const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
+        const float rstd = rsqrt_nr(warp_sum(q) / (float)C + eps);
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
             const int c = lane + 32 * i;
@@ -503,7 +501,7 @@ __global__ void __launch_bounds__(256) upsample_cn_kernel(const float* __restric
             const float dlt = v[i] - mean;
             q += (lane + 32 * i < C) ? dlt * dlt : 0.f;
         }
-        const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
+        const float rstd = rsqrt_nr(warp_sum(q) / (float)C + eps);
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
             const int c = lane + 32 * i;
@@ -755,7 +753,7 @@ __global__ void __launch_bounds__(256) upsample_cn_vec_kernel(const float* __res
                         q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
                     }
                 }
-                rstd = 1.0f / sqrtf(group_sum<GS>(q) * inv_c + eps);
+                rstd = rsqrt_nr(group_sum<GS>(q) * inv_c + eps);
             }
             if (!ok[u]) continue;
             float4* orow = reinterpret_cast<float4*>(out + (base + u * RW + sub) * C);
@@ -818,7 +816,7 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restr
                     q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
                 }
             }
-            const float rstd = 1.0f / sqrtf(group_sum<GS>(q) * inv_c + eps);
+            const float rstd = rsqrt_nr(group_sum<GS>(q) * inv_c + eps);
             const long long row = base + u * RW + sub;
             if (row >= M) continue;
 #pragma unroll
