@@ -114,12 +114,14 @@ __global__ void __launch_bounds__(kThreads, 2) decoder_tail_kernel(const Params 
             const float in[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
             uint32_t pk[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int c0 = ch * 8 + 2 * e;
-                const float s0 = __sinf(s_par[2 * kC + c0] * in[2 * e]);
-                const float s1 = __sinf(s_par[2 * kC + c0 + 1] * in[2 * e + 1]);
-                const __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaf(s_par[3 * kC + c0], s0 * s0, in[2 * e]),
-                                                                fmaf(s_par[3 * kC + c0 + 1], s1 * s1, in[2 * e + 1]));
+            for (int e = 0; e < 4; ++e) {       // packed f32x2: same rounding as the scalar ops, half the issue slots
+                const float2 al = *reinterpret_cast<const float2*>(s_par + 2 * kC + ch * 8 + 2 * e);
+                const float2 ia = *reinterpret_cast<const float2*>(s_par + 3 * kC + ch * 8 + 2 * e);
+                const float2 xin = make_float2(in[2 * e], in[2 * e + 1]);
+                const float2 t = fmul2(al, xin);
+                const float2 sn = make_float2(__sinf(t.x), __sinf(t.y));
+                const float2 r = ffma2(ia, fmul2(sn, sn), xin);
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(r.x, r.y);
                 pk[e] = *reinterpret_cast<const uint32_t*>(&h2);
             }
             *reinterpret_cast<uint4*>(a_buf + swz(row, ch)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -159,20 +161,30 @@ __global__ void __launch_bounds__(kThreads, 2) decoder_tail_kernel(const Params 
                     }
                 }
             }
+            float cb[3][2], al1[3][2], ia1[3][2];       // conv bias, alpha1, 1/(alpha1+eps) of this lane's column pairs
+#pragma unroll
+            for (int n = 0; n < 3; ++n) {
+                const int col = n * 8 + (lane & 3) * 2;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    cb[n][e] = s_par[col + e];
+                    al1[n][e] = s_par[4 * kC + col + e];
+                    ia1[n][e] = s_par[5 * kC + col + e];
+                }
+            }
 #pragma unroll
             for (int i = 0; i < kMT; ++i) {
                 const int r0 = (warp + i * (kThreads / 32)) * 16;
 #pragma unroll
                 for (int n = 0; n < 3; ++n) {
-                    const int col = n * 8 + (lane & 3) * 2;
 #pragma unroll
                     for (int hrow = 0; hrow < 2; ++hrow) {
                         const int row = r0 + (lane >> 2) + hrow * 8;
-                        float v0 = acc[i][n][2 * hrow] + s_par[col], v1 = acc[i][n][2 * hrow + 1] + s_par[col + 1];
-                        const float s0 = __sinf(s_par[4 * kC + col] * v0), s1 = __sinf(s_par[4 * kC + col + 1] * v1);
-                        v0 = fmaf(s_par[5 * kC + col], s0 * s0, v0);
-                        v1 = fmaf(s_par[5 * kC + col + 1], s1 * s1, v1);
-                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+                        const float2 v = fadd2(make_float2(acc[i][n][2 * hrow], acc[i][n][2 * hrow + 1]), make_float2(cb[n][0], cb[n][1]));
+                        const float2 t = fmul2(make_float2(al1[n][0], al1[n][1]), v);
+                        const float2 sn = make_float2(__sinf(t.x), __sinf(t.y));
+                        const float2 r = ffma2(make_float2(ia1[n][0], ia1[n][1]), fmul2(sn, sn), v);
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(r.x, r.y);
                         *reinterpret_cast<uint32_t*>(h_buf + swz(row, n) + (lane & 3) * 4) = *reinterpret_cast<const uint32_t*>(&h2);
                     }
                 }
