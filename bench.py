@@ -77,6 +77,10 @@ class ClockSampler(threading.Thread):
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            # prime both queries outside the timed region: the first call of each initialises NVML state lazily and has
+            # been seen to stall kernel launches for tens of milliseconds
+            pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
         except Exception:
             self.nv = None
 

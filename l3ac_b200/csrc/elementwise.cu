@@ -519,7 +519,7 @@ __global__ void __launch_bounds__(256) upsample_cn_kernel(const float* __restric
 // ------------------------------------------------------------------------------------------
 constexpr int kEnhReach = 23;
 constexpr int kEnhChunk = 1024;   // time steps per stats block (partials granularity)
-constexpr int kEnhTile = 128;     // time steps per apply block
+constexpr int kEnhTile = 512;     // time steps per apply block (128 made ~30k tiny CTAs per full-rate launch: 1.4 TB/s)
 
 // Computes y_j[t0 + i] for i in [0, CH) into ys[j][i] (shared, [4][CH]).  xs/ms/ps: [CH + 2*kEnhReach].
 template <int CH>
@@ -851,6 +851,13 @@ __global__ void __launch_bounds__(256) enhance_apply_vec_kernel(const float* __r
     __shared__ float ys[4 * CH];
     __shared__ float s_scale[4], s_shift[4];
     const int b = blockIdx.y, t0 = blockIdx.x * CH;
+    {   // The branch signals below need only channel 0; start pulling the whole (tile x C) block towards L2 now so that the
+        // streaming phase at the end does not begin with a cold HBM round trip.
+        const char* tile = reinterpret_cast<const char*>(x + ((long long)b * T + t0) * C);
+        const long long tile_bytes = (long long)min(CH, T - t0) * C * 4;
+        for (long long off = (long long)threadIdx.x * 128; off < tile_bytes; off += (long long)blockDim.x * 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(tile + off));
+    }
     if (threadIdx.x < 4) {
         const int j = threadIdx.x;
         double s = 0.0, q = 0.0;
