@@ -143,3 +143,24 @@ def test_fused_convunit_mlp(cuda_lib, M, C):
     e_two, e_fused = max_abs(two.cpu(), want), max_abs(got.cpu(), want)
     print(f"[mlp M={M} C={C}] max-abs vs fp64(bf16 hidden): fused {e_fused:.2e}  two-GEMM {e_two:.2e}; fused-vs-two {max_abs(got, two):.2e}")
     assert e_fused < 2e-2 * max(1.0, float(want.abs().max())) and e_fused < 3 * e_two + 1e-3
+
+
+@pytest.mark.parametrize("M,C", [(128 * 148 * 6 + 33, 48), (128 * 148 * 4 + 90, 96), (128 * 148 * 3 + 7, 256)])
+def test_fused_convunit_mlp_is_deterministic(cuda_lib, M, C):
+    """The fused kernel hands buffers between TMA, two MMA issuers and 16 epilogue warps through ~50 mbarriers: a missed
+    hand-over would show up as run-to-run differences.  Many tiles per CTA, repeated launches, bitwise comparison."""
+    a = bf(rnd(1, M, C, seed=11)).to(DEV)
+    w1, w2 = bf(rnd(4 * C, C, seed=12, scale=C ** -0.5)).to(DEV), bf(rnd(C, 4 * C, seed=13, scale=(4 * C) ** -0.5)).to(DEV)
+    b1, b2 = rnd(4 * C, seed=14, scale=0.1).to(DEV), rnd(C, seed=15, scale=0.1).to(DEV)
+    alpha, scale, shift = (0.5 + torch.rand(4 * C)).to(DEV), (1 + rnd(4 * C, seed=16, scale=0.1)).to(DEV), rnd(4 * C, seed=17, scale=0.1).to(DEV)
+    x = rnd(1, M, C, seed=18).to(DEV)
+    first = ops.convunit_mlp(a, w1, b1, alpha, scale, shift, w2, b2, x)
+    for _ in range(8):
+        again = ops.convunit_mlp(a, w1, b1, alpha, scale, shift, w2, b2, x)
+        assert torch.equal(first, again)
+    # identical rows in different tiles / CTAs must give identical results (tile-position independence)
+    a2, x2 = a.clone(), x.clone()
+    a2[0, 128 * 200 + 5] = a2[0, 3]
+    x2[0, 128 * 200 + 5] = x2[0, 3]
+    out = ops.convunit_mlp(a2, w1, b1, alpha, scale, shift, w2, b2, x2)
+    assert torch.equal(out[0, 128 * 200 + 5], out[0, 3])
