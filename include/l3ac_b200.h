@@ -137,11 +137,13 @@ int l3ac_convunit_mlp_tc(const void* a, const void* w1, const float* b1, const f
 
 /* Whole Residual(ConvUnit) (l3ac/modules.py:10-44) for the thin full-rate encoder stage (C = 24, hidden 96) as one fp32
  * kernel: depthwise conv k7 + LayerNorm + pw_conv1 + Snake + GRN affine + pw_conv2 + residual; the hidden activation
- * never leaves registers.  x/out (B,T,24) fp32; dw_w [7][24]; w1 [96][24]; w2 [24][96]; b1/alpha/scale/shift [96]. */
+ * never leaves registers.  x (B,T,24) fp32; dw_w [7][24]; w1 [96][24]; w2 [24][96]; b1/alpha/scale/shift [96].
+ * out_dtype L3AC_F32: out (B,T,24) fp32, out_lo ignored.  L3AC_BF16X2: out / out_lo (B,T,24) bf16 = the split pair
+ * (hi = bf16(v), lo = bf16(v - hi)) that the strided down-conv GEMM of the stage consumes. */
 int l3ac_convunit_thin_f32(const float* x, int B, int T, int C, const float* dw_w, const float* dw_b, const float* ln_w,
                            const float* ln_b, float eps, const float* w1, const float* b1, const float* alpha,
-                           const float* scale, const float* shift, const float* w2, const float* b2, float* out,
-                           l3ac_stream_t stream);
+                           const float* scale, const float* shift, const float* w2, const float* b2, void* out,
+                           void* out_lo, int out_dtype, l3ac_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Block-local causal attention.  Replaces LocalAttention.forward of local-attention==1.11.2 as

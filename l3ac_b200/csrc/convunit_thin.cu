@@ -27,6 +27,9 @@ struct Smem {
     float c[4 * kC];         // dw_b, ln_w, ln_b, b2
 };
 
+// SPLIT: write the result as the split-bf16 pair (hi = bf16(v), lo = bf16(v - hi)) the next tcgen05 GEMM consumes, instead
+// of fp32 -- same bytes, and the separate fp32 -> split conversion pass (a full read + write of the tensor) disappears.
+template <bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 4) convunit_thin_kernel(const float* __restrict__ x, int B, int T,
                                                                  const float* __restrict__ dw_w, const float* __restrict__ dw_b,
                                                                  const float* __restrict__ ln_w, const float* __restrict__ ln_b,
@@ -34,7 +37,7 @@ __global__ void __launch_bounds__(kThreads, 4) convunit_thin_kernel(const float*
                                                                  const float* __restrict__ b1, const float* __restrict__ alpha,
                                                                  const float* __restrict__ scale, const float* __restrict__ shift,
                                                                  const float* __restrict__ w2, const float* __restrict__ b2,
-                                                                 float* __restrict__ out) {
+                                                                 void* __restrict__ out_v, void* __restrict__ out_lo_v) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
@@ -157,10 +160,31 @@ __global__ void __launch_bounds__(kThreads, 4) convunit_thin_kernel(const float*
     for (int s = 0; s < kSPT; ++s) {
         const int t = t0 + tid + s * kThreads;
         if (t >= T) continue;
-        float4* o = reinterpret_cast<float4*>(out + ((long long)b * T + t) * kC);
+        const long long base = ((long long)b * T + t) * kC;
+        if (!SPLIT) {
+            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_v) + base);
 #pragma unroll
-        for (int c4 = 0; c4 < kC / 4; ++c4)
-            o[c4] = make_float4(acc2[s][2 * c4].x, acc2[s][2 * c4].y, acc2[s][2 * c4 + 1].x, acc2[s][2 * c4 + 1].y);
+            for (int c4 = 0; c4 < kC / 4; ++c4)
+                o[c4] = make_float4(acc2[s][2 * c4].x, acc2[s][2 * c4].y, acc2[s][2 * c4 + 1].x, acc2[s][2 * c4 + 1].y);
+        } else {
+            uint4* oh = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out_v) + base);
+            uint4* ol = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out_lo_v) + base);
+#pragma unroll
+            for (int c8 = 0; c8 < kC / 8; ++c8) {
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 v = acc2[s][4 * c8 + e];
+                    const __nv_bfloat162 hi = __floats2bfloat162_rn(v.x, v.y);
+                    const float2 hf = __bfloat1622float2(hi);
+                    const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x - hf.x, v.y - hf.y);
+                    h[e] = *reinterpret_cast<const uint32_t*>(&hi);
+                    l[e] = *reinterpret_cast<const uint32_t*>(&lo);
+                }
+                oh[c8] = make_uint4(h[0], h[1], h[2], h[3]);
+                ol[c8] = make_uint4(l[0], l[1], l[2], l[3]);
+            }
+        }
     }
 }
 
@@ -170,16 +194,20 @@ __global__ void __launch_bounds__(kThreads, 4) convunit_thin_kernel(const float*
 extern "C" int l3ac_convunit_thin_f32(const float* x, int B, int T, int C, const float* dw_w, const float* dw_b,
                                       const float* ln_w, const float* ln_b, float eps, const float* w1, const float* b1,
                                       const float* alpha, const float* scale, const float* shift, const float* w2,
-                                      const float* b2, float* out, l3ac_stream_t stream) {
+                                      const float* b2, void* out, void* out_lo, int out_dtype, l3ac_stream_t stream) {
     using namespace l3ac::thin;
     L3AC_CHECK_ARG(x && dw_w && dw_b && ln_w && ln_b && w1 && b1 && alpha && scale && shift && w2 && b2 && out);
     L3AC_CHECK_ARG(B > 0 && B <= 65535 && T > 0);
+    L3AC_CHECK_ARG(out_dtype == L3AC_F32 || (out_dtype == L3AC_BF16X2 && out_lo));
     if (C != kC) return L3AC_EUNSUPPORTED;
-    L3AC_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0);
+    L3AC_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(out_lo)) & 15) == 0);
     dim3 grid(l3ac_cdiv(T, kTile), B);
-    cudaError_t e = cudaFuncSetAttribute(convunit_thin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-    if (e != cudaSuccess) return (int)e;
-    convunit_thin_kernel<<<grid, kThreads, sizeof(Smem), (cudaStream_t)stream>>>(x, B, T, dw_w, dw_b, ln_w, ln_b, eps, w1, b1, alpha, scale,
-                                                                 shift, w2, b2, out);
-    return l3ac_launch_status();
+    auto launch = [&](auto kernel) -> int {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+        if (e != cudaSuccess) return (int)e;
+        kernel<<<grid, kThreads, sizeof(Smem), (cudaStream_t)stream>>>(x, B, T, dw_w, dw_b, ln_w, ln_b, eps, w1, b1, alpha, scale, shift,
+                                                                       w2, b2, out, out_lo);
+        return l3ac_launch_status();
+    };
+    return out_dtype == L3AC_F32 ? launch(convunit_thin_kernel<false>) : launch(convunit_thin_kernel<true>);
 }

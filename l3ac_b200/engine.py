@@ -268,22 +268,27 @@ class Engine:
         """fp32 activation -> GEMM A operand of the requested kind."""
         if kind == torch.float32:
             return x
+        if isinstance(x, ops.Split):          # the producer already wrote the split pair
+            return x
         if kind == ops.SPLIT:
             return ops.split_bf16(x)
         return x.to(kind)
 
-    def _run_conv_unit(self, x, u, act_dtype):
+    def _run_conv_unit(self, x, u, act_dtype, out_kind=torch.float32):
         """Residual(ConvUnit) -- l3ac/modules.py:32-44.
 
         The 4C-wide hidden tensor is the largest activation of the path.  Optionally (``hidden_block_bytes`` > 0) the
         two point-wise GEMMs run back to back over row blocks sized so that one block of the hidden tensor stays in the
         126 MB L2.  Measured on B200 (profiles/r01_bench_history.md) this LOSES: blocks of ~20 k rows are only ~4 tiles
         per CTA, and the fill/drain of the persistent GEMM costs more than the saved HBM traffic (C=256 pw_conv2: 636
-        -> 331 TFLOP/s), so it is off by default; keeping the hidden tensor on chip needs the fused MLP kernel."""
+        -> 331 TFLOP/s), so it is off by default; keeping the hidden tensor on chip needs the fused MLP kernel.
+
+        ``out_kind=ops.SPLIT`` (encode side, last unit before a GEMM consumer): the result is written as the split-bf16
+        pair directly by the producing kernel, which removes a separate fp32 -> split pass over the tensor."""
         B, T, C = x.shape
         if C == 24 and act_dtype != torch.bfloat16:      # thin full-rate encoder stage: one fused fp32 kernel
             return ops.convunit_thin(x, u["dw_w"], u["dw_b"], u["ln_w"], u["ln_b"], EPS, u["pw1"].w32, u["pw1"].bias,
-                                     u["alpha"], u["scale"], u["shift"], u["pw2"].w32, u["pw2"].bias)
+                                     u["alpha"], u["scale"], u["shift"], u["pw2"].w32, u["pw2"].bias, out_dtype=out_kind)
         a = ops.dwconv7_ln(x, u["dw_w"], u["dw_b"], u["ln_w"], u["ln_b"], EPS, out_dtype=act_dtype)
         M = B * T
         esz = {torch.float32: 4, torch.bfloat16: 2, ops.SPLIT: 4}[act_dtype]
@@ -294,7 +299,7 @@ class Engine:
         if self.hidden_block_bytes <= 0 or act_dtype == torch.float32 or M <= rows_blk + rows_blk // 2:
             h = self._lin(a, u["pw1"], B, T, C, act=ops.ACT_SNAKE, alpha=u["alpha"], scale=u["scale"], shift=u["shift"],
                           out_dtype=act_dtype)
-            return self._lin(h, u["pw2"], B, T, 4 * C, residual=x)
+            return self._lin(h, u["pw2"], B, T, 4 * C, residual=x, out_dtype=out_kind)
         out = torch.empty_like(x)
         a2, x2, o2 = a.view(M, C), x.view(M, C), out.view(M, C)
         split = act_dtype == ops.SPLIT
@@ -339,18 +344,21 @@ class Engine:
         x = ops.stem(audio.contiguous(), **self.stem)      # (B, T, 24)
         if taps is not None:
             taps["enc_stem"] = x
+        # The last ConvUnit before a GEMM consumer writes that GEMM's operand kind directly (split pair on the tensor-core
+        # path); only when debug taps want the fp32 tensor, or the operand is fp32 anyway, is the stream kept in fp32.
+        direct = f32 if (f32 == ops.SPLIT and self.hidden_block_bytes <= 0) else torch.float32
         for si, st in enumerate(self.enc_stages):
-            for u in st["units"]:
-                x = self._run_conv_unit(x, u, f32)
             B_, T_, C_ = x.shape
+            for ui, u in enumerate(st["units"]):
+                x = self._run_conv_unit(x, u, f32, out_kind=direct if ui == len(st["units"]) - 1 else torch.float32)
             s = st["stride"]
             x = self._lin(self._as_operand(x, f32), st["down"], B_, T_ // s, s * C_)   # Conv1d(k=s, stride=s) as a GEMM
             x = ops.layernorm(x, st["cn_w"], st["cn_b"], EPS)                       # channels-first ChannelNorm
             if taps is not None:
                 taps[f"enc_down{si}"] = x
-        for u in self.enc_last:
-            x = self._run_conv_unit(x, u, f32)
         B_, T_, C_ = x.shape
+        for ui, u in enumerate(self.enc_last):
+            x = self._run_conv_unit(x, u, f32, out_kind=direct if ui == len(self.enc_last) - 1 else torch.float32)
         x = self._lin(self._as_operand(x, f32), self.enc_out, B_, T_, C_, taps=3, tap_shift0=-1)   # Conv1d(k3, pad 1)
         if taps is not None:
             taps["enc_feature"] = x

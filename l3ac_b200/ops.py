@@ -241,16 +241,18 @@ def convunit_mlp(a: torch.Tensor, w1, b1, alpha, scale, shift, w2, b2, residual:
     return out
 
 
-def convunit_thin(x: torch.Tensor, dw_w, dw_b, ln_w, ln_b, eps: float, w1, b1, alpha, scale, shift, w2, b2) -> torch.Tensor:
-    """Fused fp32 Residual(ConvUnit) for C = 24 (x (B, T, 24) fp32 -> same shape)."""
+def convunit_thin(x: torch.Tensor, dw_w, dw_b, ln_w, ln_b, eps: float, w1, b1, alpha, scale, shift, w2, b2, out_dtype=torch.float32):
+    """Fused fp32 Residual(ConvUnit) for C = 24 (x (B, T, 24) fp32 -> same shape; ``out_dtype=SPLIT`` returns the split pair)."""
     _chk(x, name="x")
     B, T, Cc = x.shape
-    out = torch.empty_like(x)
+    if out_dtype not in (torch.float32, SPLIT):
+        raise ValueError("convunit_thin emits fp32 or the split-bf16 pair")
+    out, hi, lo = _empty_act(tuple(x.shape), x.device, out_dtype)
     _count()
-    with _hook("convunit_thin_f32", _nbytes(x, out), 2.0 * B * T * (7 * Cc + 8 * Cc * Cc)), torch.cuda.device(x.device):
+    with _hook("convunit_thin_f32", _nbytes(x) + B * T * Cc * 4, 2.0 * B * T * (7 * Cc + 8 * Cc * Cc)), torch.cuda.device(x.device):
         check(_lib.load().l3ac_convunit_thin_f32(_ptr(x), B, T, Cc, _ptr(dw_w), _ptr(dw_b), _ptr(ln_w), _ptr(ln_b), eps, _ptr(w1),
-                                                 _ptr(b1), _ptr(alpha), _ptr(scale), _ptr(shift), _ptr(w2), _ptr(b2), _ptr(out),
-                                                 _stream(x)), "l3ac_convunit_thin_f32")
+                                                 _ptr(b1), _ptr(alpha), _ptr(scale), _ptr(shift), _ptr(w2), _ptr(b2), _ptr(hi),
+                                                 _ptr(lo), _DT[out_dtype], _stream(x)), "l3ac_convunit_thin_f32")
     return out
 
 

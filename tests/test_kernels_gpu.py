@@ -294,3 +294,10 @@ def test_fused_thin_convunit(cuda_lib, T):
                             d(sd["u.act.alpha"].flatten()), d(1 + sd["u.grn.gamma"].flatten()), d(sd["u.grn.beta"].flatten()),
                             d(sd["u.pw_conv2.weight"]), d(sd["u.pw_conv2.bias"]))
     assert max_abs(cf(got), want) < 3e-5
+    # split output = exactly what the separate fp32 -> split pass would have produced from the fp32 result
+    sp = ops.convunit_thin(cl(x), d(sd["u.dw_conv.weight"][:, 0].t()), d(sd["u.dw_conv.bias"]), d(sd["u.norm.weight"]),
+                           d(sd["u.norm.bias"]), 1e-8, d(sd["u.pw_conv1.weight"]), d(sd["u.pw_conv1.bias"]),
+                           d(sd["u.act.alpha"].flatten()), d(1 + sd["u.grn.gamma"].flatten()), d(sd["u.grn.beta"].flatten()),
+                           d(sd["u.pw_conv2.weight"]), d(sd["u.pw_conv2.bias"]), out_dtype=ops.SPLIT)
+    ref = ops.split_bf16(got)
+    assert torch.equal(sp.hi, ref.hi) and torch.equal(sp.lo, ref.lo)
