@@ -223,11 +223,21 @@ __global__ void __launch_bounds__(256) dwconv7_ln_vec_kernel(const float* __rest
         const int t0 = (int)(rr - (long long)b * runs_per_sample) * R;
         const float4* xb = reinterpret_cast<const float4*>(x + (long long)b * T * C) + g;
         float4 xr[R + 6];
+        // Interior runs (no clip edge inside the R + 6 rows, true for all but two runs per clip) take a warp-uniform fast
+        // path: one base pointer, 32-bit row offsets, no per-row range predicates or zero-fill selects.
+        const bool interior = __all_sync(0xffffffffu, run_ok && t0 >= 3 && t0 + R + 3 <= T);
+        if (interior) {
+            const float4* p0 = xb + (long long)(t0 - 3) * C4;
 #pragma unroll
-        for (int r = 0; r < R + 6; ++r) {
-            const int t = t0 + r - 3;
-            xr[r] = (act && t >= 0 && t < T) ? __ldg(xb + (long long)t * C4) : z4;
+            for (int r = 0; r < R + 6; ++r) xr[r] = act ? __ldg(p0 + r * C4) : z4;
+        } else {
+#pragma unroll
+            for (int r = 0; r < R + 6; ++r) {
+                const int t = t0 + r - 3;
+                xr[r] = (act && t >= 0 && t < T) ? __ldg(xb + (long long)t * C4) : z4;
+            }
         }
+        const long long out_row0 = ((long long)b * T + t0) * C + 4 * g;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             float4 a = bias;
@@ -241,8 +251,8 @@ __global__ void __launch_bounds__(256) dwconv7_ln_vec_kernel(const float* __rest
             const float dx = a.x - mean, dy = a.y - mean, dz = a.z - mean, dw = a.w - mean;
             const float q = act ? (dx * dx + dy * dy) + (dz * dz + dw * dw) : 0.f;
             const float rstd = rsqrt_nr(group_sum<GS>(q) * inv_c + eps);
-            if (act && run_ok && t0 + r < T) {
-                const long long i = ((long long)b * T + t0 + r) * C + 4 * g;
+            if (act && (interior || (run_ok && t0 + r < T))) {
+                const long long i = out_row0 + r * C;
                 store_act4<OutT>(out, out_lo, i,
                                  make_float4(dx * rstd * lw.x + lb.x, dy * rstd * lw.y + lb.y, dz * rstd * lw.z + lb.z,
                                              dw * rstd * lw.w + lb.w));
