@@ -270,20 +270,29 @@ def main():
     ops.OP_HOOK = hook
     eng = codec.network.engine
     saved_streams, eng.num_streams = eng.num_streams, 1      # per-launch durations must not include overlap with other streams
+    # Two instrumented passes; every launch keeps the shorter of its two durations, so that a one-off stall (another tenant,
+    # a clock dip) in either pass does not end up in the per-kernel numbers.  The launch sequence is deterministic.
+    passes, inst = [], []
     with torch.inference_mode():
         step_resident(0)                         # untimed: first single-stream pass (allocator warm-up for this stream layout)
-        records.clear()
-        e_all0, e_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e_all0.record()
-        step_resident(0)
-        e_all1.record()
-    torch.cuda.synchronize()
+        for _ in range(2):
+            records.clear()
+            e_all0, e_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e_all0.record()
+            step_resident(0)
+            e_all1.record()
+            torch.cuda.synchronize()
+            passes.append([(k, f, b, a.elapsed_time(c)) for k, f, b, a, c in records])
+            inst.append(e_all0.elapsed_time(e_all1))
     ops.OP_HOOK = None
     eng.num_streams = saved_streams
-    inst_ms = e_all0.elapsed_time(e_all1)
+    inst_ms = min(inst)
+    if len(passes[0]) == len(passes[1]) and all(p[0] == q[0] for p, q in zip(*passes)):
+        records = [(k, f, b, min(t0, t1)) for (k, f, b, t0), (_, _, _, t1) in zip(*passes)]
+    else:                                        # (cannot happen for a fixed workload; keep the faster pass as a whole)
+        records = passes[inst.index(inst_ms)]
     by_op = {}
-    for k, f, b, a, c in records:
-        ms = a.elapsed_time(c)
+    for k, f, b, ms in records:
         o = by_op.setdefault(k, dict(launches=0, ms=0.0, gflop=0.0, mb=0.0))
         o["launches"] += 1
         o["ms"] += ms
@@ -291,16 +300,15 @@ def main():
         o["mb"] += b / 1e6
     if os.environ.get("L3AC_BENCH_DUMP"):
         with open(os.environ["L3AC_BENCH_DUMP"], "w") as fh:
-            for k, f, b, a, c in records:
-                ms = a.elapsed_time(c)
+            for k, f, b, ms in records:
                 fh.write(f"{k} gflop={f / 1e9:.2f} mb={b / 1e6:.1f} us={ms * 1e3:.1f} tflops={f / ms / 1e9:.1f} gbs={b / ms / 1e6:.0f}\n")
             fh.write(f"# instrumented step {inst_ms:.2f} ms, sum of ops {sum(o['ms'] for o in by_op.values()):.2f} ms\n")
             for k, o in sorted(by_op.items(), key=lambda kv: -kv[1]["ms"]):
                 fh.write(f"# {k:22s} n={o['launches']:4d} {o['ms']:8.2f} ms  {o['gflop'] / max(o['ms'], 1e-9):8.1f} TF/s "
                          f"{o['mb'] / max(o['ms'], 1e-9):8.0f} GB/s\n")
     TC_KINDS = ("convunit_mlp_tc", "gemm_tc", "gemm_tc_split")       # the tcgen05 kernels of the path
-    tc = [(k, f, b, a.elapsed_time(c)) for k, f, b, a, c in records if k in TC_KINDS]
-    f32 = [(f, b, a.elapsed_time(c)) for k, f, b, a, c in records if k == "gemm_f32"]
+    tc = [(k, f, b, ms) for k, f, b, ms in records if k in TC_KINDS]
+    f32 = [(f, b, ms) for k, f, b, ms in records if k == "gemm_f32"]
     tc_ms, tc_flops = sum(t for _, _, _, t in tc), sum(f for _, f, _, _ in tc)
     f32_ms, f32_flops = sum(t for _, _, t in f32), sum(f for f, _, _ in f32)
     roofline = None
@@ -338,7 +346,7 @@ def main():
                     "share_of_step": per_kernel[dom]["share_of_step"], "per_kernel": per_kernel,
                     "all_tcgen05": {"achieved": ach, "frac": ach / pk["tf_sustained"], "launches": len(tc), "share_of_step": tc_ms / inst_ms,
                                     "flops_per_step": tc_flops},
-                    "note": "durations from one single-stream instrumented step (%.2f ms), CUDA events around every launch on the "
+                    "note": "durations from two single-stream instrumented steps (per-launch minimum; %.2f ms per step), CUDA events around every launch on the "
                             "launching stream; the timed steps overlap micro-batches on %d streams.  The kernel is bound by its "
                             "snake epilogue (SFU + issue), see DESIGN.md section 3" % (inst_ms, saved_streams)}
     hbm_ops = {k: o for k, o in by_op.items() if not k.startswith("gemm") and k != "convunit_mlp_tc"}

@@ -265,13 +265,13 @@ __global__ void __launch_bounds__(256) dwconv7_ln_vec_kernel(const float* __rest
 // warp per 128 channels) handles R consecutive time steps.  The per-time-step statistics are a warp shuffle reduction
 // followed by one shared-memory exchange between the CTA's warps for all R steps at once (two exchanges: mean, then
 // centred sum of squares).  ~16 instructions per output element instead of ~34 for the one-channel-per-thread tile.
-template <int R, typename OutT>
-__global__ void __launch_bounds__(128) dwconv7_ln_wide_kernel(const float* __restrict__ x, int B, int T, int C,
-                                                              const float* __restrict__ dw_w, const float* __restrict__ dw_b,
-                                                              const float* __restrict__ ln_w, const float* __restrict__ ln_b,
-                                                              float eps, OutT* __restrict__ out, OutT* __restrict__ out_lo) {
-    __shared__ float s_part[2][R][4];
-    const int g = threadIdx.x, lane = g & 31, warp = g >> 5, nwarps = blockDim.x >> 5;
+template <int R, int NW, typename OutT>
+__global__ void __launch_bounds__(32 * NW) dwconv7_ln_wide_kernel(const float* __restrict__ x, int B, int T, int C,
+                                                                  const float* __restrict__ dw_w, const float* __restrict__ dw_b,
+                                                                  const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                                                                  float eps, OutT* __restrict__ out, OutT* __restrict__ out_lo) {
+    __shared__ __align__(16) float s_part[2][R][4];      // per-warp partial sums, read back as one float4 per row
+    const int g = threadIdx.x, lane = g & 31, warp = g >> 5;
     const int C4 = C >> 2;
     const int b = blockIdx.y, t0 = blockIdx.x * R;
     float4 w[7];
@@ -280,10 +280,17 @@ __global__ void __launch_bounds__(128) dwconv7_ln_wide_kernel(const float* __res
     const float4 bias = __ldg(reinterpret_cast<const float4*>(dw_b) + g);
     const float4* xb = reinterpret_cast<const float4*>(x + (long long)b * T * C) + g;
     float4 xr[R + 6];
+    const bool interior = t0 >= 3 && t0 + R + 3 <= T;      // block-uniform: no clip edge inside the R + 6 rows
+    if (interior) {
+        const float4* p0 = xb + (long long)(t0 - 3) * C4;
 #pragma unroll
-    for (int r = 0; r < R + 6; ++r) {
-        const int t = t0 + r - 3;
-        xr[r] = (t >= 0 && t < T) ? __ldg(xb + (long long)t * C4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < R + 6; ++r) xr[r] = __ldg(p0 + r * C4);
+    } else {
+#pragma unroll
+        for (int r = 0; r < R + 6; ++r) {
+            const int t = t0 + r - 3;
+            xr[r] = (t >= 0 && t < T) ? __ldg(xb + (long long)t * C4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
     float4 y[R];
 #pragma unroll
@@ -301,24 +308,28 @@ __global__ void __launch_bounds__(128) dwconv7_ln_wide_kernel(const float* __res
     }
     __syncthreads();
     const float inv_c = 1.0f / (float)C;
+    auto total = [](const float4 p) {      // sum of the NW per-warp partials, in warp order
+        float m = p.x;
+        if (NW > 1) m += p.y;
+        if (NW > 2) m += p.z;
+        if (NW > 3) m += p.w;
+        return m;
+    };
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        float m = 0.f;
-        for (int q = 0; q < nwarps; ++q) m += s_part[0][r][q];
-        m *= inv_c;
+        const float m = total(*reinterpret_cast<const float4*>(s_part[0][r])) * inv_c;
         y[r].x -= m; y[r].y -= m; y[r].z -= m; y[r].w -= m;
         const float s = warp_sum((y[r].x * y[r].x + y[r].y * y[r].y) + (y[r].z * y[r].z + y[r].w * y[r].w));
         if (lane == 0) s_part[1][r][warp] = s;
     }
     __syncthreads();
     const float4 lw = __ldg(reinterpret_cast<const float4*>(ln_w) + g), lb = __ldg(reinterpret_cast<const float4*>(ln_b) + g);
+    const long long out_row0 = ((long long)b * T + t0) * C + 4 * g;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        if (t0 + r >= T) break;
-        float q = 0.f;
-        for (int k = 0; k < nwarps; ++k) q += s_part[1][r][k];
-        const float rstd = rsqrt_nr(q * inv_c + eps);
-        store_act4<OutT>(out, out_lo, ((long long)b * T + t0 + r) * C + 4 * g,
+        if (!interior && t0 + r >= T) break;
+        const float rstd = rsqrt_nr(total(*reinterpret_cast<const float4*>(s_part[1][r])) * inv_c + eps);
+        store_act4<OutT>(out, out_lo, out_row0 + (long long)r * C,
                          make_float4(y[r].x * rstd * lw.x + lb.x, y[r].y * rstd * lw.y + lb.y, y[r].z * rstd * lw.z + lb.z,
                                      y[r].w * rstd * lw.w + lb.w));
     }
@@ -1046,11 +1057,22 @@ extern "C" int l3ac_dwconv7_ln(const float* x, int B, int T, int C, const float*
           reinterpret_cast<uintptr_t>(ln_b) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(out_lo)) & 15) == 0) {
         constexpr int R = 8;
         dim3 wgrid(l3ac_cdiv(T, R), B);
-        if (out_dtype == L3AC_F32)
-            dwconv7_ln_wide_kernel<R, float><<<wgrid, C / 4, 0, st>>>(x, B, T, C, dw_w, dw_b, ln_w, ln_b, eps, (float*)out, nullptr);
-        else
-            dwconv7_ln_wide_kernel<R, __nv_bfloat16><<<wgrid, C / 4, 0, st>>>(x, B, T, C, dw_w, dw_b, ln_w, ln_b, eps,
-                                                                               (__nv_bfloat16*)out, (__nv_bfloat16*)out_lo);
+#define L3AC_DWLN_WIDE(NW)                                                                                              \
+    do {                                                                                                                \
+        if (out_dtype == L3AC_F32)                                                                                      \
+            dwconv7_ln_wide_kernel<R, NW, float><<<wgrid, 32 * NW, 0, st>>>(x, B, T, C, dw_w, dw_b, ln_w, ln_b, eps, (float*)out, \
+                                                                          nullptr);                                     \
+        else                                                                                                            \
+            dwconv7_ln_wide_kernel<R, NW, __nv_bfloat16><<<wgrid, 32 * NW, 0, st>>>(                                    \
+                x, B, T, C, dw_w, dw_b, ln_w, ln_b, eps, (__nv_bfloat16*)out, (__nv_bfloat16*)out_lo);                  \
+    } while (0)
+        switch (C / 128) {
+            case 1: L3AC_DWLN_WIDE(1); break;
+            case 2: L3AC_DWLN_WIDE(2); break;
+            case 3: L3AC_DWLN_WIDE(3); break;
+            default: L3AC_DWLN_WIDE(4); break;
+        }
+#undef L3AC_DWLN_WIDE
         return l3ac_launch_status();
     }
     if (C % 32 == 0 && C >= 128 && C <= 512 && B <= 65535) {
