@@ -211,11 +211,12 @@ int l3ac_tail_conv_tanh(const float* x, int B, int T, int C, const float* alpha,
  * Fused full-rate decoder tail: 3 x Residual(LegacyUnit) (l3ac/modules.py:47-64,174-179; dilations 1,3,9)
  * + Snake -> Conv1d(C->1,k7,pad 3) -> tanh (l3ac/modules.py:192-194) in one kernel.
  * x (B,T,24) fp32 -> out (B,T) fp32.  The k7 and 1x1 conv weights are bf16, pre-packed in mma.m16n8k16
- * B-fragment order with K padded 24 -> 32:
- *   conv_frags [3 units][7 taps][2 ksteps][3 ntiles][32 lanes][4] bf16, pw_frags [3][2][3][32][4] bf16, where the
- *   4 values of lane l are W[n][k0], W[n][k0+1], W[n][k0+8], W[n][k0+9], n = 8*ntile + l/4, k0 = 16*kstep + 2*(l%4)
- *   (W[n][k] = 0 for k >= 24).  conv_bias/pw_bias/alpha0/alpha1 are [3][24]; dilations is a HOST array of 3 ints
- *   whose receptive field 3*(d0+d1+d2)+3 must be <= 42.  alpha_f [24], w_f [7][24] (tap-major), bias_f: final conv.
+ * B-fragment order (both pointers 16-byte aligned):
+ *   conv_frags [3 units][11 ksteps][3 ntiles][32 lanes][4] bf16 over the tap-major K axis k = 24*tap + channel
+ *   (168 -> 176, zero padded); pw_frags [3][2][3][32][4] bf16 with K padded 24 -> 32.  The 4 values of lane l are
+ *   W[n][k0], W[n][k0+1], W[n][k0+8], W[n][k0+9], n = 8*ntile + l/4, k0 = 16*kstep + 2*(l%4).
+ *   conv_bias/pw_bias/alpha0/alpha1 are [3][24]; dilations is a HOST array of 3 ints, each <= 9, whose receptive
+ *   field 3*(d0+d1+d2)+3 must be <= 42.  alpha_f [24], w_f [7][24] (tap-major), bias_f: final conv.
  * ------------------------------------------------------------------------------------------ */
 int l3ac_decoder_tail(const float* x, int B, int T, int C, const void* conv_frags, const float* conv_bias,
                       const void* pw_frags, const float* pw_bias, const float* alpha0, const float* alpha1,

@@ -247,7 +247,7 @@ class Engine:
             for j in range(3):
                 q = f"{p}.0.{j}.module.block"
                 wc = fold_weight_norm(sd, f"{q}.1")                                         # (24, 24, 7)
-                convs.append(torch.stack([ops.pack_mma_b_fragments(wc[:, :, t]) for t in range(7)]))
+                convs.append(ops.pack_mma_b_fragments(_taps_major(wc), k_pad=176))          # K = tap * 24 + channel
                 pws.append(ops.pack_mma_b_fragments(fold_weight_norm(sd, f"{q}.3")[:, :, 0]))
             self.dec_tail_fused = dict(
                 conv_frags=torch.stack(convs).contiguous(), pw_frags=torch.stack(pws).contiguous(),

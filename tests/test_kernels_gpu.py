@@ -236,8 +236,9 @@ def test_fused_decoder_tail(cuda_lib, T):
         exact = O.legacy_unit(sd, f"blocks.0.block.0.{j}.module", exact, dil)
     exact = torch.tanh(F.conv1d(O.snake(exact, sd["blocks.0.block.1.alpha"]), sd["blocks.0.block.2.weight"],
                                 sd["blocks.0.block.2.bias"], padding=3))[:, 0]
-    convs = torch.stack([torch.stack([ops.pack_mma_b_fragments(sd[f"blocks.0.block.0.{j}.module.block.1.weight"][:, :, t].to(DEV))
-                                      for t in range(7)]) for j in range(3)]).contiguous()
+    convs = torch.stack([ops.pack_mma_b_fragments(                                  # K = tap * 24 + channel, 168 -> 176
+        sd[f"blocks.0.block.0.{j}.module.block.1.weight"].permute(0, 2, 1).reshape(C, 7 * C).to(DEV), k_pad=176)
+        for j in range(3)]).contiguous()
     pws = torch.stack([ops.pack_mma_b_fragments(sd[f"blocks.0.block.0.{j}.module.block.3.weight"][:, :, 0].to(DEV))
                        for j in range(3)]).contiguous()
     st = lambda key: torch.stack([sd[f"blocks.0.block.0.{j}.module.block.{key}"].flatten() for j in range(3)]).contiguous().to(DEV)
