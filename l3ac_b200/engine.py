@@ -99,6 +99,7 @@ class Engine:
         # 222 vs 298 us; at C=256 the fused kernel re-streams 1 MB of weights per 128-row tile and is L2-bound at parity
         # (282 vs 280 us), so the two-GEMM path keeps that width.
         self.fused_mlp = True
+        self.thin_tc = os.environ.get("L3AC_THIN_TC", "1") != "0"     # fused tensor-core ConvUnit for the C = 24 / 48 encoder stages
         self.fused_mlp_max_c = 256
         self.hidden_block_bytes = 0              # >0: L2-blocked ConvUnit MLP (measured slower, see _run_conv_unit)
         self.dec_dtype = torch.bfloat16 if precision == "bf16" else torch.float32
@@ -286,6 +287,10 @@ class Engine:
         ``out_kind=ops.SPLIT`` (encode side, last unit before a GEMM consumer): the result is written as the split-bf16
         pair directly by the producing kernel, which removes a separate fp32 -> split pass over the tensor."""
         B, T, C = x.shape
+        if act_dtype == ops.SPLIT and C in (24, 48) and self.thin_tc:
+            # thin encode-side stages: the whole unit in one tensor-core kernel (3-term split operands, fp32-class)
+            return ops.convunit_thin_tc(x, u["dw_w"], u["dw_b"], u["ln_w"], u["ln_b"], EPS, u["pw1"].w32, u["pw1"].bias,
+                                        u["alpha"], u["scale"], u["shift"], u["pw2"].w32, u["pw2"].bias, out_dtype=out_kind)
         if C == 24 and act_dtype != torch.bfloat16:      # thin full-rate encoder stage: one fused fp32 kernel
             return ops.convunit_thin(x, u["dw_w"], u["dw_b"], u["ln_w"], u["ln_b"], EPS, u["pw1"].w32, u["pw1"].bias,
                                      u["alpha"], u["scale"], u["shift"], u["pw2"].w32, u["pw2"].bias, out_dtype=out_kind)
