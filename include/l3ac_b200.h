@@ -60,6 +60,13 @@ int l3ac_stem(const float* audio, int B, int T, const float* branch_w, const flo
               const float* w1, const float* b1, const float* w2, const float* b2, int C, float* out,
               l3ac_stream_t stream);
 
+/* The same stem on the tensor cores at fp32-class precision (the two 1x1 convs as 3-term split-bf16 MMAs, fp32
+ * accumulate; the pooled signals by a 4-neighbour two-level scheme, i.e. a different but equally accurate fp32
+ * summation order).  Same arguments; out 8-byte aligned.  Used by the default (split-bf16) encode path. */
+int l3ac_stem_tc(const float* audio, int B, int T, const float* branch_w, const float* branch_b,
+              const float* w1, const float* b1, const float* w2, const float* b2, int C, float* out,
+              l3ac_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * ConvUnit prologue.  Replaces dw_conv + permute + norm of ConvUnit.forward
  * (l3ac/modules.py:33-35; F.layer_norm at l3ac/layers.py:80): depthwise Conv1d(C,C,k7,pad 3) then

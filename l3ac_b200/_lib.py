@@ -32,6 +32,7 @@ PROTOTYPES = {
     "l3ac_abi_version": (_i, []),
     "l3ac_error_string": (C.c_char_p, [_i]),
     "l3ac_stem": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p]),
+    "l3ac_stem_tc": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p]),
     "l3ac_dwconv7_ln": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _f, _p, _p, _i, _p]),
     "l3ac_layernorm": (_i, [_p, _ll, _i, _p, _p, _f, _p, _p, _i, _p]),
     "l3ac_split_bf16": (_i, [_p, _ll, _p, _p, _p]),

@@ -346,7 +346,8 @@ class Engine:
         T = math.ceil(T0 / hop) * hop                      # Codec.preprocess, l3ac/codec.py:79-84
         if T != T0:
             audio = torch.nn.functional.pad(audio, (0, T - T0))
-        x = ops.stem(audio.contiguous(), **self.stem)      # (B, T, 24)
+        stem = ops.stem_tc if (f32 == ops.SPLIT and self.thin_tc) else ops.stem
+        x = stem(audio.contiguous(), **self.stem)          # (B, T, 24)
         if taps is not None:
             taps["enc_stem"] = x
         # The last ConvUnit before a GEMM consumer writes that GEMM's operand kind directly (split pair on the tensor-core

@@ -121,6 +121,19 @@ def stem(audio: torch.Tensor, branch_w, branch_b, w1, b1, w2, b2) -> torch.Tenso
     return out
 
 
+def stem_tc(audio: torch.Tensor, branch_w, branch_b, w1, b1, w2, b2) -> torch.Tensor:
+    """Encoder stem with the two 1x1 convs as 3-term split-bf16 tensor-core MMAs (fp32-class)."""
+    _chk(audio, name="audio")
+    B, T = audio.shape
+    Cout = w2.shape[0]
+    out = torch.empty((B, T, Cout), device=audio.device, dtype=torch.float32)
+    _count()
+    with _hook("stem_tc", _nbytes(audio, out), 2.0 * audio.numel() * 3700), torch.cuda.device(audio.device):
+        check(_lib.load().l3ac_stem_tc(_ptr(audio), B, T, _ptr(branch_w), _ptr(branch_b), _ptr(w1), _ptr(b1), _ptr(w2),
+                                       _ptr(b2), Cout, _ptr(out), _stream(audio)), "l3ac_stem_tc")
+    return out
+
+
 def dwconv7_ln(x, dw_w, dw_b, ln_w, ln_b, eps: float, out_dtype=torch.float32) -> torch.Tensor:
     _chk(x, name="x")
     B, T, Cc = x.shape

@@ -40,6 +40,27 @@ def test_stem(cuda_lib):
     assert max_abs(cf(got), want) < 2e-5
 
 
+@pytest.mark.parametrize("T", [1, 40, 255, 256, 1000, 2717])
+def test_stem_tc(cuda_lib, T):
+    """Tensor-core stem (3-term split-bf16 1x1 convs, two-level pooling) against the oracle's first_block."""
+    B = 3
+    sd = {}
+    for i in range(5):
+        sd[f"s.blocks.{i}.1.weight"], sd[f"s.blocks.{i}.1.bias"] = rnd(4, 1, 7, seed=i, scale=0.3), rnd(4, seed=10 + i, scale=0.1)
+    sd["s.conv_1.weight"], sd["s.conv_1.bias"] = rnd(80, 20, 1, seed=20, scale=0.2), rnd(80, seed=21, scale=0.1)
+    sd["s.conv_2.weight"], sd["s.conv_2.bias"] = rnd(24, 81, 1, seed=22, scale=0.2), rnd(24, seed=23, scale=0.1)
+    x = rnd(B, 1, T, seed=30, scale=0.3)
+    want = O.first_block(sd, "s", x)
+    bw = torch.stack([sd[f"s.blocks.{i}.1.weight"][:, 0] for i in range(5)]).contiguous().to(DEV)
+    bb = torch.cat([sd[f"s.blocks.{i}.1.bias"] for i in range(5)]).to(DEV)
+    args = (x[:, 0].contiguous().to(DEV), bw, bb, sd["s.conv_1.weight"][:, :, 0].contiguous().to(DEV),
+            sd["s.conv_1.bias"].to(DEV), sd["s.conv_2.weight"][:, :, 0].contiguous().to(DEV), sd["s.conv_2.bias"].to(DEV))
+    got = ops.stem_tc(*args)
+    err = max_abs(cf(got), want)
+    print(f"[stem_tc T={T}] max-abs vs oracle {err:.2e}; vs fp32 SIMT stem {max_abs(got, ops.stem(*args)):.2e}")
+    assert err < 3e-5 * max(1.0, float(want.abs().max()))       # fp32-class (2^-16 level)
+
+
 @pytest.mark.parametrize("C,T", [(24, 300), (48, 1001), (96, 77), (128, 9), (192, 50), (256, 133), (384, 20), (512, 40)])
 def test_dwconv7_ln(cuda_lib, C, T):
     x = rnd(2, C, T, seed=1)
