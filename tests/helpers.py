@@ -50,3 +50,33 @@ def snr_db(ref: torch.Tensor, test: torch.Tensor) -> float:
 
 def max_abs(a: torch.Tensor, b: torch.Tensor) -> float:
     return float((a.double() - b.double()).abs().max())
+
+
+class bf16_operand_emulation:
+    """Context manager: the oracle's dense decode-side ops (conv1d with groups == 1 and >= 24 input channels, linear with
+    >= 24 input features) see their input and weight rounded to bf16, products accumulated in fp32 -- the arithmetic model
+    of the tensor-core decode path ("bf16-in / fp32-accumulate").  Depthwise, 1-channel and quantiser layers stay fp32, as
+    they do in the kernels.  Attention products are not rounded, so the emulation is, if anything, slightly MORE accurate
+    than the real path."""
+
+    def __enter__(self):
+        import torch.nn.functional as F
+        self.F, self.conv1d, self.linear = F, F.conv1d, F.linear
+        bf = lambda t: t.to(torch.bfloat16).to(torch.float32)
+
+        def conv1d(x, w, b=None, stride=1, padding=0, dilation=1, groups=1):
+            if groups == 1 and w.shape[1] >= 24 and w.shape[0] > 1:
+                x, w = bf(x), bf(w)
+            return self.conv1d(x, w, b, stride, padding, dilation, groups)
+
+        def linear(x, w, b=None):
+            if w.shape[1] >= 24:
+                x, w = bf(x), bf(w)
+            return self.linear(x, w, b)
+
+        F.conv1d, F.linear = conv1d, linear
+        return self
+
+    def __exit__(self, *exc):
+        self.F.conv1d, self.F.linear = self.conv1d, self.linear
+        return False

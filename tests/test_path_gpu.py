@@ -4,7 +4,7 @@ import pytest
 import torch
 
 import l3ac_b200
-from helpers import CONFIGS, golden_case, make_audio, max_abs, model_config, snr_db
+from helpers import CONFIGS, bf16_operand_emulation, golden_case, make_audio, max_abs, model_config, snr_db
 from l3ac_b200.config import CONFIG_DIR, L3ACConfig
 from l3ac_b200.spec import init_state_dicts
 from oracle import l3ac_oracle as O
@@ -154,14 +154,19 @@ def test_other_configs_at_baseline_sizes(cuda_lib, name, seconds, batch, t_tok, 
         with torch.inference_mode():
             wav32 = codec32.decode_audio(indices=idx["indices"][:1])
         snr32 = snr_db(owav, wav32.cpu())
-        print(f"[{name} {seconds:g} s] index agreement {agree:.5f}, decode SNR vs oracle: fp32 mode {snr32:.1f} dB, bf16 mode {snr:.1f} dB")
+        with bf16_operand_emulation():
+            ewav = orc.decode_audio(indices=idx["indices"][:1].cpu())
+        snr_emu = snr_db(owav, ewav)
+        print(f"[{name} {seconds:g} s] index agreement {agree:.5f}, decode SNR vs oracle: fp32 mode {snr32:.1f} dB, bf16 mode {snr:.1f} dB, "
+              f"bf16-operand emulation of the oracle {snr_emu:.1f} dB")
         assert agree >= 0.999           # north-star bound for the default (split-bf16 encode) mode
         assert snr32 > 60.0             # fp32 mode: the 1e-5 class (measured 74-91 dB)
         # bf16 decode side: these jittered random-init networks amplify operand rounding by 6-10 dB per decoder stage
-        # (tools/snr_diag.py: dec_feature 47 dB -> dec_up3 15 dB -> waveform 6-19 dB depending on config and seed, while every
-        # kernel matches its bf16-operand emulation); the stated tolerance lives in test_bf16_mode_tolerance on the golden
-        # weights.  Here only gross failure is excluded.
-        assert snr > 3.0
+        # (tools/snr_diag.py: dec_feature 47 dB -> dec_up3 15 dB -> waveform 6-19 dB depending on config and seed).  The bound is
+        # therefore relative: the kernels must be as accurate as the "bf16-in / fp32-accumulate" model of the same network
+        # (the oracle with its dense operands rounded to bf16), within 4 dB; the absolute tolerance on the golden weights is
+        # stated in test_bf16_mode_tolerance.
+        assert snr > snr_emu - 4.0 and snr > 3.0
 
 
 def test_micro_batching_is_transparent(cuda_lib):
