@@ -219,7 +219,9 @@ __global__ void __launch_bounds__(256) dwconv7_ln_vec_kernel(const float* __rest
         const long long run = base + sub;
         const bool run_ok = run < total_runs;
         const long long rr = run_ok ? run : total_runs - 1;
-        const int b = (int)(rr / runs_per_sample);
+        int b;
+        if (total_runs <= 0x7fffffffLL) b = (int)((unsigned)rr / (unsigned)runs_per_sample);     // the 64-bit division costs ~60 instructions
+        else b = (int)(rr / runs_per_sample);
         const int t0 = (int)(rr - (long long)b * runs_per_sample) * R;
         const float4* xb = reinterpret_cast<const float4*>(x + (long long)b * T * C) + g;
         float4 xr[R + 6];
@@ -483,7 +485,8 @@ __global__ void __launch_bounds__(256) upsample_cn_kernel(const float* __restric
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     const int To = T * scale;
-    const long long rows = (long long)B * To;
+    const int bclip = blockIdx.y;                // one clip per grid row: no per-row division by To (~20 instructions per row and lane)
+    const long long rows = To;
     const float rscale = (float)(1.0 / (double)scale);
     for (long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows;
          row += (long long)gridDim.x * warps_per_block) {
@@ -706,7 +709,8 @@ __global__ void __launch_bounds__(256) upsample_cn_vec_kernel(const float* __res
     const int lane = threadIdx.x & 31, g = lane % GS, sub = lane / GS;
     const int C4 = C >> 2;
     const int To = T * scale;
-    const long long rows = (long long)B * To;
+    const int bclip = blockIdx.y;                // one clip per grid row: no per-row division by To (~20 instructions per row and lane)
+    const long long rows = To;
     const float rscale = (float)(1.0 / (double)scale);
     const float inv_c = 1.0f / (float)C;
     float4 w4[VPL], b4[VPL];
@@ -726,15 +730,8 @@ __global__ void __launch_bounds__(256) upsample_cn_vec_kernel(const float* __res
         for (int u = 0; u < U; ++u) {
             const long long row = base + u * RW + sub;
             ok[u] = row < rows;
-            const long long rr = ok[u] ? row : rows - 1;
-            int b, j;
-            if (rows <= 0x7fffffffLL) {          // 32-bit division (the 64-bit one costs ~60 instructions per row and lane)
-                b = (int)((unsigned)rr / (unsigned)To);
-                j = (int)((unsigned)rr - (unsigned)b * (unsigned)To);
-            } else {
-                b = (int)(rr / To);
-                j = (int)(rr - (long long)b * To);
-            }
+            const int j = (int)(ok[u] ? row : rows - 1);
+            const int b = bclip;
             float src = fmaf(rscale, (float)j + 0.5f, -0.5f);   // ATen contracts this to one fma
             src = src < 0.f ? 0.f : src;
             int i0 = (int)src;
@@ -777,7 +774,7 @@ __global__ void __launch_bounds__(256) upsample_cn_vec_kernel(const float* __res
                 rstd = rsqrt_nr(group_sum<GS>(q) * inv_c + eps);
             }
             if (!ok[u]) continue;
-            float4* orow = reinterpret_cast<float4*>(out + (base + u * RW + sub) * C);
+            float4* orow = reinterpret_cast<float4*>(out + ((long long)bclip * To + base + u * RW + sub) * C);
 #pragma unroll
             for (int v = 0; v < VPL; ++v) {
                 const int c4 = g + GS * v;
@@ -988,6 +985,14 @@ static inline int grid_for_rows(long long rows, int rows_per_block) {
     return (int)g;
 }
 
+// grid.x of a (row blocks, clip) grid: the same ~32 blocks per SM in total as grid_for_rows (each block loops)
+static inline int ups_grid_x(long long rows_per_clip, int rows_per_block, int B) {
+    long long g = (rows_per_clip + rows_per_block - 1) / rows_per_block;
+    const long long cap = (148LL * 32 + B - 1) / B;
+    if (g > cap) g = cap;
+    return (int)(g < 1 ? 1 : g);
+}
+
 }  // namespace l3ac
 
 using namespace l3ac;
@@ -1161,7 +1166,7 @@ extern "C" int l3ac_snake(const float* x, long long M, int C, const float* alpha
 
 extern "C" int l3ac_upsample_linear_cn(const float* x, int B, int T, int C, int scale, const float* cn_w,
                                        const float* cn_b, float eps, float* out, l3ac_stream_t stream) {
-    L3AC_CHECK_ARG(x && out && B > 0 && T > 0 && C > 0 && C <= 512 && scale >= 1);
+    L3AC_CHECK_ARG(x && out && B > 0 && B <= 65535 && T > 0 && C > 0 && C <= 512 && scale >= 1 && (long long)T * scale <= 0x7fffffffLL);
     L3AC_CHECK_ARG((cn_w == nullptr) == (cn_b == nullptr));
     cudaStream_t st = (cudaStream_t)stream;
     const long long rows = (long long)B * T * scale;
@@ -1169,8 +1174,8 @@ extern "C" int l3ac_upsample_linear_cn(const float* x, int B, int T, int C, int 
         (!cn_w || ((reinterpret_cast<uintptr_t>(cn_w) | reinterpret_cast<uintptr_t>(cn_b)) & 15) == 0)) {
         const int C4 = C / 4;
 #define L3AC_UPS(GS, VPL, U)                                                                                      \
-    upsample_cn_vec_kernel<GS, VPL, U><<<grid_for_rows(rows, 8 * (32 / GS) * U), 256, 0, st>>>(x, B, T, C, scale, cn_w, \
-                                                                                                cn_b, eps, out)
+    upsample_cn_vec_kernel<GS, VPL, U><<<dim3(ups_grid_x((long long)T * scale, 8 * (32 / GS) * U, B), B), 256, 0, st>>>( \
+        x, B, T, C, scale, cn_w, cn_b, eps, out)
         if (C4 <= 8) L3AC_UPS(8, 1, 4);
         else if (C4 <= 16) L3AC_UPS(16, 1, 4);
         else if (C4 <= 32) L3AC_UPS(32, 1, 4);

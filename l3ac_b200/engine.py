@@ -442,7 +442,12 @@ class Engine:
         """L3AC.encode_audio -- l3ac/__init__.py:108-114."""
         if audio.dim() != 2:
             raise RuntimeError(f"encode_audio expects a (batch, samples) tensor, got shape {tuple(audio.shape)}")
-        audio = audio.to(device=self.device, dtype=torch.float32)
+        # A pinned host batch that will be processed in several micro-batches is uploaded micro-batch by micro-batch on the
+        # streams that consume it, so that the copies overlap the kernels of the other micro-batches.
+        staged_on_host = (audio.device.type == "cpu" and audio.dtype == torch.float32 and audio.is_pinned()
+                          and len(self._chunks(*audio.shape)) > 1 and taps is None)
+        if not staged_on_host:
+            audio = audio.to(device=self.device, dtype=torch.float32)
         if audio.shape[0] == 0 or audio.shape[1] == 0:            # empty batch: empty results of the right shapes
             if audio.shape[1] == 0:
                 raise RuntimeError("encode_audio got clips of length 0")
@@ -457,7 +462,8 @@ class Engine:
         n_all = audio.shape[0]
 
         def run(lo, hi):
-            t = self.encode_features(audio[lo:hi], taps if (lo == 0 and hi == n_all) else None)
+            a = audio[lo:hi].to(self.device, non_blocking=True) if staged_on_host else audio[lo:hi]
+            t = self.encode_features(a, taps if (lo == 0 and hi == n_all) else None)
             if taps is not None:
                 taps["trans_feature"] = t
             q, idx, lvl, z = self.quantize(t, want_z=taps is not None)

@@ -186,6 +186,19 @@ def test_micro_batching_is_transparent(cuda_lib):
     assert torch.equal(wav[5:6], wav1)
 
 
+def test_pinned_host_input_is_uploaded_per_micro_batch(cuda_lib):
+    """A pinned host batch spanning several micro-batches is uploaded chunk by chunk inside encode_audio; same results."""
+    codec = l3ac_b200.get_model("1kbps", pretrained=False)
+    codec.network.cuda()
+    codec.network.engine.max_chunk_samples = 16000 * 12
+    codec.network.engine.graph_max_samples = 0
+    host = make_audio(5, 5.0, seed=41).pin_memory()
+    with torch.inference_mode():
+        q0, idx0 = codec.encode_audio(host.to(DEV))
+        q1, idx1 = codec.encode_audio(host)
+    assert q1.device.type == "cuda" and torch.equal(idx0["indices"], idx1["indices"]) and torch.equal(q0, q1)
+
+
 def test_cuda_graph_path_matches_eager(cuda_lib):
     """Small batches replay a captured CUDA graph; results must be bit-identical to the eager launch sequence."""
     codec = l3ac_b200.get_model("1kbps", pretrained=False)
