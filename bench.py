@@ -352,7 +352,7 @@ def main():
                             "snake epilogue (SFU + issue), see DESIGN.md section 3" % (inst_ms, saved_streams)}
     # The register-level tensor-core kernels (mma.sync: 24..48-channel layers and the windowed attention cannot feed a 128 x N
     # tcgen05 tile) are compute kernels as well; only the stencil / norm / quantiser kernels are judged against HBM.
-    MMA_KINDS = ("decoder_tail", "convunit_thin_tc", "stem_tc", "local_attention_tc", "local_attention_tc_split")
+    MMA_KINDS = ("decoder_tail", "convunit_thin_tc", "convunit_thin_tc_bf16", "stem_tc", "local_attention_tc", "local_attention_tc_split")
     mma_ops = {k: o for k, o in by_op.items() if k in MMA_KINDS}
     mma_ms, mma_gflop = sum(o["ms"] for o in mma_ops.values()), sum(o["gflop"] for o in mma_ops.values())
     hbm_ops = {k: o for k, o in by_op.items() if not k.startswith("gemm") and k != "convunit_mlp_tc" and k not in MMA_KINDS

@@ -156,11 +156,12 @@ int l3ac_convunit_thin_f32(const float* x, int B, int T, int C, const float* dw_
  * encode-side stages with C = 24 and C = 48: dwconv7 + LayerNorm in registers, pw_conv1 / pw_conv2 as 3-term
  * split-bf16 MMAs (hi*Whi + lo*Whi + hi*Wlo, fp32 accumulate) with the hidden activation kept in registers.
  * Arguments as l3ac_convunit_thin_f32 (fp32 weights: w1 [4C][C], w2 [C][4C]; they are split on the fly);
- * x / out / out_lo 16-byte aligned. */
+ * x / out / out_lo 16-byte aligned.  operand_dtype L3AC_BF16X2: 3-term split products (encode side);
+ * L3AC_BF16: plain bf16 operands, fp32 accumulate (the decode side's arithmetic; used for its C = 48 unit). */
 int l3ac_convunit_thin_tc(const float* x, int B, int T, int C, const float* dw_w, const float* dw_b, const float* ln_w,
                           const float* ln_b, float eps, const float* w1, const float* b1, const float* alpha,
                           const float* scale, const float* shift, const float* w2, const float* b2, void* out,
-                          void* out_lo, int out_dtype, l3ac_stream_t stream);
+                          void* out_lo, int out_dtype, int operand_dtype, l3ac_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Block-local causal attention.  Replaces LocalAttention.forward of local-attention==1.11.2 as

@@ -41,7 +41,7 @@ PROTOTYPES = {
     "l3ac_gemm_bf16_tc": (_i, [C.POINTER(GemmDesc), _p]),
     "l3ac_convunit_mlp_tc": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _ll, _i, _p]),
     "l3ac_convunit_thin_f32": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p]),
-    "l3ac_convunit_thin_tc": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p]),
+    "l3ac_convunit_thin_tc": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
     "l3ac_local_attention_f32": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "l3ac_local_attention_tc": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p]),
     "l3ac_fsq_quantize": (_i, [_p, _ll, _i, _p, _p, _p, _p, C.POINTER(_i), _i, _p, _p, _p, _p, _p]),

@@ -77,6 +77,11 @@ __device__ __forceinline__ void split2(float2 v, uint32_t& hi, uint32_t& lo) {
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+__device__ __forceinline__ uint32_t pack2(float2 v) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
 __device__ __forceinline__ float quad_sum(float v) {
     v += __shfl_xor_sync(0xffffffffu, v, 1);
     v += __shfl_xor_sync(0xffffffffu, v, 2);
@@ -89,7 +94,9 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool v
 }
 
 // SPLIT: write the result as the split-bf16 pair the next tcgen05 GEMM consumes instead of fp32.
-template <int C, int kMT, bool SPLIT>
+// kSplitOps: 3-term split-bf16 products (fp32-class, encode side); false = plain bf16 operands with fp32 accumulation (the
+// decode side's arithmetic: A = bf16(LayerNorm(..)), hidden = bf16(snake(..)), bf16 weights), one MMA per product.
+template <int C, int kMT, bool SPLIT, bool kSplitOps>
 __global__ void __launch_bounds__(kThreads, 1) convunit_tc_split_kernel(const Params p) {
     using G = Geo<C, kMT>;
     constexpr int H = G::H, kNT = G::kNT, kK16 = G::kK16, kKS1 = G::kKS1, kPitch = G::kPitch, kRows = G::kRows;
@@ -236,7 +243,13 @@ __global__ void __launch_bounds__(kThreads, 1) convunit_tc_split_kernel(const Pa
                     for (int n = 0; n < kNT; ++n) {
                         const float2 lw = *reinterpret_cast<const float2*>(cpar + 8 * C + n * 8 + t4 * 2);
                         const float2 lb = *reinterpret_cast<const float2*>(cpar + 9 * C + n * 8 + t4 * 2);
-                        split2(ffma2(fmul2(y[i][h][n], make_float2(rstd, rstd)), lw, lb), ahi[i][n][h], alo[i][n][h]);
+                        const float2 a = ffma2(fmul2(y[i][h][n], make_float2(rstd, rstd)), lw, lb);
+                        if (kSplitOps) {
+                            split2(a, ahi[i][n][h], alo[i][n][h]);
+                        } else {
+                            ahi[i][n][h] = pack2(a);
+                            alo[i][n][h] = 0;
+                        }
                     }
                 }
         }
@@ -273,12 +286,16 @@ __global__ void __launch_bounds__(kThreads, 1) convunit_tc_split_kernel(const Pa
                     for (int i = 0; i < kMT; ++i) {
                         if (ks < kK16) {
                             mma_k16(hacc[i][nt], ahi[i][2 * ks][0], ahi[i][2 * ks][1], ahi[i][2 * ks + 1][0], ahi[i][2 * ks + 1][1], w.x, w.y);
-                            mma_k16(hacc[i][nt], alo[i][2 * ks][0], alo[i][2 * ks][1], alo[i][2 * ks + 1][0], alo[i][2 * ks + 1][1], w.x, w.y);
-                            mma_k16(hacc[i][nt], ahi[i][2 * ks][0], ahi[i][2 * ks][1], ahi[i][2 * ks + 1][0], ahi[i][2 * ks + 1][1], w.z, w.w);
+                            if (kSplitOps) {
+                                mma_k16(hacc[i][nt], alo[i][2 * ks][0], alo[i][2 * ks][1], alo[i][2 * ks + 1][0], alo[i][2 * ks + 1][1], w.x, w.y);
+                                mma_k16(hacc[i][nt], ahi[i][2 * ks][0], ahi[i][2 * ks][1], ahi[i][2 * ks + 1][0], ahi[i][2 * ks + 1][1], w.z, w.w);
+                            }
                         } else {                         // trailing 8 channels
                             mma_k8(hacc[i][nt], ahi[i][kNT - 1][0], ahi[i][kNT - 1][1], w.x);
-                            mma_k8(hacc[i][nt], alo[i][kNT - 1][0], alo[i][kNT - 1][1], w.x);
-                            mma_k8(hacc[i][nt], ahi[i][kNT - 1][0], ahi[i][kNT - 1][1], w.z);
+                            if (kSplitOps) {
+                                mma_k8(hacc[i][nt], alo[i][kNT - 1][0], alo[i][kNT - 1][1], w.x);
+                                mma_k8(hacc[i][nt], ahi[i][kNT - 1][0], ahi[i][kNT - 1][1], w.z);
+                            }
                         }
                     }
                 }
@@ -295,7 +312,12 @@ __global__ void __launch_bounds__(kThreads, 1) convunit_tc_split_kernel(const Pa
                     for (int h = 0; h < 2; ++h) {
                         const float2 v = snake_affine2(make_float2(hacc[i][nt][2 * h], hacc[i][nt][2 * h + 1]), make_float2(q0.z, q0.w),
                                                        make_float2(q1.x, q1.y), make_float2(q1.z, q1.w), sh);
-                        split2(v, hhi[i][nt][h], hlo[i][nt][h]);
+                        if (kSplitOps) {
+                            split2(v, hhi[i][nt][h], hlo[i][nt][h]);
+                        } else {
+                            hhi[i][nt][h] = pack2(v);
+                            hlo[i][nt][h] = 0;
+                        }
                     }
             }
             // pw_conv2: this chunk's 32 hidden columns are two k16 steps
@@ -307,8 +329,10 @@ __global__ void __launch_bounds__(kThreads, 1) convunit_tc_split_kernel(const Pa
 #pragma unroll
                     for (int i = 0; i < kMT; ++i) {
                         mma_k16(acc[i][n], hhi[i][2 * ks][0], hhi[i][2 * ks][1], hhi[i][2 * ks + 1][0], hhi[i][2 * ks + 1][1], w.x, w.y);
-                        mma_k16(acc[i][n], hlo[i][2 * ks][0], hlo[i][2 * ks][1], hlo[i][2 * ks + 1][0], hlo[i][2 * ks + 1][1], w.x, w.y);
-                        mma_k16(acc[i][n], hhi[i][2 * ks][0], hhi[i][2 * ks][1], hhi[i][2 * ks + 1][0], hhi[i][2 * ks + 1][1], w.z, w.w);
+                        if (kSplitOps) {
+                            mma_k16(acc[i][n], hlo[i][2 * ks][0], hlo[i][2 * ks][1], hlo[i][2 * ks + 1][0], hlo[i][2 * ks + 1][1], w.x, w.y);
+                            mma_k16(acc[i][n], hhi[i][2 * ks][0], hhi[i][2 * ks][1], hhi[i][2 * ks + 1][0], hhi[i][2 * ks + 1][1], w.z, w.w);
+                        }
                     }
                 }
         }
@@ -341,7 +365,7 @@ __global__ void __launch_bounds__(kThreads, 1) convunit_tc_split_kernel(const Pa
     asm volatile("cp.async.wait_all;");
 }
 
-template <int C, int kMT>
+template <int C, int kMT, bool kSplitOps>
 static int launch(const Params& p, bool split, cudaStream_t stream) {
     using G = Geo<C, kMT>;
     int dev = 0, sms = 0;
@@ -356,7 +380,7 @@ static int launch(const Params& p, bool split, cudaStream_t stream) {
         kernel<<<grid, kThreads, G::kSmemBytes, stream>>>(p);
         return l3ac_launch_status();
     };
-    return split ? go(convunit_tc_split_kernel<C, kMT, true>) : go(convunit_tc_split_kernel<C, kMT, false>);
+    return split ? go(convunit_tc_split_kernel<C, kMT, true, kSplitOps>) : go(convunit_tc_split_kernel<C, kMT, false, kSplitOps>);
 }
 
 }  // namespace thintc
@@ -365,15 +389,22 @@ static int launch(const Params& p, bool split, cudaStream_t stream) {
 extern "C" int l3ac_convunit_thin_tc(const float* x, int B, int T, int C, const float* dw_w, const float* dw_b,
                                      const float* ln_w, const float* ln_b, float eps, const float* w1, const float* b1,
                                      const float* alpha, const float* scale, const float* shift, const float* w2,
-                                     const float* b2, void* out, void* out_lo, int out_dtype, l3ac_stream_t stream) {
+                                     const float* b2, void* out, void* out_lo, int out_dtype, int operand_dtype,
+                                     l3ac_stream_t stream) {
     using namespace l3ac::thintc;
     L3AC_CHECK_ARG(x && dw_w && dw_b && ln_w && ln_b && w1 && b1 && alpha && scale && shift && w2 && b2 && out);
     L3AC_CHECK_ARG(B > 0 && T > 0);
     L3AC_CHECK_ARG(out_dtype == L3AC_F32 || (out_dtype == L3AC_BF16X2 && out_lo));
+    L3AC_CHECK_ARG(operand_dtype == L3AC_BF16X2 || operand_dtype == L3AC_BF16);
     L3AC_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(out_lo)) & 15) == 0);
     Params p{x, dw_w, dw_b, ln_w, ln_b, w1, b1, alpha, scale, shift, w2, b2, eps, B, T, out, out_lo};
     const bool split = out_dtype == L3AC_BF16X2;
-    if (C == 24) return launch<24, 2>(p, split, (cudaStream_t)stream);
-    if (C == 48) return launch<48, 1>(p, split, (cudaStream_t)stream);
+    if (operand_dtype == L3AC_BF16X2) {
+        if (C == 24) return launch<24, 2, true>(p, split, (cudaStream_t)stream);
+        if (C == 48) return launch<48, 1, true>(p, split, (cudaStream_t)stream);
+    } else {
+        if (C == 24) return launch<24, 2, false>(p, split, (cudaStream_t)stream);
+        if (C == 48) return launch<48, 1, false>(p, split, (cudaStream_t)stream);
+    }
     return L3AC_EUNSUPPORTED;
 }

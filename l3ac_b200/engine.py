@@ -100,6 +100,10 @@ class Engine:
         # (282 vs 280 us), so the two-GEMM path keeps that width.
         self.fused_mlp = True
         self.thin_tc = os.environ.get("L3AC_THIN_TC", "1") != "0"     # fused tensor-core ConvUnit for the C = 24 / 48 encoder stages
+        # The same kernel with plain bf16 operands for the decode-side C = 48 unit: measured SLOWER than dwconv7_ln + the tcgen05
+        # fused MLP (664 vs 190 + 256 us per 24 clips: with one m-tile per warp and 16 warps per SM the kernel is latency-bound,
+        # 21 % issue efficiency), so it is off; kept as a tested operand mode of the entry point.
+        self.thin_tc_decode = os.environ.get("L3AC_THIN_TC_DECODE", "0") != "0"
         self.fused_mlp_max_c = 256
         self.hidden_block_bytes = 0              # >0: L2-blocked ConvUnit MLP (measured slower, see _run_conv_unit)
         self.dec_dtype = torch.bfloat16 if precision == "bf16" else torch.float32
@@ -291,6 +295,11 @@ class Engine:
             # thin encode-side stages: the whole unit in one tensor-core kernel (3-term split operands, fp32-class)
             return ops.convunit_thin_tc(x, u["dw_w"], u["dw_b"], u["ln_w"], u["ln_b"], EPS, u["pw1"].w32, u["pw1"].bias,
                                         u["alpha"], u["scale"], u["shift"], u["pw2"].w32, u["pw2"].bias, out_dtype=out_kind)
+        if act_dtype == torch.bfloat16 and C == 48 and self.thin_tc_decode and out_kind == torch.float32:
+            # decode-side C = 48 unit (1.9 M rows per 24 clips): dwconv + LN + MLP in one register-resident mma.sync kernel
+            # with the decode side's bf16 operands, instead of dwconv7_ln + the (HBM-bound at this width) tcgen05 fused MLP
+            return ops.convunit_thin_tc(x, u["dw_w"], u["dw_b"], u["ln_w"], u["ln_b"], EPS, u["pw1"].w32, u["pw1"].bias,
+                                        u["alpha"], u["scale"], u["shift"], u["pw2"].w32, u["pw2"].bias, operands=torch.bfloat16)
         if C == 24 and act_dtype != torch.bfloat16:      # thin full-rate encoder stage: one fused fp32 kernel
             return ops.convunit_thin(x, u["dw_w"], u["dw_b"], u["ln_w"], u["ln_b"], EPS, u["pw1"].w32, u["pw1"].bias,
                                      u["alpha"], u["scale"], u["shift"], u["pw2"].w32, u["pw2"].bias, out_dtype=out_kind)

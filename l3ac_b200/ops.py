@@ -269,19 +269,23 @@ def convunit_thin(x: torch.Tensor, dw_w, dw_b, ln_w, ln_b, eps: float, w1, b1, a
     return out
 
 
-def convunit_thin_tc(x: torch.Tensor, dw_w, dw_b, ln_w, ln_b, eps: float, w1, b1, alpha, scale, shift, w2, b2, out_dtype=torch.float32):
-    """Fused Residual(ConvUnit) for C = 24 / 48 on the tensor cores with 3-term split-bf16 operands (fp32-class):
-    x (B, T, C) fp32 -> same shape; ``out_dtype=SPLIT`` returns the split pair."""
+def convunit_thin_tc(x: torch.Tensor, dw_w, dw_b, ln_w, ln_b, eps: float, w1, b1, alpha, scale, shift, w2, b2, out_dtype=torch.float32,
+                     operands=None):
+    """Fused Residual(ConvUnit) for C = 24 / 48 on the tensor cores: x (B, T, C) fp32 -> same shape; ``out_dtype=SPLIT``
+    returns the split pair.  ``operands``: SPLIT (default) = 3-term split-bf16 products (fp32-class, encode side);
+    torch.bfloat16 = plain bf16 operands with fp32 accumulation (decode side)."""
+    operands = SPLIT if operands is None else operands
     _chk(x, name="x")
     B, T, Cc = x.shape
     if out_dtype not in (torch.float32, SPLIT):
         raise ValueError("convunit_thin_tc emits fp32 or the split-bf16 pair")
     out, hi, lo = _empty_act(tuple(x.shape), x.device, out_dtype)
     _count()
-    with _hook("convunit_thin_tc", _nbytes(x) + B * T * Cc * 4, 2.0 * B * T * (7 * Cc + 8 * Cc * Cc)), torch.cuda.device(x.device):
+    kind = "convunit_thin_tc" if operands == SPLIT else "convunit_thin_tc_bf16"
+    with _hook(kind, _nbytes(x) + B * T * Cc * 4, 2.0 * B * T * (7 * Cc + 8 * Cc * Cc)), torch.cuda.device(x.device):
         check(_lib.load().l3ac_convunit_thin_tc(_ptr(x), B, T, Cc, _ptr(dw_w), _ptr(dw_b), _ptr(ln_w), _ptr(ln_b), eps, _ptr(w1),
                                                 _ptr(b1), _ptr(alpha), _ptr(scale), _ptr(shift), _ptr(w2), _ptr(b2), _ptr(hi),
-                                                _ptr(lo), _DT[out_dtype], _stream(x)), "l3ac_convunit_thin_tc")
+                                                _ptr(lo), _DT[out_dtype], _DT[operands], _stream(x)), "l3ac_convunit_thin_tc")
     return out
 
 

@@ -301,6 +301,18 @@ def test_fused_thin_convunit_tc(cuda_lib, C, T):
     sp = ops.convunit_thin_tc(cl(x), *args, out_dtype=ops.SPLIT)
     ref = ops.split_bf16(got)
     assert torch.equal(sp.hi, ref.hi) and torch.equal(sp.lo, ref.lo)
+    # plain bf16 operands (decode side): same distance from the oracle as the bf16-operand emulation of the same unit
+    got16 = ops.convunit_thin_tc(cl(x), *args, operands=torch.bfloat16)
+    bf = lambda t: t.to(torch.bfloat16).float()
+    a = bf(F.layer_norm(F.conv1d(x, sd["u.dw_conv.weight"], sd["u.dw_conv.bias"], padding=3, groups=C).permute(0, 2, 1), (C,),
+                        sd["u.norm.weight"], sd["u.norm.bias"], 1e-8))
+    lin = F.linear(a, bf(sd["u.pw_conv1.weight"]), sd["u.pw_conv1.bias"])
+    al = sd["u.act.alpha"].flatten()
+    hid = bf((lin + torch.sin(al * lin).pow(2) / (al + 1e-8)) * (1 + sd["u.grn.gamma"].flatten()) + sd["u.grn.beta"].flatten())
+    emu = (F.linear(hid, bf(sd["u.pw_conv2.weight"]), sd["u.pw_conv2.bias"])).permute(0, 2, 1) + x
+    e_k, e_e = max_abs(cf(got16), want), max_abs(emu, want)
+    print(f"[thin_tc bf16 C={C} T={T}] max-abs vs oracle: kernel {e_k:.2e}, emulation {e_e:.2e}, kernel-vs-emulation {max_abs(cf(got16), emu):.2e}")
+    assert e_k < 2.0 * e_e + 1e-3
 
 
 @pytest.mark.parametrize("T,w", [(100, 40), (333, 100), (593, 250), (64, 200), (257, 64), (1779, 750)])

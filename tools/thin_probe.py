@@ -27,7 +27,7 @@ def timed(fn, n=6):
     return sorted(ts)[len(ts) // 2], out
 
 
-for C, T in ((24, 160110), (48, 26685)):
+for C, T in ((24, 160110), (48, 26685), (48, 80055)):
     B = 24
     x = rnd(B, T, C)
     args = (rnd(7, C, scale=0.3), rnd(C, scale=0.1), 1 + rnd(C, scale=0.1), rnd(C, scale=0.1), 1e-8, rnd(4 * C, C, scale=0.2),
@@ -42,3 +42,5 @@ for C, T in ((24, 160110), (48, 26685)):
             r = ref if kind == torch.float32 else ref.hi.float() + ref.lo.float()
             msg += f" | fp32 SIMT kernel {t2:.1f} us, max-abs difference {(o - r).abs().max().item():.2e}"
         print(msg, flush=True)
+    t, out = timed(lambda: ops.convunit_thin_tc(x, *args, operands=torch.bfloat16))
+    print(f"thin_tc C={C} rows={B * T} bf16 operands, f32 out: {t:.1f} us", flush=True)
