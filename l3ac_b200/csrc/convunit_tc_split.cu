@@ -21,11 +21,13 @@
 namespace l3ac {
 namespace thintc {
 
-constexpr int kWarps = 16;
-constexpr int kThreads = kWarps * 32;
-
-template <int C, int kMT>
+// Launch shapes: (C, m-tiles per warp, warps per CTA, CTAs per SM).  Measured for C = 24 on 24 clips: two m-tiles per warp with
+// 1 x 16 warps per SM (weight fragments loaded once per two tiles) 479 us; one m-tile per warp at <= 85 registers with 3 x 8 or
+// 2 x 12 warps per SM 545 / 541 us -- the extra resident warps do not pay for the doubled fragment traffic.  C = 48 needs 74 KB
+// of weight fragments and runs one m-tile per warp.
+template <int C, int kMT, int kWarps, int kCtas>
 struct Geo {
+    static constexpr int kThreads = kWarps * 32;
     static constexpr int H = 4 * C;
     static constexpr int kNT = C / 8;                    // 8-channel n-tiles of a C-wide row
     static constexpr int kK16 = C / 16;                  // full k16 steps over C
@@ -96,9 +98,10 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool v
 // SPLIT: write the result as the split-bf16 pair the next tcgen05 GEMM consumes instead of fp32.
 // kSplitOps: 3-term split-bf16 products (fp32-class, encode side); false = plain bf16 operands with fp32 accumulation (the
 // decode side's arithmetic: A = bf16(LayerNorm(..)), hidden = bf16(snake(..)), bf16 weights), one MMA per product.
-template <int C, int kMT, bool SPLIT, bool kSplitOps>
-__global__ void __launch_bounds__(kThreads, 1) convunit_tc_split_kernel(const Params p) {
-    using G = Geo<C, kMT>;
+template <int C, int kMT, int kWarps, int kCtas, bool SPLIT, bool kSplitOps>
+__global__ void __launch_bounds__(kWarps * 32, kCtas) convunit_tc_split_kernel(const Params p) {
+    using G = Geo<C, kMT, kWarps, kCtas>;
+    constexpr int kThreads = G::kThreads;
     constexpr int H = G::H, kNT = G::kNT, kK16 = G::kK16, kKS1 = G::kKS1, kPitch = G::kPitch, kRows = G::kRows;
     extern __shared__ __align__(16) uint8_t smem[];
     float* xs = reinterpret_cast<float*>(smem);                               // [kWarps][2][kRows + 6][kPitch]
@@ -365,22 +368,23 @@ __global__ void __launch_bounds__(kThreads, 1) convunit_tc_split_kernel(const Pa
     asm volatile("cp.async.wait_all;");
 }
 
-template <int C, int kMT, bool kSplitOps>
+template <int C, int kMT, int kWarps, int kCtas, bool kSplitOps>
 static int launch(const Params& p, bool split, cudaStream_t stream) {
-    using G = Geo<C, kMT>;
+    using G = Geo<C, kMT, kWarps, kCtas>;
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
         return L3AC_EDRIVER;
     const long long n_tiles = (long long)l3ac_cdiv(p.T, G::kRows) * p.B;           // warp tiles
     const long long ctas = (n_tiles + kWarps - 1) / kWarps;
-    const int grid = (int)(ctas < sms ? ctas : sms);
+    const int grid = (int)(ctas < (long long)sms * kCtas ? ctas : (long long)sms * kCtas);
     auto go = [&](auto kernel) -> int {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::kSmemBytes);
         if (e != cudaSuccess) return (int)e;
-        kernel<<<grid, kThreads, G::kSmemBytes, stream>>>(p);
+        kernel<<<grid, G::kThreads, G::kSmemBytes, stream>>>(p);
         return l3ac_launch_status();
     };
-    return split ? go(convunit_tc_split_kernel<C, kMT, true, kSplitOps>) : go(convunit_tc_split_kernel<C, kMT, false, kSplitOps>);
+    return split ? go(convunit_tc_split_kernel<C, kMT, kWarps, kCtas, true, kSplitOps>)
+                 : go(convunit_tc_split_kernel<C, kMT, kWarps, kCtas, false, kSplitOps>);
 }
 
 }  // namespace thintc
@@ -400,11 +404,11 @@ extern "C" int l3ac_convunit_thin_tc(const float* x, int B, int T, int C, const 
     Params p{x, dw_w, dw_b, ln_w, ln_b, w1, b1, alpha, scale, shift, w2, b2, eps, B, T, out, out_lo};
     const bool split = out_dtype == L3AC_BF16X2;
     if (operand_dtype == L3AC_BF16X2) {
-        if (C == 24) return launch<24, 2, true>(p, split, (cudaStream_t)stream);
-        if (C == 48) return launch<48, 1, true>(p, split, (cudaStream_t)stream);
+        if (C == 24) return launch<24, 2, 16, 1, true>(p, split, (cudaStream_t)stream);
+        if (C == 48) return launch<48, 1, 16, 1, true>(p, split, (cudaStream_t)stream);
     } else {
-        if (C == 24) return launch<24, 2, false>(p, split, (cudaStream_t)stream);
-        if (C == 48) return launch<48, 1, false>(p, split, (cudaStream_t)stream);
+        if (C == 24) return launch<24, 2, 16, 1, false>(p, split, (cudaStream_t)stream);
+        if (C == 48) return launch<48, 1, 16, 1, false>(p, split, (cudaStream_t)stream);
     }
     return L3AC_EUNSUPPORTED;
 }
