@@ -44,6 +44,11 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], 
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ float ex2f(float x) {       // 2^x on MUFU.EX2 (2 ulp; ex2(-inf) = +0)
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<const uint32_t*>(&h);
@@ -83,7 +88,8 @@ __global__ void __launch_bounds__(128) local_attention_tc_kernel(const __nv_bflo
     const __nv_bfloat16* base_lo = SPLIT ? qkv_lo + (long long)b * T * ld + h * kD : nullptr;
     const int koff = H * kD, voff = 2 * H * kD;
 
-    for (int i = threadIdx.x; i < 2 * window; i += 128) s_table[i] = __ldg(bias_table + (long long)h * 2 * window + i);
+    for (int i = threadIdx.x; i < 2 * window; i += 128)       // base-2 domain: bias * log2 e
+        s_table[i] = __ldg(bias_table + (long long)h * 2 * window + i) * 1.4426950408889634f;
 
     const int q_last = min(q0 + kBQ, T) - 1;
     int k_begin = (q0 / window - 1) * window;
@@ -120,7 +126,11 @@ __global__ void __launch_bounds__(128) local_attention_tc_kernel(const __nv_bflo
     int lo0 = (qpos0 / window - 1) * window, lo1 = (qpos1 / window - 1) * window;
     lo0 = lo0 < 0 ? 0 : lo0;
     lo1 = lo1 < 0 ? 0 : lo1;
-    const float scale = 0.17677669529663687f;        // 32 ** -0.5
+    constexpr float kLog2e = 1.4426950408889634f;
+    const float scale = 0.17677669529663687f * kLog2e;        // 32 ** -0.5, base-2 domain
+    const int qmin_w = q0 + warp * 16, qmax_w = qmin_w + 15;    // this warp's query rows
+    int lo_max_w = (qmax_w / window - 1) * window;              // first visible key of the last row (monotone in the row)
+    lo_max_w = lo_max_w < 0 ? 0 : lo_max_w;
 
     float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
     float o[4][4];
@@ -162,19 +172,37 @@ __global__ void __launch_bounds__(128) local_attention_tc_kernel(const __nv_bflo
                 mma_bf16(s[nt], qa[1], kl[2], kl[3]);
             }
         }
-        // ---- scale + bias + mask, online softmax on the fragments
+        // ---- scale + bias + mask, online softmax on the fragments.  Everything is kept in the base-2 domain (the scale and
+        // the bias table carry a factor log2 e), so that a probability is one FADD + MUFU.EX2 instead of the ~10
+        // instructions of expf.  Tiles that lie entirely inside every row's visible range (all but the diagonal and the
+        // window-boundary tiles) skip the per-element position / mask logic; the choice is warp-uniform.
         float mx[2] = {-INFINITY, -INFINITY};
+        const bool full = (qmax_w < T) && (k0 + kBK - 1 <= qmin_w) && (k0 >= lo_max_w);
+        if (full) {
+            const float* t0p = s_table + (qpos0 - k0 - (lane & 3) * 2);      // index qpos0 - kpos for e = 0; e = 1: one less
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
+            for (int nt = 0; nt < 8; ++nt) {
+                const float* tp = t0p - nt * 8;
+                s[nt][0] = fmaf(s[nt][0], scale, tp[0]);
+                s[nt][1] = fmaf(s[nt][1], scale, tp[-1]);
+                s[nt][2] = fmaf(s[nt][2], scale, tp[8]);
+                s[nt][3] = fmaf(s[nt][3], scale, tp[7]);
+                mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+                mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+            }
+        } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int kpos = k0 + nt * 8 + (lane & 3) * 2 + (e & 1);
-                const int qpos = (e >> 1) ? qpos1 : qpos0;
-                const int lo = (e >> 1) ? lo1 : lo0;
-                const bool ok = (qpos < T) && (kpos <= qpos) && (kpos >= lo);
-                const float v = ok ? fmaf(s[nt][e], scale, s_table[qpos - kpos]) : -INFINITY;
-                s[nt][e] = v;
-                mx[e >> 1] = fmaxf(mx[e >> 1], v);
+            for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int kpos = k0 + nt * 8 + (lane & 3) * 2 + (e & 1);
+                    const int qpos = (e >> 1) ? qpos1 : qpos0;
+                    const int lo = (e >> 1) ? lo1 : lo0;
+                    const bool ok = (qpos < T) && (kpos <= qpos) && (kpos >= lo);
+                    const float v = ok ? fmaf(s[nt][e], scale, s_table[qpos - kpos]) : -INFINITY;
+                    s[nt][e] = v;
+                    mx[e >> 1] = fmaxf(mx[e >> 1], v);
+                }
             }
         }
         float corr[2];
@@ -183,7 +211,7 @@ __global__ void __launch_bounds__(128) local_attention_tc_kernel(const __nv_bflo
             mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
             mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
             const float m_new = fmaxf(m_run[r], mx[r]);
-            corr[r] = (m_new == -INFINITY) ? 1.f : expf(m_run[r] - m_new);
+            corr[r] = (m_new == -INFINITY) ? 1.f : ex2f(m_run[r] - m_new);
             m_run[r] = m_new;
             l_run[r] *= corr[r];
         }
@@ -192,7 +220,7 @@ __global__ void __launch_bounds__(128) local_attention_tc_kernel(const __nv_bflo
         for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const float pv = expf(s[nt][e] - mref[e >> 1]);      // masked (-inf) -> 0
+                const float pv = ex2f(s[nt][e] - mref[e >> 1]);      // masked (-inf) -> 0
                 s[nt][e] = pv;
                 l_run[e >> 1] += pv;
             }
