@@ -412,8 +412,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
                             const float4 b0 = *reinterpret_cast<const float4*>(s_bias + cb + 8 * i + 4 * j);
-                            r[2 * j] = (__uint_as_float(v[8 * i + 4 * j]) + b0.x) * gelu_erf(__uint_as_float(v[8 * i + 4 * j + 1]) + b0.y);
-                            r[2 * j + 1] = (__uint_as_float(v[8 * i + 4 * j + 2]) + b0.z) * gelu_erf(__uint_as_float(v[8 * i + 4 * j + 3]) + b0.w);
+                            r[2 * j] = (__uint_as_float(v[8 * i + 4 * j]) + b0.x) * gelu_erf_fast(__uint_as_float(v[8 * i + 4 * j + 1]) + b0.y);
+                            r[2 * j + 1] = (__uint_as_float(v[8 * i + 4 * j + 2]) + b0.z) * gelu_erf_fast(__uint_as_float(v[8 * i + 4 * j + 3]) + b0.w);
                         }
                         *reinterpret_cast<float4*>(stg_wr + 4 * i) = make_float4(r[0], r[1], r[2], r[3]);
                     }

@@ -395,7 +395,14 @@ class Engine:
 
     def _chunks(self, B: int, T: int):
         per = max(1, self.max_chunk_samples // max(T, 1))
-        return [(i, min(B, i + per)) for i in range(0, B, per)]
+        n = -(-B // per)                                     # balanced micro-batches (64 clips -> 22 + 21 + 21, not 24 + 24 + 16):
+        base, extra = divmod(B, n) if n else (0, 0)          # the streams then finish together
+        out, lo = [], 0
+        for i in range(n):
+            hi = lo + base + (1 if i < extra else 0)
+            out.append((lo, hi))
+            lo = hi
+        return out
 
     # ------------------------------------------------------------------ CUDA graphs (small, launch-bound batches)
     def _graphed(self, key, fn, inp: torch.Tensor):
