@@ -855,7 +855,7 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restr
 
 // EnhanceBlock gating, vectorised: a thread owns one float4 of channels (its merge weights stay in registers) and walks
 // the rows of the tile with a stride, four rows in flight.
-template <typename OutT>
+template <typename OutT, int CH>
 __global__ void __launch_bounds__(256) enhance_apply_vec_kernel(const float* __restrict__ x, int B, int T, int C,
                                                                 const float* __restrict__ conv_w,
                                                                 const float* __restrict__ conv_b,
@@ -864,7 +864,6 @@ __global__ void __launch_bounds__(256) enhance_apply_vec_kernel(const float* __r
                                                                 const float* __restrict__ merge_b,
                                                                 const float* __restrict__ partials, int nchunk,
                                                                 OutT* __restrict__ out) {
-    constexpr int CH = kEnhTile;
     __shared__ float xs[CH + 2 * kEnhReach], ms[CH + 2 * kEnhReach], ps[CH + 2 * kEnhReach];
     __shared__ float ys[4 * CH];
     __shared__ float s_scale[4], s_shift[4];
@@ -1214,12 +1213,21 @@ extern "C" int l3ac_enhance_apply(const float* x, int B, int T, int C, const flo
     cudaStream_t st = (cudaStream_t)stream;
     if (C % 4 == 0 && C / 4 <= 256 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
         (reinterpret_cast<uintptr_t>(merge_b) & 15) == 0) {
-        if (out_dtype == L3AC_F32)
-            enhance_apply_vec_kernel<float><<<grid, 256, 0, st>>>(x, B, T, C, conv_w, conv_b, in_w, in_b, merge_w, merge_b,
-                                                                  partials, nchunk, (float*)out);
-        else
-            enhance_apply_vec_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, B, T, C, conv_w, conv_b, in_w, in_b, merge_w,
-                                                                          merge_b, partials, nchunk, (__nv_bfloat16*)out);
+        // 512-step tiles amortise the branch signals; short clips at the coarse decoder stages (T = 1779: 4 tiles per clip)
+        // would leave most SMs without a CTA, so they take 128-step tiles.
+        const bool small = (long long)grid.x * B < 2 * 148;
+        dim3 grid_s(l3ac_cdiv(T, 128), B);
+#define L3AC_ENH(OUTT, CHV, GRID)                                                                                       \
+    enhance_apply_vec_kernel<OUTT, CHV><<<GRID, 256, 0, st>>>(x, B, T, C, conv_w, conv_b, in_w, in_b, merge_w, merge_b, \
+                                                              partials, nchunk, (OUTT*)out)
+        if (out_dtype == L3AC_F32) {
+            if (small) L3AC_ENH(float, 128, grid_s);
+            else L3AC_ENH(float, kEnhTile, grid);
+        } else {
+            if (small) L3AC_ENH(__nv_bfloat16, 128, grid_s);
+            else L3AC_ENH(__nv_bfloat16, kEnhTile, grid);
+        }
+#undef L3AC_ENH
         return l3ac_launch_status();
     }
     if (out_dtype == L3AC_F32)
