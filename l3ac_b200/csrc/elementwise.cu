@@ -21,6 +21,32 @@ __device__ __forceinline__ void store_act<__nv_bfloat16>(__nv_bfloat16* hi, __nv
     if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
+// Eight simultaneous sums over a group of GS lanes (GS = 8, 16 or 32 consecutive lanes of a warp).  Three halving steps
+// (a lane keeps half of its values and trades the other half with its partner) leave every lane with ONE row's partial
+// sum, log2(GS) - 3 butterfly steps finish it: 7 + (log2(GS) - 3) shuffles instead of 8 log2(GS).  After the call lane l
+// of a group holds the group total of row (l * 8 / GS) & 7 ... see group_row8; group_bcast8 hands every total to every lane.
+template <int GS>
+__device__ __forceinline__ float group_reduce8(const float (&v)[8]) {
+    const int gl = (threadIdx.x & 31) & (GS - 1);
+    const bool b2 = gl & (GS / 2), b1 = gl & (GS / 4), b0 = gl & (GS / 8);
+    float w[4], u[2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = (b2 ? v[k + 4] : v[k]) + __shfl_xor_sync(0xffffffffu, b2 ? v[k] : v[k + 4], GS / 2);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) u[k] = (b1 ? w[k + 2] : w[k]) + __shfl_xor_sync(0xffffffffu, b1 ? w[k] : w[k + 2], GS / 4);
+    float t = (b0 ? u[1] : u[0]) + __shfl_xor_sync(0xffffffffu, b0 ? u[0] : u[1], GS / 8);
+#pragma unroll
+    for (int o = GS / 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    return t;           // total of row 4 b2 + 2 b1 + b0
+}
+// all eight totals in every lane of the group: row r sits in the group's lane r * (GS / 8)
+template <int GS>
+__device__ __forceinline__ void group_bcast8(float t, float (&v)[8]) {
+    const int base = (threadIdx.x & 31) & ~(GS - 1);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v[r] = __shfl_sync(0xffffffffu, t, base + r * (GS / 8));
+}
+
 template <int GS>
 __device__ __forceinline__ float group_sum(float v) {
 #pragma unroll
@@ -240,24 +266,37 @@ __global__ void __launch_bounds__(256) dwconv7_ln_vec_kernel(const float* __rest
             }
         }
         const long long out_row0 = ((long long)b * T + t0) * C + 4 * g;
+        static_assert(R == 8, "the statistics use the 8-row group reduction");
+        float4 a[R];
+        float st[8];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            float4 a = bias;
+            float4 acc = bias;
 #pragma unroll
             for (int j = 0; j < 7; ++j) {
-                const float2 lo = ffma2(make_float2(w[j].x, w[j].y), make_float2(xr[r + j].x, xr[r + j].y), make_float2(a.x, a.y));
-                const float2 hi = ffma2(make_float2(w[j].z, w[j].w), make_float2(xr[r + j].z, xr[r + j].w), make_float2(a.z, a.w));
-                a = make_float4(lo.x, lo.y, hi.x, hi.y);
+                const float2 lo = ffma2(make_float2(w[j].x, w[j].y), make_float2(xr[r + j].x, xr[r + j].y), make_float2(acc.x, acc.y));
+                const float2 hi = ffma2(make_float2(w[j].z, w[j].w), make_float2(xr[r + j].z, xr[r + j].w), make_float2(acc.z, acc.w));
+                acc = make_float4(lo.x, lo.y, hi.x, hi.y);
             }
-            const float mean = group_sum<GS>((a.x + a.y) + (a.z + a.w)) * inv_c;     // inactive lanes hold zeros
-            const float dx = a.x - mean, dy = a.y - mean, dz = a.z - mean, dw = a.w - mean;
-            const float q = act ? (dx * dx + dy * dy) + (dz * dz + dw * dw) : 0.f;
-            const float rstd = rsqrt_nr(group_sum<GS>(q) * inv_c + eps);
+            a[r] = acc;
+            st[r] = (acc.x + acc.y) + (acc.z + acc.w);                     // inactive lanes hold zeros
+        }
+        group_bcast8<GS>(group_reduce8<GS>(st), st);                       // row sums: 8 rows in one reduction
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float mean = st[r] * inv_c;
+            a[r].x -= mean; a[r].y -= mean; a[r].z -= mean; a[r].w -= mean;
+            st[r] = act ? (a[r].x * a[r].x + a[r].y * a[r].y) + (a[r].z * a[r].z + a[r].w * a[r].w) : 0.f;
+        }
+        group_bcast8<GS>(group_reduce8<GS>(st), st);                       // centred sums of squares
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float rstd = rsqrt_nr(st[r] * inv_c + eps);
             if (act && (interior || (run_ok && t0 + r < T))) {
                 const long long i = out_row0 + r * C;
                 store_act4<OutT>(out, out_lo, i,
-                                 make_float4(dx * rstd * lw.x + lb.x, dy * rstd * lw.y + lb.y, dz * rstd * lw.z + lb.z,
-                                             dw * rstd * lw.w + lb.w));
+                                 make_float4(a[r].x * rstd * lw.x + lb.x, a[r].y * rstd * lw.y + lb.y, a[r].z * rstd * lw.z + lb.z,
+                                             a[r].w * rstd * lw.w + lb.w));
             }
         }
     }
@@ -295,6 +334,8 @@ __global__ void __launch_bounds__(32 * NW) dwconv7_ln_wide_kernel(const float* _
         }
     }
     float4 y[R];
+    float st[8];
+    static_assert(R == 8, "the statistics use the 8-row group reduction");
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         float4 a = bias;
@@ -305,8 +346,11 @@ __global__ void __launch_bounds__(32 * NW) dwconv7_ln_wide_kernel(const float* _
             a = make_float4(lo.x, lo.y, hi.x, hi.y);
         }
         y[r] = a;
-        const float s = warp_sum((a.x + a.y) + (a.z + a.w));
-        if (lane == 0) s_part[0][r][warp] = s;
+        st[r] = (a.x + a.y) + (a.z + a.w);
+    }
+    {   // eight row sums in one reduction: lane 4 r ends up with row r's warp total
+        const float t = group_reduce8<32>(st);
+        if ((lane & 3) == 0) s_part[0][lane >> 2][warp] = t;
     }
     __syncthreads();
     const float inv_c = 1.0f / (float)C;
@@ -321,8 +365,11 @@ __global__ void __launch_bounds__(32 * NW) dwconv7_ln_wide_kernel(const float* _
     for (int r = 0; r < R; ++r) {
         const float m = total(*reinterpret_cast<const float4*>(s_part[0][r])) * inv_c;
         y[r].x -= m; y[r].y -= m; y[r].z -= m; y[r].w -= m;
-        const float s = warp_sum((y[r].x * y[r].x + y[r].y * y[r].y) + (y[r].z * y[r].z + y[r].w * y[r].w));
-        if (lane == 0) s_part[1][r][warp] = s;
+        st[r] = (y[r].x * y[r].x + y[r].y * y[r].y) + (y[r].z * y[r].z + y[r].w * y[r].w);
+    }
+    {
+        const float t = group_reduce8<32>(st);
+        if ((lane & 3) == 0) s_part[1][lane >> 2][warp] = t;
     }
     __syncthreads();
     const float4 lw = __ldg(reinterpret_cast<const float4*>(ln_w) + g), lb = __ldg(reinterpret_cast<const float4*>(ln_b) + g);
