@@ -96,6 +96,7 @@ class L3AC:
         """(B, T) fp32 -> (q_feature (B, T_tok, F), {"indices": int32 (B, T_tok), "level_indices": fp32 (B, T_tok, D)})."""
         return self.network.engine.encode(audio_data)
 
-    def decode_audio(self, audio_feature: torch.Tensor = None, indices: torch.Tensor = None) -> torch.Tensor:
-        """q_feature (B, T_tok, F) or indices (B, T_tok) -> audio (B, T_tok * hop_length) fp32."""
-        return self.network.engine.decode(audio_feature, indices)
+    def decode_audio(self, audio_feature: torch.Tensor = None, indices: torch.Tensor = None, out: torch.Tensor = None) -> torch.Tensor:
+        """q_feature (B, T_tok, F) or indices (B, T_tok) -> audio (B, T_tok * hop_length) fp32.  ``out`` (optional extension):
+        a pinned host tensor that receives the waveform, downloaded micro-batch by micro-batch while the rest decodes."""
+        return self.network.engine.decode(audio_feature, indices, out=out)

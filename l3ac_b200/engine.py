@@ -528,8 +528,15 @@ class Engine:
         return ops.tail_conv_tanh(x, self.dec_tail["alpha"], self.dec_tail["w"], self.dec_tail["bias"])
 
     def decode(self, audio_feature: Optional[torch.Tensor] = None, indices: Optional[torch.Tensor] = None,
-               taps: Optional[dict] = None) -> torch.Tensor:
-        """L3AC.decode_audio -- l3ac/__init__.py:116-121."""
+               taps: Optional[dict] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """L3AC.decode_audio -- l3ac/__init__.py:116-121.
+
+        ``out`` (an extension): a pinned host tensor (B, T_tok * hop) fp32 that receives the waveform; every micro-batch is
+        downloaded on its own stream as soon as it is decoded, overlapping the kernels of the others.  The returned tensor
+        is ``out`` and the copies are complete (the call synchronises the device)."""
+        if out is not None:
+            if out.device.type != "cpu" or not out.is_pinned() or out.dtype != torch.float32 or not out.is_contiguous():
+                raise ValueError("out must be a contiguous pinned host tensor of dtype float32")
         if audio_feature is None:
             if indices is None:
                 # the reference fails inside quantizer.to_features(None) with AttributeError
@@ -541,10 +548,30 @@ class Engine:
         B, T_tok, _ = feat.shape
         if B == 0:
             return torch.zeros((0, T_tok * self.mc.hop_length), device=self.device, dtype=torch.float32)
+        if out is not None and tuple(out.shape) != (B, T_tok * self.mc.hop_length):
+            raise ValueError(f"out must have shape {(B, T_tok * self.mc.hop_length)}, got {tuple(out.shape)}")
+
+        def finish(wav):
+            if out is None:
+                return wav
+            out.copy_(wav, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            return out
+
         if taps is None and 0 < B * T_tok * self.mc.hop_length <= self.graph_max_samples and \
                 not torch.cuda.is_current_stream_capturing():
             with torch.cuda.device(self.device):
-                return self._graphed(("dec", B, T_tok), lambda f: (self.decode_features(f),), feat)[0]
-        outs = self._run_chunks(lambda lo, hi: self.decode_features(feat[lo:hi].contiguous(), taps if (lo == 0 and hi == B) else None),
-                                self._chunks(B, T_tok * self.mc.hop_length))
-        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+                return finish(self._graphed(("dec", B, T_tok), lambda f: (self.decode_features(f),), feat)[0])
+        chunks = self._chunks(B, T_tok * self.mc.hop_length)
+
+        def run(lo, hi):
+            wav = self.decode_features(feat[lo:hi].contiguous(), taps if (lo == 0 and hi == B) else None)
+            if out is not None and len(chunks) > 1:
+                out[lo:hi].copy_(wav, non_blocking=True)          # on this micro-batch's stream
+            return wav
+
+        outs = self._run_chunks(run, chunks)
+        if out is not None and len(chunks) > 1:
+            torch.cuda.current_stream(self.device).synchronize()   # the side streams were joined into the current one
+            return out
+        return finish(outs[0] if len(outs) == 1 else torch.cat(outs, dim=0))

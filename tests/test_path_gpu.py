@@ -197,6 +197,17 @@ def test_pinned_host_input_is_uploaded_per_micro_batch(cuda_lib):
         q0, idx0 = codec.encode_audio(host.to(DEV))
         q1, idx1 = codec.encode_audio(host)
     assert q1.device.type == "cuda" and torch.equal(idx0["indices"], idx1["indices"]) and torch.equal(q0, q1)
+    # decode_audio(out=pinned host tensor): the waveform is downloaded per micro-batch inside the call
+    with torch.inference_mode():
+        wav = codec.decode_audio(indices=idx0["indices"])
+        host = torch.empty(tuple(wav.shape), dtype=torch.float32).pin_memory()
+        got = codec.decode_audio(indices=idx0["indices"], out=host)
+        small = torch.empty((1, wav.shape[1]), dtype=torch.float32).pin_memory()
+        codec.network.engine.graph_max_samples = 16000 * 40
+        got1 = codec.decode_audio(indices=idx0["indices"][:1], out=small)            # CUDA-graph path
+    assert got is host and torch.equal(host, wav.cpu()) and got1 is small and torch.equal(small, wav[:1].cpu())
+    with pytest.raises(ValueError):
+        codec.decode_audio(indices=idx0["indices"], out=torch.empty(tuple(wav.shape)))   # not pinned
 
 
 def test_cuda_graph_path_matches_eager(cuda_lib):
