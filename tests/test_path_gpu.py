@@ -169,6 +169,23 @@ def test_other_configs_at_baseline_sizes(cuda_lib, name, seconds, batch, t_tok, 
         assert snr > snr_emu - 4.0 and snr > 3.0
 
 
+def test_many_short_clips(cuda_lib):
+    """BASELINE config #5 corner: hundreds of 1 s clips (two micro-batches, sample count not a multiple of any tile size)."""
+    codec = l3ac_b200.get_model("1kbps", pretrained=False)
+    codec.network.cuda()
+    audio = make_audio(300, 1.0, seed=9).to(DEV)
+    audio[299] = audio[0]
+    with torch.inference_mode():
+        q, idx = codec.encode_audio(audio)
+        wav = codec.decode_audio(indices=idx["indices"])
+        q1, idx1 = codec.encode_audio(audio[:1])
+        wav1 = codec.decode_audio(indices=idx1["indices"])
+    assert idx["indices"].shape == (300, 60) and wav.shape == (300, 16200)
+    assert torch.equal(idx["indices"][299], idx["indices"][0]) and torch.equal(wav[299], wav[0])
+    assert torch.equal(idx1["indices"][0], idx["indices"][0]) and torch.equal(wav1[0], wav[0])
+    assert torch.isfinite(wav).all()
+
+
 def test_micro_batching_is_transparent(cuda_lib):
     """Batches larger than one 160 s micro-batch are processed in chunks; results must equal per-clip processing."""
     codec = l3ac_b200.get_model("3kbps", pretrained=False)
