@@ -900,6 +900,96 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restr
     }
 }
 
+// Linear upsample (+ ChannelNorm) by an integer factor S in {2,3,4,5}, run variant (C % 4 == 0, C <= 128): a group of GS lanes
+// (one float4 of channels per lane) produces a run of R consecutive output rows of one clip, R a multiple of S, so that the
+// input rows every output interpolates between are compile-time offsets into the NR = R/S + 2 rows the group loads ONCE
+// (0.6 - 0.75 loads per output row instead of 2), the per-row index arithmetic shrinks to one FMA for the weight, and the
+// statistics of the run share one 8-row group reduction each.  The interpolation weight is computed per row exactly like
+// ATen's upsample_linear1d (src = scale^-1 (j + 0.5) - 0.5 in fp32, clamped at 0); rows clamped at the clip edges make the
+// edge cases fall out of the same formula.
+__host__ __device__ constexpr int ups_off(int r, int S) {      // floor((r + 0.5) / S - 0.5) + 1 = i0 - ibase for output j0 + r, j0 % S == 0
+    return (2 * r + 1 - S >= 0) ? (2 * r + 1 - S) / (2 * S) + 1 : 0;
+}
+
+template <int GS, int S>
+__global__ void __launch_bounds__(256) upsample_cn_run_kernel(const float* __restrict__ x, int B, int T, int C,
+                                                              const float* __restrict__ cn_w, const float* __restrict__ cn_b,
+                                                              float eps, float* __restrict__ out) {
+    constexpr int R = (S == 3) ? 6 : (S == 5) ? 5 : 8;
+    constexpr int NR = ups_off(R - 1, S) + 2;
+    constexpr int RW = 32 / GS;
+    static_assert(R % S == 0 && R <= 8, "a run is a whole number of input intervals and fits the 8-row reduction");
+    const int lane = threadIdx.x & 31, g = lane % GS, sub = lane / GS;
+    const int C4 = C >> 2;
+    const bool act = g < C4;
+    const int b = blockIdx.y;
+    const int To = T * S;
+    const int runs = (To + R - 1) / R;
+    const float rscale = (float)(1.0 / (double)S);
+    const float inv_c = 1.0f / (float)C;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 w4 = (cn_w && act) ? __ldg(reinterpret_cast<const float4*>(cn_w) + g) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 b4 = (cn_b && act) ? __ldg(reinterpret_cast<const float4*>(cn_b) + g) : z4;
+    const float4* xb = reinterpret_cast<const float4*>(x + (long long)b * T * C) + g;
+    float* ob = out + (long long)b * To * C + 4 * g;
+    const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int nwarps = gridDim.x * (blockDim.x >> 5);
+    for (int base = warp_global * RW; base < runs; base += nwarps * RW) {
+        const int run = base + sub;
+        const bool run_ok = run < runs;
+        const int rr = run_ok ? run : runs - 1;
+        const int j0 = rr * R, ibase = rr * (R / S) - 1;
+        float4 xr[NR];
+#pragma unroll
+        for (int k = 0; k < NR; ++k) {
+            int t = ibase + k;
+            t = t < 0 ? 0 : (t > T - 1 ? T - 1 : t);
+            xr[k] = act ? __ldg(xb + (long long)t * C4) : z4;
+        }
+        float4 val[R];
+        float st[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) st[r] = 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int o = ups_off(r, S);
+            float src = fmaf(rscale, (float)(j0 + r) + 0.5f, -0.5f);      // ATen contracts this to one fma
+            float l1 = src - (float)(ibase + o);
+            if (src < 0.f) l1 = 0.f;                                       // clamped source index: weight 0 on row 0
+            const float w1 = l1, w0 = 1.0f - l1;
+            const float4 a0 = (src < 0.f) ? xr[o + 1] : xr[o], a1 = xr[o + 1];
+            float4 v;
+            v.x = __fmaf_rn(w1, a1.x, __fmul_rn(w0, a0.x));
+            v.y = __fmaf_rn(w1, a1.y, __fmul_rn(w0, a0.y));
+            v.z = __fmaf_rn(w1, a1.z, __fmul_rn(w0, a0.z));
+            v.w = __fmaf_rn(w1, a1.w, __fmul_rn(w0, a0.w));
+            val[r] = v;
+            st[r] = (v.x + v.y) + (v.z + v.w);                              // inactive lanes hold zeros
+        }
+        if (cn_w) {
+            group_bcast8<GS>(group_reduce8<GS>(st), st);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float mean = st[r] * inv_c;
+                val[r].x -= mean; val[r].y -= mean; val[r].z -= mean; val[r].w -= mean;
+                st[r] = act ? (val[r].x * val[r].x + val[r].y * val[r].y) + (val[r].z * val[r].z + val[r].w * val[r].w) : 0.f;
+            }
+            group_bcast8<GS>(group_reduce8<GS>(st), st);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (!act || !run_ok || j0 + r >= To) continue;
+            const float rstd = cn_w ? rsqrt_nr(st[r] * inv_c + eps) : 1.0f;
+            float4 o4;
+            o4.x = val[r].x * rstd * w4.x + b4.x;
+            o4.y = val[r].y * rstd * w4.y + b4.y;
+            o4.z = val[r].z * rstd * w4.z + b4.z;
+            o4.w = val[r].w * rstd * w4.w + b4.w;
+            *reinterpret_cast<float4*>(ob + (long long)(j0 + r) * C) = o4;
+        }
+    }
+}
+
 // EnhanceBlock gating, vectorised: a thread owns one float4 of channels (its merge weights stay in registers) and walks
 // the rows of the tile with a stride, four rows in flight.
 template <typename OutT, int CH>
@@ -1219,6 +1309,24 @@ extern "C" int l3ac_upsample_linear_cn(const float* x, int B, int T, int C, int 
     if (C % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
         (!cn_w || ((reinterpret_cast<uintptr_t>(cn_w) | reinterpret_cast<uintptr_t>(cn_b)) & 15) == 0)) {
         const int C4 = C / 4;
+        if (C4 <= 32 && scale >= 2 && scale <= 5) {        // run variant: input rows loaded once per run of outputs
+#define L3AC_UPR(GS, SV)                                                                                                 \
+    upsample_cn_run_kernel<GS, SV><<<dim3(ups_grid_x(((long long)T * SV + 4) / 5, 8 * (32 / GS), B), B), 256, 0, st>>>(   \
+        x, B, T, C, cn_w, cn_b, eps, out)
+#define L3AC_UPR_S(GS)                        \
+    do {                                      \
+        if (scale == 2) L3AC_UPR(GS, 2);      \
+        else if (scale == 3) L3AC_UPR(GS, 3); \
+        else if (scale == 4) L3AC_UPR(GS, 4); \
+        else L3AC_UPR(GS, 5);                 \
+    } while (0)
+            if (C4 <= 8) L3AC_UPR_S(8);
+            else if (C4 <= 16) L3AC_UPR_S(16);
+            else L3AC_UPR_S(32);
+#undef L3AC_UPR_S
+#undef L3AC_UPR
+            return l3ac_launch_status();
+        }
 #define L3AC_UPS(GS, VPL, U)                                                                                      \
     upsample_cn_vec_kernel<GS, VPL, U><<<dim3(ups_grid_x((long long)T * scale, 8 * (32 / GS) * U, B), B), 256, 0, st>>>( \
         x, B, T, C, scale, cn_w, cn_b, eps, out)

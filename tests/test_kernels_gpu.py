@@ -181,7 +181,8 @@ def test_fsq_quantize_full(cuda_lib):
     assert torch.equal(deq, gq)
 
 
-@pytest.mark.parametrize("C,T,s", [(128, 50, 3), (256, 33, 5), (24, 100, 2), (96, 7, 4)])
+@pytest.mark.parametrize("C,T,s", [(128, 50, 3), (256, 33, 5), (24, 100, 2), (96, 7, 4), (48, 1001, 3), (96, 333, 5), (24, 1, 2), (48, 2, 5),
+                                   (128, 1779, 3), (24, 4001, 4), (100, 77, 3), (48, 40, 6)])
 def test_upsample_linear_cn(cuda_lib, C, T, s):
     x = rnd(2, C, T, seed=1)
     w, b = 1 + rnd(C, seed=2, scale=0.1), rnd(C, seed=3, scale=0.1)
