@@ -214,11 +214,13 @@ int l3ac_upsample_linear_cn(const float* x, int B, int T, int C, int scale, cons
  * merge_w [C][4], merge_b [C].  out (B,T,C) fp32|bf16.
  * ------------------------------------------------------------------------------------------ */
 long long l3ac_enhance_partials_floats(int B, int T);
+/* branches (optional, 16-byte aligned): (B,T,4) fp32 -- when given, `stats` also stores the four un-normalised branch
+ * signals of every sample and `apply` streams them back instead of recomputing the pooling / convolutions per tile. */
 int l3ac_enhance_stats(const float* x, int B, int T, int C, const float* conv_w, const float* conv_b,
-                       float* partials, l3ac_stream_t stream);
+                       float* partials, float* branches, l3ac_stream_t stream);
 int l3ac_enhance_apply(const float* x, int B, int T, int C, const float* conv_w, const float* conv_b,
                        const float* in_w, const float* in_b, const float* merge_w, const float* merge_b,
-                       const float* partials, void* out, int out_dtype, l3ac_stream_t stream);
+                       const float* partials, const float* branches, void* out, int out_dtype, l3ac_stream_t stream);
 
 /* Decoder tail (l3ac/modules.py:192-194): Snake(C) -> Conv1d(C->1,k7,pad 3) -> tanh.
  * x (B,T,C) fp32 -> out (B,T) fp32.  w is [7][C] (tap-major). */

@@ -651,7 +651,7 @@ __device__ __forceinline__ void enhance_branches(const float* __restrict__ xb /*
 __global__ void __launch_bounds__(256) enhance_stats_kernel(const float* __restrict__ x, int B, int T, int C,
                                                             const float* __restrict__ conv_w,
                                                             const float* __restrict__ conv_b,
-                                                            float* __restrict__ partials) {
+                                                            float* __restrict__ partials, float4* __restrict__ branches) {
     constexpr int CH = kEnhChunk;
     __shared__ float xs[CH + 2 * kEnhReach], ms[CH + 2 * kEnhReach], ps[CH + 2 * kEnhReach];
     __shared__ float ys[4 * CH];
@@ -667,6 +667,8 @@ __global__ void __launch_bounds__(256) enhance_stats_kernel(const float* __restr
                 s[j] += y;
                 q[j] = fmaf(y, y, q[j]);
             }
+            // the four (un-normalised) branch signals of this sample, so that the apply pass is a pure streaming kernel
+            if (branches) branches[(long long)b * T + t0 + i] = make_float4(ys[i], ys[CH + i], ys[2 * CH + i], ys[3 * CH + i]);
         }
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1075,6 +1077,97 @@ __global__ void __launch_bounds__(256) enhance_apply_vec_kernel(const float* __r
     }
 }
 
+// EnhanceBlock gating, streaming variant: the branch signals come from the compact (B, T, 4) array the stats pass wrote, so
+// there is no per-tile pooling / convolution phase (strided channel-0 reads, five barriers) in front of the stream.  Warp 0
+// reduces the clip's partial sums (fp64), then a thread owns one float4 of channels and walks the tile's rows, four in flight.
+constexpr int kEnhStreamTile = 1024;
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) enhance_apply_stream_kernel(const float* __restrict__ x, int B, int T, int C,
+                                                                   const float* __restrict__ in_w, const float* __restrict__ in_b,
+                                                                   const float* __restrict__ merge_w,
+                                                                   const float* __restrict__ merge_b,
+                                                                   const float* __restrict__ partials, int nchunk,
+                                                                   const float4* __restrict__ branches, int tile,
+                                                                   OutT* __restrict__ out) {
+    __shared__ float s_scale[4], s_shift[4];
+    const int b = blockIdx.y, t0 = blockIdx.x * tile;
+    if (threadIdx.x < 32) {
+        double acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.0;
+        for (int c = threadIdx.x; c < nchunk; c += 32) {
+            const float4* pp = reinterpret_cast<const float4*>(partials + ((long long)b * nchunk + c) * 8);
+            const float4 p0 = __ldg(pp), p1 = __ldg(pp + 1);
+            acc[0] += p0.x; acc[1] += p0.y; acc[2] += p0.z; acc[3] += p0.w;
+            acc[4] += p1.x; acc[5] += p1.y; acc[6] += p1.z; acc[7] += p1.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+        if (threadIdx.x < 4) {
+            const int j = threadIdx.x;
+            const double sum = j == 0 ? acc[0] : j == 1 ? acc[2] : j == 2 ? acc[4] : acc[6];
+            const double sq = j == 0 ? acc[1] : j == 1 ? acc[3] : j == 2 ? acc[5] : acc[7];
+            const double mean = sum / (double)T;
+            double var = sq / (double)T - mean * mean;   // biased variance (InstanceNorm1d)
+            if (var < 0.0) var = 0.0;
+            const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+            const float gg = in_w[j] * rstd;
+            s_scale[j] = gg;
+            s_shift[j] = in_b[j] - (float)mean * gg;
+        }
+    }
+    __syncthreads();
+    const int nt = min(tile, T - t0);
+    const int C4 = C >> 2;
+    const int rpp = blockDim.x / C4;                  // rows per pass
+    const int c4 = threadIdx.x % C4, r0 = threadIdx.x / C4;
+    if (r0 >= rpp) return;
+    const float4 sc = make_float4(s_scale[0], s_scale[1], s_scale[2], s_scale[3]);
+    const float4 sh = make_float4(s_shift[0], s_shift[1], s_shift[2], s_shift[3]);
+    float4 mw[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) mw[q] = __ldg(reinterpret_cast<const float4*>(merge_w) + 4 * c4 + q);   // merge_w[c][0..3]
+    const float4 mb = __ldg(reinterpret_cast<const float4*>(merge_b) + c4);
+    const float4* xrow = reinterpret_cast<const float4*>(x + ((long long)b * T + t0) * C) + c4;
+    const float4* yrow = branches + (long long)b * T + t0;
+    OutT* obase = out + ((long long)b * T + t0) * C + 4 * c4;
+    for (int i0 = r0; i0 < nt; i0 += 4 * rpp) {
+        float4 xv[4], yv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * rpp;
+            const bool ok = i < nt;
+            xv[u] = ok ? __ldg(xrow + (long long)i * C4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            yv[u] = ok ? __ldg(yrow + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * rpp;
+            if (i >= nt) break;
+            const float y0 = fmaf(yv[u].x, sc.x, sh.x), y1 = fmaf(yv[u].y, sc.y, sh.y), y2 = fmaf(yv[u].z, sc.z, sh.z),
+                        y3 = fmaf(yv[u].w, sc.w, sh.w);
+            float4 r;
+            r.x = fmaf(fmaf(mw[0].w, y3, fmaf(mw[0].z, y2, fmaf(mw[0].y, y1, fmaf(mw[0].x, y0, mb.x)))), xv[u].x, xv[u].x);
+            r.y = fmaf(fmaf(mw[1].w, y3, fmaf(mw[1].z, y2, fmaf(mw[1].y, y1, fmaf(mw[1].x, y0, mb.y)))), xv[u].y, xv[u].y);
+            r.z = fmaf(fmaf(mw[2].w, y3, fmaf(mw[2].z, y2, fmaf(mw[2].y, y1, fmaf(mw[2].x, y0, mb.z)))), xv[u].z, xv[u].z);
+            r.w = fmaf(fmaf(mw[3].w, y3, fmaf(mw[3].z, y2, fmaf(mw[3].y, y1, fmaf(mw[3].x, y0, mb.w)))), xv[u].w, xv[u].w);
+            OutT* o = obase + (long long)i * C;
+            if (sizeof(OutT) == 4) {
+                *reinterpret_cast<float4*>(o) = r;
+            } else {
+                const __nv_bfloat162 h01 = __floats2bfloat162_rn(r.x, r.y), h23 = __floats2bfloat162_rn(r.z, r.w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<const uint32_t*>(&h01);
+                pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+                *reinterpret_cast<uint2*>(o) = pk;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // decoder tail: snake -> conv(C->1, k7, pad 3) -> tanh.  Block = 256 output samples.
 // ------------------------------------------------------------------------------------------
@@ -1348,17 +1441,19 @@ extern "C" long long l3ac_enhance_partials_floats(int B, int T) {
 }
 
 extern "C" int l3ac_enhance_stats(const float* x, int B, int T, int C, const float* conv_w, const float* conv_b,
-                                  float* partials, l3ac_stream_t stream) {
+                                  float* partials, float* branches, l3ac_stream_t stream) {
     L3AC_CHECK_ARG(x && conv_w && conv_b && partials && B > 0 && B <= 65535 && T > 0 && C > 0);
+    L3AC_CHECK_ARG((reinterpret_cast<uintptr_t>(branches) & 15) == 0);
     dim3 grid(l3ac_cdiv(T, kEnhChunk), B);
-    enhance_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, B, T, C, conv_w, conv_b, partials);
+    enhance_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, B, T, C, conv_w, conv_b, partials,
+                                                                 reinterpret_cast<float4*>(branches));
     return l3ac_launch_status();
 }
 
 extern "C" int l3ac_enhance_apply(const float* x, int B, int T, int C, const float* conv_w, const float* conv_b,
                                   const float* in_w, const float* in_b, const float* merge_w,
-                                  const float* merge_b, const float* partials, void* out, int out_dtype,
-                                  l3ac_stream_t stream) {
+                                  const float* merge_b, const float* partials, const float* branches, void* out,
+                                  int out_dtype, l3ac_stream_t stream) {
     L3AC_CHECK_ARG(x && conv_w && conv_b && in_w && in_b && merge_w && merge_b && partials && out);
     L3AC_CHECK_ARG(B > 0 && B <= 65535 && T > 0 && C > 0);
     L3AC_CHECK_ARG(out_dtype == L3AC_F32 || out_dtype == L3AC_BF16);
@@ -1366,6 +1461,21 @@ extern "C" int l3ac_enhance_apply(const float* x, int B, int T, int C, const flo
     dim3 grid(l3ac_cdiv(T, kEnhTile), B);
     const int nchunk = l3ac_cdiv(T, kEnhChunk);
     cudaStream_t st = (cudaStream_t)stream;
+    if (branches && C % 4 == 0 && C / 4 <= 256 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
+                                                    reinterpret_cast<uintptr_t>(merge_b) | reinterpret_cast<uintptr_t>(branches) |
+                                                    reinterpret_cast<uintptr_t>(partials)) & 15) == 0) {
+        // streaming variant; short clips take 128-row tiles so that every SM gets a CTA
+        const int tile = ((long long)l3ac_cdiv(T, kEnhStreamTile) * B >= 2 * 148) ? kEnhStreamTile : 128;
+        dim3 g1(l3ac_cdiv(T, tile), B);
+        if (out_dtype == L3AC_F32)
+            enhance_apply_stream_kernel<float><<<g1, 256, 0, st>>>(x, B, T, C, in_w, in_b, merge_w, merge_b, partials, nchunk,
+                                                                   reinterpret_cast<const float4*>(branches), tile, (float*)out);
+        else
+            enhance_apply_stream_kernel<__nv_bfloat16><<<g1, 256, 0, st>>>(x, B, T, C, in_w, in_b, merge_w, merge_b, partials, nchunk,
+                                                                           reinterpret_cast<const float4*>(branches), tile,
+                                                                           (__nv_bfloat16*)out);
+        return l3ac_launch_status();
+    }
     if (C % 4 == 0 && C / 4 <= 256 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
         (reinterpret_cast<uintptr_t>(merge_b) & 15) == 0) {
         // 512-step tiles amortise the branch signals; short clips at the coarse decoder stages (T = 1779: 4 tiles per clip)

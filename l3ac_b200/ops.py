@@ -387,19 +387,23 @@ def upsample_linear_cn(x: torch.Tensor, scale: int, cn_w=None, cn_b=None, eps: f
     return out
 
 
-def enhance(x: torch.Tensor, conv_w, conv_b, in_w, in_b, merge_w, merge_b, out_dtype=torch.float32) -> torch.Tensor:
+def enhance(x: torch.Tensor, conv_w, conv_b, in_w, in_b, merge_w, merge_b, out_dtype=torch.float32,
+            stream_branches: bool = True) -> torch.Tensor:
+    """EnhanceBlock.  ``stream_branches``: the stats pass stores the four branch signals (B, T, 4) and the apply pass streams
+    them back (default); False recomputes them per tile in the apply pass."""
     _chk(x, name="x")
     B, T, Cc = x.shape
     lib = _lib.load()
     partials = torch.empty(lib.l3ac_enhance_partials_floats(B, T), device=x.device, dtype=torch.float32)
+    branches = torch.empty((B, T, 4), device=x.device, dtype=torch.float32) if stream_branches else None
     out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
     _count(2)
     with _hook("enhance", 2 * x.numel() // x.shape[-1] * 4 + _nbytes(x, out)), torch.cuda.device(x.device):
         st = _stream(x)
-        check(lib.l3ac_enhance_stats(_ptr(x), B, T, Cc, _ptr(conv_w), _ptr(conv_b), _ptr(partials), st),
+        check(lib.l3ac_enhance_stats(_ptr(x), B, T, Cc, _ptr(conv_w), _ptr(conv_b), _ptr(partials), _ptr(branches), st),
               "l3ac_enhance_stats")
         check(lib.l3ac_enhance_apply(_ptr(x), B, T, Cc, _ptr(conv_w), _ptr(conv_b), _ptr(in_w), _ptr(in_b),
-                                     _ptr(merge_w), _ptr(merge_b), _ptr(partials), _ptr(out), _DT[out_dtype], st),
+                                     _ptr(merge_w), _ptr(merge_b), _ptr(partials), _ptr(branches), _ptr(out), _DT[out_dtype], st),
               "l3ac_enhance_apply")
     return out
 

@@ -207,6 +207,14 @@ def test_enhance_block(cuda_lib, C, T):
                       sd["e.merge_layer.0.bias"].to(DEV), sd["e.merge_layer.1.weight"][:, :, 0].contiguous().to(DEV),
                       sd["e.merge_layer.1.bias"].to(DEV))
     assert max_abs(cf(got), want) < 5e-5
+    args = (cl(x), torch.stack([sd[f"e.blocks.{k}.1.weight"][0, 0] for k in range(4)]).contiguous().to(DEV),
+            torch.cat([sd[f"e.blocks.{k}.1.bias"] for k in range(4)]).to(DEV), sd["e.merge_layer.0.weight"].to(DEV),
+            sd["e.merge_layer.0.bias"].to(DEV), sd["e.merge_layer.1.weight"][:, :, 0].contiguous().to(DEV),
+            sd["e.merge_layer.1.bias"].to(DEV))
+    recompute = ops.enhance(*args, stream_branches=False)          # the apply pass recomputing the branch signals per tile
+    assert max_abs(cf(recompute), want) < 5e-5 and max_abs(recompute, got) < 1e-5
+    got16 = ops.enhance(*args, out_dtype=torch.bfloat16)
+    assert max_abs(got16.float(), got) < 2e-2 * float(got.abs().max())
 
 
 def test_snake_and_tail(cuda_lib):
