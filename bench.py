@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--config", default="1kbps")
     ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step (weak scaling)")
     ap.add_argument("--seconds", type=float, default=10.0)
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "split"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="encdec", choices=["encdec", "decode"],
                     help="encdec = BASELINE headline; decode = decode_audio(indices=) only (BASELINE config #5 sweep)")
@@ -381,7 +381,9 @@ def main():
                                    ("encode_audio + decode_audio(indices=)" if args.mode == "encdec" else "decode_audio(indices=) only"),
                        "mode": args.mode,
                        "bitrate": args.config, "batch_per_gpu": B, "clip_seconds": secs, "parallelism": f"dp{world}",
-                       "precision": "encode side split-bf16 (3-term) tcgen05, decode side bf16 tcgen05, fp32 accumulate and residual stream" if args.precision == "bf16" else "fp32 SIMT",
+                       "precision": {"bf16": "encode side split-bf16 (3-term) tcgen05, decode side bf16 tcgen05, fp32 accumulate and residual stream",
+                                     "split": "both sides split-bf16 (3-term) on the tensor cores, fp32 accumulate and residual stream",
+                                     "fp32": "fp32 SIMT"}[args.precision],
                        "l2": f"{n_rot} rotating input batches ({n_rot * B * secs * 64e3 / 1e6:.0f} MB) and a multi-GB "
                              "activation working set per step, both larger than the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,

@@ -66,6 +66,25 @@ def test_bf16_mode_tolerance(cuda_lib, name):
     assert snr > 17.0 and err < 0.3        # random-init nets are not contractive: SURVEY.md section 8d (iii)
 
 
+@pytest.mark.parametrize("name", ["1kbps", "3kbps"])
+def test_split_mode_is_fp32_class(cuda_lib, name):
+    """precision="split": encode AND decode on the tensor cores with 3-term split-bf16 operands -- indices equal, waveform at
+    the fp32-class level (the bf16 decode of the same weights sits at 19-24 dB)."""
+    mc, weights, audio, g = golden_case(name)
+    codec = build(name, weights, "split")
+    with torch.inference_mode():
+        q, idx = codec.encode_audio(audio.to(DEV))
+        wav = codec.decode_audio(indices=torch.from_numpy(g["indices"]).to(DEV))
+    agree = float((idx["indices"].cpu().numpy() == g["indices"]).mean())
+    stride = int(g["wav_stride"])
+    ref_wav = torch.from_numpy(g["wav"])
+    snr = snr_db(ref_wav, wav.cpu()[:, ::stride])
+    err = max_abs(wav.cpu()[:, ::stride], ref_wav)
+    print(f"[{name}] split: index agreement {agree:.5f}  wav snr {snr:.1f} dB  max-abs {err:.3e}")
+    assert agree >= 0.999
+    assert snr > 55.0 and err < 5e-3
+
+
 def test_api_surface_and_invariants(cuda_lib):
     name = "1k5bps"
     mc = model_config(name)
