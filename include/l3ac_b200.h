@@ -180,6 +180,17 @@ int l3ac_local_attention_f32(const float* qkv, const float* bias_table, int B, i
 int l3ac_local_attention_tc(const void* qkv_hi, const void* qkv_lo, const float* bias_table, int B, int T, int H,
                             int D, int window, void* out, void* out_lo, int out_dtype, l3ac_stream_t stream);
 
+/* Rotary-position path (en_coder_dynamic_pos = false: LocalMHA(use_rotary_pos_emb=True), l3ac/local_trans.py:29,36;
+ * replaces SinusoidalEmbeddings + apply_rotary_pos_emb of local-attention inside LocalAttention.forward).
+ * l3ac_rotary_pack: qkv (B,T,3*H*D) fp32 [q | k | v] -> one segment per attention window, (B*ceil(T/window), 2*window,
+ * 3*H*D) in fp32 / bf16 / bf16 (hi, lo) pair, keys rotated by their bucket position 0..2w-1 and queries by w..2w-1
+ * (cos_table / sin_table: (2*window, D) fp32, host-computed like the reference).  The attention entry points above then
+ * run on the segments with T = 2*window and a zero bias table; l3ac_rotary_unpack gathers the (B,T,row_bytes) result rows
+ * back from the (B*ceil(T/window), 2*window, row_bytes) segment output.  D must be 32. */
+int l3ac_rotary_pack(const float* qkv, int B, int T, int H, int D, int window, const float* cos_table,
+                     const float* sin_table, void* out, void* out_lo, int out_dtype, l3ac_stream_t stream);
+int l3ac_rotary_unpack(const void* seg, void* out, int B, int T, int window, int row_bytes, l3ac_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * FSQ bottleneck.  Replaces VQEmbed.forward (l3ac/vq/__init__.py:25-30) = project_in ->
  * SuperFSQ.forward (l3ac/vq/fsq.py:30-68; tanh_act l3ac/vq/fsq_act.py:38-39) -> project_out, and

@@ -19,13 +19,14 @@ log = logging.getLogger("L3AC")
 
 
 def list_models() -> list[str]:
-    """l3ac/__init__.py:17-18."""
+    """l3ac/__init__.py:17-18: the TOML stems under configs/ (``debug`` included, like the reference)."""
     return sorted(p.relative_to(CONFIG_DIR).stem for p in CONFIG_DIR.rglob("*.toml"))
 
 
 def get_model(config_name, pretrained: bool = True, precision: str = "bf16") -> "L3AC":
-    """l3ac/__init__.py:21-25.  ``pretrained`` loads ``<model_dir>/<name>.<version>/*.pt`` when present (there is
-    no download step here: the box has no network); otherwise the seeded random initialisation is kept."""
+    """l3ac/__init__.py:21-25.  ``pretrained=True`` (the reference's only behaviour) downloads the per-module ``.pt`` files
+    that are missing under ``<model_dir>/<name>.<version>/`` and loads them; it RAISES when they cannot be had (no silent
+    random-weight codec).  ``pretrained=False`` (extension) keeps the seeded random initialisation."""
     config = L3ACConfig(config_file=CONFIG_DIR / f"{config_name}.toml")
     codec = L3AC(config, precision=precision)
     if pretrained:
@@ -88,8 +89,28 @@ class L3AC:
         self.config = config
         self.network = EnCodec(config.network_config, precision=precision)
 
+    def download_weights(self):
+        """l3ac/__init__.py:90-102: fetch every missing ``<module>.pt`` from ``config.weight_url`` (HTTP errors raise)."""
+        import requests
+        self.config.model_path.mkdir(parents=True, exist_ok=True)
+        for module_name in self.network.trainable_modules:
+            weight_url = self.config.weight_url.format(module_name)
+            weight_path = self.config.model_path / f"{module_name}.pt"
+            if weight_path.exists():
+                log.info(f"{module_name}({weight_path}) already exists, skip download")
+                continue
+            log.warning(f"Downloading {module_name}({weight_url}) to {weight_path}")
+            response = requests.get(weight_url, timeout=60)
+            response.raise_for_status()
+            weight_path.write_bytes(response.content)
+
     def load_pretrained(self):
-        """l3ac/__init__.py:104-106 without the HTTP download (l3ac/__init__.py:90-102)."""
+        """l3ac/__init__.py:104-106.  Unlike the reference's ``load_model`` (which only logs a missing file), a module file
+        that is still absent after the download step is an error: the caller asked for pretrained weights."""
+        self.download_weights()
+        missing = [n for n in self.network.trainable_modules if not (self.config.model_path / f"{n}.pt").exists()]
+        if missing:
+            raise FileNotFoundError(f"pretrained weights missing under {self.config.model_path}: {missing}")
         self.network.load_model(model_path=self.config.model_path)
 
     def encode_audio(self, audio_data: torch.Tensor):

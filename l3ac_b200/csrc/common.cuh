@@ -18,6 +18,20 @@ static inline int l3ac_launch_status() {
     return e == cudaSuccess ? L3AC_OK : (int)e;
 }
 
+// SM count of the CURRENT device (cached per device id: one process may drive several GPUs).
+static inline int l3ac_sm_count() {
+    static int cache[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        return n;
+    }
+    if (cache[dev] == 0) cudaDeviceGetAttribute(&cache[dev], cudaDevAttrMultiProcessorCount, dev);
+    return cache[dev];
+}
+
 static inline int l3ac_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // shared argument validation of the two GEMM entry points (defined in gemm_f32.cu)

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(kThreads, 4) convunit_thin_kernel(const float*
 #pragma unroll
         for (int s = 0; s < kSPT; ++s) {
             float h = hp[s].x + hp[s].y;
-            const float sn = __sinf(p0.y * h);
+            const float sn = sinf(p0.y * h);            // parity mode: libm-accurate sine (not the MUFU approximation)
             h = fmaf(p0.z, sn * sn, h);
             h = fmaf(h, p0.w, shift_u);
             hh[s] = make_float2(h, h);

@@ -532,8 +532,7 @@ __global__ void __launch_bounds__(256) upsample_cn_kernel(const float* __restric
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     const int To = T * scale;
-    const int bclip = blockIdx.y;                // one clip per grid row: no per-row division by To (~20 instructions per row and lane)
-    const long long rows = To;
+    const long long rows = (long long)B * To;    // scalar fallback (C % 4 != 0 or unaligned pointers): 1-D grid over all clips
     const float rscale = (float)(1.0 / (double)scale);
     for (long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows;
          row += (long long)gridDim.x * warps_per_block) {

@@ -672,12 +672,7 @@ extern "C" int l3ac_gemm_bf16_tc(const l3ac_gemm_desc* d, l3ac_stream_t stream) 
     if (!fn) return L3AC_EUNSUPPORTED;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int sms = l3ac_sm_count();
     const long long tiles = (long long)p.num_m_tiles * p.num_n_tiles;
     const long long max_ctas = occ2 ? 2LL * sms : sms;
     const int grid = (int)(tiles < max_ctas ? tiles : max_ctas);

@@ -678,12 +678,7 @@ extern "C" int l3ac_convunit_mlp_tc(const void* a, const void* w1, const float* 
         return L3AC_EINVAL;
     cudaError_t e = cudaFuncSetAttribute(convunit_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e != cudaSuccess) return (int)e;
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int sms = l3ac_sm_count();
     const int grid = (int)(mt < sms ? mt : sms);
     convunit_mlp_kernel<<<grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(tmA, tmW1, tmW2, p);
     return l3ac_launch_status();

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(kStemThreads) stem_kernel(const float* __restr
         float2 g[kStemSPT];
 #pragma unroll
         for (int sp = 0; sp < kStemSPT; ++sp) {
-            const float gv = gelu_erf_fast(ap[sp].x + ap[sp].y);
+            const float gv = gelu_erf(ap[sp].x + ap[sp].y);          // parity mode: erff (not the A&S / MUFU approximation)
             g[sp] = make_float2(gv, gv);
         }
         const float4* w2r = reinterpret_cast<const float4*>(s_w2t + u * CO);

@@ -74,8 +74,6 @@ class Engine:
         encoder_precision = encoder_precision or ("fp32" if precision == "fp32" else "split")
         if encoder_precision not in ("fp32", "split"):
             raise ValueError(f"encoder_precision must be 'fp32' or 'split', got {encoder_precision!r}")
-        if not mc.en_coder_dynamic_pos:
-            raise NotImplementedError("rotary position path (en_coder_dynamic_pos=false) is not built yet")
         if mc.decoder_last_layer != "legacy" or mc.base_unit != "normal" or not mc.use_norm or not mc.use_snake_act:
             raise NotImplementedError("only the layer options used by the four named configs are built")
         if mc.en_coder_cache_size != 0:
@@ -92,7 +90,9 @@ class Engine:
         # the kernel sequence of a given (batch, length) is captured once into a CUDA graph and replayed.
         self.graph_max_samples = int(40.0 * 16000)
         self.graph_cache_size = 8
+        self.graph_capture_after = int(os.environ.get("L3AC_GRAPH_AFTER", 2))   # capture a shape on its n-th appearance
         self._graphs = {}
+        self._graph_seen = {}
         # Micro-batches are independent, so they are issued round-robin on a few streams: the HBM-bound stencil kernels of
         # one micro-batch then overlap the tensor-core GEMMs (one persistent, shared-memory-heavy CTA per SM) of another.
         self.num_streams = int(os.environ.get("L3AC_STREAMS", 4))    # measured: 2 -> +11 %, 4 -> +14 % at 64 x 10 s
@@ -158,13 +158,26 @@ class Engine:
         self.enc_out = _Linear(_taps_major(fold_weight_norm(sd, f"blocks.{blk + 1}")), sd[f"blocks.{blk + 1}.bias"], ek)
 
     def _local_trans(self, sd, p, depth, window, kind):
-        """LocalTrans weights + the DynamicPositionBias table f[h][d], d = q_pos - k_pos in [0, 2w)
-        (l3ac/local_trans.py:30,43; the MLP input is the integer distance, so the table is input-independent)."""
+        """LocalTrans weights + the position term.  Dynamic mode (l3ac/local_trans.py:30,43): the DynamicPositionBias table
+        f[h][d], d = q_pos - k_pos in [0, 2w) (the MLP input is the integer distance, so the table is input-independent).
+        Rotary mode (l3ac/local_trans.py:29,36): cos / sin of the bucket angles t * inv_freq, t in [0, 2w), computed on the
+        CPU in fp32 exactly like SinusoidalEmbeddings (the attention kernels then see a zero bias table)."""
         q = f"{p}.dynamic_pos_bias.mlp"
-        d = torch.arange(2 * window, dtype=torch.float32, device=self.device)[:, None]
-        h = torch.nn.functional.silu(torch.nn.functional.linear(d, sd[f"{q}.0.weight"].float(), sd[f"{q}.0.bias"].float()))
-        h = torch.nn.functional.silu(torch.nn.functional.linear(h, sd[f"{q}.2.weight"].float(), sd[f"{q}.2.bias"].float()))
-        table = torch.nn.functional.linear(h, sd[f"{q}.4.weight"].float(), sd[f"{q}.4.bias"].float()).t().contiguous()
+        rotary = None
+        if self.mc.en_coder_dynamic_pos:
+            d = torch.arange(2 * window, dtype=torch.float32, device=self.device)[:, None]
+            h = torch.nn.functional.silu(torch.nn.functional.linear(d, sd[f"{q}.0.weight"].float(), sd[f"{q}.0.bias"].float()))
+            h = torch.nn.functional.silu(torch.nn.functional.linear(h, sd[f"{q}.2.weight"].float(), sd[f"{q}.2.bias"].float()))
+            table = torch.nn.functional.linear(h, sd[f"{q}.4.weight"].float(), sd[f"{q}.4.bias"].float()).t().contiguous()
+        else:
+            table = torch.zeros((HEADS, 2 * window), device=self.device)
+            rotary = []
+            for l in range(depth):
+                inv_freq = sd[f"{p}.layers.{l}.0.attn_fn.rel_pos.inv_freq"].detach().float().cpu()
+                t = torch.arange(2 * window).type_as(inv_freq)
+                freqs = torch.einsum("i , j -> i j", t, inv_freq)
+                freqs = torch.cat((freqs, freqs), dim=-1)
+                rotary.append((freqs.cos().contiguous().to(self.device), freqs.sin().contiguous().to(self.device)))
         layers = []
         for l in range(depth):
             a, f = f"{p}.layers.{l}.0", f"{p}.layers.{l}.1"
@@ -181,7 +194,7 @@ class Engine:
                 qkv=_Linear(sd[f"{a}.to_qkv.weight"], None, kind), out=_Linear(sd[f"{a}.to_out.weight"], None, kind),
                 ln2_w=sd[f"{f}.0.weight"].float().contiguous(), ln2_b=sd[f"{f}.0.bias"].float().contiguous(),
                 ff1=_Linear(w1i, None, kind), ff2=_Linear(w2, None, kind)))
-        return dict(layers=layers, window=window, table=table)
+        return dict(layers=layers, window=window, table=table, rotary=rotary)
 
     def _pack_en_encoder(self, sd):
         mc = self.mc
@@ -334,14 +347,24 @@ class Engine:
     def _run_local_trans(self, x, lt, act_dtype):
         """LocalTrans.forward -- l3ac/local_trans.py:42-48 (LocalMHA prenorm + GEGLU FeedForward)."""
         B, T, D = x.shape
-        for L in lt["layers"]:
+        for li, L in enumerate(lt["layers"]):
             a = ops.layernorm(x, L["ln1_w"], L["ln1_b"], LN_EPS, out_dtype=act_dtype)
-            if act_dtype == torch.float32:
+            w = lt["window"]
+            if lt["rotary"] is not None:
+                # rotary mode: fp32 q/k/v -> rotated per-window segments in the attention operand kind (rotary.cu)
+                cos_t, sin_t = lt["rotary"][li]
+                seg = ops.rotary_pack(self._lin(a, L["qkv"], B, T, D), HEADS, w, cos_t, sin_t, out_dtype=act_dtype)
+                if act_dtype == torch.float32:
+                    o = ops.local_attention(seg, lt["table"], HEADS, w)
+                else:
+                    o = ops.local_attention_tc(seg, lt["table"], HEADS, w, out_dtype=act_dtype)
+                o = ops.rotary_unpack(o, B, T, w)
+            elif act_dtype == torch.float32:
                 qkv = self._lin(a, L["qkv"], B, T, D)                               # fp32 (B,T,576)
-                o = ops.local_attention(qkv, lt["table"], HEADS, lt["window"])
+                o = ops.local_attention(qkv, lt["table"], HEADS, w)
             else:   # q/k/v stay in the GEMM operand format (bf16 or split pair) and feed the tensor-core attention
                 qkv = self._lin(a, L["qkv"], B, T, D, out_dtype=act_dtype)
-                o = ops.local_attention_tc(qkv, lt["table"], HEADS, lt["window"], out_dtype=act_dtype)
+                o = ops.local_attention_tc(qkv, lt["table"], HEADS, w, out_dtype=act_dtype)
             x = self._lin(o, L["out"], B, T, o.shape[-1], residual=x)
             a = ops.layernorm(x, L["ln2_w"], L["ln2_b"], LN_EPS, out_dtype=act_dtype)
             g = self._lin(a, L["ff1"], B, T, D, act=ops.ACT_GEGLU, out_dtype=act_dtype)   # (B,T,352)
@@ -349,15 +372,10 @@ class Engine:
         return x
 
     # ------------------------------------------------------------------ encode
-    def encode_features(self, audio: torch.Tensor, taps: Optional[dict] = None) -> torch.Tensor:
-        """preprocess + encoder + en_encoder (l3ac/__init__.py:109-111) -> trans_feature (B, T_tok, F)."""
-        mc = self.mc
+    def conv_encoder(self, audio: torch.Tensor, taps: Optional[dict] = None) -> torch.Tensor:
+        """Encoder.forward -- l3ac/modules.py:71-116.  audio (B, T) fp32 -> feature (B, T_f, F) channels-last fp32.
+        A length that is not a multiple of a stage's stride is floored like the reference's strided Conv1d does."""
         f32 = self.enc_dtype            # operand kind of the encode-side GEMMs (fp32 SIMT or split-bf16 tcgen05)
-        B, T0 = audio.shape
-        hop = mc.hop_length
-        T = math.ceil(T0 / hop) * hop                      # Codec.preprocess, l3ac/codec.py:79-84
-        if T != T0:
-            audio = torch.nn.functional.pad(audio, (0, T - T0))
         stem = ops.stem_tc if (f32 == ops.SPLIT and self.thin_tc) else ops.stem
         x = stem(audio.contiguous(), **self.stem)          # (B, T, 24)
         if taps is not None:
@@ -367,10 +385,14 @@ class Engine:
         direct = f32 if (f32 == ops.SPLIT and self.hidden_block_bytes <= 0) else torch.float32
         for si, st in enumerate(self.enc_stages):
             B_, T_, C_ = x.shape
-            for ui, u in enumerate(st["units"]):
-                x = self._run_conv_unit(x, u, f32, out_kind=direct if ui == len(st["units"]) - 1 else torch.float32)
             s = st["stride"]
-            x = self._lin(self._as_operand(x, f32), st["down"], B_, T_ // s, s * C_)   # Conv1d(k=s, stride=s) as a GEMM
+            keep = (T_ // s) * s
+            last_kind = direct if keep == T_ else torch.float32
+            for ui, u in enumerate(st["units"]):
+                x = self._run_conv_unit(x, u, f32, out_kind=last_kind if ui == len(st["units"]) - 1 else torch.float32)
+            if keep != T_:
+                x = x[:, :keep].contiguous()
+            x = self._lin(self._as_operand(x, f32), st["down"], B_, keep // s, s * C_)   # Conv1d(k=s, stride=s) as a GEMM
             x = ops.layernorm(x, st["cn_w"], st["cn_b"], EPS)                       # channels-first ChannelNorm
             if taps is not None:
                 taps[f"enc_down{si}"] = x
@@ -380,12 +402,30 @@ class Engine:
         x = self._lin(self._as_operand(x, f32), self.enc_out, B_, T_, C_, taps=3, tap_shift0=-1)   # Conv1d(k3, pad 1)
         if taps is not None:
             taps["enc_feature"] = x
-        if self.enc_trans_frame is not None:                                        # l3ac/local_trans.py:138-142,161-165
-            x = self._run_local_trans(x, self.enc_trans_frame, f32)
-            r = mc.en_coder_compress_rate
-            x = self._lin(self._as_operand(x, f32), self.enc_trans_down, B_, T_ // r, r * x.shape[-1])
-        x = self._run_local_trans(x, self.enc_trans_token, f32)
         return x
+
+    def en_encoder(self, x: torch.Tensor) -> torch.Tensor:
+        """LocalEncoder / CompressedLocalEncoderWithCache.forward -- l3ac/local_trans.py:63-74,138-142,161-165.
+        feature (B, T_f, F) channels-last -> trans_feature (B, T_tok, F)."""
+        f32 = self.enc_dtype
+        if self.enc_trans_frame is not None:
+            B_, T_, _ = x.shape
+            x = self._run_local_trans(x, self.enc_trans_frame, f32)
+            r = self.mc.en_coder_compress_rate
+            keep = (T_ // r) * r
+            if keep != T_:
+                x = x[:, :keep].contiguous()
+            x = self._lin(self._as_operand(x, f32), self.enc_trans_down, B_, keep // r, r * x.shape[-1])
+        return self._run_local_trans(x, self.enc_trans_token, f32)
+
+    def encode_features(self, audio: torch.Tensor, taps: Optional[dict] = None) -> torch.Tensor:
+        """preprocess + encoder + en_encoder (l3ac/__init__.py:109-111) -> trans_feature (B, T_tok, F)."""
+        B, T0 = audio.shape
+        hop = self.mc.hop_length
+        T = math.ceil(T0 / hop) * hop                      # Codec.preprocess, l3ac/codec.py:79-84
+        if T != T0:
+            audio = torch.nn.functional.pad(audio, (0, T - T0))
+        return self.en_encoder(self.conv_encoder(audio, taps))
 
     def quantize(self, trans_feature: torch.Tensor, want_z: bool = False):
         """VQEmbed.forward -- l3ac/vq/__init__.py:25-30."""
@@ -409,9 +449,21 @@ class Engine:
 
     # ------------------------------------------------------------------ CUDA graphs (small, launch-bound batches)
     def _graphed(self, key, fn, inp: torch.Tensor):
-        """Runs ``fn(static copy of inp)`` through a cached CUDA graph; returns fresh clones of its outputs."""
+        """Runs ``fn(inp)`` through a cached CUDA graph once the shape has been seen before; returns fresh outputs.
+
+        A shape is captured on its SECOND appearance (variable-length workloads would otherwise pay warm-up + capture +
+        instantiation, ~3x the eager cost, on almost every call and evict useful graphs); the first call runs eagerly.
+        Capture uses the thread-local error mode (a DataLoader pin-memory thread issuing CUDA calls must not abort it) and
+        any capture failure falls back to eager execution for that shape."""
         slot = self._graphs.get(key)
         if slot is None:
+            seen = self._graph_seen.get(key, 0)
+            if seen < 0 or seen + 1 < self.graph_capture_after:
+                if seen >= 0:
+                    if len(self._graph_seen) > 4096:
+                        self._graph_seen.clear()
+                    self._graph_seen[key] = seen + 1
+                return fn(inp)
             if len(self._graphs) >= self.graph_cache_size:
                 self._graphs.pop(next(iter(self._graphs)))          # drop the oldest capture (and its memory pool)
             static_in = inp.clone()
@@ -422,8 +474,13 @@ class Engine:
                 fn(static_in)
             cur.wait_stream(side)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                outs = fn(static_in)
+            try:
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                    outs = fn(static_in)
+            except RuntimeError:
+                self._graph_seen[key] = -1                           # never try this shape again
+                torch.cuda.synchronize(self.device)
+                return fn(inp)
             slot = (graph, static_in, outs)
             self._graphs[key] = slot
         graph, static_in, outs = slot
@@ -498,16 +555,19 @@ class Engine:
         return q, {"indices": idx, "level_indices": lvl}
 
     # ------------------------------------------------------------------ decode
-    def decode_features(self, feat: torch.Tensor, taps: Optional[dict] = None) -> torch.Tensor:
-        """en_decoder + decoder (l3ac/__init__.py:119-120).  feat (B, T_tok, F) fp32 -> audio (B, T)."""
-        mc = self.mc
+    def en_decoder(self, feat: torch.Tensor) -> torch.Tensor:
+        """LocalDecoder / CompressedLocalDecoderWithCache.forward -- l3ac/local_trans.py:86-94,123-126,182-186.
+        q_trans_feature (B, T_tok, F) -> q_feature (B, T_f, F), channels-last."""
         adt = self.dec_dtype
         x = self._run_local_trans(feat, self.dec_trans_token, adt)
         if self.dec_trans_frame is not None:                                        # UpTransV2, l3ac/local_trans.py:123-126
-            x = ops.upsample_linear_cn(x, mc.en_coder_compress_rate)
+            x = ops.upsample_linear_cn(x, self.mc.en_coder_compress_rate)
             x = self._run_local_trans(x, self.dec_trans_frame, adt)
-        if taps is not None:
-            taps["dec_feature"] = x
+        return x
+
+    def conv_decoder(self, x: torch.Tensor, taps: Optional[dict] = None) -> torch.Tensor:
+        """Decoder.forward -- l3ac/modules.py:135-201.  q_feature (B, T_f, F) channels-last -> audio (B, T)."""
+        adt = self.dec_dtype
         B, T, F = x.shape
         x = self._lin(self._as_operand(x, adt), self.dec_in, B, T, F, taps=3, tap_shift0=-1)   # Conv1d(k3, pad 1)
         for si, st in enumerate(self.dec_stages):
@@ -529,6 +589,50 @@ class Engine:
                           alpha=u["alpha1"], out_dtype=adt)
             x = self._lin(h, u["pw"], B, T, C, residual=x)
         return ops.tail_conv_tanh(x, self.dec_tail["alpha"], self.dec_tail["w"], self.dec_tail["bias"])
+
+    def decode_features(self, feat: torch.Tensor, taps: Optional[dict] = None) -> torch.Tensor:
+        """en_decoder + decoder (l3ac/__init__.py:119-120).  feat (B, T_tok, F) fp32 -> audio (B, T)."""
+        x = self.en_decoder(feat)
+        if taps is not None:
+            taps["dec_feature"] = x
+        return self.conv_decoder(x, taps)
+
+    # ------------------------------------------------------------------ stage-level entry points (EnCodec sub-modules)
+    def run_stage(self, name: str, x: torch.Tensor) -> torch.Tensor:
+        """One trainable module of the reference on a whole batch (micro-batched like encode / decode):
+        ``conv_encoder`` (B, T) -> (B, T_f, F); ``en_encoder`` (B, T_f, F) -> (B, T_tok, F); ``en_decoder`` (B, T_tok, F) ->
+        (B, T_f, F); ``conv_decoder`` (B, T_f, F) -> (B, T).  All channels-last."""
+        fn = getattr(self, name)
+        x = x.to(device=self.device, dtype=torch.float32).contiguous()
+        frame = math.prod(self.mc.compress_rates)
+        per_item = {"conv_encoder": 1, "en_encoder": frame, "en_decoder": self.mc.hop_length, "conv_decoder": frame}[name]
+        if x.shape[0] == 0:
+            raise RuntimeError(f"{name} got an empty batch")
+        outs = self._run_chunks(lambda lo, hi: fn(x[lo:hi].contiguous()), self._chunks(x.shape[0], x.shape[1] * per_item))
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+
+    def forward_all(self, audio: torch.Tensor) -> dict:
+        """EnCodec.forward -- l3ac/en_codec.py:53-72: every intermediate the reference returns, channels-last."""
+        if audio.dim() != 2:
+            raise RuntimeError(f"forward expects a (batch, samples) tensor, got shape {tuple(audio.shape)}")
+        audio = audio.to(device=self.device, dtype=torch.float32)
+        hop = self.mc.hop_length
+        T0 = audio.shape[1]
+        T = math.ceil(T0 / hop) * hop
+        if T != T0:
+            audio = torch.nn.functional.pad(audio, (0, T - T0))
+
+        def run(lo, hi):
+            feature = self.conv_encoder(audio[lo:hi])
+            trans = self.en_encoder(feature)
+            q, idx, lvl, _ = self.quantize(trans)
+            q_feature = self.en_decoder(q)
+            return feature, trans, q, idx, lvl, q_feature, self.conv_decoder(q_feature)
+
+        outs = self._run_chunks(run, self._chunks(*audio.shape))
+        keys = ("encoded_feature", "encoded_trans_feature", "quantized_trans_feature", "indices", "level_indices",
+                "quantized_feature", "audio")
+        return {k: (outs[0][i] if len(outs) == 1 else torch.cat([o[i] for o in outs], dim=0)) for i, k in enumerate(keys)}
 
     def decode(self, audio_feature: Optional[torch.Tensor] = None, indices: Optional[torch.Tensor] = None,
                taps: Optional[dict] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:

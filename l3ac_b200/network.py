@@ -49,6 +49,8 @@ class _Stage(ParamTree):
         super().__init__(tensors)
         object.__setattr__(self, "_owner", owner)
         self._fn_name = fn_name
+        # module.load_state_dict(sd) on one stage (the reference's load_model does exactly this) must drop the packed engine
+        self.register_load_state_dict_post_hook(lambda module, incompatible: owner.invalidate())
 
     def forward(self, *args, **kwargs):
         return getattr(self._owner, self._fn_name)(*args, **kwargs)
@@ -71,6 +73,7 @@ class EnCodec(nn.Module):
         self.quantizer.to_features = self._to_features      # VQEmbed.to_features, l3ac/vq/__init__.py:20-23
         self._engine: Optional[Engine] = None
         self._engine_key = None
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate())
 
     # ---- reference helpers ----------------------------------------------------------------------
     @property
@@ -126,7 +129,9 @@ class EnCodec(nn.Module):
     @property
     def engine(self) -> Engine:
         dev = next(self.parameters()).device
-        key = (str(dev), self.precision, self.encoder_precision)
+        # the packed engine (folded weight-norm, bf16 / split copies, bias tables, CUDA graphs) is keyed on the parameters'
+        # version counters too, so in-place edits (p.copy_, p.mul_, optimiser steps) repack instead of serving stale weights
+        key = (str(dev), self.precision, self.encoder_precision, sum(p._version for p in self.parameters()))
         if self._engine is None or self._engine_key != key:
             weights = {n: m.state_dict() for n, m in self.trainable_modules.items()}
             self._engine = Engine(self.mc, weights, dev, precision=self.precision,
@@ -136,29 +141,110 @@ class EnCodec(nn.Module):
 
     # ---- stage entry points (channels-first at this boundary, like the reference modules) ----------
     def _call_encoder(self, audio_b1t: torch.Tensor):
-        raise NotImplementedError("call codec.encode_audio(); the conv encoder is fused with en_encoder in this build")
+        """Encoder.forward, l3ac/modules.py:114-116: (B, 1, T) -> (B, F, T_f)."""
+        if audio_b1t.dim() != 3 or audio_b1t.shape[1] != 1:
+            raise RuntimeError(f"encoder expects (batch, 1, samples), got {tuple(audio_b1t.shape)}")
+        return self.engine.run_stage("conv_encoder", audio_b1t[:, 0]).permute(0, 2, 1)
 
-    def _call_en_encoder(self, feature):
-        raise NotImplementedError("call codec.encode_audio(); the conv encoder is fused with en_encoder in this build")
+    def _call_en_encoder(self, feature: torch.Tensor):
+        """LocalEncoder / CompressedLocalEncoderWithCache.forward: (B, F, T_f) -> (B, T_tok, F)."""
+        return self.engine.run_stage("en_encoder", feature.permute(0, 2, 1))
 
     def _call_quantizer(self, trans_feature: torch.Tensor):
+        """VQEmbed.forward, l3ac/vq/__init__.py:25-30: (q_features, indices dict, vq_loss = [0.])."""
         q, idx, lvl, _ = self.engine.quantize(trans_feature.to(torch.float32))
         return q, {"indices": idx, "level_indices": lvl}, torch.zeros(1, device=q.device, dtype=q.dtype)
 
     def _to_features(self, indices: torch.Tensor):
         return self.engine.dequantize(indices)
 
-    def _call_en_decoder(self, q_feature):
-        raise NotImplementedError("call codec.decode_audio(); en_decoder is fused with the conv decoder in this build")
+    def _call_en_decoder(self, q_trans_feature: torch.Tensor):
+        """LocalDecoder / CompressedLocalDecoderWithCache.forward: (B, T_tok, F) -> (B, F, T_f)."""
+        return self.engine.run_stage("en_decoder", q_trans_feature).permute(0, 2, 1)
 
-    def _call_decoder(self, feature):
-        raise NotImplementedError("call codec.decode_audio(); en_decoder is fused with the conv decoder in this build")
+    def _call_decoder(self, q_feature: torch.Tensor):
+        """Decoder.forward, l3ac/modules.py:200-201: (B, F, T_f) -> (B, 1, T)."""
+        return self.engine.run_stage("conv_decoder", q_feature.permute(0, 2, 1)).unsqueeze(1)
 
     def forward(self, audio_data: torch.Tensor):
-        """EnCodec.forward, l3ac/en_codec.py:53-72 (inference subset of the returned dict)."""
+        """EnCodec.forward, l3ac/en_codec.py:53-72: the same keys, shapes and layouts as the reference's dict."""
         length = audio_data.shape[-1]
-        q, idx = self.engine.encode(audio_data)
-        y = self.engine.decode(q)
-        return {"generated_audio": y[..., :length], "indices": idx["indices"],
-                "commit_loss": torch.zeros(1, device=y.device),
-                "hidden_feature": dict(quantized_trans_feature=q)}
+        r = self.engine.forward_all(audio_data)
+        q_feature = r["quantized_feature"].permute(0, 2, 1)
+        return {"generated_audio": r["audio"][..., :length],
+                "embedded_audio": q_feature,
+                "indices": r["indices"],
+                "commit_loss": torch.zeros(1, device=q_feature.device, dtype=q_feature.dtype),
+                "hidden_feature": dict(encoded_feature=r["encoded_feature"].permute(0, 2, 1),
+                                       encoded_trans_feature=r["encoded_trans_feature"],
+                                       quantized_trans_feature=r["quantized_trans_feature"],
+                                       quantized_feature=q_feature)}
+
+    # ---- legacy chunked API of the base Codec (l3ac/codec.py:111-161) ---------------------------------
+    def compress(self, audio_data: torch.Tensor):
+        """Codec.compress, l3ac/codec.py:111-114: encoder -> quantizer (the base class's path: no en_encoder).
+        audio_data (B, 1, T) -> (indices dict, q_feature (B, T_f, F))."""
+        feature = self._call_encoder(audio_data).permute(0, 2, 1)
+        q_feature, indices, _ = self._call_quantizer(feature.contiguous())
+        return indices, q_feature
+
+    def decompress(self, indices: torch.Tensor = None, q_feature: torch.Tensor = None):
+        """Codec.decompress, l3ac/codec.py:116-120: (to_features ->) decoder; returns (B, 1, T)."""
+        if q_feature is None:
+            q_feature = self._to_features(indices)
+        return self._call_decoder(q_feature.permute(0, 2, 1))
+
+    @torch.no_grad()
+    def extract_unit(self, audio_data: torch.Tensor, process_window: int = 5 * 16000):
+        """Codec.extract_unit, l3ac/codec.py:122-147: chunked compress of one long clip (1, T) with one-hop overlap.
+        Returns (ChunkData of index chunks, ChunkData of q_feature chunks).  The reference feeds ``compress`` an index DICT
+        per chunk and takes ``indices[0]``, which raises KeyError there; here the chunk's ``indices`` tensor is used."""
+        assert len(audio_data) == 1, "Only support batch size 1"
+        audio_data, _ = self.preprocess(audio_data)
+        process_window = process_window // self.fill_length * self.fill_length
+        chunk_audio = ChunkData(chunk_len=process_window, prefix_len=self.fill_length, original_data=audio_data[0])
+        chunk_indices, chunk_q_feature = [], []
+        for x in chunk_audio.chunk_data:
+            indices, q_feature = self.compress(x[None, None, :])
+            chunk_indices.append(indices["indices"][0])
+            chunk_q_feature.append(q_feature[0])
+        codec_chunk_len, codec_prefix_len = process_window // self.mc.hop_length, self.fill_length // self.mc.hop_length
+        return (ChunkData(chunk_len=codec_chunk_len, prefix_len=codec_prefix_len, chunk_data=chunk_indices),
+                ChunkData(chunk_len=codec_chunk_len, prefix_len=codec_prefix_len, chunk_data=chunk_q_feature))
+
+    @torch.no_grad()
+    def decode_unit(self, chunk_indices=None, chunk_q_feature=None, audio_length: int = None):
+        """Codec.decode_unit, l3ac/codec.py:149-156: decode every chunk, drop each later chunk's one-hop prefix, concatenate."""
+        if chunk_q_feature is None:
+            chunk_audio = [self.decompress(indices=x[None, :])[0, 0] for x in chunk_indices.chunk_data]
+        else:
+            chunk_audio = [self.decompress(q_feature=x[None, :, :])[0, 0] for x in chunk_q_feature.chunk_data]
+        chunk_audio = ChunkData(chunk_len=len(chunk_audio[0]), prefix_len=self.fill_length, chunk_data=chunk_audio)
+        return chunk_audio.data[None, :]
+
+
+class ChunkData:
+    """l3ac/codec.py:164-195: a sequence either whole (``original_data``) or as overlapping chunks (``chunk_data``): chunk 0 is
+    ``[0, chunk_len)``, chunk i > 0 is ``[i*chunk_len - prefix_len, (i+1)*chunk_len)``; ``data`` drops the prefixes again."""
+
+    def __init__(self, chunk_len: int, prefix_len: int, original_data=None, chunk_data=None):
+        assert chunk_len > prefix_len
+        self.chunk_len = chunk_len
+        self.prefix_len = prefix_len
+        self._original_data = original_data
+        self._chunk_data = chunk_data
+
+    @property
+    def data(self):
+        if self._original_data is not None:
+            return self._original_data
+        parts = [self._chunk_data[0]] + [x[self.prefix_len:] for x in self._chunk_data[1:]]
+        return torch.cat(parts, dim=0)
+
+    @property
+    def chunk_data(self):
+        if self._chunk_data is not None:
+            return self._chunk_data
+        n = len(self._original_data)
+        return [self._original_data[:self.chunk_len] if i == 0 else self._original_data[i - self.prefix_len:i + self.chunk_len]
+                for i in range(0, n, self.chunk_len)]

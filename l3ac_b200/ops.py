@@ -328,6 +328,41 @@ def local_attention_tc(qkv, bias_table: torch.Tensor, heads: int, window: int, o
     return out
 
 
+def rotary_pack(qkv: torch.Tensor, heads: int, window: int, cos_table: torch.Tensor, sin_table: torch.Tensor,
+                out_dtype=torch.float32):
+    """fp32 (B, T, 3*heads*32) q|k|v -> rotated per-window segments (B*ceil(T/window), 2*window, 3*heads*32) of the requested kind."""
+    _chk(qkv, name="qkv")
+    _chk(cos_table, name="cos_table")
+    _chk(sin_table, name="sin_table")
+    B, T, three_hd = qkv.shape
+    D = three_hd // (3 * heads)
+    if tuple(cos_table.shape) != (2 * window, D) or tuple(sin_table.shape) != (2 * window, D):
+        raise ValueError(f"rotary tables must be (2*window, {D})")
+    nw = -(-T // window)
+    out, hi, lo = _empty_act((B * nw, 2 * window, three_hd), qkv.device, out_dtype)
+    _count()
+    with _hook("rotary_pack", _nbytes(qkv, out)), torch.cuda.device(qkv.device):
+        check(_lib.load().l3ac_rotary_pack(_ptr(qkv), B, T, heads, D, window, _ptr(cos_table), _ptr(sin_table), _ptr(hi),
+                                           _ptr(lo), _DT[out_dtype], _stream(qkv)), "l3ac_rotary_pack")
+    return out
+
+
+def rotary_unpack(seg, B: int, T: int, window: int):
+    """Segment attention output (B*ceil(T/window), 2*window, C) -> (B, T, C); same kind as ``seg`` (tensor or Split)."""
+    planes = (seg.hi, seg.lo) if isinstance(seg, Split) else (seg,)
+    outs = []
+    for pl in planes:
+        if not pl.is_cuda or not pl.is_contiguous():
+            raise ValueError("seg must be a contiguous CUDA tensor")
+        o = torch.empty((B, T, pl.shape[-1]), device=pl.device, dtype=pl.dtype)
+        _count()
+        with _hook("rotary_unpack", _nbytes(o, o)), torch.cuda.device(pl.device):
+            check(_lib.load().l3ac_rotary_unpack(_ptr(pl), _ptr(o), B, T, window, pl.shape[-1] * pl.element_size(),
+                                                 _stream(pl)), "l3ac_rotary_unpack")
+        outs.append(o)
+    return Split(*outs) if isinstance(seg, Split) else outs[0]
+
+
 def fsq_quantize(x: torch.Tensor, w_in, b_in, w_out, b_out, levels: Sequence[int], want_z: bool = False):
     _chk(x, name="x")
     F = x.shape[-1]

@@ -22,6 +22,7 @@ MODULE_NAMES = ("encoder", "quantizer", "decoder", "en_encoder", "en_decoder")
 
 # init kinds
 TRUNC, ZEROS, ONES, UNIFORM, WN_G = "trunc_normal_0.02", "zeros", "ones", "uniform_fan_in", "weight_norm_g"
+INV_FREQ = "rotary_inv_freq"        # SinusoidalEmbeddings buffer: 1 / theta ** (arange(0, d, 2) / d), theta = 10000
 Spec = "OrderedDict[str, Tuple[Tuple[int, ...], str, object]]"
 
 
@@ -120,6 +121,8 @@ def _local_trans(spec, p, dim, depth, dynamic_pos):
     for l in range(depth):
         _norm(spec, f"{p}.layers.{l}.0.norm", dim)
         _plain(spec, f"{p}.layers.{l}.0.to_qkv", (3 * inner, dim), bias=False)
+        if not dynamic_pos:     # use_rotary_pos_emb (l3ac/local_trans.py:29,36): the angle table's persistent buffer
+            spec[f"{p}.layers.{l}.0.attn_fn.rel_pos.inv_freq"] = ((dim_head // 2,), INV_FREQ, dim_head)
         _plain(spec, f"{p}.layers.{l}.0.to_out", (dim, inner), bias=False)
         _norm(spec, f"{p}.layers.{l}.1.0", dim)
         _plain(spec, f"{p}.layers.{l}.1.1", (2 * ff_inner, dim), bias=False)
@@ -205,6 +208,8 @@ def init_state_dicts(mc: ModelConfig, seed: int = 0, jitter: bool = False) -> Di
                 if jitter:
                     std = 0.1 if (".grn." in key or ".norm." in key or ".merge_layer.0." in key) else 0.02
                     t = std * torch.randn(shape, generator=g)
+            elif kind == INV_FREQ:
+                t = 1.0 / (10000 ** (torch.arange(0, arg, 2).float() / arg))
             elif kind == WN_G:
                 t = None    # filled below from v
             else:

@@ -179,19 +179,35 @@ def decoder(sd: SD, cfg: dict, x: torch.Tensor, taps: dict | None = None) -> tor
 def dynamic_position_bias(sd: SD, p: str, w: int) -> torch.Tensor:
     """DynamicPositionBias(dim=64, heads)(w, 2w) -> (heads, w, 2w); l3ac/local_trans.py:30,43."""
     j = 2 * w
-    d = torch.arange(j, dtype=torch.float32)[:, None]
+    w0 = sd[f"{p}.mlp.0.weight"]
+    d = torch.arange(j, dtype=w0.dtype, device=w0.device)[:, None]         # fp32 in the reference (fp64 only in tools/fp32_floor.py)
     h = F.silu(F.linear(d, sd[f"{p}.mlp.0.weight"], sd[f"{p}.mlp.0.bias"]))
     h = F.silu(F.linear(h, sd[f"{p}.mlp.2.weight"], sd[f"{p}.mlp.2.bias"]))
     table = F.linear(h, sd[f"{p}.mlp.4.weight"], sd[f"{p}.mlp.4.bias"])          # (2w, heads)
-    idx = (torch.arange(w, j)[:, None] - torch.arange(j)[None, :]).abs()
+    idx = (torch.arange(w, j, device=w0.device)[:, None] - torch.arange(j, device=w0.device)[None, :]).abs()
     return table[idx].permute(2, 0, 1)
 
 
-def local_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, bias: torch.Tensor, w: int) -> torch.Tensor:
+def rotary_tables(inv_freq: torch.Tensor, n: int):
+    """SinusoidalEmbeddings.forward of local-attention: angles t * inv_freq (fp32 product) for t = 0..n-1, duplicated to the
+    full head dim; returns (cos, sin) of shape (n, d)."""
+    t = torch.arange(n, device=inv_freq.device).type_as(inv_freq)
+    freqs = torch.einsum("i , j -> i j", t, inv_freq)
+    freqs = torch.cat((freqs, freqs), dim=-1)
+    return freqs.cos(), freqs.sin()
+
+
+def rotate_half(x: torch.Tensor) -> torch.Tensor:
+    x1, x2 = x.reshape(*x.shape[:-1], 2, x.shape[-1] // 2).unbind(dim=-2)
+    return torch.cat((-x2, x1), dim=-1)
+
+
+def local_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, bias, w: int, inv_freq=None) -> torch.Tensor:
     """LocalAttention(window_size=w, causal, look_backward=1, look_forward=0, autopad, exact_windowsize=False).
 
     q,k,v: (B*heads, n, d).  Keys of window i are [window i-1 ; window i]; window -1 is padding
-    (value -1, masked out).  bias: (heads, w, 2w).
+    (value -1, masked out).  bias: (heads, w, 2w) or None; ``inv_freq`` (rotary mode, l3ac/local_trans.py:29,36): keys are
+    rotated by their position 0..2w-1 inside [previous ; own], queries by w..2w-1, after q has been scaled.
     """
     bh, n0, d = q.shape
     rem = (-n0) % w
@@ -199,7 +215,7 @@ def local_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, bias: tor
         q, k, v = (F.pad(t, (0, 0, 0, rem)) for t in (q, k, v))
     n = q.shape[1]
     nw = n // w
-    pos = torch.arange(n).reshape(1, nw, w)
+    pos = torch.arange(n, device=q.device).reshape(1, nw, w)
 
     def look_around(t, pad_value):
         prev = F.pad(t, (0,) * (2 * (t.dim() - 2)) + (1, 0), value=pad_value)[:, :nw]
@@ -208,11 +224,17 @@ def local_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, bias: tor
     bq = q.reshape(bh, nw, w, d) * (d ** -0.5)
     bk = look_around(k.reshape(bh, nw, w, d), -1.)
     bv = look_around(v.reshape(bh, nw, w, d), -1.)
+    if inv_freq is not None:
+        cos, sin = rotary_tables(inv_freq, 2 * w)
+        scale = torch.ones(1, device=q.device)
+        bq = (bq * cos[-w:] * scale) + (rotate_half(bq) * sin[-w:] * scale)
+        bk = (bk * cos * scale ** -1) + (rotate_half(bk) * sin * scale ** -1)
     q_pos = pos[..., :, None]
     k_pos = look_around(pos, -1)[..., None, :]
     sim = torch.einsum("bhie,bhje->bhij", bq, bk)
-    heads = bias.shape[0]
-    sim = sim + bias.repeat(bh // heads, 1, 1)[:, None]
+    if bias is not None:
+        heads = bias.shape[0]
+        sim = sim + bias.repeat(bh // heads, 1, 1)[:, None]
     neg = -torch.finfo(sim.dtype).max
     sim = sim.masked_fill(q_pos < k_pos, neg)
     sim = sim.masked_fill(k_pos == -1, neg)
@@ -223,14 +245,15 @@ def local_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, bias: tor
 
 def local_trans(sd: SD, p: str, x: torch.Tensor, depth: int, w: int, heads: int = 6) -> torch.Tensor:
     """LocalTrans.forward, l3ac/local_trans.py:42-48; LocalMHA(prenorm) + FeedForward(GEGLU)."""
-    bias = dynamic_position_bias(sd, f"{p}.dynamic_pos_bias", w)
+    rotary = f"{p}.dynamic_pos_bias.mlp.0.weight" not in sd           # use_rotary_pos_emb = not use_dynamic_pos_bias
+    bias = None if rotary else dynamic_position_bias(sd, f"{p}.dynamic_pos_bias", w)
     b, n, dim = x.shape
     for l in range(depth):
         a = f"{p}.layers.{l}.0"
         h = F.layer_norm(x, (dim,), sd[f"{a}.norm.weight"], sd[f"{a}.norm.bias"], 1e-5)
         q, k, v = F.linear(h, sd[f"{a}.to_qkv.weight"]).chunk(3, dim=-1)
         q, k, v = (t.reshape(b, n, heads, -1).transpose(1, 2).reshape(b * heads, n, -1) for t in (q, k, v))
-        o = local_attention(q, k, v, bias, w)
+        o = local_attention(q, k, v, bias, w, sd[f"{a}.attn_fn.rel_pos.inv_freq"] if rotary else None)
         o = o.reshape(b, heads, n, -1).transpose(1, 2).reshape(b, n, -1)
         x = F.linear(o, sd[f"{a}.to_out.weight"]) + x
         f = f"{p}.layers.{l}.1"
@@ -266,28 +289,28 @@ def en_decoder(sd: SD, cfg: dict, q_feature: torch.Tensor) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------------
 # FSQ bottleneck
 # ----------------------------------------------------------------------------------------------
-def fsq_basis(levels: Sequence[int]) -> torch.Tensor:
+def fsq_basis(levels: Sequence[int], device=None) -> torch.Tensor:
     """l3ac/vq/fsq.py:15 -- cumprod([1, L0, ..., L4]); dim 0 is least significant."""
-    return torch.cumprod(torch.tensor([1] + list(levels[:-1])), dim=0, dtype=torch.int32)
+    return torch.cumprod(torch.tensor([1] + list(levels[:-1]), device=device), dim=0, dtype=torch.int32)
 
 
 def fsq_quantize(z: torch.Tensor, levels: Sequence[int]):
     """SuperFSQ.forward in eval mode, l3ac/vq/fsq.py:30-68 + fsq_act.py:38-39 + fsq.py:21."""
-    lv = torch.tensor(list(levels), dtype=torch.int32)
+    lv = torch.tensor(list(levels), dtype=torch.int32, device=z.device)
     shape = z.shape
     z2 = z.reshape(-1, len(levels))
     act = (torch.tanh(z2) + 1) / 2
     level_idx = (act * (lv - 1)).round()
     q_act = level_idx / (lv - 1)
-    indices = (level_idx * fsq_basis(levels)).sum(dim=-1).to(torch.int32)
+    indices = (level_idx * fsq_basis(levels, z.device)).sum(dim=-1).to(torch.int32)
     q_z = q_act * 2 - 1
     return q_z.reshape(shape), indices.reshape(shape[:-1]), level_idx.reshape(shape)
 
 
 def fsq_indices_to_codes(indices: torch.Tensor, levels: Sequence[int]) -> torch.Tensor:
     """l3ac/vq/fsq.py:70-81."""
-    lv = torch.tensor(list(levels), dtype=torch.int32)
-    level_idx = (indices.unsqueeze(-1) // fsq_basis(levels)) % lv
+    lv = torch.tensor(list(levels), dtype=torch.int32, device=indices.device)
+    level_idx = (indices.unsqueeze(-1) // fsq_basis(levels, indices.device)) % lv
     return (level_idx / (lv - 1)) * 2 - 1
 
 
@@ -329,14 +352,17 @@ class Oracle:
     ``cfg``: the ``[network_config]`` table of the TOML as a dict.
     """
 
-    def __init__(self, cfg: dict, weights: Dict[str, SD]):
+    def __init__(self, cfg: dict, weights: Dict[str, SD], device="cpu"):
+        """``device``: "cpu" for the oracle proper; a CUDA device only for ``bench.py --impl reference-gpu`` (the same torch
+        forward through ATen/cuBLAS/cuDNN kernels, TF32 off -- the reference's own GPU path, never a parity checker)."""
         self.cfg = dict(cfg)
-        self.w = {m: {k: v.detach().to(torch.float32).cpu() for k, v in sd.items()} for m, sd in weights.items()}
+        self.device = torch.device(device)
+        self.w = {m: {k: v.detach().to(torch.float32).to(self.device) for k, v in sd.items()} for m, sd in weights.items()}
 
     @torch.no_grad()
     def encode_audio(self, audio: torch.Tensor, taps: dict | None = None):
         """l3ac/__init__.py:108-114."""
-        audio, _ = preprocess(self.cfg, audio.to(torch.float32))
+        audio, _ = preprocess(self.cfg, audio.to(device=self.device, dtype=torch.float32))
         feature = encoder(self.w["encoder"], self.cfg, audio.unsqueeze(1), taps)
         trans = en_encoder(self.w["en_encoder"], self.cfg, feature)
         q_feature, idx, z = quantizer_forward(self.w["quantizer"], self.cfg, trans)
@@ -348,7 +374,8 @@ class Oracle:
     def decode_audio(self, audio_feature: torch.Tensor = None, indices: torch.Tensor = None, taps: dict | None = None):
         """l3ac/__init__.py:116-121."""
         if audio_feature is None:
-            audio_feature = quantizer_to_features(self.w["quantizer"], self.cfg, indices)
+            audio_feature = quantizer_to_features(self.w["quantizer"], self.cfg, indices.to(self.device))
+        audio_feature = audio_feature.to(self.device)
         q_feature = en_decoder(self.w["en_decoder"], self.cfg, audio_feature)
         if taps is not None:
             taps["dec_feature"] = q_feature

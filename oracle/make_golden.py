@@ -28,7 +28,15 @@ from oracle.l3ac_oracle import Oracle                           # noqa: E402
 
 GOLDEN = ROOT / "tests" / "golden"
 # (config, seconds, batch): 10 s clips span several attention windows (1kbps: 750 frames = 4.2 s)
-CASES = [("1kbps", 10.0, 1), ("3kbps", 6.0, 1), ("0k75bps", 3.1, 2), ("1k5bps", 3.1, 2)]
+CASES = [("1kbps", 10.0, 1), ("3kbps", 6.0, 1), ("0k75bps", 3.1, 2), ("1k5bps", 3.1, 2),
+         ("rotary", 3.1, 2)]          # tests/golden/rotary.toml: the rotary-position path (no named config uses it)
+
+
+def config_file(name: str, config_dir) -> Path:
+    """Named configs live in the package's configs/; test-only configs (rotary) next to the golden vectors."""
+    p = Path(config_dir) / f"{name}.toml"
+    return p if p.exists() else GOLDEN / f"{name}.toml"
+
 WEIGHT_SEED, AUDIO_SEED = 7, 1234
 
 
@@ -52,14 +60,17 @@ def stats(t: torch.Tensor):
     return [float(t.sum()), float((t * t).sum()), float(t.abs().max())]
 
 
-def main():
+def main(only=None):
     torch.set_num_threads(8)
-    keys = {}
+    keys_path = GOLDEN / "state_dict_keys.json"
+    keys = json.loads(keys_path.read_text()) if (only and keys_path.exists()) else {}
     for name, seconds, batch in CASES:
-        rcfg = ref_pkg.L3ACConfig(config_file=ref_pkg.CONFIG_DIR / f"{name}.toml")
+        if only and name not in only:
+            continue
+        rcfg = ref_pkg.L3ACConfig(config_file=config_file(name, ref_pkg.CONFIG_DIR))
         ref = ref_pkg.L3AC(rcfg)
         ref.network.eval()
-        mc = L3ACConfig(config_file=CONFIG_DIR / f"{name}.toml").network_config
+        mc = L3ACConfig(config_file=config_file(name, CONFIG_DIR)).network_config
         spec = network_spec(mc)
         for mod, net in ref.network.trainable_modules.items():
             sd = net.state_dict()
@@ -107,4 +118,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1:])

@@ -40,6 +40,37 @@ def _look_around(x, backward, forward, pad_value, dim=2):
     return torch.cat(parts, dim=dim)
 
 
+class SinusoidalEmbeddings(nn.Module):
+    """Rotary angle table: ``forward(x)`` -> (freqs (n, dim), scale = ones(1)) for n = x.shape[-2]; ``inv_freq`` is a
+    persistent buffer (it appears in the state dict as ``...attn_fn.rel_pos.inv_freq``)."""
+
+    def __init__(self, dim, scale_base=None, use_xpos=False, theta=10000):
+        super().__init__()
+        assert not use_xpos
+        inv_freq = 1. / (theta ** (torch.arange(0, dim, 2).float() / dim))
+        self.register_buffer('inv_freq', inv_freq)
+
+    def forward(self, x):
+        t = torch.arange(x.shape[-2], device=x.device).type_as(self.inv_freq)
+        freqs = torch.einsum('i , j -> i j', t, self.inv_freq)
+        return torch.cat((freqs, freqs), dim=-1), torch.ones(1, device=x.device)
+
+
+def rotate_half(x):
+    x1, x2 = x.reshape(*x.shape[:-1], 2, x.shape[-1] // 2).unbind(dim=-2)
+    return torch.cat((-x2, x1), dim=-1)
+
+
+def apply_rotary_pos_emb(q, k, freqs, scale=1):
+    """Window-relative rotation: keys at positions 0..2w-1 of [previous ; own], queries at the last q_len positions."""
+    q_len = q.shape[-2]
+    q_freqs = freqs[..., -q_len:, :]
+    inv_scale = scale ** -1
+    q = (q * q_freqs.cos() * scale) + (rotate_half(q) * q_freqs.sin() * scale)
+    k = (k * freqs.cos() * inv_scale) + (rotate_half(k) * freqs.sin() * inv_scale)
+    return q, k
+
+
 class LocalAttention(nn.Module):
     def __init__(self, window_size, causal=False, look_backward=1, look_forward=None, dropout=0.,
                  autopad=False, exact_windowsize=False, scale=None, dim=None,
@@ -47,9 +78,8 @@ class LocalAttention(nn.Module):
         super().__init__()
         look_forward = (0 if causal else 1) if look_forward is None else look_forward
         assert not (causal and look_forward > 0)
-        if use_rotary_pos_emb and dim is not None:
-            raise NotImplementedError("rotary path is not restated (named configs use dynamic_pos)")
         assert not use_xpos and not shared_qk and dropout == 0.
+        self.rel_pos = SinusoidalEmbeddings(dim) if (use_rotary_pos_emb and dim is not None) else None
         self.window_size, self.causal = window_size, causal
         self.look_backward, self.look_forward = look_backward, look_forward
         self.autopad, self.exact_windowsize, self.scale = autopad, exact_windowsize, scale
@@ -73,6 +103,9 @@ class LocalAttention(nn.Module):
         bq = bq * scale
         la = dict(backward=self.look_backward, forward=self.look_forward, pad_value=pad_value)
         bk, bv = _look_around(bk, **la), _look_around(bv, **la)
+        if self.rel_pos is not None:
+            pos_emb, xpos_scale = self.rel_pos(bk)
+            bq, bk = apply_rotary_pos_emb(bq, bk, pos_emb, scale=xpos_scale)
         bq_t = b_t[..., :, None]
         bq_k = _look_around(b_t, **la)[..., None, :]
         pad_mask = bq_k == pad_value

@@ -19,8 +19,14 @@ def make_audio(batch: int, seconds: float, seed: int = 1234) -> torch.Tensor:
     return (0.1 * torch.randn(batch, n, generator=g)).clamp(-1, 1)
 
 
+def config_path(name: str) -> Path:
+    """Named configs live in the package; test-only configs (``rotary``) next to the golden vectors."""
+    p = CONFIG_DIR / f"{name}.toml"
+    return p if p.exists() else GOLDEN / f"{name}.toml"
+
+
 def model_config(name: str):
-    return L3ACConfig(config_file=CONFIG_DIR / f"{name}.toml").network_config
+    return L3ACConfig(config_file=config_path(name)).network_config
 
 
 def weights_digest(weights) -> str:

@@ -49,6 +49,12 @@ def _worker(rank, world, port, n_items):
         assert torch.equal(q, rq) and torch.equal(idx["indices"], ridx["indices"])
         assert torch.equal(sharded.decode_audio(indices=idx["indices"]), ref.decode_audio(indices=ridx["indices"]))
         assert torch.equal(sharded.decode_audio(q), ref.decode_audio(rq))
+        # local-shard style: each rank brings its own utterances; async index / waveform gathers
+        ql, idxl, pending = sharded.encode_shard(local, n_items=n_items)
+        assert torch.equal(ql, rq[lo:hi]) and torch.equal(pending.wait(), ridx["indices"])
+        wl, pw = sharded.decode_shard(indices=idxl["indices"], gather=True, n_items=n_items)
+        assert torch.equal(wl, ref.decode_audio(indices=ridx["indices"])[lo:hi])
+        assert torch.equal(pw.wait(), ref.decode_audio(indices=ridx["indices"]))
     finally:
         dist.destroy_process_group()
 

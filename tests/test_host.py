@@ -17,10 +17,59 @@ ROOT = Path(__file__).resolve().parent.parent
 
 
 def test_list_models():
-    assert set(CONFIGS) <= set(l3ac_b200.list_models())
+    """l3ac/__init__.py:17-18 lists every TOML stem, ``debug`` included (which cannot be loaded, there as here)."""
+    assert set(l3ac_b200.list_models()) == set(CONFIGS) | {"debug"}
+    with pytest.raises(ValueError):
+        l3ac_b200.get_model("debug", pretrained=False)
 
 
-@pytest.mark.parametrize("name", CONFIGS)
+def test_pretrained_missing_raises(tmp_path, monkeypatch):
+    """get_model(pretrained=True) must not hand back a random-weight codec: no files and no network -> an exception."""
+    cfg = L3ACConfig(config_file=CONFIG_DIR / "1kbps.toml", model_dir=tmp_path)
+    codec = l3ac_b200.L3AC(cfg)
+    import requests
+
+    def no_network(url, **kw):
+        raise requests.ConnectionError(f"offline: {url}")
+    monkeypatch.setattr(requests, "get", no_network)
+    with pytest.raises(requests.ConnectionError):
+        codec.load_pretrained()
+    assert codec.config.weight_url.format("encoder").endswith("weights/1kbps.v1/encoder.pt")
+    # files present -> loaded without touching the network
+    codec.network.save_model(model_path=cfg.model_path)
+    codec.load_pretrained()
+
+
+def test_engine_invalidated_by_standard_weight_loading():
+    """load_state_dict on the network or one stage, and in-place parameter edits, must drop the packed engine."""
+    net = l3ac_b200.EnCodec(model_config("3kbps"), seed=1)
+    sentinel = object()
+    net._engine, net._engine_key = sentinel, None
+    net.decoder.load_state_dict(net.decoder.state_dict())
+    assert net._engine is None
+    net._engine = sentinel
+    net.load_state_dict(net.state_dict())
+    assert net._engine is None
+    v0 = sum(p._version for p in net.parameters())
+    with torch.no_grad():
+        next(net.quantizer.parameters()).mul_(1.0)
+    assert sum(p._version for p in net.parameters()) == v0 + 1      # the engine cache key changes with it
+
+
+def test_chunk_data_round_trip():
+    """ChunkData, l3ac/codec.py:164-195: chunk i > 0 carries a prefix_len overlap that ``data`` drops again."""
+    from l3ac_b200.network import ChunkData
+    x = torch.arange(1000)
+    c = ChunkData(chunk_len=300, prefix_len=50, original_data=x)
+    chunks = c.chunk_data
+    assert [len(t) for t in chunks] == [300, 350, 350, 150]
+    assert torch.equal(chunks[1], x[250:600])
+    assert torch.equal(ChunkData(chunk_len=300, prefix_len=50, chunk_data=chunks).data, x)
+    with pytest.raises(AssertionError):
+        ChunkData(chunk_len=10, prefix_len=10, original_data=x)
+
+
+@pytest.mark.parametrize("name", CONFIGS + ("rotary",))
 def test_spec_matches_reference_checkpoint_keys(name):
     """Key names and shapes equal the reference state_dicts (dumped from the reference by oracle/make_golden.py)."""
     ref = json.loads((GOLDEN / "state_dict_keys.json").read_text())[name]

@@ -182,7 +182,8 @@ def test_fsq_quantize_full(cuda_lib):
 
 
 @pytest.mark.parametrize("C,T,s", [(128, 50, 3), (256, 33, 5), (24, 100, 2), (96, 7, 4), (48, 1001, 3), (96, 333, 5), (24, 1, 2), (48, 2, 5),
-                                   (128, 1779, 3), (24, 4001, 4), (100, 77, 3), (48, 40, 6)])
+                                   (128, 1779, 3), (24, 4001, 4), (100, 77, 3), (48, 40, 6),
+                                   (30, 50, 3), (7, 33, 2), (130, 20, 5)])          # C % 4 != 0: the scalar fallback kernel (B = 2)
 def test_upsample_linear_cn(cuda_lib, C, T, s):
     x = rnd(2, C, T, seed=1)
     w, b = 1 + rnd(C, seed=2, scale=0.1), rnd(C, seed=3, scale=0.1)
@@ -370,3 +371,27 @@ def test_fused_thin_convunit(cuda_lib, T):
                            d(sd["u.pw_conv2.weight"]), d(sd["u.pw_conv2.bias"]), out_dtype=ops.SPLIT)
     ref = ops.split_bf16(got)
     assert torch.equal(sp.hi, ref.hi) and torch.equal(sp.lo, ref.lo)
+
+
+@pytest.mark.parametrize("T,w", [(100, 40), (333, 100), (64, 200), (150, 50)])
+@pytest.mark.parametrize("kind", ["fp32", "bf16", "split"])
+def test_rotary_attention(cuda_lib, T, w, kind):
+    """Rotary path: rotary_pack -> block-local attention on the per-window segments -> rotary_unpack against the oracle's
+    restatement of LocalAttention(use_rotary_pos_emb=True) (keys rotated by bucket position 0..2w-1, queries by w..2w-1)."""
+    B, H, D = 2, 6, 32
+    qkv = rnd(B, T, 3 * H * D, seed=T + w)
+    inv_freq = 1.0 / (10000 ** (torch.arange(0, D, 2).float() / D))
+    cos, sin = O.rotary_tables(inv_freq, 2 * w)
+    q, k, v = (t.reshape(B, T, H, D).transpose(1, 2).reshape(B * H, T, D) for t in qkv.chunk(3, dim=-1))
+    want = O.local_attention(q, k, v, None, w, inv_freq).reshape(B, H, T, D).transpose(1, 2).reshape(B, T, H * D)
+    dt = {"fp32": torch.float32, "bf16": torch.bfloat16, "split": ops.SPLIT}[kind]
+    seg = ops.rotary_pack(qkv.to(DEV), H, w, cos.to(DEV), sin.to(DEV), out_dtype=dt)
+    zero = torch.zeros((H, 2 * w), device=DEV)
+    if kind == "fp32":
+        o = ops.local_attention(seg, zero, H, w)
+    else:
+        o = ops.local_attention_tc(seg, zero, H, w, out_dtype=torch.float32)
+    got = ops.rotary_unpack(o, B, T, w)
+    err = max_abs(got.cpu(), want)
+    print(f"rotary attention T={T} w={w} {kind}: max-abs {err:.2e}")
+    assert err < {"fp32": 2e-5, "split": 1e-4, "bf16": 6e-2}[kind]

@@ -11,7 +11,7 @@ from l3ac_b200.spec import init_state_dicts
 from oracle import l3ac_oracle as O
 
 
-@pytest.mark.parametrize("name", ["0k75bps", "1k5bps", "3kbps"])
+@pytest.mark.parametrize("name", ["0k75bps", "1k5bps", "3kbps", "rotary"])
 def test_oracle_matches_reference_golden(name):
     mc, weights, audio, g = golden_case(name)
     orc = O.Oracle(mc.as_dict(), weights)
