@@ -12,6 +12,8 @@ e2e    : the same through the public API with pinned HOST buffers (H2D of the au
 --impl reference : the reference's CPU implementation of the path.  /root/reference is not pip-installable offline
          (hatchling absent) and its attention dependency is not vendored, so this arm times the oracle port
          (oracle/l3ac_oracle.py, bit-identical to the reference on the golden vectors) on all host cores.
+--impl reference-gpu : the same torch forward (the reference's own ATen / cuBLAS / cuDNN path) on the SAME B200, TF32 off,
+         micro-batched because it materialises the (B*6, windows, w, 2w) attention scores.
 """
 from __future__ import annotations
 
@@ -41,14 +43,17 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--config", default="1kbps")
     ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step (weak scaling)")
     ap.add_argument("--seconds", type=float, default=10.0)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "split"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="encdec", choices=["encdec", "decode"],
-                    help="encdec = BASELINE headline; decode = decode_audio(indices=) only (BASELINE config #5 sweep)")
+    ap.add_argument("--mode", default="encdec", choices=["encdec", "decode", "decode-sweep"],
+                    help="encdec = BASELINE headline; decode = decode_audio(indices=) only; decode-sweep = BASELINE config #5 "
+                         "(clip length x batch grid of decode_audio(indices=), whole-job batch sharded over the ranks)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch clips per GPU (the driver's contract); strong: --batch clips in total, sharded by utterance")
     return ap.parse_args()
 
 
@@ -151,10 +156,102 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_reference_gpu(args):
+    """BASELINE config #2's comparator: the reference forward as PyTorch runs it on this GPU (fp32, TF32 off)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from l3ac_b200.config import CONFIG_DIR, L3ACConfig
+    from l3ac_b200.spec import init_state_dicts
+    from oracle.l3ac_oracle import Oracle
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    mc = L3ACConfig(config_file=CONFIG_DIR / f"{args.config}.toml").network_config
+    orc = Oracle(mc.as_dict(), init_state_dicts(mc, seed=0), device=dev)
+    micro = max(1, int(40 // args.seconds))        # <= 40 s of audio per pass: the score tensor is 81 MB per clip, layer and copy
+    audio = synth_audio(args.batch, args.seconds, 1234).to(dev)
+
+    def step():
+        for lo in range(0, args.batch, micro):
+            _, idx = orc.encode_audio(audio[lo:lo + micro])
+            orc.decode_audio(indices=idx["indices"])
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    value = args.batch * args.seconds / (ms * 1e-3)
+    print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                      "data": "synthetic", "impl": "reference-gpu",
+                      "config": {"workload": f"{args.config}, batch {args.batch} x {args.seconds:g} s clips, encode_audio + decode_audio(indices=)",
+                                 "mode": "encdec", "bitrate": args.config, "batch_per_gpu": args.batch, "clip_seconds": args.seconds,
+                                 "note": f"torch {torch.__version__} eager fp32 on the same GPU, allow_tf32=False, micro-batches of {micro} clips, "
+                                         "oracle port of the reference forward (bit-identical to the reference on CPU)"}}))
+
+
+def run_decode_sweep(args, codec, dev, world, rank):
+    """BASELINE config #5: decode_audio(indices=) only, clip length 1-60 s x whole-job batch 1-1024, batch sharded by utterance
+    over the ranks (ranks without a clip idle, as SURVEY 8e expects for B < N).  One JSON object with the whole grid."""
+    import torch.distributed as dist
+    from l3ac_b200.dist import shard_bounds
+    mc = codec.config.network_config
+    n_codes = 1
+    for l in mc.levels:
+        n_codes *= l
+    grid = []
+    g = torch.Generator().manual_seed(99 + rank)
+    for secs in (1, 2, 5, 10, 30, 60):
+        t_tok = -(-secs * 16000 // mc.hop_length)
+        for batch in (1, 4, 16, 64, 256, 1024):
+            lo, hi = shard_bounds(batch, world, rank)
+            mine = hi - lo
+            idx = [torch.randint(0, n_codes, (mine, t_tok), generator=g, dtype=torch.int32).to(dev) for _ in range(2)] if mine else None
+            with torch.inference_mode():
+                for i in range(2):                                   # warm-up (also captures the CUDA graph of small shapes)
+                    if mine:
+                        codec.decode_audio(indices=idx[i % 2])
+                if world > 1:
+                    dist.barrier()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for i in range(args.steps):
+                    if mine:
+                        codec.decode_audio(indices=idx[i % 2])
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.steps
+            if world > 1:
+                t = torch.tensor([ms], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            grid.append({"clip_seconds": secs, "batch": batch, "ms_per_step": round(ms, 4),
+                         "audio_s_per_s": round(batch * secs / (ms * 1e-3), 1), "busy_ranks": min(world, batch)})
+            del idx
+            torch.cuda.empty_cache()
+    if rank == 0:
+        print(json.dumps({"metric": "decode_audio(indices=) audio-sec/sec", "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                          "config": {"workload": f"{args.config}, decode_audio(indices=) sweep, whole-job batch sharded by utterance",
+                                     "bitrate": args.config, "precision": args.precision}, "scaling": "strong", "grid": grid}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    if args.impl == "reference-gpu":
+        return run_reference_gpu(args)
 
     import torch.distributed as dist
     import l3ac_b200
@@ -170,13 +267,24 @@ def main():
 
     codec = l3ac_b200.get_model(args.config, pretrained=False, precision=args.precision)
     codec.network.to(dev).eval()
+    sharded = None
+    if world > 1:       # the product's multi-GPU API: utterance shards, asynchronous index gather over NCCL
+        from l3ac_b200.dist import ShardedCodec
+        sharded = ShardedCodec(codec)
     mc = codec.config.network_config
+    if args.mode == "decode-sweep":
+        return run_decode_sweep(args, codec, dev, world, rank)
     B, secs = args.batch, args.seconds
+    if args.scaling == "strong":            # fixed whole-job batch, contiguous utterance shards (l3ac_b200.dist.shard_bounds)
+        from l3ac_b200.dist import shard_bounds
+        lo, hi = shard_bounds(args.batch, world, rank)
+        B = hi - lo
+        if B == 0:
+            raise SystemExit("strong scaling needs at least one clip per rank")
     n_rot = 4       # rotate distinct input batches so that inputs exceed L2 (4 x 41 MB at B=64 x 10 s)
     dev_inputs = [synth_audio(B, secs, 1234 + 97 * rank + i).to(dev) for i in range(n_rot)]
     host_inputs = [synth_audio(B, secs, 4321 + 97 * rank + i).pin_memory() for i in range(n_rot)]
     T_tok = -(-dev_inputs[0].shape[1] // mc.hop_length)
-    gathered = torch.empty((world * B, T_tok), dtype=torch.int32, device=dev) if world > 1 else None
 
     dec_indices = None
     if args.mode == "decode":
@@ -186,10 +294,15 @@ def main():
     def step_resident(i):
         if dec_indices is not None:
             return codec.decode_audio(indices=dec_indices[i % n_rot])
-        q, idx = codec.encode_audio(dev_inputs[i % n_rot])
-        if world > 1:       # the only exchange step on the path: gather token indices (B*T_tok*4 bytes per rank)
-            dist.all_gather_into_tensor(gathered, idx["indices"])
-        return codec.decode_audio(indices=idx["indices"])
+        if sharded is None:
+            q, idx = codec.encode_audio(dev_inputs[i % n_rot])
+            return codec.decode_audio(indices=idx["indices"])
+        # the only exchange step on the path: all-gather of the token indices (B*T_tok*4 bytes per rank), issued asynchronously
+        # so that this rank's decode is queued behind its own encode, not behind the slowest rank's
+        q, idx, pending = sharded.encode_shard(dev_inputs[i % n_rot])
+        wav = sharded.decode_shard(indices=idx["indices"])
+        pending.wait()
+        return wav
 
     host_wav = torch.empty((B, T_tok * mc.hop_length), dtype=torch.float32).pin_memory()
     host_idx = torch.empty((B, T_tok), dtype=torch.int32).pin_memory()
@@ -200,31 +313,49 @@ def main():
         if host_dec_idx is not None:
             codec.decode_audio(indices=host_dec_idx[i % n_rot].to(dev, non_blocking=True), out=host_wav)
             return
-        q, idx = codec.encode_audio(host_inputs[i % n_rot])      # pinned host batch: uploaded inside the call, per micro-batch
+        if sharded is None:
+            q, idx = codec.encode_audio(host_inputs[i % n_rot])      # pinned host batch: uploaded inside the call, per micro-batch
+            host_idx.copy_(idx["indices"], non_blocking=True)
+            codec.decode_audio(indices=idx["indices"], out=host_wav)     # pinned host result: downloaded per micro-batch inside the call
+            return
+        q, idx, pending = sharded.encode_shard(host_inputs[i % n_rot])
         host_idx.copy_(idx["indices"], non_blocking=True)
-        codec.decode_audio(indices=idx["indices"], out=host_wav)     # pinned host result: downloaded per micro-batch inside the call
+        sharded.decode_shard(indices=idx["indices"], out=host_wav)
+        pending.wait()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    stats = {}
+
+    def timed(fn, steps, warmup, tag):
         with torch.inference_mode():
             for i in range(warmup):
                 fn(i)
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
             e0.record()
             for i in range(steps):
                 fn(warmup + i)
             e1.record()
+            issue_ms = (time.perf_counter() - t0) * 1e3 / steps      # host time to ISSUE a step (no device wait inside fn except e2e's final copy)
             barrier()
         ms = e0.elapsed_time(e1)
+        per_rank = [ms / steps]
+        issue = [issue_ms]
         if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            t = torch.tensor([ms / steps, issue_ms], device=dev)
+            allt = torch.empty((world, 2), device=dev)
+            dist.all_gather_into_tensor(allt, t)
+            per_rank = [float(v) for v in allt[:, 0].tolist()]
+            issue = [float(v) for v in allt[:, 1].tolist()]
+            ms = max(per_rank) * steps
+        srt = sorted(per_rank)
+        stats[tag] = {"per_rank_ms": {"min": srt[0], "median": srt[len(srt) // 2], "max": srt[-1]},
+                      "host_issue_ms_per_step": {"min": min(issue), "max": max(issue)}}
         return ms / steps
 
     if os.environ.get("L3AC_BENCH_NCU"):
@@ -247,10 +378,10 @@ def main():
             step_resident(i)
     launches_per_step = (ops.LAUNCHES - launches0) // max(1, args.warmup)
     sampler.start()
-    ms_step = timed(step_resident, args.steps, 0 if args.warmup else 0)
+    ms_step = timed(step_resident, args.steps, 0, "resident")
     clocks = sampler.stop()
-    ms_e2e = timed(step_e2e, args.steps, min(args.warmup, 2))
-    audio_s = world * B * secs
+    ms_e2e = timed(step_e2e, args.steps, min(args.warmup, 2), "e2e")
+    audio_s = (args.batch if args.scaling == "strong" else world * B) * secs
     value = audio_s / (ms_step * 1e-3)
     e2e_value = audio_s / (ms_e2e * 1e-3)
 
@@ -375,7 +506,7 @@ def main():
     }
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": f"{args.config}, batch {B} x {secs:g} s clips per GPU, " +
                                    ("encode_audio + decode_audio(indices=)" if args.mode == "encdec" else "decode_audio(indices=) only"),
@@ -389,7 +520,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(host_inputs[0].numel() * 4) if args.mode == "encdec" else int(host_idx.numel() * 4),
                     "d2h_bytes_per_step": int(host_wav.numel() * 4 + (host_idx.numel() * 4 if args.mode == "encdec" else 0))},
-            "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks, "roofline": roofline, **extras}
+            "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks, "roofline": roofline,
+            "per_rank": stats, **extras}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, t, cores = cpu_reference_run(args.config, secs, 1, 20, 2)

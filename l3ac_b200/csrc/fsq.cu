@@ -26,7 +26,27 @@ __device__ __forceinline__ void fsq_round(float z, int L, float& q_z, float& lev
     q_z = __fsub_rn(__fmul_rn(q_act, 2.0f), 1.0f);                   // fsq.py:21
 }
 
-// F == 128: lane owns features 4*lane .. 4*lane+3.
+// Lane group of dimension d: the four lanes whose bits (4, 3, 2) spell d.  The eight per-dimension partial sums of a token
+// are reduced reduce-scatter style (4 + 2 + 1 exchange shuffles leave every lane with ONE dimension summed over 8 lanes, two
+// butterfly steps finish it): 9 shuffles instead of 8 x 5, and tanh / rounding run once per dimension instead of 32 times.
+__device__ __forceinline__ int fsq_lane_dim(int lane) { return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1); }
+__device__ __forceinline__ int fsq_dim_lane(int d) { return ((d >> 2) & 1) * 16 + ((d >> 1) & 1) * 8 + (d & 1) * 4; }
+
+__device__ __forceinline__ float fsq_reduce8(const float (&p)[8], int lane) {
+    const unsigned full = 0xffffffffu;
+    const bool hA = lane & 16, hB = lane & 8, hC = lane & 4;
+    float a[4], b[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = (hA ? p[i + 4] : p[i]) + __shfl_xor_sync(full, hA ? p[i] : p[i + 4], 16);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) b[i] = (hB ? a[i + 2] : a[i]) + __shfl_xor_sync(full, hB ? a[i] : a[i + 2], 8);
+    float c = (hC ? b[1] : b[0]) + __shfl_xor_sync(full, hC ? b[0] : b[1], 4);
+    c += __shfl_xor_sync(full, c, 2);
+    c += __shfl_xor_sync(full, c, 1);
+    return c;
+}
+
+// F == 128: lane owns features 4*lane .. 4*lane+3.  One warp per token, two tokens in flight per warp.
 __global__ void __launch_bounds__(256) fsq_quantize_kernel(const float* __restrict__ x, long long M,
                                                            const float* __restrict__ w_in,
                                                            const float* __restrict__ b_in,
@@ -35,55 +55,75 @@ __global__ void __launch_bounds__(256) fsq_quantize_kernel(const float* __restri
                                                            float* __restrict__ q_feature, int32_t* __restrict__ indices,
                                                            float* __restrict__ level_indices, float* __restrict__ z_out) {
     constexpr int F = 128;
+    __shared__ __align__(16) float s_win[kFsqMaxD * F];
+    __shared__ float s_wout[F * kFsqMaxD];
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
-    // per-lane weight slices live in registers for the whole grid-stride loop
+    for (int i = threadIdx.x; i < lv.D * F; i += blockDim.x) {          // coalesced staging; lanes then take their slices
+        s_win[i] = __ldg(w_in + i);
+        s_wout[i] = __ldg(w_out + i);
+    }
+    __syncthreads();
     float4 win[kFsqMaxD];
     float wout[4][kFsqMaxD];
-    float bin[kFsqMaxD];
 #pragma unroll
     for (int d = 0; d < kFsqMaxD; ++d) {
+        win[d] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (d < lv.D) {
-            win[d] = __ldg(reinterpret_cast<const float4*>(w_in + d * F) + lane);
-            bin[d] = __ldg(b_in + d);
+            win[d] = reinterpret_cast<const float4*>(s_win + d * F)[lane];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) wout[i][d] = __ldg(w_out + (4 * lane + i) * lv.D + d);
+            for (int i = 0; i < 4; ++i) wout[i][d] = s_wout[(4 * lane + i) * lv.D + d];
         }
     }
     const float4 bo = __ldg(reinterpret_cast<const float4*>(b_out) + lane);
+    const int my_d = fsq_lane_dim(lane);
+    const bool has_dim = my_d < lv.D;
+    const float my_bin = has_dim ? __ldg(b_in + my_d) : 0.f;
+    const int my_L = has_dim ? lv.levels[my_d] : 2, my_basis = has_dim ? lv.basis[my_d] : 0;
+    const bool writer = has_dim && (lane & 3) == 0;
 
-    for (long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M;
-         row += (long long)gridDim.x * warps_per_block) {
-        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + row * F) + lane);
-        float qz[kFsqMaxD];
-        int index = 0;
+    const long long stride = (long long)gridDim.x * warps_per_block;
+    for (long long row0 = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row0 < M; row0 += 2 * stride) {
+        const long long rows[2] = {row0, row0 + stride};
+        float4 xv[2];
 #pragma unroll
-        for (int d = 0; d < kFsqMaxD; ++d) {
-            if (d < lv.D) {
-                float p = xv.x * win[d].x;
-                p = fmaf(xv.y, win[d].y, p);
-                p = fmaf(xv.z, win[d].z, p);
-                p = fmaf(xv.w, win[d].w, p);
-                const float z = warp_sum(p) + bin[d];
-                float level;
-                fsq_round(z, lv.levels[d], qz[d], level);
-                index += (int)level * lv.basis[d];
-                if (lane == 0) {
-                    if (z_out) z_out[row * lv.D + d] = z;
-                    if (level_indices) level_indices[row * lv.D + d] = level;
+        for (int u = 0; u < 2; ++u)
+            xv[u] = rows[u] < M ? __ldg(reinterpret_cast<const float4*>(x + rows[u] * F) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (rows[u] >= M) break;                           // warp-uniform
+            const long long row = rows[u];
+            float p[8];
+#pragma unroll
+            for (int d = 0; d < 8; ++d) {
+                p[d] = xv[u].x * win[d].x;
+                p[d] = fmaf(xv[u].y, win[d].y, p[d]);
+                p[d] = fmaf(xv[u].z, win[d].z, p[d]);
+                p[d] = fmaf(xv[u].w, win[d].w, p[d]);
+            }
+            const float z = fsq_reduce8(p, lane) + my_bin;
+            float my_qz, level;
+            fsq_round(z, my_L, my_qz, level);
+            int index = has_dim ? (int)level * my_basis : 0;
+            index += __shfl_xor_sync(0xffffffffu, index, 4);
+            index += __shfl_xor_sync(0xffffffffu, index, 8);
+            index += __shfl_xor_sync(0xffffffffu, index, 16);
+            if (writer) {
+                if (z_out) z_out[row * lv.D + my_d] = z;
+                if (level_indices) level_indices[row * lv.D + my_d] = level;
+            }
+            if (lane == 0) indices[row] = index;
+            float o[4] = {bo.x, bo.y, bo.z, bo.w};
+#pragma unroll
+            for (int d = 0; d < kFsqMaxD; ++d) {
+                if (d < lv.D) {
+                    const float qz = __shfl_sync(0xffffffffu, my_qz, fsq_dim_lane(d));
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) o[i] = fmaf(wout[i][d], qz, o[i]);
                 }
             }
+            reinterpret_cast<float4*>(q_feature + row * F)[lane] = make_float4(o[0], o[1], o[2], o[3]);   // read next by the decoder: keep in L2
         }
-        if (lane == 0) indices[row] = index;
-        float o[4] = {bo.x, bo.y, bo.z, bo.w};
-#pragma unroll
-        for (int d = 0; d < kFsqMaxD; ++d) {
-            if (d < lv.D) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) o[i] = fmaf(wout[i][d], qz[d], o[i]);
-            }
-        }
-        reinterpret_cast<float4*>(q_feature + row * F)[lane] = make_float4(o[0], o[1], o[2], o[3]);
     }
 }
 
@@ -110,32 +150,49 @@ __global__ void __launch_bounds__(256) fsq_dequantize_kernel(const IdxT* __restr
                                                              const float* __restrict__ b_out, FsqLevels lv,
                                                              float* __restrict__ q_feature) {
     constexpr int F = 128;
+    __shared__ float s_wout[F * kFsqMaxD];
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < lv.D * F; i += blockDim.x) s_wout[i] = __ldg(w_out + i);
+    __syncthreads();
     float wout[4][kFsqMaxD];
 #pragma unroll
     for (int d = 0; d < kFsqMaxD; ++d)
         if (d < lv.D) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) wout[i][d] = __ldg(w_out + (4 * lane + i) * lv.D + d);
+            for (int i = 0; i < 4; ++i) wout[i][d] = s_wout[(4 * lane + i) * lv.D + d];
         }
     const float4 bo = __ldg(reinterpret_cast<const float4*>(b_out) + lane);
-    for (long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M;
-         row += (long long)gridDim.x * warps_per_block) {
-        const long long idx = (long long)__ldg(indices + row);
-        float o[4] = {bo.x, bo.y, bo.z, bo.w};
+    // lane d (< D) decodes digit d of the token's index; the D codes are then broadcast.  The divisions are by per-lane
+    // constants hoisted out of the loop.
+    const bool has_dim = lane < lv.D;
+    const long long my_basis = has_dim ? lv.basis[lane] : 1;
+    const int my_L = has_dim ? lv.levels[lane] : 2;
+    const float my_lm1 = (float)(my_L - 1);
+    const long long stride = (long long)gridDim.x * warps_per_block;
+    for (long long row0 = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row0 < M; row0 += 4 * stride) {
+        long long idx[4];
 #pragma unroll
-        for (int d = 0; d < kFsqMaxD; ++d) {
-            if (d < lv.D) {
-                // (idx // basis) % L with floor semantics (l3ac/vq/fsq.py:70-71); indices are non-negative
-                const int level = (int)((idx / lv.basis[d]) % lv.levels[d]);
-                const float q_act = __fdiv_rn((float)level, (float)(lv.levels[d] - 1));
-                const float qz = __fsub_rn(__fmul_rn(q_act, 2.0f), 1.0f);
+        for (int u = 0; u < 4; ++u) idx[u] = row0 + u * stride < M ? (long long)__ldg(indices + row0 + u * stride) : 0;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) o[i] = fmaf(wout[i][d], qz, o[i]);
+        for (int u = 0; u < 4; ++u) {
+            const long long row = row0 + u * stride;
+            if (row >= M) break;                               // warp-uniform
+            // (idx // basis) % L with floor semantics (l3ac/vq/fsq.py:70-71); indices are non-negative
+            const int level = sizeof(IdxT) == 4 ? (int)(((unsigned)idx[u] / (unsigned)my_basis) % (unsigned)my_L)
+                                                : (int)((idx[u] / my_basis) % my_L);
+            const float my_qz = __fsub_rn(__fmul_rn(__fdiv_rn((float)level, my_lm1), 2.0f), 1.0f);
+            float o[4] = {bo.x, bo.y, bo.z, bo.w};
+#pragma unroll
+            for (int d = 0; d < kFsqMaxD; ++d) {
+                if (d < lv.D) {
+                    const float qz = __shfl_sync(0xffffffffu, my_qz, d);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) o[i] = fmaf(wout[i][d], qz, o[i]);
+                }
             }
+            reinterpret_cast<float4*>(q_feature + row * F)[lane] = make_float4(o[0], o[1], o[2], o[3]);   // read next by the decoder: keep in L2
         }
-        reinterpret_cast<float4*>(q_feature + row * F)[lane] = make_float4(o[0], o[1], o[2], o[3]);
     }
 }
 
@@ -157,7 +214,8 @@ static int make_levels(const int* levels, int D, FsqLevels* out) {
 
 static int fsq_grid(long long M, int rows_per_block) {
     long long g = (M + rows_per_block - 1) / rows_per_block;
-    if (g > 148LL * 16) g = 148LL * 16;
+    const long long cap = (long long)l3ac_sm_count() * 8;           // 8 resident 256-thread blocks per SM, each looping
+    if (g > cap) g = cap;
     return (int)(g < 1 ? 1 : g);
 }
 

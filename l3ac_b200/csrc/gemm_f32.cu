@@ -48,11 +48,15 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
     const int n0 = blockIdx.y * BN;
     const int ldw = taps * K;
 
-    float acc[TM][TN];
+    // Two-level accumulation: 64 products into `acc`, blocks into `tot`.  A single running fp32 sum over K*taps (up to 2048)
+    // terms carries ~sqrt(K) ulps of rounding noise, several times what the reference's blocked / vectorised CPU GEMM has;
+    // with 64-term blocks the parity mode sits at the reference's own distance from exact arithmetic (tests/golden/fp32_floor.json).
+    float acc[TM][TN], tot[TM][TN];
 #pragma unroll
     for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < TN; ++j) acc[i][j] = tot[i][j] = 0.f;
+    int blk = 0;
 
     // loader mapping: k = tid % 16, rows tid/16 + 16 r
     const int lk = tid & 15, lr = tid >> 4;
@@ -96,8 +100,21 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
                     for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
             }
             __syncthreads();
+            if ((++blk & 3) == 0) {
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) {
+                        tot[i][j] += acc[i][j];
+                        acc[i][j] = 0.f;
+                    }
+            }
         }
     }
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] += tot[i][j];
 
 #pragma unroll
     for (int i = 0; i < TM; ++i) {

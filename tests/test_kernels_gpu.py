@@ -148,7 +148,12 @@ def test_fsq_bit_exact_from_reference_latents(cuda_lib, levels):
     # exempt values within 1e-5 level units of a rounding tie (tanhf may differ by an ulp between libm and CUDA)
     a = (torch.tanh(z.double()) + 1) / 2 * (torch.tensor(levels) - 1)
     safe = ((a - a.floor() - 0.5).abs() > 1e-5).all(dim=-1)
-    assert safe.float().mean() > 0.999
+    n_exempt = int((~safe).sum())
+    n_differ_all = int((gidx.cpu() != idx).sum())            # over ALL tokens, exempt ones included
+    print(f"fsq levels {levels}: {n_exempt} of {len(z)} tokens within 1e-5 level units of a rounding tie (exempt); "
+          f"{n_differ_all} tokens differ from the reference over all {len(z)} tokens")
+    assert n_exempt <= 5                                      # measured: 0-2 of 20 000
+    assert n_differ_all <= n_exempt
     assert torch.equal(gidx.cpu()[safe], idx[safe])
     assert torch.equal(glvl.cpu()[safe], lvl[safe]) and torch.equal(gq.cpu()[safe], q_z[safe])
     # whole codebook: dequantise every index and re-quantise its latents
