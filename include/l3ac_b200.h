@@ -254,6 +254,24 @@ int l3ac_decoder_tail(const float* x, int B, int T, int C, const void* conv_frag
                       const int* dilations, const float* alpha_f, const float* w_f, float bias_f, float* out,
                       l3ac_stream_t stream);
 
+/* The same fused decoder tail on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM; the bf16 snake
+ * outputs are written to shared memory by their row-owner threads and the conv taps are row-shifted operand
+ * descriptors of that one tile).  The immutable packed weights live in a plan (handle):
+ *   l3ac_tail_plan_create  takes HOST arrays in the reference's layout, folded fp32:
+ *       conv_w [3][24 out][24 in][7 taps]  (LegacyUnit.block.1, l3ac/modules.py:54), conv_b [3][24],
+ *       pw_w [3][24 out][24 in] (block.3), pw_b [3][24], alpha0 / alpha1 [3][24] (block.0 / block.2 Snake),
+ *       dilations [3], alpha_f [24], w_f [7 taps][24], bias_f (Decoder tail, l3ac/modules.py:192-194);
+ *     converts them to bf16 operand order and uploads them to the CURRENT device (one cudaMalloc + cudaMemcpy).
+ *   l3ac_decoder_tail_tc   x (B,T,24) fp32 -> out (B,T) fp32 on `stream`; allocates nothing; graph-capturable.
+ *   l3ac_tail_plan_destroy frees the device blob.
+ * Same constraints on the dilations as l3ac_decoder_tail. */
+typedef struct l3ac_tail_plan l3ac_tail_plan;
+int l3ac_tail_plan_create(const float* conv_w, const float* conv_b, const float* pw_w, const float* pw_b,
+                          const float* alpha0, const float* alpha1, const int* dilations, const float* alpha_f,
+                          const float* w_f, float bias_f, int C, l3ac_tail_plan** plan_out);
+int l3ac_tail_plan_destroy(l3ac_tail_plan* plan);
+int l3ac_decoder_tail_tc(const l3ac_tail_plan* plan, const float* x, int B, int T, float* out, l3ac_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,592 @@
+// Fused full-rate decoder tail on tcgen05 / TMEM (l3ac/modules.py:47-64,174-179,192-194): three Residual(LegacyUnit)
+// blocks (dilations d0,d1,d2)
+//   x += Conv1x1( snake( Conv_k7,dil d( snake(x, a0) ) + b, a1 ) ) + b'
+// then Snake -> Conv1d(24 -> 1, k7, pad 3) -> tanh, in ONE persistent kernel: (B, T, 24) fp32 is read once from HBM and
+// only the (B, T) waveform is written.
+//
+// The contractions run on the 5th-generation tensor cores with the A operand written by threads (umma.cuh):
+//   * one CTA owns 1024 consecutive samples of one clip (940 outputs + a 42-sample halo per side = the receptive field
+//     3*(1+3+9)+3) as eight 128-row blocks; one THREAD owns one row of two blocks, i.e. exactly the TMEM lane its
+//     tcgen05.ld reads, and keeps the fp32 residual stream of its rows in registers;
+//   * bf16(snake(x)) is stored as 8-channel planes [3 (+1 zero)][27 guard + 1024 + 27][8]; the k7 conv of a block is 11
+//     tcgen05.mma (M=128, N=32, K=16) whose A descriptors are the SAME tile shifted by (tap-3)*dilation rows -- nine of
+//     them pair the taps (2p, 2p+1) of one 8-channel plane through LBO = dilation * 16 B, two cover tap 6 -- so the
+//     conv's 168-long K axis costs 11 K-steps instead of 7 x 2 channel-padded ones and no im2col is ever materialised;
+//   * the accumulator row comes back with tcgen05.ld, bias + snake run on registers, bf16(h) goes to the second plane
+//     buffer and two more MMAs (K = 24 -> 32) do the 1x1 conv; its result is added to the register residual;
+//   * the final Conv1d(24 -> 1, k7) has its 7 taps in the N dimension (P[t'][j] = s[t'] . w[j], A = snake(x) as a
+//     split-bf16 pair, 3 terms hi*Whi + lo*Whi + hi*Wlo: fp32-class) + a diagonal sum y[t] = sum_j P[t+j-3][j] through
+//     shared memory.
+// Warps 0-15: row owners (warp & 3 = TMEM lane quadrant, warp >> 2 = which pair of blocks).  Warps 16-18 issue the MMAs
+// through one elected lane each (16 / 17: the k7 convs and the final conv of the even / odd blocks, 18: the 1x1 convs,
+// so that a block's 1x1 conv never queues behind the other blocks' k7 convs and one issuer's barrier polls overlap the
+// other's MMAs); all hand-overs are mbarriers per 128-row block, so the tensor pipe, the SFU (168 sines per sample: the bound of this kernel) and the FMA pipe overlap
+// across blocks without any CTA-wide barrier in the steady state.  Per-channel parameters live in the kernel-parameter
+// constant bank: with one row per thread they are warp-uniform immediates of the FMUL / FFMA instructions.
+#include "common.cuh"
+#include "umma.cuh"
+
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace l3ac {
+namespace tailtc {
+
+using namespace l3ac::umma;
+
+constexpr int kC = 24;
+constexpr int kHalo = 42;
+constexpr int kGuard = 27;                       // largest conv reach (3 taps x dilation 9)
+constexpr int kBlocks = 8;
+constexpr int kRows = kBlocks * 128;             // 1024
+constexpr int kOut = kRows - 2 * kHalo;          // 940
+constexpr int kRowsTot = kRows + 2 * kGuard;     // 1078
+constexpr int kPlaneBytes = kRowsTot * 16;       // one 8-channel plane
+constexpr int kBufBytes = 4 * kPlaneBytes;       // 3 channel planes + 1 zero plane (K padding)
+constexpr int kConvMmas = 11;
+constexpr int kWConvBytes = kConvMmas * 1024;    // per unit: 11 x [2 halves][32 n][8 k] bf16
+constexpr int kWPwBytes = 2 * 1024;              // per unit: 2 x [2][32][8]
+constexpr int kWFinBytes = 2 * 2 * 512;          // {hi, lo} x 2 x [2][16][8]
+constexpr int kWBytes = 3 * kWConvBytes + 3 * kWPwBytes + kWFinBytes;
+constexpr int kPtStride = kRows + 8;             // P^T[tap][row + 4]
+constexpr int kPtBytes = 7 * kPtStride * 4;
+constexpr int kNumBars = 5 * kBlocks;
+constexpr int kWorkerWarps = 16;
+constexpr int kConvWarp = kWorkerWarps, kPwWarp = kWorkerWarps + 2;     // MMA issuers: two for the k7 convs (even / odd blocks), one for the 1x1 convs
+constexpr int kThreads = 32 * (kWorkerWarps + 3);       // 19 warps at 96 registers (the register file is granted in 32-register steps)
+constexpr int kSmemBytes = 2 * kBufBytes + kWBytes + kPtBytes + 8 * kNumBars + 16;
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+static_assert(kBufBytes % 16 == 0 && kWBytes % 16 == 0 && kPtBytes % 16 == 0, "16-byte carve-up");
+
+struct Params {
+    const float* x;
+    float* out;
+    const uint8_t* wblob;      // device: conv[3] | pw[3] | fin, already in operand order
+    int B, T;
+    int dil[3];
+    float bias_f;
+    float conv_b[3][kC], pw_b[3][kC], a0[3][kC], ia0[3][kC], a1[3][kC], ia1[3][kC], af[kC], iaf[kC];
+};
+
+#ifdef L3AC_TAIL_TRACE
+// Debug build only (tools/tail_trace.py): CTA 0 stamps clock64() at the hand-overs of its second tile.
+__device__ unsigned long long g_tail_trace[6 * 256];
+#define TAIL_TRACE(role, ev, unit, blk)                                                                              \
+    do {                                                                                                             \
+        if (blockIdx.x == 0 && it == 1 && trace_n < 255) {                                                           \
+            g_tail_trace[(role) * 256 + 1 + trace_n++] = ((unsigned long long)clock64() << 16) | ((ev) << 8) | ((unit) << 4) | (blk); \
+            g_tail_trace[(role) * 256] = trace_n;                                                                    \
+        }                                                                                                            \
+    } while (0)
+#define TAIL_TRACE_DECL unsigned int trace_n = 0;
+#else
+#define TAIL_TRACE(role, ev, unit, blk) do {} while (0)
+#define TAIL_TRACE_DECL
+#endif
+
+__device__ __forceinline__ float snake1(float v, float a, float ia) {
+    const float s = __sinf(a * v);
+    return fmaf(ia, s * s, v);
+}
+
+// this thread's row of the fp32 stream (zero outside the clip: every conv on the path zero-pads its input)
+__device__ __forceinline__ bool load_row(float (&xr)[kC], const float* __restrict__ xb, int t, int T) {
+    const bool ok = t >= 0 && t < T;
+    const float4* src = reinterpret_cast<const float4*>(xb + (long long)(ok ? t : 0) * kC);
+#pragma unroll
+    for (int i = 0; i < kC / 4; ++i) {
+        const float4 v = ok ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xr[4 * i] = v.x; xr[4 * i + 1] = v.y; xr[4 * i + 2] = v.z; xr[4 * i + 3] = v.w;
+    }
+    return ok;
+}
+
+// 24 accumulator columns of this thread's row
+__device__ __forceinline__ void ld_row24(uint32_t taddr, float (&v)[kC]) {
+    uint32_t lo[16], hi[8];
+    tmem_ld16(taddr, lo);
+    tmem_ld8(taddr + 16, hi);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(lo[i]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[16 + i] = __uint_as_float(hi[i]);
+}
+
+template <int U>
+struct UnitPhase {
+    // a = bf16(snake(x, alpha0)) -> plane buffer A
+    static __device__ __forceinline__ void snake_in(const Params& p, const float (&xr)[kC], uint32_t dst) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int e = 8 * c + 2 * i;
+                pk[i] = pack_bf16x2(snake1(xr[e], p.a0[U][e], p.ia0[U][e]), snake1(xr[e + 1], p.a0[U][e + 1], p.ia0[U][e + 1]));
+            }
+            st_shared_v4(dst + c * kPlaneBytes, pk[0], pk[1], pk[2], pk[3]);
+        }
+    }
+    // h = bf16(snake(conv + bias, alpha1)) -> plane buffer H   (8 accumulator columns at a time: 8 live registers, not 24)
+    static __device__ __forceinline__ void snake_mid(const Params& p, uint32_t taddr, uint32_t dst) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            uint32_t v[8];
+            tmem_ld8(taddr + 8 * c, v);
+            tmem_ld_wait();
+            uint32_t pk[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int e = 8 * c + 2 * i;
+                pk[i] = pack_bf16x2(snake1(__uint_as_float(v[2 * i]) + p.conv_b[U][e], p.a1[U][e], p.ia1[U][e]),
+                                    snake1(__uint_as_float(v[2 * i + 1]) + p.conv_b[U][e + 1], p.a1[U][e + 1], p.ia1[U][e + 1]));
+            }
+            st_shared_v4(dst + c * kPlaneBytes, pk[0], pk[1], pk[2], pk[3]);
+        }
+    }
+    // x += conv1x1(h) + bias  (rows outside the clip stay zero)
+    static __device__ __forceinline__ void residual(const Params& p, uint32_t taddr, float (&xr)[kC], bool valid) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            uint32_t v[8];
+            tmem_ld8(taddr + 8 * c, v);
+            tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) xr[8 * c + i] += __uint_as_float(v[i]) + p.pw_b[U][8 * c + i];
+            }
+        }
+    }
+};
+
+__global__ void __launch_bounds__(kThreads, 1) decoder_tail_tc_kernel(const __grid_constant__ Params p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t buf_a = sbase, buf_h = buf_a + kBufBytes;
+    const uint32_t w_conv = buf_h + kBufBytes, w_pw = w_conv + 3 * kWConvBytes, w_fin = w_pw + 3 * kWPwBytes;
+    const uint32_t pt_addr = w_fin + kWFinBytes;
+    float* pt = reinterpret_cast<float*>(smem + (pt_addr - sbase));
+    const uint32_t bars = pt_addr + kPtBytes;
+    const uint32_t a_ready = bars, d_ready = a_ready + 8 * kBlocks, h_ready = d_ready + 8 * kBlocks,
+                   o_ready = h_ready + 8 * kBlocks, pt_ready = o_ready + 8 * kBlocks;
+    const uint32_t tmem_slot = pt_ready + 8 * kBlocks;
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - sbase));
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+
+    // ---- once per CTA: zero both plane buffers (guard rows and the K-padding plane stay zero for good), stage the
+    // weights, barriers, TMEM
+    {
+        uint4* z = reinterpret_cast<uint4*>(smem);
+        for (int i = tid; i < 2 * kBufBytes / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+        const uint4* src = reinterpret_cast<const uint4*>(p.wblob);
+        uint4* dst = reinterpret_cast<uint4*>(smem + 2 * kBufBytes);
+        for (int i = tid; i < kWBytes / 16; i += kThreads) dst[i] = __ldg(src + i);
+        for (int i = tid; i < kPtBytes / 4; i += kThreads) pt[i] = 0.f;
+    }
+    if (tid == 0) {
+        for (int b = 0; b < kBlocks; ++b) {
+            mbar_init(a_ready + 8 * b, 4);       // the four warps that own the block's rows
+            mbar_init(d_ready + 8 * b, 1);       // tcgen05.commit
+            mbar_init(h_ready + 8 * b, 4);
+            mbar_init(o_ready + 8 * b, 1);
+            mbar_init(pt_ready + 8 * b, 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == kConvWarp) tmem_alloc(tmem_slot, 512);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    const int tiles_per_clip = (p.T + kOut - 1) / kOut;
+    const int n_tiles = tiles_per_clip * p.B;
+
+    if (warp == kConvWarp || warp == kConvWarp + 1) {
+        // =============================================================== MMA issuers 1a / 1b: the k7 convs and the final conv of the
+        // even / odd blocks.  One issuer needs ~770 cycles per block (barrier polls ~250, eleven MMAs through the uniform
+        // datapath ~300, commit) for 440 cycles of tensor-pipe work (tools/tail_trace.py); two of them keep the pipe fed.
+        const int b_first = warp - kConvWarp;
+        // Everything this warp computes runs on the uniform datapath, whose dependent-instruction latency is long: the low
+        // descriptor words (address and LBO fields) of a unit's eleven conv MMAs are computed once per unit and a block
+        // only adds its row offset -- with the descriptors rebuilt per MMA the issue loop cost ~85 cycles per MMA
+        // against the 40 the tensor core needs (tools/tail_trace.py, tools/umma_rate.cu).
+        const bool leader = elect_one();
+        const uint32_t idesc32 = make_idesc_bf16(32), idesc16 = make_idesc_bf16(16);
+        constexpr uint64_t kDescHi = (uint64_t)(((128u >> 4) & 0x3FFF) | (1u << 14)) << 32;     // SBO = 128 B, sm_100 descriptor version
+        constexpr uint32_t kBlockStep = (128 * 16) >> 4;                                        // 128 rows further down the planes
+        const uint32_t lbo_plane = (uint32_t)(kPlaneBytes >> 4) << 16, lbo_w32 = (512u >> 4) << 16, lbo_w16 = (256u >> 4) << 16;
+        const uint32_t rows_a = (buf_a + kGuard * 16) >> 4, rows_h = (buf_h + kGuard * 16) >> 4;
+        TAIL_TRACE_DECL
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+#pragma unroll 1
+            for (int u = 0; u < 3; ++u) {
+                const int d = u == 0 ? p.dil[0] : (u == 1 ? p.dil[1] : p.dil[2]);
+                uint32_t a_lo[kConvMmas];
+#pragma unroll
+                for (int j = 0; j < kConvMmas; ++j) {
+                    // j < 9: taps (2 (j / 3), + 1) of plane j % 3; j = 9: tap 6 of planes 0, 1; j = 10: tap 6 of plane 2 + the zero plane
+                    const int plane = j < 9 ? j % 3 : (j == 9 ? 0 : 2);
+                    const int tap = j < 9 ? 2 * (j / 3) : 6;
+                    a_lo[j] = (rows_a + (uint32_t)(plane * (kPlaneBytes >> 4)) + (uint32_t)((tap - 3) * d)) | (j < 9 ? (uint32_t)d << 16 : lbo_plane);
+                }
+                const uint32_t wc_lo = ((w_conv + u * kWConvBytes) >> 4) | lbo_w32;
+#pragma unroll 1
+                for (int b = b_first; b < kBlocks; b += 2) {
+                    if (b > 0) mbar_wait(a_ready + 8 * (b - 1), u & 1);          // the taps reach into both neighbour blocks
+                    mbar_wait(a_ready + 8 * b, u & 1);
+                    if (b + 1 < kBlocks) mbar_wait(a_ready + 8 * (b + 1), u & 1);
+                    tc_fence_after();
+                    if (leader && b_first == 0) TAIL_TRACE(4, 10, u, b);
+                    if (leader) {
+                        const uint32_t dcol = tmem_base + 64 * b, boff = kBlockStep * b;
+#pragma unroll
+                        for (int j = 0; j < kConvMmas; ++j)
+                            tc_mma_bf16(dcol, kDescHi | (a_lo[j] + boff), kDescHi | (wc_lo + j * (1024 >> 4)), idesc32, j > 0 ? 1u : 0u);
+                        TAIL_TRACE(4, 11, u, b);
+                        tc_commit(d_ready + 8 * b);
+                        TAIL_TRACE(4, 13, u, b);
+                    }
+                    __syncwarp();
+                }
+            }
+            // final conv: P = s . Wf^T with s = hi (buffer A) + lo (buffer H), Wf = hi + lo
+            const uint32_t wf_lo = (w_fin >> 4) | lbo_w16;
+#pragma unroll 1
+            for (int b = b_first; b < kBlocks; b += 2) {
+                // (only block b's rows are read, but waiting for the neighbours as well keeps every d_ready(b) phase behind the
+                // a_ready phases of blocks b-1 .. b+1: the row owners' parity waits on a neighbour's d_ready rely on that)
+                if (b > 0) mbar_wait(a_ready + 8 * (b - 1), 1);
+                mbar_wait(a_ready + 8 * b, 1);
+                if (b + 1 < kBlocks) mbar_wait(a_ready + 8 * (b + 1), 1);
+                tc_fence_after();
+                if (leader && b_first == 0) TAIL_TRACE(4, 10, 3, b);
+                if (leader) {
+                    const uint32_t ra = (rows_a + kBlockStep * b) | lbo_plane, rh = (rows_h + kBlockStep * b) | lbo_plane;
+                    const uint32_t dcol = tmem_base + 64 * b;
+#pragma unroll
+                    for (int term = 0; term < 3; ++term) {
+                        const uint32_t arow = term == 1 ? rh : ra;
+                        const uint32_t wsel = wf_lo + (term == 2 ? (1024 >> 4) : 0);
+#pragma unroll
+                        for (int m = 0; m < 2; ++m)
+                            tc_mma_bf16(dcol, kDescHi | (arow + m * (2 * kPlaneBytes >> 4)), kDescHi | (wsel + m * (512 >> 4)), idesc16,
+                                        (term | m) ? 1u : 0u);
+                    }
+                    tc_commit(d_ready + 8 * b);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == kPwWarp) {
+        // =============================================================== MMA issuer 2: the 1x1 convs, as soon as a block's h is written
+        // (its own warp: behind the conv issuer's program order the 1x1 convs of a unit would wait for all eight k7 convs)
+        const bool leader = elect_one();
+        const uint32_t idesc32 = make_idesc_bf16(32);
+        constexpr uint64_t kDescHi = (uint64_t)(((128u >> 4) & 0x3FFF) | (1u << 14)) << 32;
+        constexpr uint32_t kBlockStep = (128 * 16) >> 4;
+        const uint32_t lbo_plane = (uint32_t)(kPlaneBytes >> 4) << 16, lbo_w32 = (512u >> 4) << 16;
+        const uint32_t rows_h = (buf_h + kGuard * 16) >> 4;
+        TAIL_TRACE_DECL
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+#pragma unroll 1
+            for (int u = 0; u < 3; ++u) {
+                const uint32_t wp_lo = ((w_pw + u * kWPwBytes) >> 4) | lbo_w32;
+#pragma unroll 1
+                for (int b = 0; b < kBlocks; ++b) {
+                    mbar_wait(h_ready + 8 * b, (it + u) & 1);
+                    tc_fence_after();
+                    if (leader) TAIL_TRACE(5, 12, u, b);
+                    if (leader) {
+                        const uint32_t a0 = (rows_h + kBlockStep * b) | lbo_plane;
+#pragma unroll
+                        for (int m = 0; m < 2; ++m)
+                            tc_mma_bf16(tmem_base + 64 * b + 32, kDescHi | (a0 + m * (2 * kPlaneBytes >> 4)), kDescHi | (wp_lo + m * (1024 >> 4)),
+                                        idesc32, m > 0 ? 1u : 0u);
+                        tc_commit(o_ready + 8 * b);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp < kWorkerWarps) {
+        // =============================================================== row owners
+        const int wg = warp >> 2, quad = warp & 3;
+        const int r0 = 128 * wg + 32 * quad + lane;              // rows r0 (block wg) and r0 + 512 (block wg + 4)
+        const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
+        float xr[2][kC];
+        bool valid[2];
+        TAIL_TRACE_DECL
+        const bool tracer = quad == 0 && lane == 0;
+        int tile = blockIdx.x;
+        int clip = 0, t_first = 0;
+        if (tile < n_tiles) {
+            clip = tile / tiles_per_clip;
+            t_first = (tile - clip * tiles_per_clip) * kOut - kHalo;
+            const float* xb = p.x + (long long)clip * p.T * kC;
+#pragma unroll
+            for (int s = 0; s < 2; ++s) valid[s] = load_row(xr[s], xb, t_first + r0 + 512 * s, p.T);
+        }
+        int it = 0;
+        for (; tile < n_tiles; ++it) {
+            const int cur_clip = clip, cur_t_first = t_first;
+            // Stage order per thread: the chain of one block runs ahead as far as its data allows -- S2 (snake of the conv
+            // result), S3 (residual) and the NEXT unit's operand S1 of block wg, then the same for block wg + 4 -- so the
+            // k7 convs of unit u+1 start on the first blocks while those of unit u are still running on the last ones.
+            {
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const int b = wg + 4 * s;
+                    if (tracer) TAIL_TRACE(wg, 1, 0, b);
+                    UnitPhase<0>::snake_in(p, xr[s], buf_a + (kGuard + r0 + 512 * s) * 16);
+                    fence_async_smem();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(a_ready + 8 * b);
+                    if (tracer) TAIL_TRACE(wg, 2, 0, b);
+                }
+            }
+#define L3AC_TAIL_UNIT(U)                                                                                     \
+            _Pragma("unroll") for (int s = 0; s < 2; ++s) {                                                   \
+                const int b = wg + 4 * s;                                                                     \
+                const uint32_t row_off = (kGuard + r0 + 512 * s) * 16;                                        \
+                mbar_wait_tag(d_ready + 8 * b, U & 1, 10 + 4 * s);                                            \
+                tc_fence_after();                                                                             \
+                if (tracer) TAIL_TRACE(wg, 3, U, b);                                                          \
+                UnitPhase<U>::snake_mid(p, tlane + 64 * b, buf_h + row_off);                                  \
+                fence_async_smem();                                                                           \
+                tc_fence_before();                                                                            \
+                __syncwarp();                                                                                 \
+                if (lane == 0) mbar_arrive(h_ready + 8 * b);                                                  \
+                if (tracer) TAIL_TRACE(wg, 4, U, b);                                                          \
+                mbar_wait_tag(o_ready + 8 * b, (it + U) & 1, 11 + 4 * s);                                     \
+                /* This block's rows of buffer A are also read by the k7 convs of both neighbour blocks (other issuers than   */ \
+                /* the one whose commit was seen above): they must be through before the rows are overwritten.  Neither      */ \
+                /* barrier can be a phase ahead: every conv of a neighbour block waits for THIS block's next a_ready first.  */ \
+                /* (Polled before the residual update so that the compiler cannot hoist the next snake above the spin loops  */ \
+                /* and spill its results.)                                                                                   */ \
+                if (b + 1 < kBlocks) mbar_wait_tag(d_ready + 8 * (b + 1), U & 1, 12 + 4 * s);                 \
+                if (b > 0) mbar_wait_tag(d_ready + 8 * (b - 1), U & 1, 13 + 4 * s);                           \
+                tc_fence_after();                                                                             \
+                if (tracer) TAIL_TRACE(wg, 5, U, b);                                                          \
+                UnitPhase<U>::residual(p, tlane + 64 * b + 32, xr[s], valid[s]);                              \
+                if (tracer) TAIL_TRACE(wg, 6, U, b);                                                          \
+                if (tracer) TAIL_TRACE(wg, 1, U + 1, b);                                                      \
+                if (U < 2) {                                                                                  \
+                    UnitPhase<(U < 2 ? U + 1 : 0)>::snake_in(p, xr[s], buf_a + row_off);                      \
+                } else {    /* final conv operand: s = snake(x, alpha_f) as a split pair, hi -> buffer A, lo -> buffer H */ \
+                    _Pragma("unroll") for (int c = 0; c < 3; ++c) {                                           \
+                        uint32_t ph[4], pl[4];                                                                \
+                        _Pragma("unroll") for (int i = 0; i < 4; ++i) {                                       \
+                            const int e = 8 * c + 2 * i;                                                      \
+                            const float s0 = snake1(xr[s][e], p.af[e], p.iaf[e]), s1 = snake1(xr[s][e + 1], p.af[e + 1], p.iaf[e + 1]); \
+                            ph[i] = pack_bf16x2(s0, s1);                                                      \
+                            pl[i] = pack_bf16x2(s0 - __uint_as_float(ph[i] << 16), s1 - __uint_as_float(ph[i] & 0xffff0000u)); \
+                        }                                                                                     \
+                        st_shared_v4(buf_a + row_off + c * kPlaneBytes, ph[0], ph[1], ph[2], ph[3]);          \
+                        st_shared_v4(buf_h + row_off + c * kPlaneBytes, pl[0], pl[1], pl[2], pl[3]);          \
+                    }                                                                                         \
+                }                                                                                             \
+                fence_async_smem();                                                                           \
+                tc_fence_before();                                                                            \
+                __syncwarp();                                                                                 \
+                if (lane == 0) mbar_arrive(a_ready + 8 * b);                                                  \
+                if (tracer) TAIL_TRACE(wg, 2, U + 1, b);                                                      \
+            }
+            L3AC_TAIL_UNIT(0)
+            L3AC_TAIL_UNIT(1)
+            L3AC_TAIL_UNIT(2)
+#undef L3AC_TAIL_UNIT
+            // the residual registers are dead: fetch the next tile's rows while the final conv runs
+            tile += gridDim.x;
+            if (tile < n_tiles) {
+                clip = tile / tiles_per_clip;
+                t_first = (tile - clip * tiles_per_clip) * kOut - kHalo;
+                const float* xb = p.x + (long long)clip * p.T * kC;
+#pragma unroll
+                for (int s = 0; s < 2; ++s) valid[s] = load_row(xr[s], xb, t_first + r0 + 512 * s, p.T);
+            }
+            // P rows -> P^T in shared memory
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int b = wg + 4 * s;
+                mbar_wait(d_ready + 8 * b, 1);
+                tc_fence_after();
+                if (tracer) TAIL_TRACE(wg, 7, 3, b);
+                uint32_t v[8];
+                tmem_ld8(tlane + 64 * b, v);
+                tmem_ld_wait();
+                float* dst = pt + 4 + r0 + 512 * s;
+#pragma unroll
+                for (int j = 0; j < 7; ++j) dst[j * kPtStride] = __uint_as_float(v[j]);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(pt_ready + 8 * b);
+            }
+            // y[t] = tanh(bias + sum_j P[t + j - 3][j])
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int b = wg + 4 * s;
+                const int r = r0 + 512 * s;
+                if (b > 0) mbar_wait(pt_ready + 8 * (b - 1), it & 1);
+                mbar_wait(pt_ready + 8 * b, it & 1);
+                if (b + 1 < kBlocks) mbar_wait(pt_ready + 8 * (b + 1), it & 1);
+                const int t = cur_t_first + r;
+                if (r >= kHalo && r < kRows - kHalo && t < p.T) {
+                    const float* src = pt + 4 + r - 3;
+                    float acc = p.bias_f;
+#pragma unroll
+                    for (int j = 0; j < 7; ++j) acc += src[j * kPtStride + j];
+                    float y;
+                    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(acc));
+                    p.out[(long long)cur_clip * p.T + t] = y;
+                }
+                if (tracer) TAIL_TRACE(wg, 8, 3, b);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kConvWarp) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace tailtc
+}  // namespace l3ac
+
+#ifdef L3AC_TAIL_TRACE
+extern "C" int l3ac_debug_tail_trace(unsigned long long* host_buf) {      // host_buf: 6 * 256 entries
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(host_buf, l3ac::tailtc::g_tail_trace, 6 * 256 * sizeof(unsigned long long));
+    return 0;
+}
+#endif
+
+struct l3ac_tail_plan {
+    l3ac::tailtc::Params params;
+    void* dev_blob;
+    int device;
+};
+
+static inline uint16_t bf16_bits(float v) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    uint16_t b;
+    memcpy(&b, &h, 2);
+    return b;
+}
+static inline float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+extern "C" int l3ac_tail_plan_create(const float* conv_w, const float* conv_b, const float* pw_w, const float* pw_b,
+                                     const float* alpha0, const float* alpha1, const int* dilations, const float* alpha_f,
+                                     const float* w_f, float bias_f, int C, l3ac_tail_plan** plan_out) {
+    using namespace l3ac::tailtc;
+    L3AC_CHECK_ARG(conv_w && conv_b && pw_w && pw_b && alpha0 && alpha1 && dilations && alpha_f && w_f && plan_out);
+    if (C != kC) return L3AC_EUNSUPPORTED;
+    int reach = 3;
+    for (int i = 0; i < 3; ++i) {
+        L3AC_CHECK_ARG(dilations[i] >= 1);
+        if (3 * dilations[i] > kGuard) return L3AC_EUNSUPPORTED;      // a conv's reach must fit the guard rows
+        reach += 3 * dilations[i];
+    }
+    if (reach > kHalo) return L3AC_EUNSUPPORTED;                      // receptive field must fit the 42-sample halo
+    std::vector<uint16_t> blob(kWBytes / 2, 0);
+    // conv: [unit][mma j][half h][n 32][k 8]; W[u][n][ch][tap] at conv_w[((u * 24 + n) * 24 + ch) * 7 + tap]
+    for (int u = 0; u < 3; ++u)
+        for (int j = 0; j < kConvMmas; ++j)
+            for (int h = 0; h < 2; ++h) {
+                int tap, plane;
+                if (j < 9) { tap = 2 * (j / 3) + h; plane = j % 3; }
+                else if (j == 9) { tap = 6; plane = h; }
+                else { tap = 6; plane = h == 0 ? 2 : -1; }
+                for (int n = 0; n < kC && plane >= 0; ++n)
+                    for (int k = 0; k < 8; ++k)
+                        blob[(size_t)u * kWConvBytes / 2 + j * 512 + h * 256 + n * 8 + k] =
+                            bf16_bits(conv_w[(((size_t)u * kC + n) * kC + 8 * plane + k) * 7 + tap]);
+            }
+    const size_t pw0 = 3 * kWConvBytes / 2;
+    for (int u = 0; u < 3; ++u)
+        for (int m = 0; m < 2; ++m)
+            for (int h = 0; h < 2; ++h)
+                for (int n = 0; n < kC; ++n)
+                    for (int k = 0; k < 8; ++k) {
+                        const int ch = 16 * m + 8 * h + k;
+                        if (ch < kC) blob[pw0 + (size_t)u * kWPwBytes / 2 + m * 512 + h * 256 + n * 8 + k] = bf16_bits(pw_w[((size_t)u * kC + n) * kC + ch]);
+                    }
+    const size_t fin0 = pw0 + 3 * kWPwBytes / 2;
+    for (int part = 0; part < 2; ++part)                    // hi, lo
+        for (int m = 0; m < 2; ++m)
+            for (int h = 0; h < 2; ++h)
+                for (int n = 0; n < 7; ++n)
+                    for (int k = 0; k < 8; ++k) {
+                        const int ch = 16 * m + 8 * h + k;
+                        if (ch >= kC) continue;
+                        const float w = w_f[n * kC + ch], hi = bf16_round(w);
+                        blob[fin0 + part * 512 + m * 256 + h * 128 + n * 8 + k] = bf16_bits(part == 0 ? hi : w - hi);
+                    }
+    l3ac_tail_plan* plan = new (std::nothrow) l3ac_tail_plan();
+    if (!plan) return L3AC_EINVAL;
+    if (cudaGetDevice(&plan->device) != cudaSuccess) { delete plan; return L3AC_EDRIVER; }
+    cudaError_t e = cudaMalloc(&plan->dev_blob, kWBytes);
+    if (e != cudaSuccess) { delete plan; return (int)e; }
+    e = cudaMemcpy(plan->dev_blob, blob.data(), kWBytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(plan->dev_blob); delete plan; return (int)e; }
+    Params& p = plan->params;
+    p = Params{};
+    p.wblob = static_cast<const uint8_t*>(plan->dev_blob);
+    p.bias_f = bias_f;
+    for (int u = 0; u < 3; ++u) {
+        p.dil[u] = dilations[u];
+        for (int c = 0; c < kC; ++c) {
+            p.conv_b[u][c] = conv_b[u * kC + c];
+            p.pw_b[u][c] = pw_b[u * kC + c];
+            p.a0[u][c] = alpha0[u * kC + c];
+            p.ia0[u][c] = 1.0f / (alpha0[u * kC + c] + l3ac::kEps);
+            p.a1[u][c] = alpha1[u * kC + c];
+            p.ia1[u][c] = 1.0f / (alpha1[u * kC + c] + l3ac::kEps);
+        }
+    }
+    for (int c = 0; c < kC; ++c) {
+        p.af[c] = alpha_f[c];
+        p.iaf[c] = 1.0f / (alpha_f[c] + l3ac::kEps);
+    }
+    *plan_out = plan;
+    return L3AC_OK;
+}
+
+extern "C" int l3ac_tail_plan_destroy(l3ac_tail_plan* plan) {
+    if (!plan) return L3AC_OK;
+    cudaFree(plan->dev_blob);
+    delete plan;
+    return L3AC_OK;
+}
+
+extern "C" int l3ac_decoder_tail_tc(const l3ac_tail_plan* plan, const float* x, int B, int T, float* out, l3ac_stream_t stream) {
+    using namespace l3ac::tailtc;
+    L3AC_CHECK_ARG(plan && x && out && B > 0 && T > 0);
+    L3AC_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) return L3AC_EDRIVER;
+    L3AC_CHECK_ARG(dev == plan->device);
+    const long long n_tiles = (long long)l3ac_cdiv(T, kOut) * B;
+    L3AC_CHECK_ARG(n_tiles < (1LL << 30));
+    Params p = plan->params;
+    p.x = x;
+    p.out = out;
+    p.B = B;
+    p.T = T;
+    cudaError_t e = cudaFuncSetAttribute(decoder_tail_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    const int sms = l3ac_sm_count();
+    decoder_tail_tc_kernel<<<(int)(n_tiles < sms ? n_tiles : sms), kThreads, kSmemBytes, (cudaStream_t)stream>>>(p);
+    return l3ac_launch_status();
+}

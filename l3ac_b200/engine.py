@@ -20,6 +20,7 @@ Precision modes
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, Optional
 
 import torch
@@ -270,6 +271,17 @@ class Engine:
                 wc = fold_weight_norm(sd, f"{q}.1")                                         # (24, 24, 7)
                 convs.append(ops.pack_mma_b_fragments(_taps_major(wc), k_pad=176))          # K = tap * 24 + channel
                 pws.append(ops.pack_mma_b_fragments(fold_weight_norm(sd, f"{q}.3")[:, :, 0]))
+            # product path: the tcgen05 kernel (weights packed into a plan by the library); the register-level mma.sync
+            # kernel below stays as a cross-check (L3AC_TAIL_IMPL=mma_sync)
+            self.dec_tail_plan = None
+            if os.environ.get("L3AC_TAIL_IMPL", "tcgen05") == "tcgen05":
+                self.dec_tail_plan = ops.TailPlan(
+                    torch.stack([fold_weight_norm(sd, f"{p}.0.{j}.module.block.1") for j in range(3)]),
+                    torch.stack([u["conv"].bias for u in self.dec_legacy]),
+                    torch.stack([fold_weight_norm(sd, f"{p}.0.{j}.module.block.3")[:, :, 0] for j in range(3)]),
+                    torch.stack([u["pw"].bias for u in self.dec_legacy]),
+                    torch.stack([u["alpha0"] for u in self.dec_legacy]), torch.stack([u["alpha1"] for u in self.dec_legacy]),
+                    [u["dil"] for u in self.dec_legacy], self.dec_tail["alpha"], self.dec_tail["w"], self.dec_tail["bias"], self.device)
             self.dec_tail_fused = dict(
                 conv_frags=torch.stack(convs).contiguous(), pw_frags=torch.stack(pws).contiguous(),
                 conv_bias=torch.stack([u["conv"].bias for u in self.dec_legacy]).contiguous(),
@@ -581,6 +593,8 @@ class Engine:
                 taps[f"dec_up{si}"] = x
         B, T, C = x.shape
         if self.dec_tail_fused is not None:                                         # 3 LegacyUnits + tail conv in one kernel
+            if self.dec_tail_plan is not None:
+                return ops.decoder_tail_tc(x, self.dec_tail_plan)
             return ops.decoder_tail(x, **self.dec_tail_fused)
         for u in self.dec_legacy:                                                   # Residual(LegacyUnit), modules.py:47-64
             d = u["dil"]

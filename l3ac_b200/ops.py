@@ -482,3 +482,41 @@ def decoder_tail(x: torch.Tensor, conv_frags, conv_bias, pw_frags, pw_bias, alph
                                             _ptr(alpha0), _ptr(alpha1), dil, _ptr(alpha_f), _ptr(w_f), float(bias_f), _ptr(out),
                                             _stream(x)), "l3ac_decoder_tail")
     return out
+
+
+class TailPlan:
+    """Packed weights of the tcgen05 decoder tail (``l3ac_tail_plan``): built once from folded fp32 host arrays."""
+
+    def __init__(self, conv_w, conv_b, pw_w, pw_b, alpha0, alpha1, dilations, alpha_f, w_f, bias_f: float, device):
+        host = lambda t: t.detach().to("cpu", torch.float32).contiguous()
+        self._keep = [host(t) for t in (conv_w, conv_b, pw_w, pw_b, alpha0, alpha1, alpha_f, w_f)]
+        cw, cb, pw, pb, a0, a1, af, wf = self._keep
+        if cw.shape != (3, 24, 24, 7) or pw.shape != (3, 24, 24) or wf.shape != (7, 24):
+            raise ValueError("TailPlan: conv_w (3,24,24,7), pw_w (3,24,24), w_f (7,24) expected")
+        dil = (C.c_int * 3)(*[int(d) for d in dilations])
+        self.handle = C.c_void_p()
+        self.device = torch.device(device)
+        with torch.cuda.device(self.device):
+            check(_lib.load().l3ac_tail_plan_create(cw.data_ptr(), cb.data_ptr(), pw.data_ptr(), pb.data_ptr(), a0.data_ptr(),
+                                                    a1.data_ptr(), dil, af.data_ptr(), wf.data_ptr(), float(bias_f), 24,
+                                                    C.byref(self.handle)), "l3ac_tail_plan_create")
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            try:
+                _lib.load().l3ac_tail_plan_destroy(h)
+            except Exception:
+                pass
+
+
+def decoder_tail_tc(x: torch.Tensor, plan: TailPlan) -> torch.Tensor:
+    _chk(x, name="x")
+    B, T, Cc = x.shape
+    if Cc != 24:
+        raise ValueError("decoder_tail_tc: 24 channels expected")
+    out = torch.empty((B, T), device=x.device, dtype=torch.float32)
+    _count()
+    with _hook("decoder_tail_tc", _nbytes(x, out), 2.0 * B * T * (3 * (7 * 24 * 24 + 24 * 24) + 7 * 24)), torch.cuda.device(x.device):
+        check(_lib.load().l3ac_decoder_tail_tc(plan.handle, _ptr(x), B, T, _ptr(out), _stream(x)), "l3ac_decoder_tail_tc")
+    return out

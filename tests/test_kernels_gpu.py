@@ -244,9 +244,11 @@ def test_argument_validation(cuda_lib):
         ops.fsq_quantize_latents(torch.zeros(4, 6, device=DEV), (1, 7, 7, 7, 7, 7))       # level < 2
 
 
-@pytest.mark.parametrize("T", [50, 300, 1000, 2717])
-def test_fused_decoder_tail(cuda_lib, T):
-    """3 x Residual(LegacyUnit) + Snake + Conv(24->1,k7) + tanh in one kernel vs the oracle's decoder tail (bf16 operands)."""
+@pytest.mark.parametrize("impl", ["tcgen05", "mma_sync"])
+@pytest.mark.parametrize("T", [50, 300, 1000, 2717, 9401, 80011])
+def test_fused_decoder_tail(cuda_lib, T, impl):
+    """3 x Residual(LegacyUnit) + Snake + Conv(24->1,k7) + tanh in one kernel vs the oracle's decoder tail (bf16 operands).
+    impl = tcgen05: l3ac_decoder_tail_tc (the product path); mma_sync: the register-level l3ac_decoder_tail."""
     C = 24
     sd = {}
     for j in range(3):
@@ -278,9 +280,16 @@ def test_fused_decoder_tail(cuda_lib, T):
     pws = torch.stack([ops.pack_mma_b_fragments(sd[f"blocks.0.block.0.{j}.module.block.3.weight"][:, :, 0].to(DEV))
                        for j in range(3)]).contiguous()
     st = lambda key: torch.stack([sd[f"blocks.0.block.0.{j}.module.block.{key}"].flatten() for j in range(3)]).contiguous().to(DEV)
-    got = ops.decoder_tail(cl(x), convs, st("1.bias"), pws, st("3.bias"), st("0.alpha"), st("2.alpha"), (1, 3, 9),
-                           sd["blocks.0.block.1.alpha"].flatten().to(DEV), sd["blocks.0.block.2.weight"][0].t().contiguous().to(DEV),
-                           float(sd["blocks.0.block.2.bias"]))
+    if impl == "tcgen05":
+        plan = ops.TailPlan(torch.stack([sd[f"blocks.0.block.0.{j}.module.block.1.weight"] for j in range(3)]), st("1.bias"),
+                            torch.stack([sd[f"blocks.0.block.0.{j}.module.block.3.weight"][:, :, 0] for j in range(3)]), st("3.bias"),
+                            st("0.alpha"), st("2.alpha"), (1, 3, 9), sd["blocks.0.block.1.alpha"].flatten(),
+                            sd["blocks.0.block.2.weight"][0].t(), float(sd["blocks.0.block.2.bias"]), DEV)
+        got = ops.decoder_tail_tc(cl(x), plan)
+    else:
+        got = ops.decoder_tail(cl(x), convs, st("1.bias"), pws, st("3.bias"), st("0.alpha"), st("2.alpha"), (1, 3, 9),
+                               sd["blocks.0.block.1.alpha"].flatten().to(DEV), sd["blocks.0.block.2.weight"][0].t().contiguous().to(DEV),
+                               float(sd["blocks.0.block.2.bias"]))
     # The kernel and the CPU emulation round the same operands to bf16, but a 1-ulp fp32 difference upstream can flip a
     # bf16 rounding, so the two agree only statistically: both must sit at the same distance from the exact oracle.
     e_kernel, e_emul = max_abs(got.cpu(), exact), max_abs(want, exact)
