@@ -484,8 +484,13 @@ def main():
     MMA_KINDS = ("decoder_tail", "convunit_thin_tc", "convunit_thin_tc_bf16", "stem_tc", "local_attention_tc", "local_attention_tc_split")
     mma_ops = {k: o for k, o in by_op.items() if k in MMA_KINDS}
     mma_ms, mma_gflop = sum(o["ms"] for o in mma_ops.values()), sum(o["gflop"] for o in mma_ops.values())
+    # tcgen05 kernels whose operands are produced by threads (decoder tail, windowed attention, ...): tensor-core contractions
+    # with TMEM accumulators, bound by the SFU / issue work of their snake or softmax stages rather than by the MMAs
+    UMMA_KINDS = ("decoder_tail_tc", "local_attention_tc_umma", "local_attention_tc_split_umma", "convunit_thin_umma", "stem_umma")
+    umma_ops = {k: o for k, o in by_op.items() if k in UMMA_KINDS}
+    umma_ms, umma_gflop = sum(o["ms"] for o in umma_ops.values()), sum(o["gflop"] for o in umma_ops.values())
     hbm_ops = {k: o for k, o in by_op.items() if not k.startswith("gemm") and k != "convunit_mlp_tc" and k not in MMA_KINDS
-               and k not in ("stem", "convunit_thin_f32", "local_attention")}
+               and k not in UMMA_KINDS and k not in ("stem", "convunit_thin_f32", "local_attention")}
     hbm_ms, hbm_mb = sum(o["ms"] for o in hbm_ops.values()), sum(o["mb"] for o in hbm_ops.values())
     total_gflop = GFLOP_PER_10S.get(args.config, 0.0) * secs / 10.0 * B
     extras = {
@@ -498,6 +503,12 @@ def main():
                               "frac": (mma_gflop / mma_ms / pk["tf_sustained"]) if mma_ms else None, "share_of_step": mma_ms / inst_ms,
                               "per_kernel": {k: {"launches": o["launches"], "ms": round(o["ms"], 3), "achieved": o["gflop"] / o["ms"]}
                                              for k, o in mma_ops.items()}},
+        "roofline_tcgen05_fused": {"bound": "tensor", "kernel": "tcgen05 kernels with thread-produced operands (" + ", ".join(sorted(umma_ops)) + "): "
+                                   "TMEM accumulators, snake / softmax stages on the SFU; algorithmic flops",
+                                   "achieved": (umma_gflop / umma_ms) if umma_ms else None, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                                   "frac": (umma_gflop / umma_ms / pk["tf_sustained"]) if umma_ms else None, "share_of_step": umma_ms / inst_ms,
+                                   "per_kernel": {k: {"launches": o["launches"], "ms": round(o["ms"], 3), "achieved": o["gflop"] / o["ms"]}
+                                                  for k, o in umma_ops.items()}},
         "roofline_hbm": {"bound": "hbm", "kernel": "HBM-bound kernels of one step (" + ", ".join(sorted(hbm_ops)) + "), algorithmic bytes",
                          "per_kernel": {k: {"launches": o["launches"], "ms": round(o["ms"], 3), "achieved": o["mb"] / o["ms"]} for k, o in hbm_ops.items()},
                          "achieved": (hbm_mb / hbm_ms) if hbm_ms else None, "peak": pk["hbm"], "unit": "GB/s",

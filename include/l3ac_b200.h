@@ -180,6 +180,13 @@ int l3ac_local_attention_f32(const float* qkv, const float* bias_table, int B, i
 int l3ac_local_attention_tc(const void* qkv_hi, const void* qkv_lo, const float* bias_table, int B, int T, int H,
                             int D, int window, void* out, void* out_lo, int out_dtype, l3ac_stream_t stream);
 
+/* The same attention on the 5th-generation tensor cores (tcgen05.mma, S and O accumulators in TMEM; one thread per query
+ * row does the softmax on its TMEM lane; V is consumed in its natural layout as an MN-major operand and the row sums come
+ * out of the P.V product through a ones column).  Same arguments and results as l3ac_local_attention_tc; additionally
+ * out / out_lo must be 16-byte aligned.  This is the product path; the mma.sync kernel above is kept as a cross-check. */
+int l3ac_local_attention_umma(const void* qkv_hi, const void* qkv_lo, const float* bias_table, int B, int T, int H,
+                              int D, int window, void* out, void* out_lo, int out_dtype, l3ac_stream_t stream);
+
 /* Rotary-position path (en_coder_dynamic_pos = false: LocalMHA(use_rotary_pos_emb=True), l3ac/local_trans.py:29,36;
  * replaces SinusoidalEmbeddings + apply_rotary_pos_emb of local-attention inside LocalAttention.forward).
  * l3ac_rotary_pack: qkv (B,T,3*H*D) fp32 [q | k | v] -> one segment per attention window, (B*ceil(T/window), 2*window,

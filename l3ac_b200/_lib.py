@@ -44,6 +44,7 @@ PROTOTYPES = {
     "l3ac_convunit_thin_tc": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
     "l3ac_local_attention_f32": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "l3ac_local_attention_tc": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p]),
+    "l3ac_local_attention_umma": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p]),
     "l3ac_rotary_pack": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p]),
     "l3ac_rotary_unpack": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "l3ac_fsq_quantize": (_i, [_p, _ll, _i, _p, _p, _p, _p, C.POINTER(_i), _i, _p, _p, _p, _p, _p]),

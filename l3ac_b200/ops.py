@@ -7,6 +7,7 @@ the same device.  Activations are channels-last ``(B, T, C)``.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence
 
 import torch
@@ -304,8 +305,15 @@ def local_attention(qkv: torch.Tensor, bias_table: torch.Tensor, heads: int, win
     return out
 
 
-def local_attention_tc(qkv, bias_table: torch.Tensor, heads: int, window: int, out_dtype=torch.float32):
-    """Tensor-core attention over bf16 q/k/v: ``qkv`` is a bf16 tensor or a ``Split`` pair of shape (B, T, 3*heads*32)."""
+# "auto": tcgen05 (l3ac_local_attention_umma) once a clip has >= 8 query tiles of 128 -- the frame-rate layers, 85 % of the
+# attention work; the token-rate layers (T ~ 600: 1-5 key tiles per CTA, set-up bound) stay on the register-level kernel,
+# measured 35 vs 37 us per 24 clips.  "tcgen05" / "mma_sync" force one kernel.
+ATTENTION_IMPL = os.environ.get("L3AC_ATT_IMPL", "auto")
+
+
+def local_attention_tc(qkv, bias_table: torch.Tensor, heads: int, window: int, out_dtype=torch.float32, impl: Optional[str] = None):
+    """Tensor-core attention over bf16 q/k/v: ``qkv`` is a bf16 tensor or a ``Split`` pair of shape (B, T, 3*heads*32).
+    impl = "tcgen05": l3ac_local_attention_umma (TMEM accumulators); "mma_sync": the register-level l3ac_local_attention_tc."""
     split = isinstance(qkv, Split)
     hi = qkv.hi if split else qkv
     _chk(hi, torch.bfloat16, "qkv")
@@ -320,11 +328,15 @@ def local_attention_tc(qkv, bias_table: torch.Tensor, heads: int, window: int, o
     _count()
     # useful MACs: query p sees (w if p >= w else 0) + (p mod w) + 1 keys; two products of D MACs each
     keys = sum((window if p >= window else 0) + (p % window) + 1 for p in range(T)) if OP_HOOK is not None else 0
-    with _hook("local_attention_tc_split" if split else "local_attention_tc", _nbytes(qkv, out),
+    with _hook(("local_attention_tc_split" if split else "local_attention_tc") + ("_umma" if (impl or ATTENTION_IMPL) == "tcgen05" or ((impl or ATTENTION_IMPL) == "auto" and T >= 897) else ""), _nbytes(qkv, out),
                2.0 * 2 * B * heads * keys * D * (1 if not split else 1)), torch.cuda.device(hi.device):
-        check(_lib.load().l3ac_local_attention_tc(_ptr(hi), _ptr(qkv.lo) if split else None, _ptr(bias_table), B, T, heads, D,
-                                                  window, _ptr(o_hi), _ptr(o_lo), _DT[out_dtype], _stream(hi)),
-              "l3ac_local_attention_tc")
+        lib = _lib.load()
+        which = impl or ATTENTION_IMPL
+        if which == "auto":
+            which = "tcgen05" if T >= 897 else "mma_sync"
+        fn = lib.l3ac_local_attention_umma if which == "tcgen05" else lib.l3ac_local_attention_tc
+        check(fn(_ptr(hi), _ptr(qkv.lo) if split else None, _ptr(bias_table), B, T, heads, D,
+                 window, _ptr(o_hi), _ptr(o_lo), _DT[out_dtype], _stream(hi)), "l3ac_local_attention_tc")
     return out
 
 

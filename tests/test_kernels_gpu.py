@@ -339,10 +339,12 @@ def test_fused_thin_convunit_tc(cuda_lib, C, T):
     assert e_k < 2.0 * e_e + 1e-3
 
 
-@pytest.mark.parametrize("T,w", [(100, 40), (333, 100), (593, 250), (64, 200), (257, 64), (1779, 750)])
+@pytest.mark.parametrize("impl", ["tcgen05", "mma_sync"])
+@pytest.mark.parametrize("T,w", [(100, 40), (333, 100), (593, 250), (64, 200), (257, 64), (1779, 750), (1, 7), (128, 128), (1025, 96)])
 @pytest.mark.parametrize("split", [False, True])
-def test_local_attention_tc(cuda_lib, T, w, split):
-    """Tensor-core attention vs the oracle on the bf16-rounded (or hi+lo) q/k/v it actually consumes."""
+def test_local_attention_tc(cuda_lib, T, w, split, impl):
+    """Tensor-core attention vs the oracle on the bf16-rounded (or hi+lo) q/k/v it actually consumes.
+    impl = tcgen05: l3ac_local_attention_umma (the product path); mma_sync: the register-level l3ac_local_attention_tc."""
     B, H, D = 2, 6, 32
     qkv = rnd(B, T, 3 * H * D, seed=T)
     table = rnd(H, 2 * w, seed=w, scale=0.5)
@@ -353,11 +355,31 @@ def test_local_attention_tc(cuda_lib, T, w, split):
     idx = (torch.arange(w, 2 * w)[:, None] - torch.arange(2 * w)[None, :]).abs()
     want = O.local_attention(q, k, v, table[:, idx], w).reshape(B, H, T, D).transpose(1, 2).reshape(B, T, H * D)
     arg = ops.Split(hi.to(DEV), lo.to(DEV)) if split else hi.to(DEV)
-    got = ops.local_attention_tc(arg, table.to(DEV), H, w)
+    got = ops.local_attention_tc(arg, table.to(DEV), H, w, impl=impl)
     tol = 3e-5 if split else 2e-2          # split: fp32-class; plain: P is rounded to bf16 before the second product
     assert max_abs(got.cpu(), want) < tol
-    got2 = ops.local_attention_tc(arg, table.to(DEV), H, w, out_dtype=ops.SPLIT)
+    got2 = ops.local_attention_tc(arg, table.to(DEV), H, w, out_dtype=ops.SPLIT, impl=impl)
     assert max_abs(got2.float().cpu(), got.cpu()) < 3e-5
+    got3 = ops.local_attention_tc(arg, table.to(DEV), H, w, out_dtype=torch.bfloat16, impl=impl)
+    assert max_abs(got3.float().cpu(), got.cpu()) < 2e-2
+
+
+@pytest.mark.parametrize("impl", ["tcgen05", "mma_sync"])
+@pytest.mark.parametrize("slope", [-0.7, 0.4, 25.0])
+def test_local_attention_steep_bias(cuda_lib, slope, impl):
+    """DynamicPositionBias is an MLP of the RAW distance (0 .. 2w-1): its table can span hundreds of units, far more than the
+    logits.  The softmax reference (an upper bound per half tile in the tcgen05 kernel) must stay tight under such tables, and
+    under large logits."""
+    B, H, D, T, w = 1, 6, 32, 1100, 400
+    qkv = rnd(B, T, 3 * H * D, seed=3) * (4.0 if slope > 1 else 1.0)
+    table = rnd(H, 2 * w, seed=5, scale=0.5) + slope * torch.arange(2 * w)[None, :] * torch.linspace(-1, 1, H)[:, None]
+    hi = qkv.to(torch.bfloat16)
+    q, k, v = (t.reshape(B, T, H, D).transpose(1, 2).reshape(B * H, T, D) for t in hi.float().chunk(3, dim=-1))
+    idx = (torch.arange(w, 2 * w)[:, None] - torch.arange(2 * w)[None, :]).abs()
+    want = O.local_attention(q, k, v, table[:, idx], w).reshape(B, H, T, D).transpose(1, 2).reshape(B, T, H * D)
+    got = ops.local_attention_tc(hi.to(DEV), table.to(DEV), H, w, impl=impl)
+    assert torch.isfinite(got).all()
+    assert max_abs(got.cpu(), want) < 3e-2
 
 
 @pytest.mark.parametrize("T", [1, 100, 129, 1000])

@@ -17,14 +17,15 @@ for T, w in ((1779, 750), (593, 250)):
     hi = qkv.to(torch.bfloat16)
     sp = ops.Split(hi, (qkv - hi.float()).to(torch.bfloat16))
     for name, arg in (("bf16", hi), ("split", sp)):
+      for impl in ("tcgen05", "mma_sync"):
         ts = []
         for i in range(8):
             junk.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            out = ops.local_attention_tc(arg, table, H, w, out_dtype=torch.bfloat16 if name == "bf16" else ops.SPLIT)
+            out = ops.local_attention_tc(arg, table, H, w, out_dtype=torch.bfloat16 if name == "bf16" else ops.SPLIT, impl=impl)
             e1.record()
             torch.cuda.synchronize()
             if i >= 2:
                 ts.append(e0.elapsed_time(e1) * 1e3)
-        print(f"local_attention_tc {name} B={B} T={T} w={w}: {sorted(ts)[len(ts) // 2]:.1f} us", flush=True)
+        print(f"local_attention {impl:8s} {name} B={B} T={T} w={w}: {sorted(ts)[len(ts) // 2]:.1f} us", flush=True)
