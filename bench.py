@@ -372,13 +372,13 @@ def main():
         return
 
     sampler = ClockSampler(local)
-    launches0 = ops.LAUNCHES
     with torch.inference_mode():
         for i in range(args.warmup):
             step_resident(i)
-    launches_per_step = (ops.LAUNCHES - launches0) // max(1, args.warmup)
     sampler.start()
+    launches0 = ops.LAUNCHES
     ms_step = timed(step_resident, args.steps, 0, "resident")
+    launches_per_step = (ops.LAUNCHES - launches0) // max(1, args.steps)      # this library's kernels (inside replayed CUDA graphs included)
     clocks = sampler.stop()
     ms_e2e = timed(step_e2e, args.steps, min(args.warmup, 2), "e2e")
     audio_s = (args.batch if args.scaling == "strong" else world * B) * secs

@@ -90,7 +90,11 @@ class Engine:
         # Small batches are launch-bound (~220 kernels per encode+decode step, ~1 ms of GPU work for one 10 s clip):
         # the kernel sequence of a given (batch, length) is captured once into a CUDA graph and replayed.
         self.graph_max_samples = int(40.0 * 16000)
-        self.graph_cache_size = 8
+        self.graph_cache_size = 32
+        # Large batches: every micro-batch (encode and decode separately, one graph instance per micro-batch slot so that the
+        # instances can run concurrently on their streams) is captured into a CUDA graph on its second appearance and
+        # replayed from then on -- ~360 ctypes launches (10 ms of host time per 64 x 10 s step) become six graph launches.
+        self.graph_chunks = os.environ.get("L3AC_GRAPH_CHUNKS", "1") != "0"
         self.graph_capture_after = int(os.environ.get("L3AC_GRAPH_AFTER", 2))   # capture a shape on its n-th appearance
         self._graphs = {}
         self._graph_seen = {}
@@ -475,10 +479,10 @@ class Engine:
                     if len(self._graph_seen) > 4096:
                         self._graph_seen.clear()
                     self._graph_seen[key] = seen + 1
-                return fn(inp)
+                return fn(inp.to(self.device, non_blocking=True))
             if len(self._graphs) >= self.graph_cache_size:
                 self._graphs.pop(next(iter(self._graphs)))          # drop the oldest capture (and its memory pool)
-            static_in = inp.clone()
+            static_in = inp.to(self.device, copy=True)
             cur = torch.cuda.current_stream(self.device)
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(cur)
@@ -486,18 +490,21 @@ class Engine:
                 fn(static_in)
             cur.wait_stream(side)
             graph = torch.cuda.CUDAGraph()
+            launches0 = ops.LAUNCHES
             try:
                 with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                     outs = fn(static_in)
             except RuntimeError:
                 self._graph_seen[key] = -1                           # never try this shape again
                 torch.cuda.synchronize(self.device)
-                return fn(inp)
-            slot = (graph, static_in, outs)
+                return fn(inp.to(self.device, non_blocking=True))
+            slot = (graph, static_in, outs, ops.LAUNCHES - launches0)
+            ops.LAUNCHES = launches0                                 # (captured, not launched)
             self._graphs[key] = slot
-        graph, static_in, outs = slot
-        static_in.copy_(inp)
+        graph, static_in, outs, n_kernels = slot
+        static_in.copy_(inp, non_blocking=True)                      # (a pinned host slice is uploaded straight into the graph's input)
         graph.replay()
+        ops.LAUNCHES += n_kernels                                    # the kernels of this library inside the replayed graph
         return tuple(o.clone() for o in outs)
 
     def _run_chunks(self, fn, chunks):
@@ -549,7 +556,13 @@ class Engine:
             return q, {"indices": idx, "level_indices": lvl}
         n_all = audio.shape[0]
 
+        chunks = self._chunks(*audio.shape)
+        use_graphs = (self.graph_chunks and len(chunks) > 1 and taps is None and ops.OP_HOOK is None
+                      and not torch.cuda.is_current_stream_capturing())
+
         def run(lo, hi):
+            if use_graphs:
+                return self._graphed(("encc", chunks.index((lo, hi)), hi - lo, audio.shape[1]), self._encode_one_chunk, audio[lo:hi])
             a = audio[lo:hi].to(self.device, non_blocking=True) if staged_on_host else audio[lo:hi]
             t = self.encode_features(a, taps if (lo == 0 and hi == n_all) else None)
             if taps is not None:
@@ -559,7 +572,7 @@ class Engine:
                 taps["z"] = z
             return q, idx, lvl
 
-        outs = self._run_chunks(run, self._chunks(*audio.shape))
+        outs = self._run_chunks(run, chunks)
         if len(outs) == 1:
             q, idx, lvl = outs[0]
         else:
@@ -685,8 +698,14 @@ class Engine:
                 return finish(self._graphed(("dec", B, T_tok), lambda f: (self.decode_features(f),), feat)[0])
         chunks = self._chunks(B, T_tok * self.mc.hop_length)
 
+        use_graphs = (self.graph_chunks and len(chunks) > 1 and taps is None and ops.OP_HOOK is None
+                      and not torch.cuda.is_current_stream_capturing())
+
         def run(lo, hi):
-            wav = self.decode_features(feat[lo:hi].contiguous(), taps if (lo == 0 and hi == B) else None)
+            if use_graphs:
+                wav = self._graphed(("decc", chunks.index((lo, hi)), hi - lo, T_tok), lambda f: (self.decode_features(f),), feat[lo:hi])[0]
+            else:
+                wav = self.decode_features(feat[lo:hi].contiguous(), taps if (lo == 0 and hi == B) else None)
             if out is not None and len(chunks) > 1:
                 out[lo:hi].copy_(wav, non_blocking=True)          # on this micro-batch's stream
             return wav

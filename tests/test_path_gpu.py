@@ -4,6 +4,7 @@ import pytest
 import torch
 
 import l3ac_b200
+from l3ac_b200 import ops
 from helpers import CONFIGS, bf16_operand_emulation, config_path, golden_case, make_audio, max_abs, model_config, snr_db
 from l3ac_b200.config import CONFIG_DIR, L3ACConfig
 from l3ac_b200.spec import init_state_dicts
@@ -257,6 +258,34 @@ def test_pinned_host_input_is_uploaded_per_micro_batch(cuda_lib):
     assert got is host and torch.equal(host, wav.cpu()) and got1 is small and torch.equal(small, wav[:1].cpu())
     with pytest.raises(ValueError):
         codec.decode_audio(indices=idx0["indices"], out=torch.empty(tuple(wav.shape)))   # not pinned
+
+
+def test_micro_batch_graphs_match_eager(cuda_lib):
+    """Large batches: each micro-batch is captured into its own CUDA graph on its second appearance and replayed on its stream
+    (pinned host input uploaded straight into the graph's input); results must be bit-identical to the eager launch sequence."""
+    codec = l3ac_b200.get_model("1kbps", pretrained=False)
+    codec.network.cuda()
+    eng = codec.network.engine
+    eng.max_chunk_samples = 16000 * 12                            # 4 micro-batches for 7 clips of 5 s
+    eng.graph_max_samples = 0
+    a, b = make_audio(7, 5.0, seed=51), make_audio(7, 5.0, seed=52).pin_memory()
+    with torch.inference_mode():
+        eng.graph_chunks = False
+        ref = []
+        for x in (a.to(DEV), b):
+            q, idx = codec.encode_audio(x)
+            ref.append((q, idx["indices"], codec.decode_audio(indices=idx["indices"])))
+        eng.graph_chunks = True
+        launches0 = ops.LAUNCHES
+        for rep in range(3):                                      # eager, capture, replay
+            for x, (q0, i0, w0) in zip((a.to(DEV), b), ref):
+                q, idx = codec.encode_audio(x)
+                w = codec.decode_audio(indices=idx["indices"])
+                assert torch.equal(q, q0) and torch.equal(idx["indices"], i0) and torch.equal(w, w0), rep
+            if rep == 0:
+                per_pass = ops.LAUNCHES - launches0
+        assert len(eng._graphs) == 2 * len(eng._chunks(7, 80000)) >= 6      # micro-batch slots x (encode, decode)
+        assert ops.LAUNCHES - launches0 == 3 * per_pass           # replayed kernels are counted like launched ones
 
 
 def test_cuda_graph_path_matches_eager(cuda_lib):
