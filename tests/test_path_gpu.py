@@ -272,20 +272,22 @@ def test_micro_batch_graphs_match_eager(cuda_lib):
     with torch.inference_mode():
         eng.graph_chunks = False
         ref = []
+        launches0 = ops.LAUNCHES
         for x in (a.to(DEV), b):
             q, idx = codec.encode_audio(x)
             ref.append((q, idx["indices"], codec.decode_audio(indices=idx["indices"])))
+        per_call = (ops.LAUNCHES - launches0) // 2                # kernels of one encode + decode of this batch
         eng.graph_chunks = True
         launches0 = ops.LAUNCHES
-        for rep in range(3):                                      # eager, capture, replay
+        for rep in range(3):                                      # (eager, capture + replay), replay, replay
             for x, (q0, i0, w0) in zip((a.to(DEV), b), ref):
                 q, idx = codec.encode_audio(x)
                 w = codec.decode_audio(indices=idx["indices"])
                 assert torch.equal(q, q0) and torch.equal(idx["indices"], i0) and torch.equal(w, w0), rep
-            if rep == 0:
-                per_pass = ops.LAUNCHES - launches0
         assert len(eng._graphs) == 2 * len(eng._chunks(7, 80000)) >= 6      # micro-batch slots x (encode, decode)
-        assert ops.LAUNCHES - launches0 == 3 * per_pass           # replayed kernels are counted like launched ones
+        # replayed kernels are counted like launched ones: 1 eager call + the capture's warm-up run + 5 replays (the few kernels
+        # outside the graphs -- dequantize -- are not repeated by the warm-up run)
+        assert abs((ops.LAUNCHES - launches0) - 7 * per_call) <= 8
 
 
 def test_cuda_graph_path_matches_eager(cuda_lib):
