@@ -46,7 +46,10 @@ __device__ __forceinline__ float fsq_reduce8(const float (&p)[8], int lane) {
     return c;
 }
 
-// F == 128: lane owns features 4*lane .. 4*lane+3.  One warp per token, two tokens in flight per warp.
+// F == 128: lane owns features 4*lane .. 4*lane+3.  One warp per token, kInFlight tokens (512 B each) requested per warp before
+// the first is consumed: with ~16 resident warps per SM (the per-lane weight slices cost ~64 registers) that is 32 KB in
+// flight per SM -- what 6.4 TB/s x ~800 ns of HBM latency needs; two in flight ran at 0.28 of the HBM peak.
+constexpr int kFsqInFlight = 4;
 __global__ void __launch_bounds__(256) fsq_quantize_kernel(const float* __restrict__ x, long long M,
                                                            const float* __restrict__ w_in,
                                                            const float* __restrict__ b_in,
@@ -83,14 +86,16 @@ __global__ void __launch_bounds__(256) fsq_quantize_kernel(const float* __restri
     const bool writer = has_dim && (lane & 3) == 0;
 
     const long long stride = (long long)gridDim.x * warps_per_block;
-    for (long long row0 = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row0 < M; row0 += 2 * stride) {
-        const long long rows[2] = {row0, row0 + stride};
-        float4 xv[2];
+    for (long long row0 = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row0 < M; row0 += kFsqInFlight * stride) {
+        long long rows[kFsqInFlight];
+        float4 xv[kFsqInFlight];
 #pragma unroll
-        for (int u = 0; u < 2; ++u)
-            xv[u] = rows[u] < M ? __ldg(reinterpret_cast<const float4*>(x + rows[u] * F) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int u = 0; u < kFsqInFlight; ++u) {
+            rows[u] = row0 + u * stride;
+            xv[u] = rows[u] < M ? __ldcs(reinterpret_cast<const float4*>(x + rows[u] * F) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < kFsqInFlight; ++u) {
             if (rows[u] >= M) break;                           // warp-uniform
             const long long row = rows[u];
             float p[8];
