@@ -272,6 +272,17 @@ int l3ac_decoder_tail(const float* x, int B, int T, int C, const void* conv_frag
  *   l3ac_decoder_tail_tc   x (B,T,24) fp32 -> out (B,T) fp32 on `stream`; allocates nothing; graph-capturable.
  *   l3ac_tail_plan_destroy frees the device blob.
  * Same constraints on the dilations as l3ac_decoder_tail. */
+/* The encoder stem (V3FirstBlock, see l3ac_stem above) on the 5th-generation tensor cores: the two 1x1 convs are 3-term
+ * split-bf16 tcgen05.mma with TMEM accumulators (fp32-class results), one thread per sample does the pooling taps, GELU and
+ * operand splitting.  Weights go into a plan built once from HOST arrays in the reference's layout (folded fp32):
+ *   branch_w [5][4][7], branch_b [20], w1 [80][20], b1 [80], w2 [24][81], b2 [24].
+ * l3ac_stem_umma: audio (B,T) fp32 -> out (B,T,24) fp32 (16-byte aligned) on `stream`; allocates nothing. */
+typedef struct l3ac_stem_plan l3ac_stem_plan;
+int l3ac_stem_plan_create(const float* branch_w, const float* branch_b, const float* w1, const float* b1, const float* w2,
+                          const float* b2, int C, l3ac_stem_plan** plan_out);
+int l3ac_stem_plan_destroy(l3ac_stem_plan* plan);
+int l3ac_stem_umma(const l3ac_stem_plan* plan, const float* audio, int B, int T, float* out, l3ac_stream_t stream);
+
 typedef struct l3ac_tail_plan l3ac_tail_plan;
 int l3ac_tail_plan_create(const float* conv_w, const float* conv_b, const float* pw_w, const float* pw_b,
                           const float* alpha0, const float* alpha1, const int* dilations, const float* alpha_f,

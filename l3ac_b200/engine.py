@@ -149,6 +149,8 @@ class Engine:
             branch_w=bw.contiguous(), branch_b=bb.contiguous(),
             w1=fold_weight_norm(sd, "blocks.0.conv_1")[:, :, 0].contiguous(), b1=sd["blocks.0.conv_1.bias"].float(),
             w2=fold_weight_norm(sd, "blocks.0.conv_2")[:, :, 0].contiguous(), b2=sd["blocks.0.conv_2.bias"].float())
+        self.stem_plan = None                                                 # tcgen05 stem: packed lazily on first use
+        self.stem_impl = os.environ.get("L3AC_STEM_IMPL", "tcgen05")          # "mma_sync": the register-level cross-check kernel
         self.enc_stages = []
         blk = 1
         for i, stride in enumerate(mc.compress_rates):
@@ -392,8 +394,13 @@ class Engine:
         """Encoder.forward -- l3ac/modules.py:71-116.  audio (B, T) fp32 -> feature (B, T_f, F) channels-last fp32.
         A length that is not a multiple of a stage's stride is floored like the reference's strided Conv1d does."""
         f32 = self.enc_dtype            # operand kind of the encode-side GEMMs (fp32 SIMT or split-bf16 tcgen05)
-        stem = ops.stem_tc if (f32 == ops.SPLIT and self.thin_tc) else ops.stem
-        x = stem(audio.contiguous(), **self.stem)          # (B, T, 24)
+        if f32 == ops.SPLIT and self.thin_tc and self.stem_impl == "tcgen05":
+            if self.stem_plan is None:
+                self.stem_plan = ops.StemPlan(**self.stem, device=self.device)
+            x = ops.stem_umma(audio.contiguous(), self.stem_plan)               # (B, T, 24)
+        else:
+            stem = ops.stem_tc if (f32 == ops.SPLIT and self.thin_tc) else ops.stem
+            x = stem(audio.contiguous(), **self.stem)
         if taps is not None:
             taps["enc_stem"] = x
         # The last ConvUnit before a GEMM consumer writes that GEMM's operand kind directly (split pair on the tensor-core

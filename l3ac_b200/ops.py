@@ -532,3 +532,37 @@ def decoder_tail_tc(x: torch.Tensor, plan: TailPlan) -> torch.Tensor:
     with _hook("decoder_tail_tc", _nbytes(x, out), 2.0 * B * T * (3 * (7 * 24 * 24 + 24 * 24) + 7 * 24)), torch.cuda.device(x.device):
         check(_lib.load().l3ac_decoder_tail_tc(plan.handle, _ptr(x), B, T, _ptr(out), _stream(x)), "l3ac_decoder_tail_tc")
     return out
+
+
+class StemPlan:
+    """Packed weights of the tcgen05 encoder stem (``l3ac_stem_plan``): built once from folded fp32 tensors."""
+
+    def __init__(self, branch_w, branch_b, w1, b1, w2, b2, device):
+        host = lambda t: t.detach().to("cpu", torch.float32).contiguous()
+        self._keep = [host(t) for t in (branch_w, branch_b, w1, b1, w2, b2)]
+        bw, bb, w1h, b1h, w2h, b2h = self._keep
+        if bw.numel() != 140 or bb.numel() != 20 or tuple(w1h.shape) != (80, 20) or tuple(w2h.shape) != (24, 81):
+            raise ValueError("StemPlan: branch_w (5,4,7), branch_b (20), w1 (80,20), w2 (24,81) expected")
+        self.handle = C.c_void_p()
+        self.device = torch.device(device)
+        with torch.cuda.device(self.device):
+            check(_lib.load().l3ac_stem_plan_create(bw.data_ptr(), bb.data_ptr(), w1h.data_ptr(), b1h.data_ptr(), w2h.data_ptr(),
+                                                    b2h.data_ptr(), 24, C.byref(self.handle)), "l3ac_stem_plan_create")
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            try:
+                _lib.load().l3ac_stem_plan_destroy(h)
+            except Exception:
+                pass
+
+
+def stem_umma(audio: torch.Tensor, plan: StemPlan) -> torch.Tensor:
+    _chk(audio, name="audio")
+    B, T = audio.shape
+    out = torch.empty((B, T, 24), device=audio.device, dtype=torch.float32)
+    _count()
+    with _hook("stem_umma", _nbytes(audio, out), 2.0 * audio.numel() * 3700), torch.cuda.device(audio.device):
+        check(_lib.load().l3ac_stem_umma(plan.handle, _ptr(audio), B, T, _ptr(out), _stream(audio)), "l3ac_stem_umma")
+    return out

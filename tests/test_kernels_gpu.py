@@ -40,9 +40,11 @@ def test_stem(cuda_lib):
     assert max_abs(cf(got), want) < 2e-5
 
 
-@pytest.mark.parametrize("T", [1, 40, 255, 256, 1000, 2717])
-def test_stem_tc(cuda_lib, T):
-    """Tensor-core stem (3-term split-bf16 1x1 convs, two-level pooling) against the oracle's first_block."""
+@pytest.mark.parametrize("impl", ["tcgen05", "mma_sync"])
+@pytest.mark.parametrize("T", [1, 40, 255, 256, 511, 513, 1000, 2717, 80011])
+def test_stem_tc(cuda_lib, T, impl):
+    """Tensor-core stem (3-term split-bf16 1x1 convs, two-level pooling) against the oracle's first_block.
+    impl = tcgen05: l3ac_stem_umma (the product path); mma_sync: the register-level l3ac_stem_tc."""
     B = 3
     sd = {}
     for i in range(5):
@@ -55,7 +57,11 @@ def test_stem_tc(cuda_lib, T):
     bb = torch.cat([sd[f"s.blocks.{i}.1.bias"] for i in range(5)]).to(DEV)
     args = (x[:, 0].contiguous().to(DEV), bw, bb, sd["s.conv_1.weight"][:, :, 0].contiguous().to(DEV),
             sd["s.conv_1.bias"].to(DEV), sd["s.conv_2.weight"][:, :, 0].contiguous().to(DEV), sd["s.conv_2.bias"].to(DEV))
-    got = ops.stem_tc(*args)
+    if impl == "tcgen05":
+        plan = ops.StemPlan(bw, bb, *args[3:], DEV)
+        got = ops.stem_umma(args[0], plan)
+    else:
+        got = ops.stem_tc(*args)
     err = max_abs(cf(got), want)
     print(f"[stem_tc T={T}] max-abs vs oracle {err:.2e}; vs fp32 SIMT stem {max_abs(got, ops.stem(*args)):.2e}")
     assert err < 3e-5 * max(1.0, float(want.abs().max()))       # fp32-class (2^-16 level)
@@ -251,12 +257,14 @@ def test_fused_decoder_tail(cuda_lib, T, impl):
     impl = tcgen05: l3ac_decoder_tail_tc (the product path); mma_sync: the register-level l3ac_decoder_tail."""
     C = 24
     sd = {}
+    ga = torch.Generator().manual_seed(100 + T)            # (seeded: the bf16 noise level depends on the snake alphas)
+    urand = lambda: 0.5 + torch.rand(1, C, 1, generator=ga)
     for j in range(3):
         q = f"blocks.0.block.0.{j}.module.block"
-        sd[f"{q}.0.alpha"], sd[f"{q}.2.alpha"] = (0.5 + torch.rand(1, C, 1)), (0.5 + torch.rand(1, C, 1))
+        sd[f"{q}.0.alpha"], sd[f"{q}.2.alpha"] = urand(), urand()
         sd[f"{q}.1.weight"], sd[f"{q}.1.bias"] = rnd(C, C, 7, seed=10 + j, scale=0.08), rnd(C, seed=20 + j, scale=0.05)
         sd[f"{q}.3.weight"], sd[f"{q}.3.bias"] = rnd(C, C, 1, seed=30 + j, scale=0.15), rnd(C, seed=40 + j, scale=0.05)
-    sd["blocks.0.block.1.alpha"] = 0.5 + torch.rand(1, C, 1)
+    sd["blocks.0.block.1.alpha"] = urand()
     sd["blocks.0.block.2.weight"], sd["blocks.0.block.2.bias"] = rnd(1, C, 7, seed=50, scale=0.1), rnd(1, seed=51, scale=0.05)
     x = rnd(2, C, T, seed=1, scale=0.7)
     bf = lambda t: t.to(torch.bfloat16).float()
@@ -297,7 +305,7 @@ def test_fused_decoder_tail(cuda_lib, T, impl):
     r_kernel, r_emul, r_between = rms(got.cpu(), exact), rms(want, exact), rms(got.cpu(), want)
     print(f"[tail T={T}] max-abs vs exact: kernel {e_kernel:.4f} emulation {e_emul:.4f}; rms {r_kernel:.5f} / {r_emul:.5f}; "
           f"kernel-vs-emulation rms {r_between:.5f}")
-    assert e_kernel < 6e-2 and r_kernel < 1.5 * r_emul + 1e-4
+    assert e_kernel < max(6e-2, 1.3 * e_emul) and r_kernel < 1.5 * r_emul + 1e-4
     assert r_between < 1.5 * r_emul + 1e-4
 
 

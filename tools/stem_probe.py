@@ -15,7 +15,8 @@ B, T = 24, 160110
 args = (rnd(B, T, scale=0.1), rnd(5, 4, 7, scale=0.3), rnd(20, scale=0.1), rnd(80, 20, scale=0.2), rnd(80, scale=0.1),
         rnd(24, 81, scale=0.2), rnd(24, scale=0.1))
 res = {}
-for name, fn in (("stem_tc", ops.stem_tc), ("stem", ops.stem)):
+plan = ops.StemPlan(*args[1:], DEV)
+for name, fn in (("stem_umma", lambda *a: ops.stem_umma(a[0], plan)), ("stem_tc", ops.stem_tc), ("stem", ops.stem)):
     ts = []
     for i in range(8):
         junk.zero_()
@@ -27,4 +28,5 @@ for name, fn in (("stem_tc", ops.stem_tc), ("stem", ops.stem)):
         if i >= 2:
             ts.append(e0.elapsed_time(e1) * 1e3)
     print(f"{name}: {sorted(ts)[len(ts) // 2]:.1f} us for {B * T} samples", flush=True)
+print(f"umma vs fp32 SIMT: {(res['stem_umma'] - res['stem']).abs().max().item():.2e}")
 print(f"max-abs difference {(res['stem_tc'] - res['stem']).abs().max().item():.2e} (values up to {res['stem'].abs().max().item():.2f})")
