@@ -272,6 +272,20 @@ int l3ac_decoder_tail(const float* x, int B, int T, int C, const void* conv_frag
  *   l3ac_decoder_tail_tc   x (B,T,24) fp32 -> out (B,T) fp32 on `stream`; allocates nothing; graph-capturable.
  *   l3ac_tail_plan_destroy frees the device blob.
  * Same constraints on the dilations as l3ac_decoder_tail. */
+/* The fused Residual(ConvUnit) of the thin encode-side stages (C = 24 / 48; see l3ac_convunit_thin_tc) on the 5th-generation
+ * tensor cores: pw_conv1 / pw_conv2 as 3-term split-bf16 tcgen05.mma with TMEM accumulators (fp32-class), one thread per time
+ * step does dwconv7 + LayerNorm, snake + GRN affine and the operand splitting.  Weights go into a plan built once from HOST
+ * arrays (layouts of l3ac_convunit_thin_f32: dw_w [7][C], w1 [4C][C], w2 [C][4C], b1/alpha/scale/shift [4C]).
+ * l3ac_convunit_umma: x (B,T,C) fp32 -> out fp32 (out_dtype L3AC_F32) or the split pair out / out_lo (L3AC_BF16X2); all
+ * pointers 16-byte aligned; allocates nothing. */
+typedef struct l3ac_convunit_plan l3ac_convunit_plan;
+int l3ac_convunit_plan_create(int C, const float* dw_w, const float* dw_b, const float* ln_w, const float* ln_b, float eps,
+                              const float* w1, const float* b1, const float* alpha, const float* scale, const float* shift,
+                              const float* w2, const float* b2, l3ac_convunit_plan** plan_out);
+int l3ac_convunit_plan_destroy(l3ac_convunit_plan* plan);
+int l3ac_convunit_umma(const l3ac_convunit_plan* plan, const float* x, int B, int T, void* out, void* out_lo, int out_dtype,
+                       l3ac_stream_t stream);
+
 /* The encoder stem (V3FirstBlock, see l3ac_stem above) on the 5th-generation tensor cores: the two 1x1 convs are 3-term
  * split-bf16 tcgen05.mma with TMEM accumulators (fp32-class results), one thread per sample does the pooling taps, GELU and
  * operand splitting.  Weights go into a plan built once from HOST arrays in the reference's layout (folded fp32):

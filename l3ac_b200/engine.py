@@ -112,6 +112,7 @@ class Engine:
         # fused MLP (664 vs 190 + 256 us per 24 clips: with one m-tile per warp and 16 warps per SM the kernel is latency-bound,
         # 21 % issue efficiency), so it is off; kept as a tested operand mode of the entry point.
         self.thin_tc_decode = os.environ.get("L3AC_THIN_TC_DECODE", "0") != "0"
+        self.thin_impl = os.environ.get("L3AC_THIN_IMPL", "tcgen05")  # "mma_sync": the register-level cross-check kernel
         self.fused_mlp_max_c = 256
         self.hidden_block_bytes = 0              # >0: L2-blocked ConvUnit MLP (measured slower, see _run_conv_unit)
         self.dec_dtype = {"bf16": torch.bfloat16, "split": ops.SPLIT, "fp32": torch.float32}[precision]
@@ -325,8 +326,14 @@ class Engine:
         ``out_kind=ops.SPLIT`` (encode side, last unit before a GEMM consumer): the result is written as the split-bf16
         pair directly by the producing kernel, which removes a separate fp32 -> split pass over the tensor."""
         B, T, C = x.shape
+        if act_dtype == ops.SPLIT and C in (24, 48) and self.thin_tc and self.thin_impl == "tcgen05":
+            # thin encode-side stages: the whole unit in one tcgen05 kernel (3-term split operands, fp32-class)
+            if u.get("plan") is None:
+                u["plan"] = ops.ConvUnitPlan(u["dw_w"], u["dw_b"], u["ln_w"], u["ln_b"], EPS, u["pw1"].w32, u["pw1"].bias, u["alpha"],
+                                             u["scale"], u["shift"], u["pw2"].w32, u["pw2"].bias, self.device)
+            return ops.convunit_umma(x, u["plan"], out_dtype=out_kind)
         if act_dtype == ops.SPLIT and C in (24, 48) and self.thin_tc:
-            # thin encode-side stages: the whole unit in one tensor-core kernel (3-term split operands, fp32-class)
+            # (cross-check path, L3AC_THIN_IMPL=mma_sync: the register-level kernel)
             return ops.convunit_thin_tc(x, u["dw_w"], u["dw_b"], u["ln_w"], u["ln_b"], EPS, u["pw1"].w32, u["pw1"].bias,
                                         u["alpha"], u["scale"], u["shift"], u["pw2"].w32, u["pw2"].bias, out_dtype=out_kind)
         if act_dtype == torch.bfloat16 and C == 48 and self.thin_tc_decode and out_kind == torch.float32:

@@ -566,3 +566,44 @@ def stem_umma(audio: torch.Tensor, plan: StemPlan) -> torch.Tensor:
     with _hook("stem_umma", _nbytes(audio, out), 2.0 * audio.numel() * 3700), torch.cuda.device(audio.device):
         check(_lib.load().l3ac_stem_umma(plan.handle, _ptr(audio), B, T, _ptr(out), _stream(audio)), "l3ac_stem_umma")
     return out
+
+
+class ConvUnitPlan:
+    """Packed weights of the tcgen05 thin ConvUnit (``l3ac_convunit_plan``, C = 24 / 48): built once from folded fp32 tensors."""
+
+    def __init__(self, dw_w, dw_b, ln_w, ln_b, eps: float, w1, b1, alpha, scale, shift, w2, b2, device):
+        host = lambda t: t.detach().to("cpu", torch.float32).contiguous()
+        self._keep = [host(t) for t in (dw_w, dw_b, ln_w, ln_b, w1, b1, alpha, scale, shift, w2, b2)]
+        dw, db, lw, lb, w1h, b1h, al, sc, sh, w2h, b2h = self._keep
+        self.C = int(db.numel())
+        if tuple(dw.shape) != (7, self.C) or tuple(w1h.shape) != (4 * self.C, self.C) or tuple(w2h.shape) != (self.C, 4 * self.C):
+            raise ValueError("ConvUnitPlan: dw_w (7,C), w1 (4C,C), w2 (C,4C) expected")
+        self.handle = C.c_void_p()
+        self.device = torch.device(device)
+        with torch.cuda.device(self.device):
+            check(_lib.load().l3ac_convunit_plan_create(self.C, dw.data_ptr(), db.data_ptr(), lw.data_ptr(), lb.data_ptr(), float(eps),
+                                                        w1h.data_ptr(), b1h.data_ptr(), al.data_ptr(), sc.data_ptr(), sh.data_ptr(),
+                                                        w2h.data_ptr(), b2h.data_ptr(), C.byref(self.handle)), "l3ac_convunit_plan_create")
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            try:
+                _lib.load().l3ac_convunit_plan_destroy(h)
+            except Exception:
+                pass
+
+
+def convunit_umma(x: torch.Tensor, plan: ConvUnitPlan, out_dtype=torch.float32):
+    """Fused Residual(ConvUnit) for C = 24 / 48 on tcgen05: x (B, T, C) fp32 -> same shape (fp32, or the split pair)."""
+    _chk(x, name="x")
+    B, T, Cc = x.shape
+    if Cc != plan.C:
+        raise ValueError(f"convunit_umma: plan is for C = {plan.C}, got {Cc}")
+    if out_dtype not in (torch.float32, SPLIT):
+        raise ValueError("convunit_umma emits fp32 or the split-bf16 pair")
+    out, hi, lo = _empty_act(tuple(x.shape), x.device, out_dtype)
+    _count()
+    with _hook("convunit_thin_umma", _nbytes(x) + B * T * Cc * 4, 2.0 * B * T * (7 * Cc + 8 * Cc * Cc)), torch.cuda.device(x.device):
+        check(_lib.load().l3ac_convunit_umma(plan.handle, _ptr(x), B, T, _ptr(hi), _ptr(lo), _DT[out_dtype], _stream(x)), "l3ac_convunit_umma")
+    return out

@@ -310,6 +310,31 @@ def test_fused_decoder_tail(cuda_lib, T, impl):
 
 
 @pytest.mark.parametrize("C", [24, 48])
+@pytest.mark.parametrize("T", [1, 100, 255, 256, 257, 515, 1000, 2717, 40011])
+def test_fused_thin_convunit_umma(cuda_lib, C, T):
+    """tcgen05 Residual(ConvUnit) for C = 24 / 48 (l3ac_convunit_umma, 3-term split-bf16 operands) against the oracle's conv_unit."""
+    ga = torch.Generator().manual_seed(7)
+    sd = {"u.dw_conv.weight": rnd(C, 1, 7, seed=1, scale=0.3), "u.dw_conv.bias": rnd(C, seed=2, scale=0.1),
+          "u.norm.weight": 1 + rnd(C, seed=3, scale=0.1), "u.norm.bias": rnd(C, seed=4, scale=0.1),
+          "u.pw_conv1.weight": rnd(4 * C, C, seed=5, scale=0.2), "u.pw_conv1.bias": rnd(4 * C, seed=6, scale=0.1),
+          "u.act.alpha": 0.5 + torch.rand(1, 1, 4 * C, generator=ga), "u.grn.gamma": rnd(1, 4 * C, seed=7, scale=0.1),
+          "u.grn.beta": rnd(1, 4 * C, seed=8, scale=0.1),
+          "u.pw_conv2.weight": rnd(C, 4 * C, seed=9, scale=0.1), "u.pw_conv2.bias": rnd(C, seed=10, scale=0.1)}
+    x = rnd(3, C, T, seed=11)
+    want = O.conv_unit(sd, "u", x)
+    plan = ops.ConvUnitPlan(sd["u.dw_conv.weight"][:, 0].t(), sd["u.dw_conv.bias"], sd["u.norm.weight"], sd["u.norm.bias"], 1e-8,
+                            sd["u.pw_conv1.weight"], sd["u.pw_conv1.bias"], sd["u.act.alpha"].flatten(), 1 + sd["u.grn.gamma"].flatten(),
+                            sd["u.grn.beta"].flatten(), sd["u.pw_conv2.weight"], sd["u.pw_conv2.bias"], DEV)
+    got = ops.convunit_umma(cl(x), plan)
+    err = max_abs(cf(got), want)
+    print(f"[thin_umma C={C} T={T}] max-abs vs oracle {err:.2e}")
+    assert err < 3e-5 * max(1.0, float(want.abs().max()))      # fp32-class (2^-16 level), same bound as the split tcgen05 GEMM
+    sp = ops.convunit_umma(cl(x), plan, out_dtype=ops.SPLIT)
+    ref = ops.split_bf16(got)
+    assert torch.equal(sp.hi, ref.hi) and torch.equal(sp.lo, ref.lo)
+
+
+@pytest.mark.parametrize("C", [24, 48])
 @pytest.mark.parametrize("T", [1, 100, 515, 1000, 2717])
 def test_fused_thin_convunit_tc(cuda_lib, C, T):
     """Tensor-core Residual(ConvUnit) for C = 24 / 48 (3-term split-bf16 operands) against the oracle's conv_unit."""

@@ -33,7 +33,10 @@ for C, T in ((24, 160110), (48, 26685), (48, 80055)):
     args = (rnd(7, C, scale=0.3), rnd(C, scale=0.1), 1 + rnd(C, scale=0.1), rnd(C, scale=0.1), 1e-8, rnd(4 * C, C, scale=0.2),
             rnd(4 * C, scale=0.1), (0.5 + torch.rand(4 * C, generator=g)).to(DEV), 1 + rnd(4 * C, scale=0.1), rnd(4 * C, scale=0.1),
             rnd(C, 4 * C, scale=0.1), rnd(C, scale=0.1))
+    plan = ops.ConvUnitPlan(*args, DEV)
     for kind in (torch.float32, ops.SPLIT):
+        tu, outu = timed(lambda: ops.convunit_umma(x, plan, out_dtype=kind))
+        print(f"thin_umma (tcgen05) C={C} rows={B * T} out={'split' if kind == ops.SPLIT else 'f32'}: {tu:.1f} us", flush=True)
         t, out = timed(lambda: ops.convunit_thin_tc(x, *args, out_dtype=kind))
         o = out if kind == torch.float32 else out.hi.float() + out.lo.float()
         msg = f"thin_tc C={C} rows={B * T} out={'split' if kind == ops.SPLIT else 'f32'}: {t:.1f} us ({B * T * C * 8 / t / 1e3:.0f} GB/s)"
