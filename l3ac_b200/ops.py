@@ -305,10 +305,9 @@ def local_attention(qkv: torch.Tensor, bias_table: torch.Tensor, heads: int, win
     return out
 
 
-# "auto": tcgen05 (l3ac_local_attention_umma) once a clip has >= 8 query tiles of 128 -- the frame-rate layers, 85 % of the
-# attention work; the token-rate layers (T ~ 600: 1-5 key tiles per CTA, set-up bound) stay on the register-level kernel,
-# measured 35 vs 37 us per 24 clips.  "tcgen05" / "mma_sync" force one kernel.
-ATTENTION_IMPL = os.environ.get("L3AC_ATT_IMPL", "auto")
+# "tcgen05": l3ac_local_attention_umma everywhere (the product path).  "auto" keeps the token-rate layers (T < 897: 1-5 key tiles
+# per CTA, set-up bound; 35 vs 37 us per 24 clips) on the register-level mma.sync kernel; "mma_sync" forces that kernel.
+ATTENTION_IMPL = os.environ.get("L3AC_ATT_IMPL", "tcgen05")
 
 
 def local_attention_tc(qkv, bias_table: torch.Tensor, heads: int, window: int, out_dtype=torch.float32, impl: Optional[str] = None):
@@ -328,12 +327,12 @@ def local_attention_tc(qkv, bias_table: torch.Tensor, heads: int, window: int, o
     _count()
     # useful MACs: query p sees (w if p >= w else 0) + (p mod w) + 1 keys; two products of D MACs each
     keys = sum((window if p >= window else 0) + (p % window) + 1 for p in range(T)) if OP_HOOK is not None else 0
-    with _hook(("local_attention_tc_split" if split else "local_attention_tc") + ("_umma" if (impl or ATTENTION_IMPL) == "tcgen05" or ((impl or ATTENTION_IMPL) == "auto" and T >= 897) else ""), _nbytes(qkv, out),
+    which = impl or ATTENTION_IMPL
+    if which == "auto":
+        which = "tcgen05" if T >= 897 else "mma_sync"
+    with _hook(("local_attention_tc_split" if split else "local_attention_tc") + ("_umma" if which == "tcgen05" else ""), _nbytes(qkv, out),
                2.0 * 2 * B * heads * keys * D * (1 if not split else 1)), torch.cuda.device(hi.device):
         lib = _lib.load()
-        which = impl or ATTENTION_IMPL
-        if which == "auto":
-            which = "tcgen05" if T >= 897 else "mma_sync"
         fn = lib.l3ac_local_attention_umma if which == "tcgen05" else lib.l3ac_local_attention_tc
         check(fn(_ptr(hi), _ptr(qkv.lo) if split else None, _ptr(bias_table), B, T, heads, D,
                  window, _ptr(o_hi), _ptr(o_lo), _DT[out_dtype], _stream(hi)), "l3ac_local_attention_tc")
