@@ -5,24 +5,29 @@
 // only the (B, T) waveform is written.
 //
 // The contractions run on the 5th-generation tensor cores with the A operand written by threads (umma.cuh):
-//   * one CTA owns 1024 consecutive samples of one clip (940 outputs + a 42-sample halo per side = the receptive field
-//     3*(1+3+9)+3) as eight 128-row blocks; one THREAD owns one row of two blocks, i.e. exactly the TMEM lane its
-//     tcgen05.ld reads, and keeps the fp32 residual stream of its rows in registers;
-//   * bf16(snake(x)) is stored as 8-channel planes [3 (+1 zero)][27 guard + 1024 + 27][8]; the k7 conv of a block is 11
+//   * one CTA owns 896 consecutive samples of one clip (812 outputs + a 42-sample halo per side = the receptive field
+//     3*(1+3+9)+3) as seven 128-row blocks; one THREAD owns one row, i.e. exactly the TMEM lane its tcgen05.ld reads;
+//   * the fp32 RESIDUAL STREAM LIVES IN TMEM (24 columns of the row's lane): the 1x1 conv of every LegacyUnit is issued with
+//     accumulate = 1 INTO it, so `x += conv1x1(h)` costs no instruction at all, nothing is carried in registers between
+//     stages (64 registers per thread, 31 warps per SM), and a stage that needs x reads the row back and adds the biases
+//     accumulated so far (kernel-parameter constants).  With the residual in registers (two rows per thread, 16 row-owner
+//     warps) the same kernel needed 1843 instead of ~1200 warp-instructions per row and ran at 494 us per 24 clips; this
+//     version takes 347 us (mma.sync kernel: 537 us);
+//   * bf16(snake(x)) is stored as 8-channel planes [3 (+1 zero)][27 guard + 896 + 27][8]; the k7 conv of a block is 11
 //     tcgen05.mma (M=128, N=32, K=16) whose A descriptors are the SAME tile shifted by (tap-3)*dilation rows -- nine of
 //     them pair the taps (2p, 2p+1) of one 8-channel plane through LBO = dilation * 16 B, two cover tap 6 -- so the
 //     conv's 168-long K axis costs 11 K-steps instead of 7 x 2 channel-padded ones and no im2col is ever materialised;
 //   * the accumulator row comes back with tcgen05.ld, bias + snake run on registers, bf16(h) goes to the second plane
-//     buffer and two more MMAs (K = 24 -> 32) do the 1x1 conv; its result is added to the register residual;
+//     buffer (h = 0 on rows outside the clip, whose residual row must stay zero) and two more MMAs (K = 24 -> 32) do the 1x1 conv;
 //   * the final Conv1d(24 -> 1, k7) has its 7 taps in the N dimension (P[t'][j] = s[t'] . w[j], A = snake(x) as a
 //     split-bf16 pair, 3 terms hi*Whi + lo*Whi + hi*Wlo: fp32-class) + a diagonal sum y[t] = sum_j P[t+j-3][j] through
 //     shared memory.
-// Warps 0-15: row owners (warp & 3 = TMEM lane quadrant, warp >> 2 = which pair of blocks).  Warps 16-18 issue the MMAs
-// through one elected lane each (16 / 17: the k7 convs and the final conv of the even / odd blocks, 18: the 1x1 convs,
-// so that a block's 1x1 conv never queues behind the other blocks' k7 convs and one issuer's barrier polls overlap the
-// other's MMAs); all hand-overs are mbarriers per 128-row block, so the tensor pipe, the SFU (168 sines per sample: the bound of this kernel) and the FMA pipe overlap
+// Warps 0-27: row owners (warp & 3 = TMEM lane quadrant, warp >> 2 = block).  Warps 28-30 issue the MMAs through one elected
+// lane each (28 / 29: the k7 convs and the final conv of the even / odd blocks, 30: the 1x1 convs, so that a block's 1x1
+// conv never queues behind the other blocks' k7 convs and one issuer's barrier polls overlap the other's MMAs); all
+// hand-overs are mbarriers per 128-row block, so the tensor pipe, the SFU (168 sines per sample) and the FMA pipe overlap
 // across blocks without any CTA-wide barrier in the steady state.  Per-channel parameters live in the kernel-parameter
-// constant bank: with one row per thread they are warp-uniform immediates of the FMUL / FFMA instructions.
+// constant bank: with one row per thread they are warp-uniform operands of the FMUL / FFMA instructions.
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -38,10 +43,10 @@ using namespace l3ac::umma;
 constexpr int kC = 24;
 constexpr int kHalo = 42;
 constexpr int kGuard = 27;                       // largest conv reach (3 taps x dilation 9)
-constexpr int kBlocks = 8;
-constexpr int kRows = kBlocks * 128;             // 1024
-constexpr int kOut = kRows - 2 * kHalo;          // 940
-constexpr int kRowsTot = kRows + 2 * kGuard;     // 1078
+constexpr int kBlocks = 7;
+constexpr int kRows = kBlocks * 128;             // 896
+constexpr int kOut = kRows - 2 * kHalo;          // 812
+constexpr int kRowsTot = kRows + 2 * kGuard;     // 950
 constexpr int kPlaneBytes = kRowsTot * 16;       // one 8-channel plane
 constexpr int kBufBytes = 4 * kPlaneBytes;       // 3 channel planes + 1 zero plane (K padding)
 constexpr int kConvMmas = 11;
@@ -52,9 +57,9 @@ constexpr int kWBytes = 3 * kWConvBytes + 3 * kWPwBytes + kWFinBytes;
 constexpr int kPtStride = kRows + 8;             // P^T[tap][row + 4]
 constexpr int kPtBytes = 7 * kPtStride * 4;
 constexpr int kNumBars = 5 * kBlocks;
-constexpr int kWorkerWarps = 16;
+constexpr int kWorkerWarps = 4 * kBlocks;        // one row per thread: 28 row-owner warps
 constexpr int kConvWarp = kWorkerWarps, kPwWarp = kWorkerWarps + 2;     // MMA issuers: two for the k7 convs (even / odd blocks), one for the 1x1 convs
-constexpr int kThreads = 32 * (kWorkerWarps + 3);       // 19 warps at 96 registers (the register file is granted in 32-register steps)
+constexpr int kThreads = 32 * (kWorkerWarps + 3);       // 31 warps at 64 registers
 constexpr int kSmemBytes = 2 * kBufBytes + kWBytes + kPtBytes + 8 * kNumBars + 16;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 static_assert(kBufBytes % 16 == 0 && kWBytes % 16 == 0 && kPtBytes % 16 == 0, "16-byte carve-up");
@@ -66,7 +71,7 @@ struct Params {
     int B, T;
     int dil[3];
     float bias_f;
-    float conv_b[3][kC], pw_b[3][kC], a0[3][kC], ia0[3][kC], a1[3][kC], ia1[3][kC], af[kC], iaf[kC];
+    float conv_b[3][kC], cum_b[3][kC], a0[3][kC], ia0[3][kC], a1[3][kC], ia1[3][kC], af[kC], iaf[kC];      // cum_b[u] = pw_b[0] + .. + pw_b[u]
 };
 
 #ifdef L3AC_TAIL_TRACE
@@ -129,8 +134,9 @@ struct UnitPhase {
             st_shared_v4(dst + c * kPlaneBytes, pk[0], pk[1], pk[2], pk[3]);
         }
     }
-    // h = bf16(snake(conv + bias, alpha1)) -> plane buffer H   (8 accumulator columns at a time: 8 live registers, not 24)
-    static __device__ __forceinline__ void snake_mid(const Params& p, uint32_t taddr, uint32_t dst) {
+    // h = bf16(snake(conv + bias, alpha1)) -> plane buffer H   (8 accumulator columns at a time; rows outside the clip: h = 0,
+    // so that the 1x1 conv adds nothing to their -- zero -- residual row)
+    static __device__ __forceinline__ void snake_mid(const Params& p, uint32_t taddr, uint32_t dst, bool valid) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             uint32_t v[8];
@@ -142,21 +148,20 @@ struct UnitPhase {
                 const int e = 8 * c + 2 * i;
                 pk[i] = pack_bf16x2(snake1(__uint_as_float(v[2 * i]) + p.conv_b[U][e], p.a1[U][e], p.ia1[U][e]),
                                     snake1(__uint_as_float(v[2 * i + 1]) + p.conv_b[U][e + 1], p.a1[U][e + 1], p.ia1[U][e + 1]));
+                pk[i] = valid ? pk[i] : 0u;
             }
             st_shared_v4(dst + c * kPlaneBytes, pk[0], pk[1], pk[2], pk[3]);
         }
     }
-    // x += conv1x1(h) + bias  (rows outside the clip stay zero)
-    static __device__ __forceinline__ void residual(const Params& p, uint32_t taddr, float (&xr)[kC], bool valid) {
+    // the residual stream after unit U: the TMEM row the 1x1 convs accumulated into + their biases (zero outside the clip)
+    static __device__ __forceinline__ void load_x(const Params& p, uint32_t taddr, float (&xr)[kC], bool valid) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             uint32_t v[8];
             tmem_ld8(taddr + 8 * c, v);
             tmem_ld_wait();
-            if (valid) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) xr[8 * c + i] += __uint_as_float(v[i]) + p.pw_b[U][8 * c + i];
-            }
+            for (int i = 0; i < 8; ++i) xr[8 * c + i] = valid ? __uint_as_float(v[i]) + p.cum_b[U][8 * c + i] : 0.f;
         }
     }
 };
@@ -245,7 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_tail_tc_kernel(const __gr
                     tc_fence_after();
                     if (leader && b_first == 0) TAIL_TRACE(4, 10, u, b);
                     if (leader) {
-                        const uint32_t dcol = tmem_base + 64 * b, boff = kBlockStep * b;
+                        const uint32_t dcol = tmem_base + 64 * b + 32, boff = kBlockStep * b;
 #pragma unroll
                         for (int j = 0; j < kConvMmas; ++j)
                             tc_mma_bf16(dcol, kDescHi | (a_lo[j] + boff), kDescHi | (wc_lo + j * (1024 >> 4)), idesc32, j > 0 ? 1u : 0u);
@@ -269,7 +274,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_tail_tc_kernel(const __gr
                 if (leader && b_first == 0) TAIL_TRACE(4, 10, 3, b);
                 if (leader) {
                     const uint32_t ra = (rows_a + kBlockStep * b) | lbo_plane, rh = (rows_h + kBlockStep * b) | lbo_plane;
-                    const uint32_t dcol = tmem_base + 64 * b;
+                    const uint32_t dcol = tmem_base + 64 * b + 32;
 #pragma unroll
                     for (int term = 0; term < 3; ++term) {
                         const uint32_t arow = term == 1 ? rh : ra;
@@ -308,8 +313,8 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_tail_tc_kernel(const __gr
                         const uint32_t a0 = (rows_h + kBlockStep * b) | lbo_plane;
 #pragma unroll
                         for (int m = 0; m < 2; ++m)
-                            tc_mma_bf16(tmem_base + 64 * b + 32, kDescHi | (a0 + m * (2 * kPlaneBytes >> 4)), kDescHi | (wp_lo + m * (1024 >> 4)),
-                                        idesc32, m > 0 ? 1u : 0u);
+                            tc_mma_bf16(tmem_base + 64 * b, kDescHi | (a0 + m * (2 * kPlaneBytes >> 4)), kDescHi | (wp_lo + m * (1024 >> 4)),
+                                        idesc32, 1u);            // accumulates INTO the residual row: x += conv1x1(h)
                         tc_commit(o_ready + 8 * b);
                     }
                     __syncwarp();
@@ -317,76 +322,74 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_tail_tc_kernel(const __gr
             }
         }
     } else if (warp < kWorkerWarps) {
-        // =============================================================== row owners
-        const int wg = warp >> 2, quad = warp & 3;
-        const int r0 = 128 * wg + 32 * quad + lane;              // rows r0 (block wg) and r0 + 512 (block wg + 4)
-        const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
-        float xr[2][kC];
-        bool valid[2];
+        // =============================================================== row owners: one row of one block per thread.  The fp32
+        // residual row lives in TMEM columns [64 b, 64 b + 24) of the thread's lane: the 1x1 convs accumulate into it, a stage
+        // that needs it reads it back (+ the accumulated biases), nothing is carried in registers between stages.
+        const int blk = warp >> 2, quad = warp & 3;
+        const int r = 128 * blk + 32 * quad + lane;
+        const uint32_t tx = tmem_base + ((uint32_t)(quad * 32) << 16) + 64 * blk, td = tx + 32;
+        const uint32_t row_off = (uint32_t)(kGuard + r) * 16;
+        float xr[kC];
+        bool valid = false;
         TAIL_TRACE_DECL
-        const bool tracer = quad == 0 && lane == 0;
+        const bool tracer = quad == 0 && lane == 0 && (blk & 1) == 0;
+        [[maybe_unused]] const int wg = blk >> 1;                     // (trace role)
         int tile = blockIdx.x;
         int clip = 0, t_first = 0;
         if (tile < n_tiles) {
             clip = tile / tiles_per_clip;
             t_first = (tile - clip * tiles_per_clip) * kOut - kHalo;
-            const float* xb = p.x + (long long)clip * p.T * kC;
-#pragma unroll
-            for (int s = 0; s < 2; ++s) valid[s] = load_row(xr[s], xb, t_first + r0 + 512 * s, p.T);
+            valid = load_row(xr, p.x + (long long)clip * p.T * kC, t_first + r, p.T);
         }
         int it = 0;
         for (; tile < n_tiles; ++it) {
             const int cur_clip = clip, cur_t_first = t_first;
-            // Stage order per thread: the chain of one block runs ahead as far as its data allows -- S2 (snake of the conv
-            // result), S3 (residual) and the NEXT unit's operand S1 of block wg, then the same for block wg + 4 -- so the
-            // k7 convs of unit u+1 start on the first blocks while those of unit u are still running on the last ones.
-            {
+            const bool cur_valid = valid;
+            // ---- the tile's rows -> TMEM; unit 0's operand straight from the registers
+            if (tracer) TAIL_TRACE(wg, 1, 0, blk);
 #pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    const int b = wg + 4 * s;
-                    if (tracer) TAIL_TRACE(wg, 1, 0, b);
-                    UnitPhase<0>::snake_in(p, xr[s], buf_a + (kGuard + r0 + 512 * s) * 16);
-                    fence_async_smem();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(a_ready + 8 * b);
-                    if (tracer) TAIL_TRACE(wg, 2, 0, b);
-                }
+            for (int c = 0; c < 3; ++c) {
+                uint32_t v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = __float_as_uint(xr[8 * c + i]);
+                tmem_st8(tx + 8 * c, v);
             }
+            UnitPhase<0>::snake_in(p, xr, buf_a + row_off);
+            tmem_st_wait();
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_ready + 8 * blk);
+            if (tracer) TAIL_TRACE(wg, 2, 0, blk);
 #define L3AC_TAIL_UNIT(U)                                                                                     \
-            _Pragma("unroll") for (int s = 0; s < 2; ++s) {                                                   \
-                const int b = wg + 4 * s;                                                                     \
-                const uint32_t row_off = (kGuard + r0 + 512 * s) * 16;                                        \
-                mbar_wait_tag(d_ready + 8 * b, U & 1, 10 + 4 * s);                                            \
+            {                                                                                                 \
+                mbar_wait_tag(d_ready + 8 * blk, U & 1, 10);                                                  \
                 tc_fence_after();                                                                             \
-                if (tracer) TAIL_TRACE(wg, 3, U, b);                                                          \
-                UnitPhase<U>::snake_mid(p, tlane + 64 * b, buf_h + row_off);                                  \
+                if (tracer) TAIL_TRACE(wg, 3, U, blk);                                                        \
+                UnitPhase<U>::snake_mid(p, td, buf_h + row_off, cur_valid);                                   \
                 fence_async_smem();                                                                           \
                 tc_fence_before();                                                                            \
                 __syncwarp();                                                                                 \
-                if (lane == 0) mbar_arrive(h_ready + 8 * b);                                                  \
-                if (tracer) TAIL_TRACE(wg, 4, U, b);                                                          \
-                mbar_wait_tag(o_ready + 8 * b, (it + U) & 1, 11 + 4 * s);                                     \
+                if (lane == 0) mbar_arrive(h_ready + 8 * blk);                                                \
+                if (tracer) TAIL_TRACE(wg, 4, U, blk);                                                        \
+                mbar_wait_tag(o_ready + 8 * blk, (it + U) & 1, 11);                                           \
                 /* This block's rows of buffer A are also read by the k7 convs of both neighbour blocks (other issuers than   */ \
                 /* the one whose commit was seen above): they must be through before the rows are overwritten.  Neither      */ \
                 /* barrier can be a phase ahead: every conv of a neighbour block waits for THIS block's next a_ready first.  */ \
-                /* (Polled before the residual update so that the compiler cannot hoist the next snake above the spin loops  */ \
-                /* and spill its results.)                                                                                   */ \
-                if (b + 1 < kBlocks) mbar_wait_tag(d_ready + 8 * (b + 1), U & 1, 12 + 4 * s);                 \
-                if (b > 0) mbar_wait_tag(d_ready + 8 * (b - 1), U & 1, 13 + 4 * s);                           \
+                if (blk + 1 < kBlocks) mbar_wait_tag(d_ready + 8 * (blk + 1), U & 1, 12);                     \
+                if (blk > 0) mbar_wait_tag(d_ready + 8 * (blk - 1), U & 1, 13);                               \
                 tc_fence_after();                                                                             \
-                if (tracer) TAIL_TRACE(wg, 5, U, b);                                                          \
-                UnitPhase<U>::residual(p, tlane + 64 * b + 32, xr[s], valid[s]);                              \
-                if (tracer) TAIL_TRACE(wg, 6, U, b);                                                          \
-                if (tracer) TAIL_TRACE(wg, 1, U + 1, b);                                                      \
+                if (tracer) TAIL_TRACE(wg, 5, U, blk);                                                        \
+                UnitPhase<U>::load_x(p, tx, xr, cur_valid);                                                   \
+                if (tracer) TAIL_TRACE(wg, 1, U + 1, blk);                                                    \
                 if (U < 2) {                                                                                  \
-                    UnitPhase<(U < 2 ? U + 1 : 0)>::snake_in(p, xr[s], buf_a + row_off);                      \
+                    UnitPhase<(U < 2 ? U + 1 : 0)>::snake_in(p, xr, buf_a + row_off);                         \
                 } else {    /* final conv operand: s = snake(x, alpha_f) as a split pair, hi -> buffer A, lo -> buffer H */ \
                     _Pragma("unroll") for (int c = 0; c < 3; ++c) {                                           \
                         uint32_t ph[4], pl[4];                                                                \
                         _Pragma("unroll") for (int i = 0; i < 4; ++i) {                                       \
                             const int e = 8 * c + 2 * i;                                                      \
-                            const float s0 = snake1(xr[s][e], p.af[e], p.iaf[e]), s1 = snake1(xr[s][e + 1], p.af[e + 1], p.iaf[e + 1]); \
+                            const float s0 = snake1(xr[e], p.af[e], p.iaf[e]), s1 = snake1(xr[e + 1], p.af[e + 1], p.iaf[e + 1]); \
                             ph[i] = pack_bf16x2(s0, s1);                                                      \
                             pl[i] = pack_bf16x2(s0 - __uint_as_float(ph[i] << 16), s1 - __uint_as_float(ph[i] & 0xffff0000u)); \
                         }                                                                                     \
@@ -397,47 +400,40 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_tail_tc_kernel(const __gr
                 fence_async_smem();                                                                           \
                 tc_fence_before();                                                                            \
                 __syncwarp();                                                                                 \
-                if (lane == 0) mbar_arrive(a_ready + 8 * b);                                                  \
-                if (tracer) TAIL_TRACE(wg, 2, U + 1, b);                                                      \
+                if (lane == 0) mbar_arrive(a_ready + 8 * blk);                                                \
+                if (tracer) TAIL_TRACE(wg, 2, U + 1, blk);                                                    \
             }
             L3AC_TAIL_UNIT(0)
             L3AC_TAIL_UNIT(1)
             L3AC_TAIL_UNIT(2)
 #undef L3AC_TAIL_UNIT
-            // the residual registers are dead: fetch the next tile's rows while the final conv runs
+            // the row registers are dead: fetch the next tile's row while the final conv runs
             tile += gridDim.x;
             if (tile < n_tiles) {
                 clip = tile / tiles_per_clip;
                 t_first = (tile - clip * tiles_per_clip) * kOut - kHalo;
-                const float* xb = p.x + (long long)clip * p.T * kC;
-#pragma unroll
-                for (int s = 0; s < 2; ++s) valid[s] = load_row(xr[s], xb, t_first + r0 + 512 * s, p.T);
+                valid = load_row(xr, p.x + (long long)clip * p.T * kC, t_first + r, p.T);
             }
-            // P rows -> P^T in shared memory
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                const int b = wg + 4 * s;
-                mbar_wait(d_ready + 8 * b, 1);
+            // P row -> P^T in shared memory
+            {
+                mbar_wait(d_ready + 8 * blk, 1);
                 tc_fence_after();
-                if (tracer) TAIL_TRACE(wg, 7, 3, b);
+                if (tracer) TAIL_TRACE(wg, 7, 3, blk);
                 uint32_t v[8];
-                tmem_ld8(tlane + 64 * b, v);
+                tmem_ld8(td, v);
                 tmem_ld_wait();
-                float* dst = pt + 4 + r0 + 512 * s;
+                float* dst = pt + 4 + r;
 #pragma unroll
                 for (int j = 0; j < 7; ++j) dst[j * kPtStride] = __uint_as_float(v[j]);
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(pt_ready + 8 * b);
+                if (lane == 0) mbar_arrive(pt_ready + 8 * blk);
             }
             // y[t] = tanh(bias + sum_j P[t + j - 3][j])
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                const int b = wg + 4 * s;
-                const int r = r0 + 512 * s;
-                if (b > 0) mbar_wait(pt_ready + 8 * (b - 1), it & 1);
-                mbar_wait(pt_ready + 8 * b, it & 1);
-                if (b + 1 < kBlocks) mbar_wait(pt_ready + 8 * (b + 1), it & 1);
+            {
+                if (blk > 0) mbar_wait(pt_ready + 8 * (blk - 1), it & 1);
+                mbar_wait(pt_ready + 8 * blk, it & 1);
+                if (blk + 1 < kBlocks) mbar_wait(pt_ready + 8 * (blk + 1), it & 1);
                 const int t = cur_t_first + r;
                 if (r >= kHalo && r < kRows - kHalo && t < p.T) {
                     const float* src = pt + 4 + r - 3;
@@ -448,7 +444,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_tail_tc_kernel(const __gr
                     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(acc));
                     p.out[(long long)cur_clip * p.T + t] = y;
                 }
-                if (tracer) TAIL_TRACE(wg, 8, 3, b);
+                if (tracer) TAIL_TRACE(wg, 8, 3, blk);
             }
         }
     }
@@ -548,7 +544,7 @@ extern "C" int l3ac_tail_plan_create(const float* conv_w, const float* conv_b, c
         p.dil[u] = dilations[u];
         for (int c = 0; c < kC; ++c) {
             p.conv_b[u][c] = conv_b[u * kC + c];
-            p.pw_b[u][c] = pw_b[u * kC + c];
+            p.cum_b[u][c] = pw_b[u * kC + c] + (u > 0 ? p.cum_b[u - 1][c] : 0.f);
             p.a0[u][c] = alpha0[u * kC + c];
             p.ia0[u][c] = 1.0f / (alpha0[u * kC + c] + l3ac::kEps);
             p.a1[u][c] = alpha1[u * kC + c];
