@@ -304,6 +304,76 @@ int l3ac_tail_plan_create(const float* conv_w, const float* conv_b, const float*
 int l3ac_tail_plan_destroy(l3ac_tail_plan* plan);
 int l3ac_decoder_tail_tc(const l3ac_tail_plan* plan, const float* x, int B, int T, float* out, l3ac_stream_t stream);
 
+/* ==========================================================================================
+ * Step-level interface: the two methods of the hot path as two calls.
+ *   l3ac_encode = L3AC.encode_audio (l3ac/__init__.py:108-114): preprocess -> Encoder -> LocalEncoder /
+ *                 CompressedLocalEncoderWithCache -> VQEmbed;
+ *   l3ac_decode = L3AC.decode_audio (l3ac/__init__.py:116-121): VQEmbed.to_features -> LocalDecoder /
+ *                 CompressedLocalDecoderWithCache -> Decoder.
+ * A handle (l3ac_codec) owns the packed weights and the launch sequence over the operator-level entry points above, in the
+ * product precision (encode side 3-term split-bf16, decode side bf16, fp32 accumulation and residual stream).
+ *
+ * l3ac_create takes the reference's checkpoint as HOST fp32 tensors named "<module>.<state_dict key>" with module in
+ * encoder / quantizer / decoder / en_encoder / en_decoder (the five <module>.pt files of l3ac/xtract/nn/module.py:36-54,
+ * weight-norm pairs parametrizations.weight.original0/1 included) and the ModelConfig fields of the TOML
+ * (l3ac/codec.py:13-36, l3ac/en_codec.py:9-19); it folds / packs them and uploads them to the CURRENT device.
+ * Restrictions (L3AC_EUNSUPPORTED otherwise): feature_dim 128, first encoder / last decoder width 24, base_unit 'normal',
+ * use_norm, use_snake_act, decoder_last_layer 'legacy', en_coder_dynamic_pos true, en_coder_cache_size 0 -- the four
+ * published configs.  l3ac_last_error() names the offending tensor / field (thread-local string).
+ *
+ * l3ac_encode / l3ac_decode take DEVICE pointers, allocate nothing, never synchronise and enqueue everything on `stream`
+ * (graph-capturable).  Activations live in `workspace` (16-byte aligned device memory of at least
+ * l3ac_workspace_bytes(codec, B, T) bytes, T in samples; one workspace per concurrently running call).
+ *   l3ac_encode: audio (B, T) fp32, any T >= 1 (right-padded to a multiple of the hop like Codec.preprocess) ->
+ *                indices (B, T_tok) int32, T_tok = ceil(T / hop); q_feature (B, T_tok, feature_dim) fp32 and
+ *                level_indices (B, T_tok, n_levels) fp32 are optional (NULL).
+ *   l3ac_decode: indices (B, T_tok) int32 / int64 (indices_are_i64) or, when q_feature != NULL, the quantized features
+ *                (B, T_tok, feature_dim) fp32 -> audio (B, T_tok * hop) fp32.
+ * l3ac_encode_host / l3ac_decode_host take HOST pointers (pinned memory makes the copies asynchronous): micro-batches of
+ * <= 330 s of audio are uploaded, processed and downloaded on up to four internal streams so that copies overlap kernels;
+ * device staging and workspaces are owned by the handle and grow on demand; the calls return when the results are in
+ * host memory.  Not re-entrant per handle.
+ * ========================================================================================== */
+#define L3AC_MAX_STAGES 8
+typedef struct l3ac_codec_config {
+    int feature_dim;
+    int n_encoder_stages;                 /* len(encoder_dims) = len(compress_rates) + 1 */
+    int encoder_dims[L3AC_MAX_STAGES];
+    int encoder_depths[L3AC_MAX_STAGES];
+    int compress_rates[L3AC_MAX_STAGES];
+    int en_coder_depth;
+    int en_coder_window_size;
+    int en_coder_compress_rate;
+    int en_coder_dynamic_pos;
+    int n_levels;                         /* vq_config.levels */
+    int levels[8];
+    int n_decoder_stages;                 /* len(decoder_dims) = len(decode_rates) + 1 */
+    int decoder_dims[L3AC_MAX_STAGES];
+    int decoder_depths[L3AC_MAX_STAGES];
+    int decode_rates[L3AC_MAX_STAGES];
+} l3ac_codec_config;
+
+typedef struct l3ac_tensor {
+    const char* name;   /* "<module>.<state_dict key>", e.g. "decoder.blocks.0.parametrizations.weight.original1" */
+    const float* data;  /* host, fp32, contiguous */
+    long long numel;
+} l3ac_tensor;
+
+typedef struct l3ac_codec l3ac_codec;
+
+int l3ac_create(const l3ac_codec_config* config, const l3ac_tensor* tensors, int n_tensors, l3ac_codec** codec_out);
+int l3ac_destroy(l3ac_codec* codec);
+const char* l3ac_last_error(void);
+int l3ac_hop_length(const l3ac_codec* codec);
+long long l3ac_workspace_bytes(const l3ac_codec* codec, int B, int T);
+long long l3ac_launch_count(const l3ac_codec* codec); /* kernels launched through this handle so far */
+int l3ac_encode(l3ac_codec* codec, const float* audio, int B, int T, void* workspace, long long workspace_bytes,
+                float* q_feature, int32_t* indices, float* level_indices, l3ac_stream_t stream);
+int l3ac_decode(l3ac_codec* codec, const void* indices, int indices_are_i64, const float* q_feature, int B, int T_tok,
+                void* workspace, long long workspace_bytes, float* audio, l3ac_stream_t stream);
+int l3ac_encode_host(l3ac_codec* codec, const float* audio, int B, int T, int32_t* indices, float* q_feature);
+int l3ac_decode_host(l3ac_codec* codec, const int32_t* indices, int B, int T_tok, float* audio);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,6 +27,24 @@ class GemmDesc(C.Structure):
     ]
 
 
+MAX_STAGES = 8
+
+
+class CodecConfig(C.Structure):
+    """``l3ac_codec_config`` (include/l3ac_b200.h, step-level interface)."""
+    _fields_ = [
+        ("feature_dim", _i), ("n_encoder_stages", _i), ("encoder_dims", _i * MAX_STAGES), ("encoder_depths", _i * MAX_STAGES),
+        ("compress_rates", _i * MAX_STAGES), ("en_coder_depth", _i), ("en_coder_window_size", _i), ("en_coder_compress_rate", _i),
+        ("en_coder_dynamic_pos", _i), ("n_levels", _i), ("levels", _i * 8), ("n_decoder_stages", _i),
+        ("decoder_dims", _i * MAX_STAGES), ("decoder_depths", _i * MAX_STAGES), ("decode_rates", _i * MAX_STAGES),
+    ]
+
+
+class Tensor(C.Structure):
+    """``l3ac_tensor``: a named host fp32 array."""
+    _fields_ = [("name", C.c_char_p), ("data", _p), ("numel", _ll)]
+
+
 # name -> (restype, argtypes); must list every symbol the header declares (tests check this against the header)
 PROTOTYPES = {
     "l3ac_abi_version": (_i, []),
@@ -65,6 +83,17 @@ PROTOTYPES = {
     "l3ac_tail_plan_create": (_i, [_p, _p, _p, _p, _p, _p, C.POINTER(_i), _p, _p, _f, _i, C.POINTER(_p)]),
     "l3ac_tail_plan_destroy": (_i, [_p]),
     "l3ac_decoder_tail_tc": (_i, [_p, _p, _i, _i, _p, _p]),
+    # step-level interface (csrc/codec.cu)
+    "l3ac_create": (_i, [C.POINTER(CodecConfig), C.POINTER(Tensor), _i, C.POINTER(_p)]),
+    "l3ac_destroy": (_i, [_p]),
+    "l3ac_last_error": (C.c_char_p, []),
+    "l3ac_hop_length": (_i, [_p]),
+    "l3ac_workspace_bytes": (_ll, [_p, _i, _i]),
+    "l3ac_launch_count": (_ll, [_p]),
+    "l3ac_encode": (_i, [_p, _p, _i, _i, _p, _ll, _p, _p, _p, _p]),
+    "l3ac_decode": (_i, [_p, _p, _i, _p, _i, _i, _p, _ll, _p, _p]),
+    "l3ac_encode_host": (_i, [_p, _p, _i, _i, _p, _p]),
+    "l3ac_decode_host": (_i, [_p, _p, _i, _i, _p]),
 }
 
 _lib = None

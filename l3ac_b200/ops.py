@@ -606,3 +606,102 @@ def convunit_umma(x: torch.Tensor, plan: ConvUnitPlan, out_dtype=torch.float32):
     with _hook("convunit_thin_umma", _nbytes(x) + B * T * Cc * 4, 2.0 * B * T * (7 * Cc + 8 * Cc * Cc)), torch.cuda.device(x.device):
         check(_lib.load().l3ac_convunit_umma(plan.handle, _ptr(x), B, T, _ptr(hi), _ptr(lo), _DT[out_dtype], _stream(x)), "l3ac_convunit_umma")
     return out
+
+
+class NativeCodec:
+    """Step-level handle (``l3ac_codec``, csrc/codec.cu): the library packs the reference's checkpoint tensors and owns the
+    launch sequence of ``encode_audio`` / ``decode_audio`` in the product precision.  Torch provides the device buffers
+    (inputs, outputs, one workspace per call) and the stream; everything else happens behind ``l3ac_encode`` / ``l3ac_decode``."""
+
+    def __init__(self, mc, weights, device):
+        lib = _lib.load()
+        cfg = _lib.CodecConfig()
+        cfg.feature_dim = mc.feature_dim
+        cfg.n_encoder_stages = len(mc.encoder_dims)
+        cfg.n_decoder_stages = len(mc.decoder_dims)
+        if max(cfg.n_encoder_stages, cfg.n_decoder_stages) > _lib.MAX_STAGES or len(mc.levels) > 8:
+            raise ValueError("NativeCodec: too many stages / levels")
+        for name in ("encoder_dims", "encoder_depths", "compress_rates", "decoder_dims", "decoder_depths", "decode_rates"):
+            for i, v in enumerate(getattr(mc, name)):
+                getattr(cfg, name)[i] = int(v)
+        cfg.en_coder_depth, cfg.en_coder_window_size = mc.en_coder_depth, mc.en_coder_window_size
+        cfg.en_coder_compress_rate, cfg.en_coder_dynamic_pos = mc.en_coder_compress_rate, int(mc.en_coder_dynamic_pos)
+        cfg.n_levels = len(mc.levels)
+        for i, v in enumerate(mc.levels):
+            cfg.levels[i] = int(v)
+        keep, names = [], []
+        for mod, sd in weights.items():
+            for key, t in sd.items():
+                keep.append(t.detach().to("cpu", torch.float32).contiguous())
+                names.append(f"{mod}.{key}".encode())
+        arr = (_lib.Tensor * len(keep))()
+        for i, (n, t) in enumerate(zip(names, keep)):
+            arr[i].name, arr[i].data, arr[i].numel = n, t.data_ptr(), t.numel()
+        self.handle = C.c_void_p()
+        self.device = torch.device(device)
+        self.feature_dim, self.n_levels = mc.feature_dim, len(mc.levels)
+        with torch.cuda.device(self.device):
+            rc = lib.l3ac_create(C.byref(cfg), arr, len(keep), C.byref(self.handle))
+        if rc != 0:
+            raise (ValueError if rc in (-1, -2) else RuntimeError)(
+                f"l3ac_create failed: {lib.l3ac_last_error().decode()} ({lib.l3ac_error_string(rc).decode()}, code {rc})")
+        self.hop = lib.l3ac_hop_length(self.handle)
+        self._ws = {}
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            try:
+                _lib.load().l3ac_destroy(h)
+            except Exception:
+                pass
+
+    def _workspace(self, B: int, T: int) -> torch.Tensor:
+        n = self._ws.get((B, T))
+        if n is None:
+            n = _lib.load().l3ac_workspace_bytes(self.handle, B, T)
+            if n < 0:
+                raise RuntimeError(f"l3ac_workspace_bytes failed: {_lib.load().l3ac_last_error().decode()}")
+            if len(self._ws) > 4096:
+                self._ws.clear()
+            self._ws[(B, T)] = n
+        return torch.empty(n, device=self.device, dtype=torch.uint8)
+
+    def _call(self, what, fn, *args):
+        lib = _lib.load()
+        n0 = lib.l3ac_launch_count(self.handle)
+        with torch.cuda.device(self.device):
+            rc = fn(*args)
+        _count(lib.l3ac_launch_count(self.handle) - n0)
+        if rc != 0:
+            raise (ValueError if rc in (-1, -2) else RuntimeError)(
+                f"{what} failed: {lib.l3ac_last_error().decode()} ({lib.l3ac_error_string(rc).decode()}, code {rc})")
+
+    def encode(self, audio: torch.Tensor):
+        """audio (B, T) fp32 on the device -> (q_feature (B, T_tok, F), indices (B, T_tok) int32, level_indices (B, T_tok, D))."""
+        _chk(audio, name="audio")
+        B, T = audio.shape
+        t_tok = -(-T // self.hop)
+        q = torch.empty((B, t_tok, self.feature_dim), device=audio.device, dtype=torch.float32)
+        idx = torch.empty((B, t_tok), device=audio.device, dtype=torch.int32)
+        lvl = torch.empty((B, t_tok, self.n_levels), device=audio.device, dtype=torch.float32)
+        ws = self._workspace(B, T)
+        self._call("l3ac_encode", _lib.load().l3ac_encode, self.handle, _ptr(audio), B, T, _ptr(ws), ws.numel(), _ptr(q), _ptr(idx),
+                   _ptr(lvl), _stream(audio))
+        return q, idx, lvl
+
+    def decode(self, feat: Optional[torch.Tensor] = None, indices: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """q_feature (B, T_tok, F) fp32, or indices (B, T_tok) int32 / int64 -> audio (B, T_tok * hop) fp32."""
+        src = feat if feat is not None else indices
+        if feat is not None:
+            _chk(feat, name="audio_feature")
+        else:
+            if indices.dtype not in (torch.int32, torch.int64):
+                raise ValueError(f"indices must be int32 or int64, got {indices.dtype}")
+            _chk(indices, indices.dtype, "indices")
+        B, t_tok = src.shape[0], src.shape[1]
+        wav = torch.empty((B, t_tok * self.hop), device=src.device, dtype=torch.float32)
+        ws = self._workspace(B, t_tok * self.hop)
+        self._call("l3ac_decode", _lib.load().l3ac_decode, self.handle, _ptr(indices) if feat is None else None,
+                   int(feat is None and indices.dtype == torch.int64), _ptr(feat), B, t_tok, _ptr(ws), ws.numel(), _ptr(wav), _stream(src))
+        return wav
