@@ -303,6 +303,10 @@ int l3ac_tail_plan_create(const float* conv_w, const float* conv_b, const float*
                           const float* w_f, float bias_f, int C, l3ac_tail_plan** plan_out);
 int l3ac_tail_plan_destroy(l3ac_tail_plan* plan);
 int l3ac_decoder_tail_tc(const l3ac_tail_plan* plan, const float* x, int B, int T, float* out, l3ac_stream_t stream);
+/* The same kernel with 3-term split-bf16 operands for every contraction (snake outputs and weights as (hi, lo) bf16 pairs:
+ * hi*Whi + lo*Whi + hi*Wlo, fp32 accumulation in TMEM) and a libm-accurate tanh: fp32-class results for precision "split".
+ * Same plan, same arguments. */
+int l3ac_decoder_tail_tc_split(const l3ac_tail_plan* plan, const float* x, int B, int T, float* out, l3ac_stream_t stream);
 
 /* ==========================================================================================
  * Step-level interface: the two methods of the hot path as two calls.

@@ -83,6 +83,7 @@ PROTOTYPES = {
     "l3ac_tail_plan_create": (_i, [_p, _p, _p, _p, _p, _p, C.POINTER(_i), _p, _p, _f, _i, C.POINTER(_p)]),
     "l3ac_tail_plan_destroy": (_i, [_p]),
     "l3ac_decoder_tail_tc": (_i, [_p, _p, _i, _i, _p, _p]),
+    "l3ac_decoder_tail_tc_split": (_i, [_p, _p, _i, _i, _p, _p]),
     # step-level interface (csrc/codec.cu)
     "l3ac_create": (_i, [C.POINTER(CodecConfig), C.POINTER(Tensor), _i, C.POINTER(_p)]),
     "l3ac_destroy": (_i, [_p]),

@@ -43,26 +43,38 @@ using namespace l3ac::umma;
 constexpr int kC = 24;
 constexpr int kHalo = 42;
 constexpr int kGuard = 27;                       // largest conv reach (3 taps x dilation 9)
-constexpr int kBlocks = 7;
-constexpr int kRows = kBlocks * 128;             // 896
-constexpr int kOut = kRows - 2 * kHalo;          // 812
-constexpr int kRowsTot = kRows + 2 * kGuard;     // 950
-constexpr int kPlaneBytes = kRowsTot * 16;       // one 8-channel plane
-constexpr int kBufBytes = 4 * kPlaneBytes;       // 3 channel planes + 1 zero plane (K padding)
 constexpr int kConvMmas = 11;
-constexpr int kWConvBytes = kConvMmas * 1024;    // per unit: 11 x [2 halves][32 n][8 k] bf16
-constexpr int kWPwBytes = 2 * 1024;              // per unit: 2 x [2][32][8]
+constexpr int kWConvBytes = kConvMmas * 1024;    // per unit and part: 11 x [2 halves][32 n][8 k] bf16
+constexpr int kWPwBytes = 2 * 1024;              // per unit and part: 2 x [2][32][8]
 constexpr int kWFinBytes = 2 * 2 * 512;          // {hi, lo} x 2 x [2][16][8]
-constexpr int kWBytes = 3 * kWConvBytes + 3 * kWPwBytes + kWFinBytes;
-constexpr int kPtStride = kRows + 8;             // P^T[tap][row + 4]
-constexpr int kPtBytes = 7 * kPtStride * 4;
-constexpr int kNumBars = 5 * kBlocks;
-constexpr int kWorkerWarps = 4 * kBlocks;        // one row per thread: 28 row-owner warps
-constexpr int kConvWarp = kWorkerWarps, kPwWarp = kWorkerWarps + 2;     // MMA issuers: two for the k7 convs (even / odd blocks), one for the 1x1 convs
-constexpr int kThreads = 32 * (kWorkerWarps + 3);       // 31 warps at 64 registers
-constexpr int kSmemBytes = 2 * kBufBytes + kWBytes + kPtBytes + 8 * kNumBars + 16;
-static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
-static_assert(kBufBytes % 16 == 0 && kWBytes % 16 == 0 && kPtBytes % 16 == 0, "16-byte carve-up");
+
+// kSplit = false: bf16 operands (the decode side's default arithmetic), seven 128-row blocks per CTA.
+// kSplit = true:  3-term split-bf16 operands (a = hi + lo, W = Whi + Wlo; hi*Whi + lo*Whi + hi*Wlo, fp32 accumulate):
+//                 fp32-class results for precision="split".  Twice the operand planes and weights in shared memory, so four
+//                 blocks per CTA; three times the MMAs, which then set the pace (the row owners' work grows by ~30 %).
+template <bool kSplit>
+struct Cfg {
+    static constexpr int kBlocks = kSplit ? 4 : 7;
+    static constexpr int kRows = kBlocks * 128;             // 896 / 512
+    static constexpr int kOut = kRows - 2 * kHalo;          // 812 / 428
+    static constexpr int kRowsTot = kRows + 2 * kGuard;
+    static constexpr int kPlaneBytes = kRowsTot * 16;       // one 8-channel plane
+    static constexpr int kBufBytes = 3 * kPlaneBytes;       // 24 channels; the K-padding plane (zeros) is shared by all buffers
+    static constexpr int kParts = kSplit ? 2 : 1;           // operand parts: hi (, lo)
+    static constexpr int kTerms = kSplit ? 3 : 1;
+    static constexpr int kNumBufs = 2 * kParts;             // A hi, H hi (, A lo, H lo)
+    static constexpr int kWBytes = kParts * 3 * (kWConvBytes + kWPwBytes) + kWFinBytes;
+    static constexpr int kPtStride = kRows + 8;             // P^T[tap][row + 4]
+    static constexpr int kPtBytes = 7 * kPtStride * 4;
+    static constexpr int kNumBars = 5 * kBlocks;
+    static constexpr int kWorkerWarps = 4 * kBlocks;        // one row per thread
+    static constexpr int kConvWarp = kWorkerWarps, kPwWarp = kWorkerWarps + 2;     // MMA issuers: two for the k7 convs (even / odd blocks), one for the 1x1 convs
+    static constexpr int kThreads = 32 * (kWorkerWarps + 3);
+    static constexpr int kSmemBytes = kNumBufs * kBufBytes + kPlaneBytes + kWBytes + kPtBytes + 8 * kNumBars + 16;
+    static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+    static_assert(kBufBytes % 16 == 0 && kWBytes % 16 == 0 && kPtBytes % 16 == 0, "16-byte carve-up");
+    static_assert(kBlocks * 64 <= 512, "TMEM columns");
+};
 
 struct Params {
     const float* x;
@@ -119,38 +131,49 @@ __device__ __forceinline__ void ld_row24(uint32_t taddr, float (&v)[kC]) {
     for (int i = 0; i < 8; ++i) v[16 + i] = __uint_as_float(hi[i]);
 }
 
-template <int U>
+// bf16 pair (hi) and, for the split operand, the bf16 pair of the remainders (lo)
+template <bool kSplit>
+__device__ __forceinline__ void pack_parts(float s0, float s1, uint32_t& hi, uint32_t& lo) {
+    hi = pack_bf16x2(s0, s1);
+    if (kSplit) lo = pack_bf16x2(s0 - __uint_as_float(hi << 16), s1 - __uint_as_float(hi & 0xffff0000u));
+}
+
+template <int U, bool kSplit>
 struct UnitPhase {
-    // a = bf16(snake(x, alpha0)) -> plane buffer A
-    static __device__ __forceinline__ void snake_in(const Params& p, const float (&xr)[kC], uint32_t dst) {
+    using K = Cfg<kSplit>;
+    // a = snake(x, alpha0) as bf16 (or the split pair) -> plane buffer A (dst_lo: the lo-part buffer)
+    static __device__ __forceinline__ void snake_in(const Params& p, const float (&xr)[kC], uint32_t dst, uint32_t dst_lo) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            uint32_t pk[4];
+            uint32_t pk[4], pl[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int e = 8 * c + 2 * i;
-                pk[i] = pack_bf16x2(snake1(xr[e], p.a0[U][e], p.ia0[U][e]), snake1(xr[e + 1], p.a0[U][e + 1], p.ia0[U][e + 1]));
+                pack_parts<kSplit>(snake1(xr[e], p.a0[U][e], p.ia0[U][e]), snake1(xr[e + 1], p.a0[U][e + 1], p.ia0[U][e + 1]), pk[i], pl[i]);
             }
-            st_shared_v4(dst + c * kPlaneBytes, pk[0], pk[1], pk[2], pk[3]);
+            st_shared_v4(dst + c * K::kPlaneBytes, pk[0], pk[1], pk[2], pk[3]);
+            if (kSplit) st_shared_v4(dst_lo + c * K::kPlaneBytes, pl[0], pl[1], pl[2], pl[3]);
         }
     }
-    // h = bf16(snake(conv + bias, alpha1)) -> plane buffer H   (8 accumulator columns at a time; rows outside the clip: h = 0,
+    // h = snake(conv + bias, alpha1) -> plane buffer H   (8 accumulator columns at a time; rows outside the clip: h = 0,
     // so that the 1x1 conv adds nothing to their -- zero -- residual row)
-    static __device__ __forceinline__ void snake_mid(const Params& p, uint32_t taddr, uint32_t dst, bool valid) {
+    static __device__ __forceinline__ void snake_mid(const Params& p, uint32_t taddr, uint32_t dst, uint32_t dst_lo, bool valid) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             uint32_t v[8];
             tmem_ld8(taddr + 8 * c, v);
             tmem_ld_wait();
-            uint32_t pk[4];
+            uint32_t pk[4], pl[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int e = 8 * c + 2 * i;
-                pk[i] = pack_bf16x2(snake1(__uint_as_float(v[2 * i]) + p.conv_b[U][e], p.a1[U][e], p.ia1[U][e]),
-                                    snake1(__uint_as_float(v[2 * i + 1]) + p.conv_b[U][e + 1], p.a1[U][e + 1], p.ia1[U][e + 1]));
+                pack_parts<kSplit>(snake1(__uint_as_float(v[2 * i]) + p.conv_b[U][e], p.a1[U][e], p.ia1[U][e]),
+                                   snake1(__uint_as_float(v[2 * i + 1]) + p.conv_b[U][e + 1], p.a1[U][e + 1], p.ia1[U][e + 1]), pk[i], pl[i]);
                 pk[i] = valid ? pk[i] : 0u;
+                if (kSplit) pl[i] = valid ? pl[i] : 0u;
             }
-            st_shared_v4(dst + c * kPlaneBytes, pk[0], pk[1], pk[2], pk[3]);
+            st_shared_v4(dst + c * K::kPlaneBytes, pk[0], pk[1], pk[2], pk[3]);
+            if (kSplit) st_shared_v4(dst_lo + c * K::kPlaneBytes, pl[0], pl[1], pl[2], pl[3]);
         }
     }
     // the residual stream after unit U: the TMEM row the 1x1 convs accumulated into + their biases (zero outside the clip)
@@ -166,14 +189,24 @@ struct UnitPhase {
     }
 };
 
-__global__ void __launch_bounds__(kThreads, 1) decoder_tail_tc_kernel(const __grid_constant__ Params p) {
+template <bool kSplit>
+__global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) decoder_tail_tc_kernel(const __grid_constant__ Params p) {
+    using K = Cfg<kSplit>;
+    constexpr int kBlocks = K::kBlocks, kPlaneBytes = K::kPlaneBytes, kBufBytes = K::kBufBytes, kRows = K::kRows, kOut = K::kOut;
+    constexpr int kPtStride = K::kPtStride, kThreads = K::kThreads, kWorkerWarps = K::kWorkerWarps, kConvWarp = K::kConvWarp, kPwWarp = K::kPwWarp;
+    constexpr int kTerms = K::kTerms;
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
+    // plane buffers: A hi, H hi (, A lo, H lo), then the shared all-zero K-padding plane
     const uint32_t buf_a = sbase, buf_h = buf_a + kBufBytes;
-    const uint32_t w_conv = buf_h + kBufBytes, w_pw = w_conv + 3 * kWConvBytes, w_fin = w_pw + 3 * kWPwBytes;
+    const uint32_t buf_a_lo = kSplit ? buf_h + kBufBytes : buf_a, buf_h_lo = kSplit ? buf_a_lo + kBufBytes : buf_h;
+    const uint32_t zero_plane = sbase + K::kNumBufs * kBufBytes;
+    const uint32_t fin_lo = kSplit ? buf_a_lo : buf_h;        // lo part of the final conv's operand (bf16 mode borrows buffer H)
+    // weights: conv [part][unit] | pw [part][unit] | fin
+    const uint32_t w_conv = zero_plane + kPlaneBytes, w_pw = w_conv + K::kParts * 3 * kWConvBytes, w_fin = w_pw + K::kParts * 3 * kWPwBytes;
     const uint32_t pt_addr = w_fin + kWFinBytes;
     float* pt = reinterpret_cast<float*>(smem + (pt_addr - sbase));
-    const uint32_t bars = pt_addr + kPtBytes;
+    const uint32_t bars = pt_addr + K::kPtBytes;
     const uint32_t a_ready = bars, d_ready = a_ready + 8 * kBlocks, h_ready = d_ready + 8 * kBlocks,
                    o_ready = h_ready + 8 * kBlocks, pt_ready = o_ready + 8 * kBlocks;
     const uint32_t tmem_slot = pt_ready + 8 * kBlocks;
@@ -182,15 +215,15 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_tail_tc_kernel(const __gr
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
 
-    // ---- once per CTA: zero both plane buffers (guard rows and the K-padding plane stay zero for good), stage the
+    // ---- once per CTA: zero the plane buffers (guard rows and the K-padding plane stay zero for good), stage the
     // weights, barriers, TMEM
     {
         uint4* z = reinterpret_cast<uint4*>(smem);
-        for (int i = tid; i < 2 * kBufBytes / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < (K::kNumBufs * kBufBytes + kPlaneBytes) / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
         const uint4* src = reinterpret_cast<const uint4*>(p.wblob);
-        uint4* dst = reinterpret_cast<uint4*>(smem + 2 * kBufBytes);
-        for (int i = tid; i < kWBytes / 16; i += kThreads) dst[i] = __ldg(src + i);
-        for (int i = tid; i < kPtBytes / 4; i += kThreads) pt[i] = 0.f;
+        uint4* dst = reinterpret_cast<uint4*>(smem + (w_conv - sbase));
+        for (int i = tid; i < K::kWBytes / 16; i += kThreads) dst[i] = __ldg(src + i);
+        for (int i = tid; i < K::kPtBytes / 4; i += kThreads) pt[i] = 0.f;
     }
     if (tid == 0) {
         for (int b = 0; b < kBlocks; ++b) {
@@ -212,6 +245,12 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_tail_tc_kernel(const __gr
     const int tiles_per_clip = (p.T + kOut - 1) / kOut;
     const int n_tiles = tiles_per_clip * p.B;
 
+    constexpr uint64_t kDescHi = (uint64_t)(((128u >> 4) & 0x3FFF) | (1u << 14)) << 32;     // SBO = 128 B, sm_100 descriptor version
+    constexpr uint32_t kBlockStep = (128 * 16) >> 4;                                        // 128 rows further down the planes
+    const uint32_t lbo_plane = (uint32_t)(kPlaneBytes >> 4) << 16, lbo_w32 = (512u >> 4) << 16, lbo_w16 = (256u >> 4) << 16;
+    // K halves (plane 2, zero plane): LBO = distance from the buffer's third plane to the shared zero plane
+    auto lbo_zero = [&](uint32_t buf) { return ((zero_plane - (buf + 2 * kPlaneBytes)) >> 4) << 16; };
+
     if (warp == kConvWarp || warp == kConvWarp + 1) {
         // =============================================================== MMA issuers 1a / 1b: the k7 convs and the final conv of the
         // even / odd blocks.  One issuer needs ~770 cycles per block (barrier polls ~250, eleven MMAs through the uniform
@@ -223,25 +262,27 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_tail_tc_kernel(const __gr
         // against the 40 the tensor core needs (tools/tail_trace.py, tools/umma_rate.cu).
         const bool leader = elect_one();
         const uint32_t idesc32 = make_idesc_bf16(32), idesc16 = make_idesc_bf16(16);
-        constexpr uint64_t kDescHi = (uint64_t)(((128u >> 4) & 0x3FFF) | (1u << 14)) << 32;     // SBO = 128 B, sm_100 descriptor version
-        constexpr uint32_t kBlockStep = (128 * 16) >> 4;                                        // 128 rows further down the planes
-        const uint32_t lbo_plane = (uint32_t)(kPlaneBytes >> 4) << 16, lbo_w32 = (512u >> 4) << 16, lbo_w16 = (256u >> 4) << 16;
-        const uint32_t rows_a = (buf_a + kGuard * 16) >> 4, rows_h = (buf_h + kGuard * 16) >> 4;
         TAIL_TRACE_DECL
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
 #pragma unroll 1
             for (int u = 0; u < 3; ++u) {
                 const int d = u == 0 ? p.dil[0] : (u == 1 ? p.dil[1] : p.dil[2]);
-                uint32_t a_lo[kConvMmas];
+                uint32_t a_lo[K::kParts][kConvMmas];
 #pragma unroll
-                for (int j = 0; j < kConvMmas; ++j) {
-                    // j < 9: taps (2 (j / 3), + 1) of plane j % 3; j = 9: tap 6 of planes 0, 1; j = 10: tap 6 of plane 2 + the zero plane
-                    const int plane = j < 9 ? j % 3 : (j == 9 ? 0 : 2);
-                    const int tap = j < 9 ? 2 * (j / 3) : 6;
-                    a_lo[j] = (rows_a + (uint32_t)(plane * (kPlaneBytes >> 4)) + (uint32_t)((tap - 3) * d)) | (j < 9 ? (uint32_t)d << 16 : lbo_plane);
+                for (int part = 0; part < K::kParts; ++part) {
+                    const uint32_t buf = part == 0 ? buf_a : buf_a_lo;
+                    const uint32_t rows = (buf + kGuard * 16) >> 4;
+#pragma unroll
+                    for (int j = 0; j < kConvMmas; ++j) {
+                        // j < 9: taps (2 (j / 3), + 1) of plane j % 3; j = 9: tap 6 of planes 0, 1; j = 10: tap 6 of plane 2 + the zero plane
+                        const int plane = j < 9 ? j % 3 : (j == 9 ? 0 : 2);
+                        const int tap = j < 9 ? 2 * (j / 3) : 6;
+                        a_lo[part][j] = (rows + (uint32_t)(plane * (kPlaneBytes >> 4)) + (uint32_t)((tap - 3) * d)) |
+                                        (j < 9 ? (uint32_t)d << 16 : (j == 9 ? lbo_plane : lbo_zero(buf)));
+                    }
                 }
-                const uint32_t wc_lo = ((w_conv + u * kWConvBytes) >> 4) | lbo_w32;
+                const uint32_t wc_lo = ((w_conv + u * kWConvBytes) >> 4) | lbo_w32;               // part 0 (hi); part 1 follows the three hi units
 #pragma unroll 1
                 for (int b = b_first; b < kBlocks; b += 2) {
                     if (b > 0) mbar_wait(a_ready + 8 * (b - 1), u & 1);          // the taps reach into both neighbour blocks
@@ -252,8 +293,13 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_tail_tc_kernel(const __gr
                     if (leader) {
                         const uint32_t dcol = tmem_base + 64 * b + 32, boff = kBlockStep * b;
 #pragma unroll
-                        for (int j = 0; j < kConvMmas; ++j)
-                            tc_mma_bf16(dcol, kDescHi | (a_lo[j] + boff), kDescHi | (wc_lo + j * (1024 >> 4)), idesc32, j > 0 ? 1u : 0u);
+                        for (int term = 0; term < kTerms; ++term) {                              // hi*Whi (, lo*Whi, hi*Wlo)
+                            const uint32_t wsel = wc_lo + (term == 2 ? (3 * kWConvBytes) >> 4 : 0);
+#pragma unroll
+                            for (int j = 0; j < kConvMmas; ++j)
+                                tc_mma_bf16(dcol, kDescHi | (a_lo[term == 1 ? K::kParts - 1 : 0][j] + boff), kDescHi | (wsel + j * (1024 >> 4)), idesc32,
+                                            (term | j) ? 1u : 0u);
+                        }
                         TAIL_TRACE(4, 11, u, b);
                         tc_commit(d_ready + 8 * b);
                         TAIL_TRACE(4, 13, u, b);
@@ -261,7 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_tail_tc_kernel(const __gr
                     __syncwarp();
                 }
             }
-            // final conv: P = s . Wf^T with s = hi (buffer A) + lo (buffer H), Wf = hi + lo
+            // final conv: P = s . Wf^T with s = hi (buffer A) + lo (fin_lo), Wf = hi + lo
             const uint32_t wf_lo = (w_fin >> 4) | lbo_w16;
 #pragma unroll 1
             for (int b = b_first; b < kBlocks; b += 2) {
@@ -273,16 +319,17 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_tail_tc_kernel(const __gr
                 tc_fence_after();
                 if (leader && b_first == 0) TAIL_TRACE(4, 10, 3, b);
                 if (leader) {
-                    const uint32_t ra = (rows_a + kBlockStep * b) | lbo_plane, rh = (rows_h + kBlockStep * b) | lbo_plane;
+                    const uint32_t ra = ((buf_a + kGuard * 16) >> 4) + kBlockStep * b, rl = ((fin_lo + kGuard * 16) >> 4) + kBlockStep * b;
                     const uint32_t dcol = tmem_base + 64 * b + 32;
 #pragma unroll
                     for (int term = 0; term < 3; ++term) {
-                        const uint32_t arow = term == 1 ? rh : ra;
+                        const uint32_t arow = term == 1 ? rl : ra;
+                        const uint32_t abuf = term == 1 ? fin_lo : buf_a;
                         const uint32_t wsel = wf_lo + (term == 2 ? (1024 >> 4) : 0);
 #pragma unroll
                         for (int m = 0; m < 2; ++m)
-                            tc_mma_bf16(dcol, kDescHi | (arow + m * (2 * kPlaneBytes >> 4)), kDescHi | (wsel + m * (512 >> 4)), idesc16,
-                                        (term | m) ? 1u : 0u);
+                            tc_mma_bf16(dcol, kDescHi | ((arow + m * (2 * kPlaneBytes >> 4)) | (m == 0 ? lbo_plane : lbo_zero(abuf))),
+                                        kDescHi | (wsel + m * (512 >> 4)), idesc16, (term | m) ? 1u : 0u);
                     }
                     tc_commit(d_ready + 8 * b);
                 }
@@ -294,27 +341,28 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_tail_tc_kernel(const __gr
         // (its own warp: behind the conv issuer's program order the 1x1 convs of a unit would wait for all eight k7 convs)
         const bool leader = elect_one();
         const uint32_t idesc32 = make_idesc_bf16(32);
-        constexpr uint64_t kDescHi = (uint64_t)(((128u >> 4) & 0x3FFF) | (1u << 14)) << 32;
-        constexpr uint32_t kBlockStep = (128 * 16) >> 4;
-        const uint32_t lbo_plane = (uint32_t)(kPlaneBytes >> 4) << 16, lbo_w32 = (512u >> 4) << 16;
-        const uint32_t rows_h = (buf_h + kGuard * 16) >> 4;
         TAIL_TRACE_DECL
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
 #pragma unroll 1
             for (int u = 0; u < 3; ++u) {
-                const uint32_t wp_lo = ((w_pw + u * kWPwBytes) >> 4) | lbo_w32;
+                const uint32_t wp_lo = ((w_pw + u * kWPwBytes) >> 4) | lbo_w32;                   // part 0 (hi); part 1 follows the three hi units
 #pragma unroll 1
                 for (int b = 0; b < kBlocks; ++b) {
                     mbar_wait(h_ready + 8 * b, (it + u) & 1);
                     tc_fence_after();
                     if (leader) TAIL_TRACE(5, 12, u, b);
                     if (leader) {
-                        const uint32_t a0 = (rows_h + kBlockStep * b) | lbo_plane;
 #pragma unroll
-                        for (int m = 0; m < 2; ++m)
-                            tc_mma_bf16(tmem_base + 64 * b, kDescHi | (a0 + m * (2 * kPlaneBytes >> 4)), kDescHi | (wp_lo + m * (1024 >> 4)),
-                                        idesc32, 1u);            // accumulates INTO the residual row: x += conv1x1(h)
+                        for (int term = 0; term < kTerms; ++term) {
+                            const uint32_t hbuf = term == 1 ? buf_h_lo : buf_h;
+                            const uint32_t a0 = ((hbuf + kGuard * 16) >> 4) + kBlockStep * b;
+                            const uint32_t wsel = wp_lo + (term == 2 ? (3 * kWPwBytes) >> 4 : 0);
+#pragma unroll
+                            for (int m = 0; m < 2; ++m)
+                                tc_mma_bf16(tmem_base + 64 * b, kDescHi | ((a0 + m * (2 * kPlaneBytes >> 4)) | (m == 0 ? lbo_plane : lbo_zero(hbuf))),
+                                            kDescHi | (wsel + m * (1024 >> 4)), idesc32, 1u);     // accumulates INTO the residual row: x += conv1x1(h)
+                        }
                         tc_commit(o_ready + 8 * b);
                     }
                     __syncwarp();
@@ -354,7 +402,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_tail_tc_kernel(const __gr
                 for (int i = 0; i < 8; ++i) v[i] = __float_as_uint(xr[8 * c + i]);
                 tmem_st8(tx + 8 * c, v);
             }
-            UnitPhase<0>::snake_in(p, xr, buf_a + row_off);
+            UnitPhase<0, kSplit>::snake_in(p, xr, buf_a + row_off, buf_a_lo + row_off);
             tmem_st_wait();
             fence_async_smem();
             tc_fence_before();
@@ -366,7 +414,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_tail_tc_kernel(const __gr
                 mbar_wait_tag(d_ready + 8 * blk, U & 1, 10);                                                  \
                 tc_fence_after();                                                                             \
                 if (tracer) TAIL_TRACE(wg, 3, U, blk);                                                        \
-                UnitPhase<U>::snake_mid(p, td, buf_h + row_off, cur_valid);                                   \
+                UnitPhase<U, kSplit>::snake_mid(p, td, buf_h + row_off, buf_h_lo + row_off, cur_valid);       \
                 fence_async_smem();                                                                           \
                 tc_fence_before();                                                                            \
                 __syncwarp();                                                                                 \
@@ -380,21 +428,19 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_tail_tc_kernel(const __gr
                 if (blk > 0) mbar_wait_tag(d_ready + 8 * (blk - 1), U & 1, 13);                               \
                 tc_fence_after();                                                                             \
                 if (tracer) TAIL_TRACE(wg, 5, U, blk);                                                        \
-                UnitPhase<U>::load_x(p, tx, xr, cur_valid);                                                   \
+                UnitPhase<U, kSplit>::load_x(p, tx, xr, cur_valid);                                           \
                 if (tracer) TAIL_TRACE(wg, 1, U + 1, blk);                                                    \
                 if (U < 2) {                                                                                  \
-                    UnitPhase<(U < 2 ? U + 1 : 0)>::snake_in(p, xr, buf_a + row_off);                         \
-                } else {    /* final conv operand: s = snake(x, alpha_f) as a split pair, hi -> buffer A, lo -> buffer H */ \
+                    UnitPhase<(U < 2 ? U + 1 : 0), kSplit>::snake_in(p, xr, buf_a + row_off, buf_a_lo + row_off); \
+                } else {    /* final conv operand: s = snake(x, alpha_f) as a split pair, hi -> buffer A, lo -> fin_lo */ \
                     _Pragma("unroll") for (int c = 0; c < 3; ++c) {                                           \
                         uint32_t ph[4], pl[4];                                                                \
                         _Pragma("unroll") for (int i = 0; i < 4; ++i) {                                       \
                             const int e = 8 * c + 2 * i;                                                      \
-                            const float s0 = snake1(xr[e], p.af[e], p.iaf[e]), s1 = snake1(xr[e + 1], p.af[e + 1], p.iaf[e + 1]); \
-                            ph[i] = pack_bf16x2(s0, s1);                                                      \
-                            pl[i] = pack_bf16x2(s0 - __uint_as_float(ph[i] << 16), s1 - __uint_as_float(ph[i] & 0xffff0000u)); \
+                            pack_parts<true>(snake1(xr[e], p.af[e], p.iaf[e]), snake1(xr[e + 1], p.af[e + 1], p.iaf[e + 1]), ph[i], pl[i]); \
                         }                                                                                     \
                         st_shared_v4(buf_a + row_off + c * kPlaneBytes, ph[0], ph[1], ph[2], ph[3]);          \
-                        st_shared_v4(buf_h + row_off + c * kPlaneBytes, pl[0], pl[1], pl[2], pl[3]);          \
+                        st_shared_v4(fin_lo + row_off + c * kPlaneBytes, pl[0], pl[1], pl[2], pl[3]);         \
                     }                                                                                         \
                 }                                                                                             \
                 fence_async_smem();                                                                           \
@@ -441,7 +487,8 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_tail_tc_kernel(const __gr
 #pragma unroll
                     for (int j = 0; j < 7; ++j) acc += src[j * kPtStride + j];
                     float y;
-                    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(acc));
+                    if (kSplit) y = tanhf(acc);                                  // fp32-class mode: libm-accurate tanh
+                    else asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(acc));
                     p.out[(long long)cur_clip * p.T + t] = y;
                 }
                 if (tracer) TAIL_TRACE(wg, 8, 3, blk);
@@ -470,7 +517,8 @@ extern "C" int l3ac_debug_tail_trace(unsigned long long* host_buf) {      // hos
 
 struct l3ac_tail_plan {
     l3ac::tailtc::Params params;
-    void* dev_blob;
+    void* dev_blob;          // bf16 operand weights
+    void* dev_blob_split;    // (hi, lo) operand weights of the 3-term split variant
     int device;
 };
 
@@ -481,6 +529,51 @@ static inline uint16_t bf16_bits(float v) {
     return b;
 }
 static inline float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+// part 0: bf16(w); part 1: bf16(w - bf16(w))
+static inline uint16_t bf16_part(float w, int part) { return bf16_bits(part == 0 ? w : w - bf16_round(w)); }
+
+// Weights in operand order: conv [part][unit][mma j][half h][n 32][k 8] | pw [part][unit][m][h][n 32][k 8] | fin {hi, lo}[m][h][n 16][k 8]
+static std::vector<uint16_t> tail_weight_blob(int parts, const float* conv_w, const float* pw_w, const float* w_f) {
+    using namespace l3ac::tailtc;
+    const size_t total = ((size_t)parts * 3 * (kWConvBytes + kWPwBytes) + kWFinBytes) / 2;
+    std::vector<uint16_t> blob(total, 0);
+    // W[u][n][ch][tap] at conv_w[((u * 24 + n) * 24 + ch) * 7 + tap]
+    for (int part = 0; part < parts; ++part)
+        for (int u = 0; u < 3; ++u)
+            for (int j = 0; j < kConvMmas; ++j)
+                for (int h = 0; h < 2; ++h) {
+                    int tap, plane;
+                    if (j < 9) { tap = 2 * (j / 3) + h; plane = j % 3; }
+                    else if (j == 9) { tap = 6; plane = h; }
+                    else { tap = 6; plane = h == 0 ? 2 : -1; }
+                    for (int n = 0; n < kC && plane >= 0; ++n)
+                        for (int k = 0; k < 8; ++k)
+                            blob[(size_t)(part * 3 + u) * kWConvBytes / 2 + j * 512 + h * 256 + n * 8 + k] =
+                                bf16_part(conv_w[(((size_t)u * kC + n) * kC + 8 * plane + k) * 7 + tap], part);
+                }
+    const size_t pw0 = (size_t)parts * 3 * kWConvBytes / 2;
+    for (int part = 0; part < parts; ++part)
+        for (int u = 0; u < 3; ++u)
+            for (int m = 0; m < 2; ++m)
+                for (int h = 0; h < 2; ++h)
+                    for (int n = 0; n < kC; ++n)
+                        for (int k = 0; k < 8; ++k) {
+                            const int ch = 16 * m + 8 * h + k;
+                            if (ch < kC)
+                                blob[pw0 + (size_t)(part * 3 + u) * kWPwBytes / 2 + m * 512 + h * 256 + n * 8 + k] =
+                                    bf16_part(pw_w[((size_t)u * kC + n) * kC + ch], part);
+                        }
+    const size_t fin0 = pw0 + (size_t)parts * 3 * kWPwBytes / 2;
+    for (int part = 0; part < 2; ++part)                    // hi, lo
+        for (int m = 0; m < 2; ++m)
+            for (int h = 0; h < 2; ++h)
+                for (int n = 0; n < 7; ++n)
+                    for (int k = 0; k < 8; ++k) {
+                        const int ch = 16 * m + 8 * h + k;
+                        if (ch < kC) blob[fin0 + part * 512 + m * 256 + h * 128 + n * 8 + k] = bf16_part(w_f[n * kC + ch], part);
+                    }
+    return blob;
+}
 
 extern "C" int l3ac_tail_plan_create(const float* conv_w, const float* conv_b, const float* pw_w, const float* pw_b,
                                      const float* alpha0, const float* alpha1, const int* dilations, const float* alpha_f,
@@ -495,47 +588,22 @@ extern "C" int l3ac_tail_plan_create(const float* conv_w, const float* conv_b, c
         reach += 3 * dilations[i];
     }
     if (reach > kHalo) return L3AC_EUNSUPPORTED;                      // receptive field must fit the 42-sample halo
-    std::vector<uint16_t> blob(kWBytes / 2, 0);
-    // conv: [unit][mma j][half h][n 32][k 8]; W[u][n][ch][tap] at conv_w[((u * 24 + n) * 24 + ch) * 7 + tap]
-    for (int u = 0; u < 3; ++u)
-        for (int j = 0; j < kConvMmas; ++j)
-            for (int h = 0; h < 2; ++h) {
-                int tap, plane;
-                if (j < 9) { tap = 2 * (j / 3) + h; plane = j % 3; }
-                else if (j == 9) { tap = 6; plane = h; }
-                else { tap = 6; plane = h == 0 ? 2 : -1; }
-                for (int n = 0; n < kC && plane >= 0; ++n)
-                    for (int k = 0; k < 8; ++k)
-                        blob[(size_t)u * kWConvBytes / 2 + j * 512 + h * 256 + n * 8 + k] =
-                            bf16_bits(conv_w[(((size_t)u * kC + n) * kC + 8 * plane + k) * 7 + tap]);
-            }
-    const size_t pw0 = 3 * kWConvBytes / 2;
-    for (int u = 0; u < 3; ++u)
-        for (int m = 0; m < 2; ++m)
-            for (int h = 0; h < 2; ++h)
-                for (int n = 0; n < kC; ++n)
-                    for (int k = 0; k < 8; ++k) {
-                        const int ch = 16 * m + 8 * h + k;
-                        if (ch < kC) blob[pw0 + (size_t)u * kWPwBytes / 2 + m * 512 + h * 256 + n * 8 + k] = bf16_bits(pw_w[((size_t)u * kC + n) * kC + ch]);
-                    }
-    const size_t fin0 = pw0 + 3 * kWPwBytes / 2;
-    for (int part = 0; part < 2; ++part)                    // hi, lo
-        for (int m = 0; m < 2; ++m)
-            for (int h = 0; h < 2; ++h)
-                for (int n = 0; n < 7; ++n)
-                    for (int k = 0; k < 8; ++k) {
-                        const int ch = 16 * m + 8 * h + k;
-                        if (ch >= kC) continue;
-                        const float w = w_f[n * kC + ch], hi = bf16_round(w);
-                        blob[fin0 + part * 512 + m * 256 + h * 128 + n * 8 + k] = bf16_bits(part == 0 ? hi : w - hi);
-                    }
+    const std::vector<uint16_t> blob = tail_weight_blob(1, conv_w, pw_w, w_f), blob2 = tail_weight_blob(2, conv_w, pw_w, w_f);
+    if (blob.size() * 2 != (size_t)Cfg<false>::kWBytes || blob2.size() * 2 != (size_t)Cfg<true>::kWBytes) return L3AC_EINVAL;
     l3ac_tail_plan* plan = new (std::nothrow) l3ac_tail_plan();
     if (!plan) return L3AC_EINVAL;
+    plan->dev_blob = plan->dev_blob_split = nullptr;
     if (cudaGetDevice(&plan->device) != cudaSuccess) { delete plan; return L3AC_EDRIVER; }
-    cudaError_t e = cudaMalloc(&plan->dev_blob, kWBytes);
-    if (e != cudaSuccess) { delete plan; return (int)e; }
-    e = cudaMemcpy(plan->dev_blob, blob.data(), kWBytes, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) { cudaFree(plan->dev_blob); delete plan; return (int)e; }
+    cudaError_t e = cudaMalloc(&plan->dev_blob, blob.size() * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&plan->dev_blob_split, blob2.size() * 2);
+    if (e == cudaSuccess) e = cudaMemcpy(plan->dev_blob, blob.data(), blob.size() * 2, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(plan->dev_blob_split, blob2.data(), blob2.size() * 2, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(plan->dev_blob);
+        cudaFree(plan->dev_blob_split);
+        delete plan;
+        return (int)e;
+    }
     Params& p = plan->params;
     p = Params{};
     p.wblob = static_cast<const uint8_t*>(plan->dev_blob);
@@ -562,27 +630,39 @@ extern "C" int l3ac_tail_plan_create(const float* conv_w, const float* conv_b, c
 extern "C" int l3ac_tail_plan_destroy(l3ac_tail_plan* plan) {
     if (!plan) return L3AC_OK;
     cudaFree(plan->dev_blob);
+    cudaFree(plan->dev_blob_split);
     delete plan;
     return L3AC_OK;
 }
 
-extern "C" int l3ac_decoder_tail_tc(const l3ac_tail_plan* plan, const float* x, int B, int T, float* out, l3ac_stream_t stream) {
+template <bool kSplit>
+static int launch_tail(const l3ac_tail_plan* plan, const float* x, int B, int T, float* out, l3ac_stream_t stream) {
     using namespace l3ac::tailtc;
+    using K = Cfg<kSplit>;
     L3AC_CHECK_ARG(plan && x && out && B > 0 && T > 0);
     L3AC_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     int dev = -1;
     if (cudaGetDevice(&dev) != cudaSuccess) return L3AC_EDRIVER;
     L3AC_CHECK_ARG(dev == plan->device);
-    const long long n_tiles = (long long)l3ac_cdiv(T, kOut) * B;
+    const long long n_tiles = (long long)l3ac_cdiv(T, K::kOut) * B;
     L3AC_CHECK_ARG(n_tiles < (1LL << 30));
     Params p = plan->params;
+    p.wblob = static_cast<const uint8_t*>(kSplit ? plan->dev_blob_split : plan->dev_blob);
     p.x = x;
     p.out = out;
     p.B = B;
     p.T = T;
-    cudaError_t e = cudaFuncSetAttribute(decoder_tail_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(decoder_tail_tc_kernel<kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::kSmemBytes);
     if (e != cudaSuccess) return (int)e;
     const int sms = l3ac_sm_count();
-    decoder_tail_tc_kernel<<<(int)(n_tiles < sms ? n_tiles : sms), kThreads, kSmemBytes, (cudaStream_t)stream>>>(p);
+    decoder_tail_tc_kernel<kSplit><<<(int)(n_tiles < sms ? n_tiles : sms), K::kThreads, K::kSmemBytes, (cudaStream_t)stream>>>(p);
     return l3ac_launch_status();
+}
+
+extern "C" int l3ac_decoder_tail_tc(const l3ac_tail_plan* plan, const float* x, int B, int T, float* out, l3ac_stream_t stream) {
+    return launch_tail<false>(plan, x, B, T, out, stream);
+}
+
+extern "C" int l3ac_decoder_tail_tc_split(const l3ac_tail_plan* plan, const float* x, int B, int T, float* out, l3ac_stream_t stream) {
+    return launch_tail<true>(plan, x, B, T, out, stream);
 }

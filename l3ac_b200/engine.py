@@ -283,6 +283,16 @@ class Engine:
                              bias=float(sd[f"{p}.2.bias"].float().item()))
         # fused tail (bf16 decode mode, 24 channels, dilations 1/3/9): weights in mma B-fragment order
         self.dec_tail_fused = None
+        self.dec_tail_plan = None
+        if bf16 == ops.SPLIT and mc.decoder_dims[-1] == 24 and os.environ.get("L3AC_TAIL_IMPL", "tcgen05") == "tcgen05":
+            # precision="split": the same fused tcgen05 tail with 3-term split operands (l3ac_decoder_tail_tc_split)
+            self.dec_tail_plan = ops.TailPlan(
+                torch.stack([fold_weight_norm(sd, f"{p}.0.{j}.module.block.1") for j in range(3)]),
+                torch.stack([u["conv"].bias for u in self.dec_legacy]),
+                torch.stack([fold_weight_norm(sd, f"{p}.0.{j}.module.block.3")[:, :, 0] for j in range(3)]),
+                torch.stack([u["pw"].bias for u in self.dec_legacy]),
+                torch.stack([u["alpha0"] for u in self.dec_legacy]), torch.stack([u["alpha1"] for u in self.dec_legacy]),
+                [u["dil"] for u in self.dec_legacy], self.dec_tail["alpha"], self.dec_tail["w"], self.dec_tail["bias"], self.device)
         if bf16 == torch.bfloat16 and mc.decoder_dims[-1] == 24:
             convs, pws = [], []
             for j in range(3):
@@ -292,7 +302,6 @@ class Engine:
                 pws.append(ops.pack_mma_b_fragments(fold_weight_norm(sd, f"{q}.3")[:, :, 0]))
             # product path: the tcgen05 kernel (weights packed into a plan by the library); the register-level mma.sync
             # kernel below stays as a cross-check (L3AC_TAIL_IMPL=mma_sync)
-            self.dec_tail_plan = None
             if os.environ.get("L3AC_TAIL_IMPL", "tcgen05") == "tcgen05":
                 self.dec_tail_plan = ops.TailPlan(
                     torch.stack([fold_weight_norm(sd, f"{p}.0.{j}.module.block.1") for j in range(3)]),
@@ -638,6 +647,8 @@ class Engine:
             if taps is not None:
                 taps[f"dec_up{si}"] = x
         B, T, C = x.shape
+        if adt == ops.SPLIT and self.dec_tail_plan is not None:                     # fp32-class fused tail (3-term split operands)
+            return ops.decoder_tail_tc(x, self.dec_tail_plan, split=True)
         if self.dec_tail_fused is not None:                                         # 3 LegacyUnits + tail conv in one kernel
             if self.dec_tail_plan is not None:
                 return ops.decoder_tail_tc(x, self.dec_tail_plan)

@@ -521,15 +521,18 @@ class TailPlan:
                 pass
 
 
-def decoder_tail_tc(x: torch.Tensor, plan: TailPlan) -> torch.Tensor:
+def decoder_tail_tc(x: torch.Tensor, plan: TailPlan, split: bool = False) -> torch.Tensor:
+    """Fused decoder tail on tcgen05.  ``split``: 3-term split-bf16 operands (fp32-class) instead of plain bf16."""
     _chk(x, name="x")
     B, T, Cc = x.shape
     if Cc != 24:
         raise ValueError("decoder_tail_tc: 24 channels expected")
     out = torch.empty((B, T), device=x.device, dtype=torch.float32)
     _count()
-    with _hook("decoder_tail_tc", _nbytes(x, out), 2.0 * B * T * (3 * (7 * 24 * 24 + 24 * 24) + 7 * 24)), torch.cuda.device(x.device):
-        check(_lib.load().l3ac_decoder_tail_tc(plan.handle, _ptr(x), B, T, _ptr(out), _stream(x)), "l3ac_decoder_tail_tc")
+    name = "decoder_tail_tc_split" if split else "decoder_tail_tc"
+    with _hook(name, _nbytes(x, out), 2.0 * B * T * (3 * (7 * 24 * 24 + 24 * 24) + 7 * 24)), torch.cuda.device(x.device):
+        fn = _lib.load().l3ac_decoder_tail_tc_split if split else _lib.load().l3ac_decoder_tail_tc
+        check(fn(plan.handle, _ptr(x), B, T, _ptr(out), _stream(x)), "l3" + "ac_" + name)
     return out
 
 

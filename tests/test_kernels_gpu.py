@@ -309,6 +309,47 @@ def test_fused_decoder_tail(cuda_lib, T, impl):
     assert r_between < 1.5 * r_emul + 1e-4
 
 
+@pytest.mark.parametrize("T", [1, 50, 300, 427, 428, 429, 1000, 2717, 9401, 80011])
+def test_fused_decoder_tail_split(cuda_lib, T):
+    """The fused tcgen05 decoder tail with 3-term split-bf16 operands (l3ac_decoder_tail_tc_split, precision="split") against
+    the oracle's exact fp32 decoder tail: fp32-class (the bf16 variant above sits at ~1e-2).  T around 428 = one tile's outputs."""
+    C = 24
+    sd = {}
+    ga = torch.Generator().manual_seed(100 + T)
+    urand = lambda: 0.5 + torch.rand(1, C, 1, generator=ga)
+    for j in range(3):
+        q = f"blocks.0.block.0.{j}.module.block"
+        sd[f"{q}.0.alpha"], sd[f"{q}.2.alpha"] = urand(), urand()
+        sd[f"{q}.1.weight"], sd[f"{q}.1.bias"] = rnd(C, C, 7, seed=10 + j, scale=0.08), rnd(C, seed=20 + j, scale=0.05)
+        sd[f"{q}.3.weight"], sd[f"{q}.3.bias"] = rnd(C, C, 1, seed=30 + j, scale=0.15), rnd(C, seed=40 + j, scale=0.05)
+    sd["blocks.0.block.1.alpha"] = urand()
+    sd["blocks.0.block.2.weight"], sd["blocks.0.block.2.bias"] = rnd(1, C, 7, seed=50, scale=0.1), rnd(1, seed=51, scale=0.05)
+    x = rnd(3, C, T, seed=1, scale=0.7)
+    exact = x.double()
+    sd64 = {k: v.double() for k, v in sd.items()}
+    for j, dil in enumerate((1, 3, 9)):
+        exact = O.legacy_unit(sd64, f"blocks.0.block.0.{j}.module", exact, dil)
+    exact = torch.tanh(F.conv1d(O.snake(exact, sd64["blocks.0.block.1.alpha"]), sd64["blocks.0.block.2.weight"],
+                                sd64["blocks.0.block.2.bias"], padding=3))[:, 0]
+    st = lambda key: torch.stack([sd[f"blocks.0.block.0.{j}.module.block.{key}"].flatten() for j in range(3)]).contiguous().to(DEV)
+    plan = ops.TailPlan(torch.stack([sd[f"blocks.0.block.0.{j}.module.block.1.weight"] for j in range(3)]), st("1.bias"),
+                        torch.stack([sd[f"blocks.0.block.0.{j}.module.block.3.weight"][:, :, 0] for j in range(3)]), st("3.bias"),
+                        st("0.alpha"), st("2.alpha"), (1, 3, 9), sd["blocks.0.block.1.alpha"].flatten(),
+                        sd["blocks.0.block.2.weight"][0].t(), float(sd["blocks.0.block.2.bias"]), DEV)
+    got = ops.decoder_tail_tc(cl(x), plan, split=True)
+    err = max_abs(got.cpu(), exact)
+    ref32 = x
+    for j, dil in enumerate((1, 3, 9)):
+        ref32 = O.legacy_unit(sd, f"blocks.0.block.0.{j}.module", ref32, dil)
+    ref32 = torch.tanh(F.conv1d(O.snake(ref32, sd["blocks.0.block.1.alpha"]), sd["blocks.0.block.2.weight"],
+                                sd["blocks.0.block.2.bias"], padding=3))[:, 0]
+    err32 = max_abs(ref32, exact)
+    print(f"[tail split T={T}] max-abs vs exact (fp64) oracle {err:.2e} (the fp32 oracle itself: {err32:.2e})")
+    # 3-term split products drop the lo*lo term (2^-16 relative per product): a few 1e-5 after three units, against
+    # ~1e-2 for the bf16 variant and ~1e-6 for the fp32 oracle
+    assert err < 3e-4
+
+
 @pytest.mark.parametrize("C", [24, 48])
 @pytest.mark.parametrize("T", [1, 100, 255, 256, 257, 515, 1000, 2717, 40011])
 def test_fused_thin_convunit_umma(cuda_lib, C, T):
