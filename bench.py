@@ -381,6 +381,44 @@ def main():
     launches_per_step = (ops.LAUNCHES - launches0) // max(1, args.steps)      # this library's kernels (inside replayed CUDA graphs included)
     clocks = sampler.stop()
     ms_e2e = timed(step_e2e, args.steps, min(args.warmup, 2), "e2e")
+    # ---- the same step through the step-level C ABI with HOST buffers (l3ac_encode_host + l3ac_decode_host, csrc/codec.cu):
+    # what a non-Python host gets.  The calls are synchronous (results in host memory on return), so the host clock around
+    # K steps is the end-to-end time; micro-batching, streams, staging and workspaces are the library's.
+    c_abi = None
+    native = getattr(codec.network.engine, "native", None)
+    if native is not None and args.mode == "encdec" and os.environ.get("L3AC_BENCH_C_ABI", "1") != "0":
+        from l3ac_b200 import _lib
+        lib = _lib.load()
+        T_in = host_inputs[0].shape[1]
+
+        def step_c(i):
+            x = host_inputs[i % n_rot]
+            rc = lib.l3ac_encode_host(native.handle, x.data_ptr(), B, T_in, host_idx.data_ptr(), None)
+            rc = rc or lib.l3ac_decode_host(native.handle, host_idx.data_ptr(), B, T_tok, host_wav.data_ptr())
+            if rc != 0:
+                raise RuntimeError(f"C ABI host call failed: {lib.l3ac_last_error().decode()} (code {rc})")
+
+        with torch.cuda.device(dev):
+            for i in range(2):
+                step_c(i)
+            barrier()
+            n0 = lib.l3ac_launch_count(native.handle)
+            t0 = time.perf_counter()
+            for i in range(args.steps):
+                step_c(2 + i)
+            ms_c = (time.perf_counter() - t0) * 1e3 / args.steps
+            n_c = (lib.l3ac_launch_count(native.handle) - n0) // max(1, args.steps)
+            barrier()
+        if world > 1:
+            t = torch.tensor([ms_c], device=dev)
+            allt = torch.empty((world, 1), device=dev)
+            dist.all_gather_into_tensor(allt, t)
+            ms_c = float(allt.max())
+        c_abi = {"value": (args.batch if args.scaling == "strong" else world * B) * secs / (ms_c * 1e-3), "unit": UNIT, "ms_per_step": ms_c,
+                 "launches_per_step": int(n_c), "h2d_bytes_per_step": B * T_in * 4 + B * T_tok * 4,
+                 "d2h_bytes_per_step": B * T_tok * 4 + B * T_tok * mc.hop_length * 4,
+                 "how": "l3ac_encode_host + l3ac_decode_host (step-level C ABI, pinned host buffers in, host buffers out; no Python "
+                        "between the launches); host wall clock around the synchronous calls, max over ranks"}
     audio_s = (args.batch if args.scaling == "strong" else world * B) * secs
     value = audio_s / (ms_step * 1e-3)
     e2e_value = audio_s / (ms_e2e * 1e-3)
@@ -528,6 +566,7 @@ def main():
                                      "fp32": "fp32 SIMT"}[args.precision],
                        "l2": f"{n_rot} rotating input batches ({n_rot * B * secs * 64e3 / 1e6:.0f} MB) and a multi-GB "
                              "activation working set per step, both larger than the 126 MB L2"},
+            "e2e_c_abi": c_abi,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(host_inputs[0].numel() * 4) if args.mode == "encdec" else int(host_idx.numel() * 4),
                     "d2h_bytes_per_step": int(host_wav.numel() * 4 + (host_idx.numel() * 4 if args.mode == "encdec" else 0))},

@@ -314,8 +314,9 @@ int l3ac_decoder_tail_tc_split(const l3ac_tail_plan* plan, const float* x, int B
  *                 CompressedLocalEncoderWithCache -> VQEmbed;
  *   l3ac_decode = L3AC.decode_audio (l3ac/__init__.py:116-121): VQEmbed.to_features -> LocalDecoder /
  *                 CompressedLocalDecoderWithCache -> Decoder.
- * A handle (l3ac_codec) owns the packed weights and the launch sequence over the operator-level entry points above, in the
- * product precision (encode side 3-term split-bf16, decode side bf16, fp32 accumulation and residual stream).
+ * A handle (l3ac_codec) owns the packed weights and the launch sequence over the operator-level entry points above, on the
+ * tensor cores: encode side 3-term split-bf16, decode side bf16 (L3AC_PRECISION_BF16) or 3-term split-bf16
+ * (L3AC_PRECISION_SPLIT), fp32 accumulation and residual stream.
  *
  * l3ac_create takes the reference's checkpoint as HOST fp32 tensors named "<module>.<state_dict key>" with module in
  * encoder / quantizer / decoder / en_encoder / en_decoder (the five <module>.pt files of l3ac/xtract/nn/module.py:36-54,
@@ -339,6 +340,8 @@ int l3ac_decoder_tail_tc_split(const l3ac_tail_plan* plan, const float* x, int B
  * host memory.  Not re-entrant per handle.
  * ========================================================================================== */
 #define L3AC_MAX_STAGES 8
+#define L3AC_PRECISION_BF16 0  /* decode side bf16 operands (the default of the Python host, precision="bf16")               */
+#define L3AC_PRECISION_SPLIT 1 /* decode side 3-term split-bf16 like the encode side: fp32-class waveform (precision="split") */
 typedef struct l3ac_codec_config {
     int feature_dim;
     int n_encoder_stages;                 /* len(encoder_dims) = len(compress_rates) + 1 */
@@ -355,6 +358,7 @@ typedef struct l3ac_codec_config {
     int decoder_dims[L3AC_MAX_STAGES];
     int decoder_depths[L3AC_MAX_STAGES];
     int decode_rates[L3AC_MAX_STAGES];
+    int precision;                        /* L3AC_PRECISION_* */
 } l3ac_codec_config;
 
 typedef struct l3ac_tensor {

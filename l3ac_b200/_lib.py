@@ -37,6 +37,7 @@ class CodecConfig(C.Structure):
         ("compress_rates", _i * MAX_STAGES), ("en_coder_depth", _i), ("en_coder_window_size", _i), ("en_coder_compress_rate", _i),
         ("en_coder_dynamic_pos", _i), ("n_levels", _i), ("levels", _i * 8), ("n_decoder_stages", _i),
         ("decoder_dims", _i * MAX_STAGES), ("decoder_depths", _i * MAX_STAGES), ("decode_rates", _i * MAX_STAGES),
+        ("precision", _i),
     ]
 
 

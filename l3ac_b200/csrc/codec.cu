@@ -175,6 +175,7 @@ struct l3ac_codec {
     l3ac_codec_config cfg{};
     int dev = 0;
     int hop = 0, frame = 0;               // samples per token / per conv-encoder frame
+    int dec_kind = L3AC_BF16;             // decode-side operand kind: bf16, or the split pair for precision "split"
     bool compressed = false;
     uint8_t* dweights = nullptr;
     l3ac_stem_plan* stem = nullptr;
@@ -319,6 +320,9 @@ void build(l3ac_codec* c, Dict& d) {
     if (g.encoder_dims[0] != 24 || g.decoder_dims[nd - 1] != 24) fail(L3AC_EUNSUPPORTED, "first encoder / last decoder width must be 24");
     if (!g.en_coder_dynamic_pos) fail(L3AC_EUNSUPPORTED, "rotary position path: use the operator-level interface");
     if (g.en_coder_compress_rate < 1 || g.en_coder_window_size < 1) fail(L3AC_EINVAL, "en_coder parameters");
+    if (g.precision != L3AC_PRECISION_BF16 && g.precision != L3AC_PRECISION_SPLIT) fail(L3AC_EINVAL, "precision must be L3AC_PRECISION_BF16 or L3AC_PRECISION_SPLIT");
+    const int dk = g.precision == L3AC_PRECISION_SPLIT ? kSplit : kBf16;      // decode-side operand kind
+    c->dec_kind = dk;
     c->compressed = g.en_coder_compress_rate != 1;
     c->frame = 1;
     for (int i = 0; i + 1 < ns; ++i) c->frame *= g.compress_rates[i];
@@ -385,14 +389,14 @@ void build(l3ac_codec* c, Dict& d) {
     d.module = "en_decoder.";
     if (c->compressed) {
         if (g.en_coder_depth < 3) fail(L3AC_EINVAL, "en_coder_depth must be >= 3 with a compressed transformer");
-        c->dec_token = pack_trans(b, d, "local_trans", F, g.en_coder_depth - 2, w, kBf16);
-        c->dec_frame = pack_trans(b, d, "up_trans.trans", F, 2, w * r, kBf16);
+        c->dec_token = pack_trans(b, d, "local_trans", F, g.en_coder_depth - 2, w, dk);
+        c->dec_frame = pack_trans(b, d, "up_trans.trans", F, 2, w * r, dk);
     } else {
-        c->dec_token = pack_trans(b, d, "local_trans", F, g.en_coder_depth, w, kBf16);
+        c->dec_token = pack_trans(b, d, "local_trans", F, g.en_coder_depth, w, dk);
     }
     // ---- decoder (l3ac/modules.py:135-198; EnhanceBlock l3ac/tconv/__init__.py:30-38)
     d.module = "decoder.";
-    c->dec_in = pack_conv(b, d, "blocks.0", g.decoder_dims[0], F, 3, kBf16);
+    c->dec_in = pack_conv(b, d, "blocks.0", g.decoder_dims[0], F, 3, dk);
     blk = 1;
     for (int i = 0; i + 1 < nd; ++i) {
         DecStage st;
@@ -401,7 +405,8 @@ void build(l3ac_codec* c, Dict& d) {
         st.C_out = g.decoder_dims[i + 1];
         if (st.C_in % 8 || st.stride < 1) fail(L3AC_EUNSUPPORTED, "decoder widths must be multiples of 8");
         for (int j = 0; j < g.decoder_depths[i]; ++j)
-            st.units.push_back(pack_unit(b, d, "blocks." + std::to_string(blk) + "." + std::to_string(j) + ".module", st.C_in, kBf16, false));
+            st.units.push_back(pack_unit(b, d, "blocks." + std::to_string(blk) + "." + std::to_string(j) + ".module", st.C_in, dk,
+                                         dk == kSplit && (st.C_in == 24 || st.C_in == 48)));
         ++blk;
         const std::string e = "blocks." + std::to_string(blk);
         std::vector<float> cw(28), cb(4);
@@ -417,7 +422,7 @@ void build(l3ac_codec* c, Dict& d) {
         st.merge_w = b.f32(d.get(e + ".merge_layer.1.weight", (long long)st.C_in * 4), (size_t)st.C_in * 4);
         st.merge_b = b.f32(d.get(e + ".merge_layer.1.bias", st.C_in), st.C_in);
         ++blk;
-        st.up = pack_conv(b, d, "blocks." + std::to_string(blk) + ".0", st.C_out, st.C_in, 1, kBf16);
+        st.up = pack_conv(b, d, "blocks." + std::to_string(blk) + ".0", st.C_out, st.C_in, 1, dk);
         st.cn_w = b.f32(d.get("blocks." + std::to_string(blk) + ".2.weight", st.C_out), st.C_out);
         st.cn_b = b.f32(d.get("blocks." + std::to_string(blk) + ".2.bias", st.C_out), st.C_out);
         ++blk;
@@ -723,7 +728,8 @@ struct Run {
                 ok(l3ac_fsq_dequantize(indices, indices_are_i64, (long long)B * T_tok, F, c->P(c->vq_w_out), c->P(c->vq_b_out), g.levels,
                                        g.n_levels, static_cast<float*>(x.hi), st), "l3ac_fsq_dequantize");
         }
-        x = local_trans(x, c->dec_token, kBf16);
+        const int dk = c->dec_kind;
+        x = local_trans(x, c->dec_token, dk);
         if (c->compressed) {                                                  // UpTransV2, l3ac/local_trans.py:123-126
             const int r = g.en_coder_compress_rate;
             Act y = make(kF32, B, x.T * r, F);
@@ -731,30 +737,31 @@ struct Run {
                 ok(l3ac_upsample_linear_cn(static_cast<const float*>(x.hi), B, x.T, F, r, nullptr, nullptr, kCnEps, static_cast<float*>(y.hi), st),
                    "l3ac_upsample_linear_cn");
             drop(x);
-            x = local_trans(y, c->dec_frame, kBf16);
+            x = local_trans(y, c->dec_frame, dk);
         }
         {
-            Act a = as_operand(x, kBf16);
+            Act a = as_operand(x, dk);
             x = gemm(a, c->dec_in, B, a.T, F, kF32, L3AC_ACT_NONE, 3, -1);         // Conv1d(k3, pad 1)
             drop(a);
         }
         for (const DecStage& s : c->dec_stages) {
-            for (const Unit& u : s.units) x = conv_unit(x, u, kBf16, kF32);
+            for (const Unit& u : s.units) x = conv_unit(x, u, dk, kF32);
             const int T = x.T, C = x.C;
             // EnhanceBlock (l3ac/tconv/__init__.py:30-44): stats pass (partial sums + branch signals), then the streaming gate
             const long long np = l3ac_enhance_partials_floats(B, T);
             float* partials = static_cast<float*>(ar.alloc((size_t)np * 4));
             float* branches = static_cast<float*>(ar.alloc((size_t)B * T * 4 * 4));
-            Act a = make(kBf16, B, T, C);
+            Act a = make(dk == kBf16 ? kBf16 : kF32, B, T, C);         // (split mode: fp32 out, split below)
             if (!dry) {
                 const float* xp = static_cast<const float*>(x.hi);
                 ok(l3ac_enhance_stats(xp, B, T, C, c->P(s.conv_w), c->P(s.conv_b), partials, branches, st), "l3ac_enhance_stats");
                 ok(l3ac_enhance_apply(xp, B, T, C, c->P(s.conv_w), c->P(s.conv_b), c->P(s.in_w), c->P(s.in_b), c->P(s.merge_w),
-                                      c->P(s.merge_b), partials, branches, a.hi, kBf16, st), "l3ac_enhance_apply");
+                                      c->P(s.merge_b), partials, branches, a.hi, a.kind, st), "l3ac_enhance_apply");
             }
             ar.free(partials);
             ar.free(branches);
             drop(x);
+            a = as_operand(a, dk);
             Act y = gemm(a, s.up, B, T, C, kF32);                                  // Conv1d 1x1
             drop(a);
             x = make(kF32, B, T * s.stride, s.C_out);                              // Upsample(linear) + ChannelNorm
@@ -763,7 +770,9 @@ struct Run {
                                            static_cast<float*>(x.hi), st), "l3ac_upsample_linear_cn");
             drop(y);
         }
-        if (!dry) ok(l3ac_decoder_tail_tc(c->tail, static_cast<const float*>(x.hi), B, x.T, audio_out, st), "l3ac_decoder_tail_tc");
+        if (!dry)
+            ok((dk == kSplit ? l3ac_decoder_tail_tc_split : l3ac_decoder_tail_tc)(c->tail, static_cast<const float*>(x.hi), B, x.T, audio_out, st),
+               "l3ac_decoder_tail_tc");
         drop(x);
     }
 };

@@ -126,9 +126,9 @@ class Engine:
         self.native = None
         knobs_default = all(os.environ.get(k, d) == d for k, d in (("L3AC_THIN_TC", "1"), ("L3AC_THIN_TC_DECODE", "0"), ("L3AC_THIN_IMPL", "tcgen05"),
                                                                     ("L3AC_STEM_IMPL", "tcgen05"), ("L3AC_TAIL_IMPL", "tcgen05"), ("L3AC_ATT_IMPL", "tcgen05")))
-        if (os.environ.get("L3AC_ENGINE", "native") == "native" and precision == "bf16" and encoder_precision == "split" and knobs_default
+        if (os.environ.get("L3AC_ENGINE", "native") == "native" and precision in ("bf16", "split") and encoder_precision == "split" and knobs_default
                 and mc.en_coder_dynamic_pos and mc.feature_dim == 128 and mc.encoder_dims[0] == 24 and mc.decoder_dims[-1] == 24):
-            self.native = ops.NativeCodec(mc, weights, self.device)
+            self.native = ops.NativeCodec(mc, weights, self.device, precision=precision)
         w = {m: {k: v.detach().to(self.device) for k, v in sd.items()} for m, sd in weights.items()}
         with torch.no_grad():
             self._pack_encoder(w["encoder"])

@@ -616,9 +616,10 @@ class NativeCodec:
     launch sequence of ``encode_audio`` / ``decode_audio`` in the product precision.  Torch provides the device buffers
     (inputs, outputs, one workspace per call) and the stream; everything else happens behind ``l3ac_encode`` / ``l3ac_decode``."""
 
-    def __init__(self, mc, weights, device):
+    def __init__(self, mc, weights, device, precision: str = "bf16"):
         lib = _lib.load()
         cfg = _lib.CodecConfig()
+        cfg.precision = {"bf16": 0, "split": 1}[precision]
         cfg.feature_dim = mc.feature_dim
         cfg.n_encoder_stages = len(mc.encoder_dims)
         cfg.n_decoder_stages = len(mc.decoder_dims)

@@ -23,12 +23,12 @@ DEV = "cuda:0"
 ROOT = Path(__file__).resolve().parent.parent
 
 
-def _engines(name, weights, monkeypatch):
+def _engines(name, weights, monkeypatch, precision="bf16"):
     mc = model_config(name)
-    native = Engine(mc, weights, DEV)
-    assert native.native is not None, "the product precision must run through the step-level ABI"
+    native = Engine(mc, weights, DEV, precision=precision)
+    assert native.native is not None, "the tensor-core precisions must run through the step-level ABI"
     monkeypatch.setenv("L3AC_ENGINE", "python")
-    python = Engine(mc, weights, DEV)
+    python = Engine(mc, weights, DEV, precision=precision)
     assert python.native is None
     return mc, native, python
 
@@ -56,12 +56,13 @@ def _prefolded(weights):
     return out
 
 
+@pytest.mark.parametrize("precision", ["bf16", "split"])
 @pytest.mark.parametrize("name", ["1kbps", "3kbps", "0k75bps"])
-def test_native_engine_is_the_python_sequence(cuda_lib, name, monkeypatch):
+def test_native_engine_is_the_python_sequence(cuda_lib, name, precision, monkeypatch):
     """l3ac_encode / l3ac_decode launch the same kernels with the same arguments as the operator-level Python sequence:
     with packer-side arithmetic taken out (pre-folded weights) the indices, features and waveforms are BIT-identical."""
     weights = _prefolded(init_state_dicts(model_config(name), seed=11, jitter=True))
-    mc, native, python = _engines(name, weights, monkeypatch)
+    mc, native, python = _engines(name, weights, monkeypatch, precision)
     audio = make_audio(3, 2.0 + 0.37, seed=5).to(DEV)          # not a multiple of the hop: the library pads
     with torch.inference_mode():
         qn, dn = native.encode(audio)
@@ -160,6 +161,7 @@ def _dump_weights(path, mc, weights):
     cfg.n_levels = len(mc.levels)
     for i, v in enumerate(mc.levels):
         cfg.levels[i] = int(v)
+    cfg.precision = 0
     items = [(f"{m}.{k}", t) for m, sd in weights.items() for k, t in sd.items()]
     with open(path, "wb") as f:
         f.write(b"L3ACW1\0\0")
