@@ -155,3 +155,25 @@ def test_get_model_info_matches_readme_table(name, tokens, codes, bps):
     gmac = float(info["macs"].split()[0])
     want = {"0k75bps": 67.29, "1kbps": 83.39, "1k5bps": 84.30, "3kbps": 72.82}[name] / 2      # SURVEY section 8d, GFLOP = 2 * GMAC
     assert abs(gmac - want) / want < 0.03, (gmac, want)
+
+
+def test_step_level_structs_match_the_header(tmp_path):
+    """ctypes mirrors of l3ac_codec_config / l3ac_tensor have the layout a C compiler gives the header's structs, and the
+    plain-C host (tests/c/codec_driver.c) compiles and links against the built library with gcc alone."""
+    import subprocess
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "l3ac_b200.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(l3ac_codec_config), offsetof(l3ac_codec_config, en_coder_depth),\n'
+                   '  offsetof(l3ac_codec_config, levels), offsetof(l3ac_codec_config, decode_rates), offsetof(l3ac_codec_config, precision),\n'
+                   '  sizeof(l3ac_tensor), offsetof(l3ac_tensor, numel)); return 0; }\n')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    cc, t = _lib.CodecConfig, _lib.Tensor
+    assert got == [ctypes.sizeof(cc), cc.en_coder_depth.offset, cc.levels.offset, cc.decode_rates.offset, cc.precision.offset,
+                   ctypes.sizeof(t), t.numel.offset]
+    if not _lib.LIB_PATH.exists():
+        import __graft_entry__
+        __graft_entry__.build()
+    subprocess.run(["gcc", "-O2", "-Wall", "-Werror", "-I", str(ROOT / "include"), str(ROOT / "tests" / "c" / "codec_driver.c"),
+                    "-L", str(_lib.LIB_PATH.parent), "-ll3ac_b200", f"-Wl,-rpath,{_lib.LIB_PATH.parent}", "-o", str(tmp_path / "driver")], check=True)
