@@ -77,6 +77,17 @@ int l3ac_dwconv7_ln(const float* x, int B, int T, int C, const float* dw_w, cons
                     const float* ln_w, const float* ln_b, float eps, void* out, void* out_lo, int out_dtype,
                     l3ac_stream_t stream);
 
+/* The same ConvUnit prologue through a plan, for the decode side's thin stages (C = 48 / 96, bf16 out): the per-channel
+ * parameters (HOST arrays at plan creation: dw_w [7][C], dw_b / ln_w / ln_b [C]) stay in the plan and travel as kernel
+ * parameters, so a thread-per-row kernel (128-row tiles staged in shared memory, taps as FFMAs against the constant bank,
+ * thread-local LayerNorm statistics) replaces the lane-group kernel.  x (B,T,C) fp32 -> out (B,T,C) bf16, both 16-byte
+ * aligned; B <= 65535.  Same arithmetic as l3ac_dwconv7_ln up to the summation order of the LayerNorm statistics. */
+typedef struct l3ac_dwconv_plan l3ac_dwconv_plan;
+int l3ac_dwconv_plan_create(int C, const float* dw_w, const float* dw_b, const float* ln_w, const float* ln_b, float eps,
+                            l3ac_dwconv_plan** plan_out);
+int l3ac_dwconv_plan_destroy(l3ac_dwconv_plan* plan);
+int l3ac_dwconv7_ln_plan(const l3ac_dwconv_plan* plan, const float* x, int B, int T, void* out, l3ac_stream_t stream);
+
 /* LayerNorm over the last dim.  Replaces channels-first ChannelNorm (l3ac/layers.py:50-56) after the
  * strided convs and nn.LayerNorm inside local_attention's LocalMHA / FeedForward. */
 int l3ac_layernorm(const float* x, long long M, int C, const float* w, const float* b, float eps,

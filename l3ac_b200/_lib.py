@@ -53,6 +53,9 @@ PROTOTYPES = {
     "l3ac_stem": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p]),
     "l3ac_stem_tc": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p]),
     "l3ac_dwconv7_ln": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _f, _p, _p, _i, _p]),
+    "l3ac_dwconv_plan_create": (_i, [_i, _p, _p, _p, _p, _f, C.POINTER(_p)]),
+    "l3ac_dwconv_plan_destroy": (_i, [_p]),
+    "l3ac_dwconv7_ln_plan": (_i, [_p, _p, _i, _i, _p, _p]),
     "l3ac_layernorm": (_i, [_p, _ll, _i, _p, _p, _f, _p, _p, _i, _p]),
     "l3ac_split_bf16": (_i, [_p, _ll, _p, _p, _p]),
     "l3ac_snake": (_i, [_p, _ll, _i, _p, _p, _i, _p]),

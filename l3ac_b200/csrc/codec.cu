@@ -143,6 +143,7 @@ Lin pack_lin(Blob& b, const std::vector<float>& w, int N, int Ktot, const float*
 struct Unit {
     int C = 0;
     l3ac_convunit_plan* plan = nullptr;            // thin encode-side stages (C = 24 / 48): whole unit in one kernel
+    l3ac_dwconv_plan* dw_plan = nullptr;           // bf16 units with C = 48 / 96: thread-per-row dwconv7 + LayerNorm
     size_t dw_w = kNone, dw_b = kNone, ln_w = kNone, ln_b = kNone, alpha = kNone, ialpha = kNone, scale = kNone, shift = kNone;
     Lin pw1, pw2;
 };
@@ -233,6 +234,10 @@ Unit pack_unit(Blob& b, const Dict& d, const std::string& p, int C, int kind, bo
                                            w2.data(), b2, &u.plan);
         if (rc != 0) fail(rc, "l3ac_convunit_plan_create(" + p + ")");
         return u;
+    }
+    if (kind == kBf16 && (C == 48 || C == 96)) {
+        int rc = l3ac_dwconv_plan_create(C, dw_t.data(), dw_b, ln_w, ln_b, kCnEps, &u.dw_plan);
+        if (rc != 0) fail(rc, "l3ac_dwconv_plan_create(" + p + ")");
     }
     u.dw_w = b.f32(dw_t);
     u.dw_b = b.f32(dw_b, C);
@@ -618,9 +623,13 @@ struct Run {
             return o;
         }
         Act a = make(act_kind, B, T, C);
-        if (!dry)
-            ok(l3ac_dwconv7_ln(static_cast<const float*>(x.hi), B, T, C, c->P(u.dw_w), c->P(u.dw_b), c->P(u.ln_w), c->P(u.ln_b), kCnEps,
-                               a.hi, a.lo, act_kind, st), "l3ac_dwconv7_ln");
+        if (!dry) {
+            if (u.dw_plan && act_kind == kBf16 && B <= 65535)
+                ok(l3ac_dwconv7_ln_plan(u.dw_plan, static_cast<const float*>(x.hi), B, T, a.hi, st), "l3ac_dwconv7_ln_plan");
+            else
+                ok(l3ac_dwconv7_ln(static_cast<const float*>(x.hi), B, T, C, c->P(u.dw_w), c->P(u.dw_b), c->P(u.ln_w), c->P(u.ln_b), kCnEps,
+                                   a.hi, a.lo, act_kind, st), "l3ac_dwconv7_ln");
+        }
         Act o;
         if (act_kind == kBf16 && out_kind == kF32 && C >= 16 && C <= 256 && C % 16 == 0) {
             o = make(kF32, B, T, C);       // fused MLP: the 4C hidden activation stays in TMEM / shared memory
@@ -873,10 +882,13 @@ extern "C" int l3ac_destroy(l3ac_codec* c) {
     if (!c) return L3AC_OK;
     DeviceGuard dg(c->dev);
     auto free_units = [](std::vector<Unit>& us) {
-        for (Unit& u : us)
+        for (Unit& u : us) {
             if (u.plan) l3ac_convunit_plan_destroy(u.plan);
+            if (u.dw_plan) l3ac_dwconv_plan_destroy(u.dw_plan);
+        }
     };
     for (EncStage& s : c->enc_stages) free_units(s.units);
+    for (DecStage& s : c->dec_stages) free_units(s.units);
     free_units(c->enc_last);
     if (c->stem) l3ac_stem_plan_destroy(c->stem);
     if (c->tail) l3ac_tail_plan_destroy(c->tail);

@@ -7,6 +7,8 @@
 //   tail                     Snake -> Conv(C->1,k7) -> tanh   l3ac/modules.py:192-194
 #include "common.cuh"
 
+#include <new>
+
 namespace l3ac {
 
 // Writes v as OutT; for the split pair (OutT = bf16 and lo != nullptr) also the low-order plane bf16(v - hi).
@@ -299,6 +301,87 @@ __global__ void __launch_bounds__(256) dwconv7_ln_vec_kernel(const float* __rest
                                              a[r].w * rstd * lw.w + lb.w));
             }
         }
+    }
+}
+
+// Thread-per-row variant for the decode side's thin stages (C = 48 / 96, bf16 out; 2.6 M / 0.85 M rows per 32 clips).  The
+// lane-group kernel above spends 36 issue slots per element there (a quarter of its lanes idle: 12 / 24 float4 columns do not
+// divide a warp; 124 registers, 25 % occupancy, ncu: profiles/r02_row_kernels_ncu.txt).  Here a block stages its 128 rows
+// (+ 3 halo rows per side, zero outside the clip) in shared memory with cp.async at a (C + 4)-float pitch -- a thread's
+// 16-byte reads of consecutive rows are then bank-conflict-free -- and ONE THREAD owns one row: the seven taps are FFMAs
+// against kernel-parameter constants (no weight registers, no weight loads), the LayerNorm statistics are thread-local (no
+// shuffles), ~15 issue slots per element.
+template <int C>
+struct DwRowParams {
+    const float* x;
+    __nv_bfloat16* out;
+    int B, T;
+    float eps;
+    float w[7][C];
+    float b[C], lw[C], lb[C];
+};
+
+template <int C>
+__global__ void __launch_bounds__(128) dwconv7_ln_thread_kernel(const __grid_constant__ DwRowParams<C> p) {
+    constexpr int RB = 128, PITCH = C + 4, CH = C / 4;
+    extern __shared__ __align__(16) float dw_tile[];                 // (RB + 6) x PITCH
+    const int b = blockIdx.y, t0 = blockIdx.x * RB;
+    const float* xb = p.x + (long long)b * p.T * C;
+    for (int i = threadIdx.x; i < (RB + 6) * CH; i += 128) {
+        const int r = i / CH, c = i - r * CH;
+        const int t = t0 - 3 + r;
+        float* dst = dw_tile + r * PITCH + 4 * c;
+        if (t >= 0 && t < p.T) {
+            const uint32_t d32 = (uint32_t)__cvta_generic_to_shared(dst);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d32), "l"(xb + (long long)t * C + 4 * c) : "memory");
+        } else {
+            *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    const int r = threadIdx.x, t = t0 + r;
+    if (t >= p.T) return;
+    float acc[C];
+    const float* row = dw_tile + r * PITCH;
+#pragma unroll
+    for (int g = 0; g < CH; ++g) {
+        float4 a = make_float4(p.b[4 * g], p.b[4 * g + 1], p.b[4 * g + 2], p.b[4 * g + 3]);
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            const float4 xv = *reinterpret_cast<const float4*>(row + j * PITCH + 4 * g);
+            a.x = fmaf(p.w[j][4 * g], xv.x, a.x);
+            a.y = fmaf(p.w[j][4 * g + 1], xv.y, a.y);
+            a.z = fmaf(p.w[j][4 * g + 2], xv.z, a.z);
+            a.w = fmaf(p.w[j][4 * g + 3], xv.w, a.w);
+        }
+        acc[4 * g] = a.x; acc[4 * g + 1] = a.y; acc[4 * g + 2] = a.z; acc[4 * g + 3] = a.w;
+    }
+    // LayerNorm over the row: four interleaved partial sums (the lane-group kernel sums four channels per lane first, too)
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int g = 0; g < CH; ++g) { s0 += acc[4 * g]; s1 += acc[4 * g + 1]; s2 += acc[4 * g + 2]; s3 += acc[4 * g + 3]; }
+    const float inv_c = 1.0f / (float)C;
+    const float mean = ((s0 + s1) + (s2 + s3)) * inv_c;
+    s0 = s1 = s2 = s3 = 0.f;
+#pragma unroll
+    for (int g = 0; g < CH; ++g) {
+        acc[4 * g] -= mean; acc[4 * g + 1] -= mean; acc[4 * g + 2] -= mean; acc[4 * g + 3] -= mean;
+        s0 = fmaf(acc[4 * g], acc[4 * g], s0); s1 = fmaf(acc[4 * g + 1], acc[4 * g + 1], s1);
+        s2 = fmaf(acc[4 * g + 2], acc[4 * g + 2], s2); s3 = fmaf(acc[4 * g + 3], acc[4 * g + 3], s3);
+    }
+    const float rstd = rsqrt_nr(((s0 + s1) + (s2 + s3)) * inv_c + p.eps);
+    uint4* orow = reinterpret_cast<uint4*>(p.out + ((long long)b * p.T + t) * C);
+#pragma unroll
+    for (int k = 0; k < C / 8; ++k) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int e = 8 * k + 2 * i;
+            const __nv_bfloat162 h = __floats2bfloat162_rn(acc[e] * rstd * p.lw[e] + p.lb[e], acc[e + 1] * rstd * p.lw[e + 1] + p.lb[e + 1]);
+            pk[i] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        orow[k] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
 }
 
@@ -1509,4 +1592,67 @@ extern "C" int l3ac_tail_conv_tanh(const float* x, int B, int T, int C, const fl
     dim3 grid(l3ac_cdiv(T, kTailTile), B);
     tail_kernel<<<grid, kTailTile, 0, (cudaStream_t)stream>>>(x, B, T, C, alpha, w, bias, out);
     return l3ac_launch_status();
+}
+
+// ------------------------------------------------------------------------------------------
+// dwconv7 + LayerNorm through a plan (C = 48 / 96, bf16 out): the per-channel parameters are kept on the HOST in the plan and
+// travel as kernel parameters, so the thread-per-row kernel reads them from the constant bank.
+// ------------------------------------------------------------------------------------------
+struct l3ac_dwconv_plan {
+    int C;
+    l3ac::DwRowParams<48> p48;
+    l3ac::DwRowParams<96> p96;
+};
+
+template <int C>
+static void fill_dw_params(l3ac::DwRowParams<C>& p, const float* dw_w, const float* dw_b, const float* ln_w, const float* ln_b, float eps) {
+    p.eps = eps;
+    for (int j = 0; j < 7; ++j)
+        for (int c = 0; c < C; ++c) p.w[j][c] = dw_w[j * C + c];
+    for (int c = 0; c < C; ++c) {
+        p.b[c] = dw_b[c];
+        p.lw[c] = ln_w[c];
+        p.lb[c] = ln_b[c];
+    }
+}
+
+extern "C" int l3ac_dwconv_plan_create(int C, const float* dw_w, const float* dw_b, const float* ln_w, const float* ln_b, float eps,
+                                       l3ac_dwconv_plan** plan_out) {
+    L3AC_CHECK_ARG(dw_w && dw_b && ln_w && ln_b && plan_out);
+    if (C != 48 && C != 96) return L3AC_EUNSUPPORTED;
+    l3ac_dwconv_plan* plan = new (std::nothrow) l3ac_dwconv_plan();
+    if (!plan) return L3AC_EINVAL;
+    plan->C = C;
+    if (C == 48) fill_dw_params(plan->p48, dw_w, dw_b, ln_w, ln_b, eps);
+    else fill_dw_params(plan->p96, dw_w, dw_b, ln_w, ln_b, eps);
+    *plan_out = plan;
+    return L3AC_OK;
+}
+
+extern "C" int l3ac_dwconv_plan_destroy(l3ac_dwconv_plan* plan) {
+    delete plan;
+    return L3AC_OK;
+}
+
+template <int C>
+static int launch_dw_thread(l3ac::DwRowParams<C> p, const float* x, int B, int T, void* out, cudaStream_t st) {
+    using namespace l3ac;
+    p.x = x;
+    p.out = static_cast<__nv_bfloat16*>(out);
+    p.B = B;
+    p.T = T;
+    constexpr int smem = (128 + 6) * (C + 4) * 4;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(dwconv7_ln_thread_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    dwconv7_ln_thread_kernel<C><<<dim3(l3ac_cdiv(T, 128), B), 128, smem, st>>>(p);
+    return l3ac_launch_status();
+}
+
+extern "C" int l3ac_dwconv7_ln_plan(const l3ac_dwconv_plan* plan, const float* x, int B, int T, void* out, l3ac_stream_t stream) {
+    L3AC_CHECK_ARG(plan && x && out && B > 0 && B <= 65535 && T > 0);
+    L3AC_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0);
+    if (plan->C == 48) return launch_dw_thread<48>(plan->p48, x, B, T, out, (cudaStream_t)stream);
+    return launch_dw_thread<96>(plan->p96, x, B, T, out, (cudaStream_t)stream);
 }

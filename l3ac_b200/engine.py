@@ -116,6 +116,7 @@ class Engine:
         self.thin_tc_decode = os.environ.get("L3AC_THIN_TC_DECODE", "0") != "0"
         self.thin_impl = os.environ.get("L3AC_THIN_IMPL", "tcgen05")  # "mma_sync": the register-level cross-check kernel
         self.fused_mlp_max_c = 256
+        self.dwconv_rows = os.environ.get("L3AC_DWCONV_ROWS", "1") != "0"   # thread-per-row dwconv7 + LN for the bf16 C = 48 / 96 units
         self.hidden_block_bytes = 0              # >0: L2-blocked ConvUnit MLP (measured slower, see _run_conv_unit)
         self.dec_dtype = {"bf16": torch.bfloat16, "split": ops.SPLIT, "fp32": torch.float32}[precision]
         self.enc_dtype = ops.SPLIT if encoder_precision == "split" else torch.float32
@@ -125,7 +126,8 @@ class Engine:
         # points and the per-launch instrumentation of bench.py (ops.OP_HOOK) -- the same kernels in the same order.
         self.native = None
         knobs_default = all(os.environ.get(k, d) == d for k, d in (("L3AC_THIN_TC", "1"), ("L3AC_THIN_TC_DECODE", "0"), ("L3AC_THIN_IMPL", "tcgen05"),
-                                                                    ("L3AC_STEM_IMPL", "tcgen05"), ("L3AC_TAIL_IMPL", "tcgen05"), ("L3AC_ATT_IMPL", "tcgen05")))
+                                                                    ("L3AC_STEM_IMPL", "tcgen05"), ("L3AC_TAIL_IMPL", "tcgen05"), ("L3AC_ATT_IMPL", "tcgen05"),
+                                                                    ("L3AC_DWCONV_ROWS", "1")))
         if (os.environ.get("L3AC_ENGINE", "native") == "native" and precision in ("bf16", "split") and encoder_precision == "split" and knobs_default
                 and mc.en_coder_dynamic_pos and mc.feature_dim == 128 and mc.encoder_dims[0] == 24 and mc.decoder_dims[-1] == 24):
             self.native = ops.NativeCodec(mc, weights, self.device, precision=precision)
@@ -365,7 +367,13 @@ class Engine:
         if C == 24 and act_dtype != torch.bfloat16:      # thin full-rate encoder stage: one fused fp32 kernel
             return ops.convunit_thin(x, u["dw_w"], u["dw_b"], u["ln_w"], u["ln_b"], EPS, u["pw1"].w32, u["pw1"].bias,
                                      u["alpha"], u["scale"], u["shift"], u["pw2"].w32, u["pw2"].bias, out_dtype=out_kind)
-        a = ops.dwconv7_ln(x, u["dw_w"], u["dw_b"], u["ln_w"], u["ln_b"], EPS, out_dtype=act_dtype)
+        if act_dtype == torch.bfloat16 and C in (48, 96) and self.dwconv_rows and B <= 65535:
+            # decode side's thin stages: thread-per-row kernel, parameters in a plan (constant bank)
+            if u.get("dw_plan") is None:
+                u["dw_plan"] = ops.DwconvPlan(u["dw_w"], u["dw_b"], u["ln_w"], u["ln_b"], EPS)
+            a = ops.dwconv7_ln_plan(x, u["dw_plan"])
+        else:
+            a = ops.dwconv7_ln(x, u["dw_w"], u["dw_b"], u["ln_w"], u["ln_b"], EPS, out_dtype=act_dtype)
         M = B * T
         esz = {torch.float32: 4, torch.bfloat16: 2, ops.SPLIT: 4}[act_dtype]
         rows_blk = max(128 * 148, (self.hidden_block_bytes // (4 * C * esz)) // 128 * 128)

@@ -146,6 +146,41 @@ def dwconv7_ln(x, dw_w, dw_b, ln_w, ln_b, eps: float, out_dtype=torch.float32) -
     return out
 
 
+class DwconvPlan:
+    """Host-side parameters of the thread-per-row dwconv7 + LayerNorm kernel (``l3ac_dwconv_plan``, C = 48 / 96, bf16 out)."""
+
+    def __init__(self, dw_w, dw_b, ln_w, ln_b, eps: float):
+        host = lambda t: t.detach().to("cpu", torch.float32).contiguous()
+        dw, db, lw, lb = (host(t) for t in (dw_w, dw_b, ln_w, ln_b))
+        self.C = int(db.numel())
+        if tuple(dw.shape) != (7, self.C):
+            raise ValueError("DwconvPlan: dw_w (7, C) expected")
+        self.handle = C.c_void_p()
+        check(_lib.load().l3ac_dwconv_plan_create(self.C, dw.data_ptr(), db.data_ptr(), lw.data_ptr(), lb.data_ptr(), float(eps),
+                                                  C.byref(self.handle)), "l3ac_dwconv_plan_create")
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            try:
+                _lib.load().l3ac_dwconv_plan_destroy(h)
+            except Exception:
+                pass
+
+
+def dwconv7_ln_plan(x: torch.Tensor, plan: DwconvPlan) -> torch.Tensor:
+    """dwconv7 + LayerNorm, thread-per-row kernel: x (B, T, C) fp32 -> (B, T, C) bf16."""
+    _chk(x, name="x")
+    B, T, Cc = x.shape
+    if Cc != plan.C:
+        raise ValueError(f"dwconv7_ln_plan: plan is for C = {plan.C}, got {Cc}")
+    out = torch.empty((B, T, Cc), device=x.device, dtype=torch.bfloat16)
+    _count()
+    with _hook("dwconv7_ln", _nbytes(x, out)), torch.cuda.device(x.device):
+        check(_lib.load().l3ac_dwconv7_ln_plan(plan.handle, _ptr(x), B, T, _ptr(out), _stream(x)), "l3ac_dwconv7_ln_plan")
+    return out
+
+
 def layernorm(x, w, b, eps: float, out_dtype=torch.float32) -> torch.Tensor:
     _chk(x, name="x")
     Cc = x.shape[-1]

@@ -79,6 +79,24 @@ def test_dwconv7_ln(cuda_lib, C, T):
     assert max_abs(got16.float().cpu(), want) < 2 ** -8 * max(1.0, float(want.abs().max()))      # bf16 rounding
 
 
+@pytest.mark.parametrize("C", [48, 96])
+@pytest.mark.parametrize("T", [1, 3, 127, 128, 129, 1001, 26667])
+def test_dwconv7_ln_plan(cuda_lib, C, T):
+    """Thread-per-row dwconv7 + LayerNorm (l3ac_dwconv7_ln_plan, bf16 out) against torch and against the lane-group kernel."""
+    x = rnd(3, C, T, seed=1)
+    w, b = rnd(C, 1, 7, seed=2, scale=0.3), rnd(C, seed=3, scale=0.1)
+    lw, lb = 1 + rnd(C, seed=4, scale=0.1), rnd(C, seed=5, scale=0.1)
+    want = F.layer_norm(F.conv1d(x, w, b, padding=3, groups=C).permute(0, 2, 1), (C,), lw, lb, 1e-8)
+    wt = w[:, 0].t().contiguous()
+    got = ops.dwconv7_ln_plan(cl(x), ops.DwconvPlan(wt, b, lw, lb, 1e-8))
+    old = ops.dwconv7_ln(cl(x), wt.to(DEV), b.to(DEV), lw.to(DEV), lb.to(DEV), 1e-8, torch.bfloat16)
+    assert got.dtype == torch.bfloat16 and got.shape == old.shape
+    assert max_abs(got.float().cpu(), want) < 2 ** -8 * max(1.0, float(want.abs().max()))      # bf16 rounding
+    # same arithmetic up to the summation order of the statistics: at most a bf16 rounding flip here and there
+    diff = (got.float() - old.float()).abs()
+    assert float((diff > 0).float().mean()) < 2e-3 and float(diff.max()) <= 2 ** -7 * max(1.0, float(want.abs().max()))
+
+
 @pytest.mark.parametrize("C", [48, 128, 192])
 def test_layernorm_is_channel_norm(cuda_lib, C):
     x = rnd(2, C, 33, seed=1)
