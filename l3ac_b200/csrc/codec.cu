@@ -927,7 +927,7 @@ extern "C" long long l3ac_workspace_bytes(const l3ac_codec* c, int B, int T) {
 extern "C" int l3ac_encode(l3ac_codec* c, const float* audio, int B, int T, void* workspace, long long workspace_bytes, float* q_feature,
                            int32_t* indices, float* level_indices, l3ac_stream_t stream) {
     if (!c || !audio || B <= 0 || T <= 0 || !workspace || workspace_bytes <= 0 || !indices) return L3AC_EINVAL;
-    if ((reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(audio)) & 15) return L3AC_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(workspace) & 15) || (reinterpret_cast<uintptr_t>(audio) & 3)) return L3AC_EINVAL;
     return guarded([&] {
         Run r(c, workspace, (size_t)workspace_bytes, (cudaStream_t)stream, false);
         r.encode(audio, B, T, q_feature, indices, level_indices);
@@ -938,7 +938,7 @@ extern "C" int l3ac_encode(l3ac_codec* c, const float* audio, int B, int T, void
 extern "C" int l3ac_decode(l3ac_codec* c, const void* indices, int indices_are_i64, const float* q_feature, int B, int T_tok, void* workspace,
                            long long workspace_bytes, float* audio, l3ac_stream_t stream) {
     if (!c || (!indices && !q_feature) || B <= 0 || T_tok <= 0 || !workspace || workspace_bytes <= 0 || !audio) return L3AC_EINVAL;
-    if ((reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(audio)) & 15) return L3AC_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(workspace) & 15) || (reinterpret_cast<uintptr_t>(audio) & 3)) return L3AC_EINVAL;
     return guarded([&] {
         Run r(c, workspace, (size_t)workspace_bytes, (cudaStream_t)stream, false);
         r.decode(indices, indices_are_i64, q_feature, B, T_tok, audio);

@@ -103,6 +103,26 @@ def test_native_engine_matches_oracle(cuda_lib, monkeypatch):
     assert snr > 18.0 and abs(snr - snr_py) < 3.0
 
 
+def test_micro_batches_of_odd_length_clips(cuda_lib, monkeypatch):
+    """Clips whose length is neither a multiple of the hop nor of four samples, processed in many micro-batches (row slices of
+    the batch are then only 4-byte aligned): every micro-batching gives the result of the one-clip-at-a-time run."""
+    mc = model_config("1kbps")
+    weights = init_state_dicts(mc, seed=13, jitter=True)
+    monkeypatch.setenv("L3AC_CHUNK_SECONDS", "3")
+    eng = Engine(mc, weights, DEV)
+    assert eng.native is not None
+    audio = make_audio(45, 16005 / 16000.0, seed=21).to(DEV)         # 45 x 16005 samples: 23 micro-batches of 2 (and 1) clips
+    assert audio.shape[1] == 16005 and len(eng._chunks(*audio.shape)) > 20
+    with torch.inference_mode():
+        q, d = eng.encode(audio)
+        wav = eng.decode(indices=d["indices"])
+        for i in (0, 1, 2, 44):
+            qi, di = eng.encode(audio[i:i + 1])
+            assert torch.equal(di["indices"], d["indices"][i:i + 1]) and torch.equal(qi, q[i:i + 1])
+            assert torch.equal(eng.decode(indices=di["indices"]), wav[i:i + 1])
+    assert wav.shape == (45, d["indices"].shape[1] * mc.hop_length)
+
+
 def test_workspace_contract(cuda_lib):
     """l3ac_workspace_bytes is the exact high-water mark: the call succeeds with it and is refused one block below it;
     bad arguments are rejected with L3AC_EINVAL, not a crash."""
