@@ -134,6 +134,7 @@ local_attention_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __g
         uint4* dst = reinterpret_cast<uint4*>(smem + L::v + st * L::kVStage + 4 * kPlane) + r;
         *dst = make_uint4(r < 128 ? 0x00003F80u : 0u, 0u, 0u, 0u);      // bf16 {1, 0, 0, 0, 0, 0, 0, 0}
     }
+    L3AC_PDL_SYNC();      // the bias table and the constant planes above are weights; q / k / v below come from the previous kernel
     for (int i = tid; i < 128 * 4; i += kThreads) {
         const int r = i >> 2, g = i & 3;
         const int t = min(q0 + r, T - 1);
@@ -459,8 +460,8 @@ static int launch(const void* hi, const void* lo, const float* table, int B, int
         cudaError_t e = cudaFuncSetAttribute(local_attention_umma_kernel<SPLIT, OUTV>,                                   \
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                    \
         if (e != cudaSuccess) return (int)e;                                                                            \
-        local_attention_umma_kernel<SPLIT, OUTV><<<grid, kThreads, smem, st>>>(tm_hi, tm_lo, (const __nv_bfloat16*)hi, (const __nv_bfloat16*)lo, \
-                                                                               table, B, T, H, window, out, out_lo);    \
+        l3ac_launch(local_attention_umma_kernel<SPLIT, OUTV>, grid, dim3(kThreads), smem, st, tm_hi, tm_lo, (const __nv_bfloat16*)hi,   \
+                    (const __nv_bfloat16*)lo, table, B, T, H, window, out, out_lo);                                      \
     } while (0)
     if (out_dtype == L3AC_F32) L3AC_ATTU_LAUNCH(L3AC_F32);
     else if (out_dtype == L3AC_BF16) L3AC_ATTU_LAUNCH(L3AC_BF16);

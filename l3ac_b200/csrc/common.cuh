@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "../../include/l3ac_b200.h"
 
@@ -31,6 +32,41 @@ static inline int l3ac_sm_count() {
     if (cache[dev] == 0) cudaDeviceGetAttribute(&cache[dev], cudaDevAttrMultiProcessorCount, dev);
     return cache[dev];
 }
+
+// Programmatic dependent launch for the kernels that support it (L3AC_PDL=0 disables): the prologue of kernel N+1 overlaps
+// the tail of kernel N; see the griddepcontrol instructions in the kernels.
+static inline bool l3ac_pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("L3AC_PDL");
+        on = (e && e[0] == '1') ? 1 : 0;
+    }
+    return on == 1;
+}
+
+// Launch with (or, when disabled, without) the programmatic-stream-serialization attribute.
+template <typename... KArgs, typename... Args>
+static inline void l3ac_launch(void (*fn)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = l3ac_pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, fn, KArgs(args)...);       // errors surface through l3ac_launch_status()
+}
+
+// Device side: call once per thread after the part of the prologue that touches only kernel parameters, weights and shared
+// memory.  No-ops when the launch does not carry the attribute.
+#define L3AC_PDL_SYNC()                                                      \
+    do {                                                                     \
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      \
+        asm volatile("griddepcontrol.wait;" ::: "memory");                   \
+    } while (0)
 
 static inline int l3ac_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 

@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(kThreads, Cfg<C>::kCtasPerSm) convunit_umma_ke
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
+    L3AC_PDL_SYNC();      // weight staging, barriers and TMEM above may overlap the previous kernel's tail
 
     if (warp >= kRowWarps) {
         // =============================================================== MMA issuers: warp kRowWarps + b owns block b
@@ -425,7 +426,7 @@ int run_plan(const l3ac_convunit_plan* plan, const float* x, int B, int T, void*
     const long long n_tiles = (long long)l3ac_cdiv(T, kRows) * B;
     if (n_tiles >= (1LL << 30)) return L3AC_EINVAL;
     const long long ctas = (long long)cfg::kCtasPerSm * l3ac_sm_count();
-    convunit_umma_kernel<C><<<(int)(n_tiles < ctas ? n_tiles : ctas), kThreads, cfg::kSmemBytes, stream>>>(p);
+    l3ac_launch(convunit_umma_kernel<C>, dim3((int)(n_tiles < ctas ? n_tiles : ctas)), dim3(kThreads), cfg::kSmemBytes, stream, p);
     return l3ac_launch_status();
 }
 

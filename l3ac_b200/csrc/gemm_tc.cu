@@ -246,6 +246,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
+    // Programmatic dependent launch (no-ops unless the launch carries the attribute): everything above -- barrier init, TMEM
+    // allocation, tensor-map prefetch -- may overlap the tail of the previous kernel in the stream; nothing below (TMA loads
+    // of A, residual reads, stores) may.  The next kernel's prologue may likewise start once every CTA of this grid is here.
+    L3AC_PDL_SYNC();
 
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
     const int terms = p.split ? 3 : 1;
@@ -676,6 +680,6 @@ extern "C" int l3ac_gemm_bf16_tc(const l3ac_gemm_desc* d, l3ac_stream_t stream) 
     const long long tiles = (long long)p.num_m_tiles * p.num_n_tiles;
     const long long max_ctas = occ2 ? 2LL * sms : sms;
     const int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
-    fn<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmW, tmA_lo, tmW_lo, p);
+    l3ac_launch(fn, dim3(grid), dim3(kThreads), smem, (cudaStream_t)stream, tmA, tmW, tmA_lo, tmW_lo, p);
     return l3ac_launch_status();
 }

@@ -259,6 +259,7 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
+    L3AC_PDL_SYNC();      // the prologue above (barriers, parameters, TMEM) may overlap the previous kernel's tail
 
     const int n_my_tiles = (p.num_m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
@@ -680,6 +681,6 @@ extern "C" int l3ac_convunit_mlp_tc(const void* a, const void* w1, const float* 
     if (e != cudaSuccess) return (int)e;
     const int sms = l3ac_sm_count();
     const int grid = (int)(mt < sms ? mt : sms);
-    convunit_mlp_kernel<<<grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(tmA, tmW1, tmW2, p);
+    l3ac_launch(convunit_mlp_kernel, dim3(grid), dim3(kThreads), smem_bytes, (cudaStream_t)stream, tmA, tmW1, tmW2, p);
     return l3ac_launch_status();
 }

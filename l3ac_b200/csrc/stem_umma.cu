@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(kThreads, 2) stem_umma_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
+    L3AC_PDL_SYNC();      // weight staging, barriers and TMEM above may overlap the previous kernel's tail
 
     if (warp >= kRowWarps) {
         // =============================================================== MMA issuers: warp kRowWarps + b owns block b
@@ -499,6 +500,6 @@ extern "C" int l3ac_stem_umma(const l3ac_stem_plan* plan, const float* audio, in
     if (e != cudaSuccess) return (int)e;
     const int sms = l3ac_sm_count();
     const long long ctas = 2LL * sms;
-    stem_umma_kernel<<<(int)(n_tiles < ctas ? n_tiles : ctas), kThreads, kSmemBytes, (cudaStream_t)stream>>>(p);
+    l3ac_launch(stem_umma_kernel, dim3((int)(n_tiles < ctas ? n_tiles : ctas)), dim3(kThreads), kSmemBytes, (cudaStream_t)stream, p);
     return l3ac_launch_status();
 }

@@ -241,6 +241,7 @@ __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) decoder_tail_tc_kern
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
+    L3AC_PDL_SYNC();      // weight staging, zeroed planes, barriers and TMEM above may overlap the previous kernel's tail
 
     const int tiles_per_clip = (p.T + kOut - 1) / kOut;
     const int n_tiles = tiles_per_clip * p.B;
@@ -655,7 +656,7 @@ static int launch_tail(const l3ac_tail_plan* plan, const float* x, int B, int T,
     cudaError_t e = cudaFuncSetAttribute(decoder_tail_tc_kernel<kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::kSmemBytes);
     if (e != cudaSuccess) return (int)e;
     const int sms = l3ac_sm_count();
-    decoder_tail_tc_kernel<kSplit><<<(int)(n_tiles < sms ? n_tiles : sms), K::kThreads, K::kSmemBytes, (cudaStream_t)stream>>>(p);
+    l3ac_launch(decoder_tail_tc_kernel<kSplit>, dim3((int)(n_tiles < sms ? n_tiles : sms)), dim3(K::kThreads), K::kSmemBytes, (cudaStream_t)stream, p);
     return l3ac_launch_status();
 }
 
