@@ -497,7 +497,7 @@ def main():
                  "gemm_tc": "gemm_tc_kernel (tcgen05 bf16 GEMM)",
                  "gemm_tc_split": "gemm_tc_kernel, 3-term split-bf16 launches (counted at their algorithmic 2*M*N*K, not 3x)"}
         traffic, traffic_note = None, None
-        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_fused_mlp_traffic.json")
+        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_fused_mlp_traffic.json")
         if dom == "convunit_mlp_tc" and os.path.exists(tpath) and args.config == "1kbps" and B == 64 and secs == 10.0:
             tj = json.load(open(tpath))
             if tj.get("launches") == len(dom_sel):
