@@ -390,6 +390,13 @@ int l3ac_encode(l3ac_codec* codec, const float* audio, int B, int T, void* works
                 float* q_feature, int32_t* indices, float* level_indices, l3ac_stream_t stream);
 int l3ac_decode(l3ac_codec* codec, const void* indices, int indices_are_i64, const float* q_feature, int B, int T_tok,
                 void* workspace, long long workspace_bytes, float* audio, l3ac_stream_t stream);
+/* The quantiser alone with the handle's weights: VQEmbed.forward (trans_feature (B,T_tok,feature_dim) fp32 -> q_feature,
+ * indices int32, level_indices fp32 or NULL) and VQEmbed.to_features (indices int32 / int64 -> q_feature);
+ * l3ac/vq/__init__.py:20-30.  Device pointers, no workspace. */
+int l3ac_quantize(l3ac_codec* codec, const float* trans_feature, int B, int T_tok, float* q_feature, int32_t* indices,
+                  float* level_indices, l3ac_stream_t stream);
+int l3ac_dequantize(l3ac_codec* codec, const void* indices, int indices_are_i64, int B, int T_tok, float* q_feature,
+                    l3ac_stream_t stream);
 int l3ac_encode_host(l3ac_codec* codec, const float* audio, int B, int T, int32_t* indices, float* q_feature);
 int l3ac_decode_host(l3ac_codec* codec, const int32_t* indices, int B, int T_tok, float* audio);
 

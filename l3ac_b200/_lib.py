@@ -97,6 +97,8 @@ PROTOTYPES = {
     "l3ac_launch_count": (_ll, [_p]),
     "l3ac_encode": (_i, [_p, _p, _i, _i, _p, _ll, _p, _p, _p, _p]),
     "l3ac_decode": (_i, [_p, _p, _i, _p, _i, _i, _p, _ll, _p, _p]),
+    "l3ac_quantize": (_i, [_p, _p, _i, _i, _p, _p, _p, _p]),
+    "l3ac_dequantize": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "l3ac_encode_host": (_i, [_p, _p, _i, _i, _p, _p]),
     "l3ac_decode_host": (_i, [_p, _p, _i, _i, _p]),
 }

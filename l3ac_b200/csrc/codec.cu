@@ -946,6 +946,27 @@ extern "C" int l3ac_decode(l3ac_codec* c, const void* indices, int indices_are_i
     });
 }
 
+// VQEmbed.forward / VQEmbed.to_features on their own (l3ac/vq/__init__.py:20-30), with the handle's quantiser weights.
+extern "C" int l3ac_quantize(l3ac_codec* c, const float* trans_feature, int B, int T_tok, float* q_feature, int32_t* indices,
+                             float* level_indices, l3ac_stream_t stream) {
+    if (!c || !trans_feature || B <= 0 || T_tok <= 0 || !q_feature || !indices) return L3AC_EINVAL;
+    const l3ac_codec_config& g = c->cfg;
+    int rc = l3ac_fsq_quantize(trans_feature, (long long)B * T_tok, g.feature_dim, c->P(c->vq_w_in), c->P(c->vq_b_in), c->P(c->vq_w_out),
+                               c->P(c->vq_b_out), g.levels, g.n_levels, q_feature, indices, level_indices, nullptr, stream);
+    if (rc == L3AC_OK) c->launches += 1;
+    return rc;
+}
+
+extern "C" int l3ac_dequantize(l3ac_codec* c, const void* indices, int indices_are_i64, int B, int T_tok, float* q_feature,
+                               l3ac_stream_t stream) {
+    if (!c || !indices || B <= 0 || T_tok <= 0 || !q_feature) return L3AC_EINVAL;
+    const l3ac_codec_config& g = c->cfg;
+    int rc = l3ac_fsq_dequantize(indices, indices_are_i64, (long long)B * T_tok, g.feature_dim, c->P(c->vq_w_out), c->P(c->vq_b_out), g.levels,
+                                 g.n_levels, q_feature, stream);
+    if (rc == L3AC_OK) c->launches += 1;
+    return rc;
+}
+
 // Host-buffer calls: upload, run and download micro-batch by micro-batch on up to four internal streams, so that the copies of one
 // micro-batch overlap the kernels of the others (pinned host memory makes the copies asynchronous; pageable memory works, slower).
 extern "C" int l3ac_encode_host(l3ac_codec* c, const float* audio, int B, int T, int32_t* indices, float* q_feature) {

@@ -156,6 +156,26 @@ def test_workspace_contract(cuda_lib):
     torch.cuda.synchronize()
 
 
+def test_quantizer_entry_points(cuda_lib):
+    """l3ac_quantize / l3ac_dequantize (the handle's VQEmbed.forward / to_features) against the operator-level calls."""
+    mc = model_config("3kbps")
+    weights = init_state_dicts(mc, seed=5, jitter=True)
+    nc = ops.NativeCodec(mc, weights, DEV)
+    eng = Engine(mc, weights, DEV)
+    lib = _lib.load()
+    feat = torch.randn(3, 211, 128, device=DEV)
+    q0, i0, l0, _ = eng.quantize(feat)
+    q = torch.empty_like(q0); idx = torch.empty_like(i0); lvl = torch.empty_like(l0)
+    st = torch.cuda.current_stream().cuda_stream
+    assert lib.l3ac_quantize(nc.handle, feat.data_ptr(), 3, 211, q.data_ptr(), idx.data_ptr(), lvl.data_ptr(), st) == 0
+    assert torch.equal(q, q0) and torch.equal(idx, i0) and torch.equal(lvl, l0)
+    for ind in (i0, i0.long()):
+        d = torch.empty_like(q0)
+        assert lib.l3ac_dequantize(nc.handle, ind.data_ptr(), int(ind.dtype == torch.int64), 3, 211, d.data_ptr(), st) == 0
+        assert torch.equal(d, eng.dequantize(ind)) and torch.equal(d, q0)
+    assert lib.l3ac_quantize(nc.handle, None, 3, 211, q.data_ptr(), idx.data_ptr(), None, st) == -1
+
+
 def test_create_rejects_bad_checkpoints(cuda_lib):
     mc = model_config("1kbps")
     weights = init_state_dicts(mc, seed=3)
