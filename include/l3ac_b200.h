@@ -153,6 +153,13 @@ int l3ac_convunit_mlp_tc(const void* a, const void* w1, const float* b1, const f
                          const float* scale, const float* shift, const void* w2, const float* b2, const float* residual,
                          float* out, long long M, int C, l3ac_stream_t stream);
 
+/* The same kernel with one more output: ch0_out (M) fp32 = channel 0 of `out` as a compact plane (NULL: none).  EnhanceBlock
+ * (l3ac/tconv/__init__.py:40-44) derives its four branch signals from channel 0 only; reading it from the (M, C) tensor costs
+ * a 128-byte line per row, so the unit in front of an EnhanceBlock emits it and l3ac_enhance_stats takes it as x with C = 1. */
+int l3ac_convunit_mlp_tc_ch0(const void* a, const void* w1, const float* b1, const float* alpha, const float* ialpha,
+                             const float* scale, const float* shift, const void* w2, const float* b2, const float* residual,
+                             float* out, float* ch0_out, long long M, int C, l3ac_stream_t stream);
+
 /* Whole Residual(ConvUnit) (l3ac/modules.py:10-44) for the thin full-rate encoder stage (C = 24, hidden 96) as one fp32
  * kernel: depthwise conv k7 + LayerNorm + pw_conv1 + Snake + GRN affine + pw_conv2 + residual; the hidden activation
  * never leaves registers.  x (B,T,24) fp32; dw_w [7][24]; w1 [96][24]; w2 [24][96]; b1/alpha/scale/shift [96].
@@ -239,6 +246,7 @@ int l3ac_upsample_linear_cn(const float* x, int B, int T, int C, int scale, cons
  * EnhanceBlock (l3ac/tconv/__init__.py:30-44): 4 x [TrendPool(k in 1,3,5,9) -> Conv1d(1->1,k7,dil 1,2,3,5)]
  * on channel 0 -> InstanceNorm1d(4, affine, eps 1e-5, stats over all T) -> Conv1d(4->C,1x1) -> x + y*x.
  * Two passes: `stats` writes per-(b,chunk) partial sums, `apply` reduces them and gates.
+ * (`stats` reads channel 0 of x only: pass a compact channel-0 plane as x with C = 1 when one is available.)
  * partials: l3ac_enhance_partials_floats(B,T) floats.  conv_w [4][7], conv_b [4], in_w/in_b [4],
  * merge_w [C][4], merge_b [C].  out (B,T,C) fp32|bf16.
  * ------------------------------------------------------------------------------------------ */

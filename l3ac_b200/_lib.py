@@ -62,6 +62,7 @@ PROTOTYPES = {
     "l3ac_gemm_f32": (_i, [C.POINTER(GemmDesc), _p]),
     "l3ac_gemm_bf16_tc": (_i, [C.POINTER(GemmDesc), _p]),
     "l3ac_convunit_mlp_tc": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _ll, _i, _p]),
+    "l3ac_convunit_mlp_tc_ch0": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _ll, _i, _p]),
     "l3ac_convunit_thin_f32": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p]),
     "l3ac_convunit_thin_tc": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
     "l3ac_local_attention_f32": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p]),

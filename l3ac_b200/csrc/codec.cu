@@ -614,7 +614,7 @@ struct Run {
 
     // Residual(ConvUnit), l3ac/modules.py:32-44.  Consumes x (fp32); the result is fp32 or, for the last unit before a GEMM
     // consumer on the encode side, the split pair written directly by the producing kernel.
-    Act conv_unit(Act& x, const Unit& u, int act_kind, int out_kind) {
+    Act conv_unit(Act& x, const Unit& u, int act_kind, int out_kind, Act* ch0 = nullptr) {
         const int B = x.B, T = x.T, C = x.C;
         if (u.plan) {
             Act o = make(out_kind, B, T, C);
@@ -633,10 +633,12 @@ struct Run {
         Act o;
         if (act_kind == kBf16 && out_kind == kF32 && C >= 16 && C <= 256 && C % 16 == 0) {
             o = make(kF32, B, T, C);       // fused MLP: the 4C hidden activation stays in TMEM / shared memory
+            if (ch0) *ch0 = make(kF32, B, T, 1);      // + channel 0 as a compact plane for the EnhanceBlock statistics
             if (!dry)
-                ok(l3ac_convunit_mlp_tc(a.hi, c->P<void>(u.pw1.w), c->P(u.pw1.bias), c->P(u.alpha), c->P(u.ialpha), c->P(u.scale),
-                                        c->P(u.shift), c->P<void>(u.pw2.w), c->P(u.pw2.bias), static_cast<const float*>(x.hi),
-                                        static_cast<float*>(o.hi), x.rows(), C, st), "l3ac_convunit_mlp_tc");
+                ok(l3ac_convunit_mlp_tc_ch0(a.hi, c->P<void>(u.pw1.w), c->P(u.pw1.bias), c->P(u.alpha), c->P(u.ialpha), c->P(u.scale),
+                                            c->P(u.shift), c->P<void>(u.pw2.w), c->P(u.pw2.bias), static_cast<const float*>(x.hi),
+                                            static_cast<float*>(o.hi), ch0 ? static_cast<float*>(ch0->hi) : nullptr, x.rows(), C, st),
+                   "l3ac_convunit_mlp_tc");
             drop(a);
         } else {
             Act h = gemm(a, u.pw1, B, T, C, act_kind, L3AC_ACT_SNAKE, 1, 0, &u);
@@ -754,7 +756,8 @@ struct Run {
             drop(a);
         }
         for (const DecStage& s : c->dec_stages) {
-            for (const Unit& u : s.units) x = conv_unit(x, u, dk, kF32);
+            Act ch0;
+            for (size_t j = 0; j < s.units.size(); ++j) x = conv_unit(x, s.units[j], dk, kF32, j + 1 == s.units.size() ? &ch0 : nullptr);
             const int T = x.T, C = x.C;
             // EnhanceBlock (l3ac/tconv/__init__.py:30-44): stats pass (partial sums + branch signals), then the streaming gate
             const long long np = l3ac_enhance_partials_floats(B, T);
@@ -763,12 +766,14 @@ struct Run {
             Act a = make(dk == kBf16 ? kBf16 : kF32, B, T, C);         // (split mode: fp32 out, split below)
             if (!dry) {
                 const float* xp = static_cast<const float*>(x.hi);
-                ok(l3ac_enhance_stats(xp, B, T, C, c->P(s.conv_w), c->P(s.conv_b), partials, branches, st), "l3ac_enhance_stats");
+                if (ch0.hi) ok(l3ac_enhance_stats(static_cast<const float*>(ch0.hi), B, T, 1, c->P(s.conv_w), c->P(s.conv_b), partials, branches, st), "l3ac_enhance_stats");
+                else ok(l3ac_enhance_stats(xp, B, T, C, c->P(s.conv_w), c->P(s.conv_b), partials, branches, st), "l3ac_enhance_stats");
                 ok(l3ac_enhance_apply(xp, B, T, C, c->P(s.conv_w), c->P(s.conv_b), c->P(s.in_w), c->P(s.in_b), c->P(s.merge_w),
                                       c->P(s.merge_b), partials, branches, a.hi, a.kind, st), "l3ac_enhance_apply");
             }
             ar.free(partials);
             ar.free(branches);
+            if (ch0.hi) drop(ch0);
             drop(x);
             a = as_operand(a, dk);
             Act y = gemm(a, s.up, B, T, C, kF32);                                  // Conv1d 1x1

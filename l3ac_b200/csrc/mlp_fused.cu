@@ -60,6 +60,7 @@ struct Params {
     const float* b2;
     const float* residual;
     float* out;
+    float* ch0;               // optional: channel 0 of the output as a compact (M) plane (what EnhanceBlock's statistics pass reads)
     long long M;
     int C, H4, HN, NC;        // channels, hidden = 4C, hidden chunk width (64), number of chunks
     int a_kb;                 // k-blocks of the activation tile = ceil(C / 64)
@@ -469,6 +470,7 @@ convunit_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     float4 val = *reinterpret_cast<const float4*>(stg_rd + 8 * q * kSlabPitch);
                     val.x += res[q].x; val.y += res[q].y; val.z += res[q].z; val.w += res[q].w;
                     *reinterpret_cast<float4*>(p.out + (row_lane + 8 * q) * p.C + col) = val;
+                    if (col == 0 && p.ch0) p.ch0[row_lane + 8 * q] = val.x;
                 }
             }
             tc_fence_before();
@@ -612,6 +614,12 @@ extern "C" int l3ac_debug_mlp_trace(unsigned long long* host_buf) {      // host
 extern "C" int l3ac_convunit_mlp_tc(const void* a, const void* w1, const float* b1, const float* alpha, const float* ialpha,
                                     const float* scale, const float* shift, const void* w2, const float* b2,
                                     const float* residual, float* out, long long M, int C, l3ac_stream_t stream) {
+    return l3ac_convunit_mlp_tc_ch0(a, w1, b1, alpha, ialpha, scale, shift, w2, b2, residual, out, nullptr, M, C, stream);
+}
+
+extern "C" int l3ac_convunit_mlp_tc_ch0(const void* a, const void* w1, const float* b1, const float* alpha, const float* ialpha,
+                                        const float* scale, const float* shift, const void* w2, const float* b2,
+                                        const float* residual, float* out, float* ch0_out, long long M, int C, l3ac_stream_t stream) {
     using namespace l3ac::mlp;
     L3AC_CHECK_ARG(a && w1 && b1 && alpha && ialpha && scale && shift && w2 && b2 && residual && out && M > 0);
     // C = 512 does not fit shared memory / TMEM (two-GEMM path); the 16-column output staging wants whole 16-column groups
@@ -632,6 +640,7 @@ extern "C" int l3ac_convunit_mlp_tc(const void* a, const void* w1, const float* 
     }
     Params p{};
     p.b1 = b1; p.alpha = alpha; p.ialpha = ialpha; p.scale = scale; p.shift = shift; p.b2 = b2; p.residual = residual; p.out = out;
+    p.ch0 = ch0_out;
     p.M = M; p.C = C; p.H4 = H4; p.HN = HN; p.NC = H4 / HN;
     p.a_kb = (C + kBK - 1) / kBK;
     p.n_halves = (C + 127) / 128;

@@ -337,7 +337,7 @@ class Engine:
             return ops.split_bf16(x)
         return x.to(kind)
 
-    def _run_conv_unit(self, x, u, act_dtype, out_kind=torch.float32):
+    def _run_conv_unit(self, x, u, act_dtype, out_kind=torch.float32, ch0_out: Optional[list] = None):
         """Residual(ConvUnit) -- l3ac/modules.py:32-44.
 
         The 4C-wide hidden tensor is the largest activation of the path.  Optionally (``hidden_block_bytes`` > 0) the
@@ -378,8 +378,12 @@ class Engine:
         esz = {torch.float32: 4, torch.bfloat16: 2, ops.SPLIT: 4}[act_dtype]
         rows_blk = max(128 * 148, (self.hidden_block_bytes // (4 * C * esz)) // 128 * 128)
         if act_dtype == torch.bfloat16 and self.fused_mlp and 16 <= C <= self.fused_mlp_max_c and C % 16 == 0:
-            return ops.convunit_mlp(a, u["pw1"].w16, u["pw1"].bias, u["alpha"], u["scale"], u["shift"], u["pw2"].w16,
-                                    u["pw2"].bias, x, ialpha=u["ialpha"])
+            r = ops.convunit_mlp(a, u["pw1"].w16, u["pw1"].bias, u["alpha"], u["scale"], u["shift"], u["pw2"].w16,
+                                 u["pw2"].bias, x, ialpha=u["ialpha"], want_ch0=ch0_out is not None)
+            if ch0_out is not None:          # (the unit in front of an EnhanceBlock also emits channel 0 as a compact plane)
+                ch0_out.append(r[1])
+                return r[0]
+            return r
         if self.hidden_block_bytes <= 0 or act_dtype == torch.float32 or M <= rows_blk + rows_blk // 2:
             h = self._lin(a, u["pw1"], B, T, C, act=ops.ACT_SNAKE, alpha=u["alpha"], scale=u["scale"], shift=u["shift"],
                           out_dtype=act_dtype)
@@ -646,10 +650,11 @@ class Engine:
         B, T, F = x.shape
         x = self._lin(self._as_operand(x, adt), self.dec_in, B, T, F, taps=3, tap_shift0=-1)   # Conv1d(k3, pad 1)
         for si, st in enumerate(self.dec_stages):
-            for u in st["units"]:
-                x = self._run_conv_unit(x, u, adt)
+            ch0 = []
+            for ui, u in enumerate(st["units"]):
+                x = self._run_conv_unit(x, u, adt, ch0_out=ch0 if ui == len(st["units"]) - 1 else None)
             B, T, C = x.shape
-            a = ops.enhance(x, out_dtype=torch.float32 if adt == ops.SPLIT else adt, **st["enh"])    # EnhanceBlock
+            a = ops.enhance(x, out_dtype=torch.float32 if adt == ops.SPLIT else adt, ch0=ch0[0] if ch0 else None, **st["enh"])    # EnhanceBlock
             y = self._lin(self._as_operand(a, adt), st["up"], B, T, C)              # Conv1d 1x1
             x = ops.upsample_linear_cn(y, st["stride"], st["cn_w"], st["cn_b"], EPS)   # Upsample + ChannelNorm
             if taps is not None:

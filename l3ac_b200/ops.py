@@ -272,8 +272,9 @@ def gemm(a, w, *, B: int, T: int, K: int, taps: int = 1, tap_shift0: int = 0, ta
     return out
 
 
-def convunit_mlp(a: torch.Tensor, w1, b1, alpha, scale, shift, w2, b2, residual: torch.Tensor, ialpha=None) -> torch.Tensor:
-    """Fused pw_conv1 -> snake/GRN -> pw_conv2 -> +residual (tcgen05, hidden activation on chip).  a (…, C) bf16."""
+def convunit_mlp(a: torch.Tensor, w1, b1, alpha, scale, shift, w2, b2, residual: torch.Tensor, ialpha=None, want_ch0: bool = False):
+    """Fused pw_conv1 -> snake/GRN -> pw_conv2 -> +residual (tcgen05, hidden activation on chip).  a (…, C) bf16.
+    ``want_ch0``: also return channel 0 of the result as a compact fp32 plane (for the EnhanceBlock statistics pass)."""
     _chk(a, torch.bfloat16, "a")
     _chk(residual, name="residual")
     Cc = a.shape[-1]
@@ -281,13 +282,14 @@ def convunit_mlp(a: torch.Tensor, w1, b1, alpha, scale, shift, w2, b2, residual:
     if tuple(w1.shape) != (4 * Cc, Cc) or tuple(w2.shape) != (Cc, 4 * Cc) or residual.numel() != a.numel():
         raise ValueError("convunit_mlp shape mismatch")
     out = torch.empty(residual.shape, device=a.device, dtype=torch.float32)
+    ch0 = torch.empty(residual.shape[:-1], device=a.device, dtype=torch.float32) if want_ch0 else None
     if ialpha is None:
         ialpha = 1.0 / (alpha + 1e-8)
     _count()
     with _hook("convunit_mlp_tc", _nbytes(a, residual, out, w1, w2), 2.0 * M * 2 * 4 * Cc * Cc), torch.cuda.device(a.device):
-        check(_lib.load().l3ac_convunit_mlp_tc(_ptr(a), _ptr(w1), _ptr(b1), _ptr(alpha), _ptr(ialpha), _ptr(scale), _ptr(shift), _ptr(w2),
-                                               _ptr(b2), _ptr(residual), _ptr(out), M, Cc, _stream(a)), "l3ac_convunit_mlp_tc")
-    return out
+        check(_lib.load().l3ac_convunit_mlp_tc_ch0(_ptr(a), _ptr(w1), _ptr(b1), _ptr(alpha), _ptr(ialpha), _ptr(scale), _ptr(shift), _ptr(w2),
+                                                   _ptr(b2), _ptr(residual), _ptr(out), _ptr(ch0), M, Cc, _stream(a)), "l3ac_convunit_mlp_tc")
+    return (out, ch0) if want_ch0 else out
 
 
 def convunit_thin(x: torch.Tensor, dw_w, dw_b, ln_w, ln_b, eps: float, w1, b1, alpha, scale, shift, w2, b2, out_dtype=torch.float32):
@@ -469,9 +471,10 @@ def upsample_linear_cn(x: torch.Tensor, scale: int, cn_w=None, cn_b=None, eps: f
 
 
 def enhance(x: torch.Tensor, conv_w, conv_b, in_w, in_b, merge_w, merge_b, out_dtype=torch.float32,
-            stream_branches: bool = True) -> torch.Tensor:
+            stream_branches: bool = True, ch0: Optional[torch.Tensor] = None) -> torch.Tensor:
     """EnhanceBlock.  ``stream_branches``: the stats pass stores the four branch signals (B, T, 4) and the apply pass streams
-    them back (default); False recomputes them per tile in the apply pass."""
+    them back (default); False recomputes them per tile in the apply pass.  ``ch0``: channel 0 of x as a compact (B, T) plane
+    (emitted by the producing kernel); the stats pass then reads it instead of one 128-byte line of x per row."""
     _chk(x, name="x")
     B, T, Cc = x.shape
     lib = _lib.load()
@@ -481,8 +484,13 @@ def enhance(x: torch.Tensor, conv_w, conv_b, in_w, in_b, merge_w, merge_b, out_d
     _count(2)
     with _hook("enhance", 2 * x.numel() // x.shape[-1] * 4 + _nbytes(x, out)), torch.cuda.device(x.device):
         st = _stream(x)
-        check(lib.l3ac_enhance_stats(_ptr(x), B, T, Cc, _ptr(conv_w), _ptr(conv_b), _ptr(partials), _ptr(branches), st),
-              "l3ac_enhance_stats")
+        if ch0 is not None and stream_branches:
+            _chk(ch0, name="ch0")
+            check(lib.l3ac_enhance_stats(_ptr(ch0), B, T, 1, _ptr(conv_w), _ptr(conv_b), _ptr(partials), _ptr(branches), st),
+                  "l3ac_enhance_stats")
+        else:
+            check(lib.l3ac_enhance_stats(_ptr(x), B, T, Cc, _ptr(conv_w), _ptr(conv_b), _ptr(partials), _ptr(branches), st),
+                  "l3ac_enhance_stats")
         check(lib.l3ac_enhance_apply(_ptr(x), B, T, Cc, _ptr(conv_w), _ptr(conv_b), _ptr(in_w), _ptr(in_b),
                                      _ptr(merge_w), _ptr(merge_b), _ptr(partials), _ptr(branches), _ptr(out), _DT[out_dtype], st),
               "l3ac_enhance_apply")

@@ -155,6 +155,8 @@ def test_fused_convunit_mlp_is_deterministic(cuda_lib, M, C):
     alpha, scale, shift = (0.5 + torch.rand(4 * C)).to(DEV), (1 + rnd(4 * C, seed=16, scale=0.1)).to(DEV), rnd(4 * C, seed=17, scale=0.1).to(DEV)
     x = rnd(1, M, C, seed=18).to(DEV)
     first = ops.convunit_mlp(a, w1, b1, alpha, scale, shift, w2, b2, x)
+    with_ch0, ch0 = ops.convunit_mlp(a, w1, b1, alpha, scale, shift, w2, b2, x, want_ch0=True)      # + channel 0 as a compact plane
+    assert torch.equal(with_ch0, first) and ch0.shape == first.shape[:-1] and torch.equal(ch0, first[..., 0])
     for _ in range(8):
         again = ops.convunit_mlp(a, w1, b1, alpha, scale, shift, w2, b2, x)
         assert torch.equal(first, again)
