@@ -524,7 +524,7 @@ def main():
     mma_ms, mma_gflop = sum(o["ms"] for o in mma_ops.values()), sum(o["gflop"] for o in mma_ops.values())
     # tcgen05 kernels whose operands are produced by threads (decoder tail, windowed attention, ...): tensor-core contractions
     # with TMEM accumulators, bound by the SFU / issue work of their snake or softmax stages rather than by the MMAs
-    UMMA_KINDS = ("decoder_tail_tc", "local_attention_tc_umma", "local_attention_tc_split_umma", "convunit_thin_umma", "stem_umma")
+    UMMA_KINDS = ("decoder_tail_tc", "decoder_tail_tc_split", "local_attention_tc_umma", "local_attention_tc_split_umma", "convunit_thin_umma", "stem_umma")
     umma_ops = {k: o for k, o in by_op.items() if k in UMMA_KINDS}
     umma_ms, umma_gflop = sum(o["ms"] for o in umma_ops.values()), sum(o["gflop"] for o in umma_ops.values())
     hbm_ops = {k: o for k, o in by_op.items() if not k.startswith("gemm") and k != "convunit_mlp_tc" and k not in MMA_KINDS

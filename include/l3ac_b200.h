@@ -242,6 +242,19 @@ int l3ac_fsq_dequantize(const void* indices, int indices_are_i64, long long M, i
 int l3ac_upsample_linear_cn(const float* x, int B, int T, int C, int scale, const float* cn_w,
                             const float* cn_b, float eps, float* out, l3ac_stream_t stream);
 
+/* The up layer's tail fused with the next ConvUnit's prologue (decode side, bf16 operands; C = 48 / 96, scale 2 / 3):
+ *   x_up = ChannelNorm(Upsample_linear(y, scale))   (l3ac/modules.py:162-163)   -> (B, T*scale, C) fp32, the next stage's residual stream
+ *   a    = LayerNorm(dwconv7(x_up))                 (l3ac/modules.py:33-35)     -> (B, T*scale, C) bf16, the operand of l3ac_convunit_mlp_tc
+ * in one kernel: x_up is written once and never read back for the depthwise conv.  The per-channel parameters (HOST arrays
+ * at plan creation: cn_w / cn_b [C], dw_w [7][C], dw_b / ln_w / ln_b [C]) stay in the plan and travel as kernel parameters.
+ * Same arithmetic as l3ac_upsample_linear_cn followed by l3ac_dwconv7_ln_plan.  y, x_up, a_out 16-byte aligned; B <= 65535. */
+typedef struct l3ac_updw_plan l3ac_updw_plan;
+int l3ac_updw_plan_create(int C, int scale, const float* cn_w, const float* cn_b, float cn_eps, const float* dw_w, const float* dw_b,
+                          const float* ln_w, const float* ln_b, float ln_eps, l3ac_updw_plan** plan_out);
+int l3ac_updw_plan_destroy(l3ac_updw_plan* plan);
+int l3ac_upsample_cn_dwconv7_ln(const l3ac_updw_plan* plan, const float* y, int B, int T, float* x_up, void* a_out,
+                                l3ac_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * EnhanceBlock (l3ac/tconv/__init__.py:30-44): 4 x [TrendPool(k in 1,3,5,9) -> Conv1d(1->1,k7,dil 1,2,3,5)]
  * on channel 0 -> InstanceNorm1d(4, affine, eps 1e-5, stats over all T) -> Conv1d(4->C,1x1) -> x + y*x.

@@ -74,6 +74,9 @@ PROTOTYPES = {
     "l3ac_fsq_quantize_latents": (_i, [_p, _ll, C.POINTER(_i), _i, _p, _p, _p, _p]),
     "l3ac_fsq_dequantize": (_i, [_p, _i, _ll, _i, _p, _p, C.POINTER(_i), _i, _p, _p]),
     "l3ac_upsample_linear_cn": (_i, [_p, _i, _i, _i, _i, _p, _p, _f, _p, _p]),
+    "l3ac_updw_plan_create": (_i, [_i, _i, _p, _p, _f, _p, _p, _p, _p, _f, C.POINTER(_p)]),
+    "l3ac_updw_plan_destroy": (_i, [_p]),
+    "l3ac_upsample_cn_dwconv7_ln": (_i, [_p, _p, _i, _i, _p, _p, _p]),
     "l3ac_enhance_partials_floats": (_ll, [_i, _i]),
     "l3ac_enhance_stats": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p]),
     "l3ac_enhance_apply": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p]),

@@ -142,6 +142,7 @@ Lin pack_lin(Blob& b, const std::vector<float>& w, int N, int Ktot, const float*
 
 struct Unit {
     int C = 0;
+    std::vector<float> h_dw, h_dwb, h_lnw, h_lnb;  // host copies of the prologue parameters (for plans built with a neighbour's)
     l3ac_convunit_plan* plan = nullptr;            // thin encode-side stages (C = 24 / 48): whole unit in one kernel
     l3ac_dwconv_plan* dw_plan = nullptr;           // bf16 units with C = 48 / 96: thread-per-row dwconv7 + LayerNorm
     size_t dw_w = kNone, dw_b = kNone, ln_w = kNone, ln_b = kNone, alpha = kNone, ialpha = kNone, scale = kNone, shift = kNone;
@@ -168,6 +169,8 @@ struct DecStage {
     size_t conv_w, conv_b, in_w, in_b, merge_w, merge_b;      // EnhanceBlock
     Lin up;
     size_t cn_w = kNone, cn_b = kNone;
+    l3ac_updw_plan* updw = nullptr;      // Upsample + ChannelNorm fused with the next stage's first dwconv7 + LayerNorm
+    std::vector<float> h_cnw, h_cnb;
 };
 
 }  // namespace
@@ -238,6 +241,10 @@ Unit pack_unit(Blob& b, const Dict& d, const std::string& p, int C, int kind, bo
     if (kind == kBf16 && (C == 48 || C == 96)) {
         int rc = l3ac_dwconv_plan_create(C, dw_t.data(), dw_b, ln_w, ln_b, kCnEps, &u.dw_plan);
         if (rc != 0) fail(rc, "l3ac_dwconv_plan_create(" + p + ")");
+        u.h_dw = dw_t;
+        u.h_dwb.assign(dw_b, dw_b + C);
+        u.h_lnw.assign(ln_w, ln_w + C);
+        u.h_lnb.assign(ln_b, ln_b + C);
     }
     u.dw_w = b.f32(dw_t);
     u.dw_b = b.f32(dw_b, C);
@@ -430,8 +437,19 @@ void build(l3ac_codec* c, Dict& d) {
         st.up = pack_conv(b, d, "blocks." + std::to_string(blk) + ".0", st.C_out, st.C_in, 1, dk);
         st.cn_w = b.f32(d.get("blocks." + std::to_string(blk) + ".2.weight", st.C_out), st.C_out);
         st.cn_b = b.f32(d.get("blocks." + std::to_string(blk) + ".2.bias", st.C_out), st.C_out);
+        st.h_cnw = d.vec("blocks." + std::to_string(blk) + ".2.weight", st.C_out);
+        st.h_cnb = d.vec("blocks." + std::to_string(blk) + ".2.bias", st.C_out);
         ++blk;
         c->dec_stages.push_back(std::move(st));
+    }
+    for (size_t i = 0; i + 1 < c->dec_stages.size(); ++i) {      // up-layer tail + next unit's prologue in one kernel
+        DecStage& st = c->dec_stages[i];
+        const std::vector<Unit>& nxt = c->dec_stages[i + 1].units;
+        if (dk != kBf16 || nxt.empty() || nxt[0].h_dw.empty() || (st.stride != 2 && st.stride != 3)) continue;
+        const Unit& u0 = nxt[0];
+        int rc = l3ac_updw_plan_create(st.C_out, st.stride, st.h_cnw.data(), st.h_cnb.data(), kCnEps, u0.h_dw.data(), u0.h_dwb.data(),
+                                       u0.h_lnw.data(), u0.h_lnb.data(), kCnEps, &st.updw);
+        if (rc != 0) fail(rc, "l3ac_updw_plan_create");
     }
     {   // three LegacyUnits (dilations 1, 3, 9) + Snake + Conv(24 -> 1, k7) + tanh, l3ac/modules.py:47-64,174-179,192-194
         const std::string p = "blocks." + std::to_string(blk) + ".block";
@@ -614,7 +632,7 @@ struct Run {
 
     // Residual(ConvUnit), l3ac/modules.py:32-44.  Consumes x (fp32); the result is fp32 or, for the last unit before a GEMM
     // consumer on the encode side, the split pair written directly by the producing kernel.
-    Act conv_unit(Act& x, const Unit& u, int act_kind, int out_kind, Act* ch0 = nullptr) {
+    Act conv_unit(Act& x, const Unit& u, int act_kind, int out_kind, Act* ch0 = nullptr, Act* a_pre = nullptr) {
         const int B = x.B, T = x.T, C = x.C;
         if (u.plan) {
             Act o = make(out_kind, B, T, C);
@@ -622,8 +640,10 @@ struct Run {
             drop(x);
             return o;
         }
-        Act a = make(act_kind, B, T, C);
-        if (!dry) {
+        Act a = a_pre ? *a_pre : make(act_kind, B, T, C);
+        if (a_pre) {
+            a_pre->hi = nullptr;         // (dwconv7 + LayerNorm already done by the fused up-layer kernel; ownership moves here)
+        } else if (!dry) {
             if (u.dw_plan && act_kind == kBf16 && B <= 65535)
                 ok(l3ac_dwconv7_ln_plan(u.dw_plan, static_cast<const float*>(x.hi), B, T, a.hi, st), "l3ac_dwconv7_ln_plan");
             else
@@ -755,9 +775,11 @@ struct Run {
             x = gemm(a, c->dec_in, B, a.T, F, kF32, L3AC_ACT_NONE, 3, -1);         // Conv1d(k3, pad 1)
             drop(a);
         }
+        Act a_pre;
         for (const DecStage& s : c->dec_stages) {
             Act ch0;
-            for (size_t j = 0; j < s.units.size(); ++j) x = conv_unit(x, s.units[j], dk, kF32, j + 1 == s.units.size() ? &ch0 : nullptr);
+            for (size_t j = 0; j < s.units.size(); ++j)
+                x = conv_unit(x, s.units[j], dk, kF32, j + 1 == s.units.size() ? &ch0 : nullptr, (j == 0 && a_pre.hi) ? &a_pre : nullptr);
             const int T = x.T, C = x.C;
             // EnhanceBlock (l3ac/tconv/__init__.py:30-44): stats pass (partial sums + branch signals), then the streaming gate
             const long long np = l3ac_enhance_partials_floats(B, T);
@@ -779,9 +801,15 @@ struct Run {
             Act y = gemm(a, s.up, B, T, C, kF32);                                  // Conv1d 1x1
             drop(a);
             x = make(kF32, B, T * s.stride, s.C_out);                              // Upsample(linear) + ChannelNorm
-            if (!dry)
+            if (s.updw && B <= 65535) {                                            // ... + the next unit's dwconv7 + LayerNorm
+                a_pre = make(kBf16, B, T * s.stride, s.C_out);
+                if (!dry)
+                    ok(l3ac_upsample_cn_dwconv7_ln(s.updw, static_cast<const float*>(y.hi), B, T, static_cast<float*>(x.hi), a_pre.hi, st),
+                       "l3ac_upsample_cn_dwconv7_ln");
+            } else if (!dry) {
                 ok(l3ac_upsample_linear_cn(static_cast<const float*>(y.hi), B, T, s.C_out, s.stride, c->P(s.cn_w), c->P(s.cn_b), kCnEps,
                                            static_cast<float*>(x.hi), st), "l3ac_upsample_linear_cn");
+            }
             drop(y);
         }
         if (!dry)
@@ -893,7 +921,10 @@ extern "C" int l3ac_destroy(l3ac_codec* c) {
         }
     };
     for (EncStage& s : c->enc_stages) free_units(s.units);
-    for (DecStage& s : c->dec_stages) free_units(s.units);
+    for (DecStage& s : c->dec_stages) {
+        free_units(s.units);
+        if (s.updw) l3ac_updw_plan_destroy(s.updw);
+    }
     free_units(c->enc_last);
     if (c->stem) l3ac_stem_plan_destroy(c->stem);
     if (c->tail) l3ac_tail_plan_destroy(c->tail);

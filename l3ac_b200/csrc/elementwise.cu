@@ -385,6 +385,154 @@ __global__ void __launch_bounds__(128) dwconv7_ln_thread_kernel(const __grid_con
     }
 }
 
+// Up-layer tail fused with the next unit's prologue (decode side, bf16 operands, C = 48 / 96):
+//   y (B, T, C) fp32 -- the 1x1 up conv's output -- -> x_up = ChannelNorm(Upsample_linear(y, S))  (B, T*S, C) fp32   (l3ac/modules.py:162-163)
+//                                                   -> a = LayerNorm(dwconv7(x_up))              (B, T*S, C) bf16   (l3ac/modules.py:33-35)
+// x_up is the residual stream of the next stage, so it has to be written, but it no longer has to be READ back for the
+// depthwise conv: a block builds its 128 (+ 2 x 3 halo) rows of x_up in shared memory from the ~47 rows of y they interpolate,
+// one thread per row (lerp weights like ATen's upsample_linear1d, ChannelNorm statistics thread-local), copies the core rows
+// out coalesced and runs the thread-per-row dwconv7 + LayerNorm of dwconv7_ln_thread_kernel on the tile.
+template <int C>
+struct UpDwParams {
+    const float* y;
+    float* xup;
+    __nv_bfloat16* a;
+    int B, T, S;
+    float cn_eps, ln_eps;
+    float cw[C], cb[C];
+    float w[7][C];
+    float b[C], lw[C], lb[C];
+};
+
+constexpr int kUpDwThreads = 160;           // 134 tile rows in one pass (five warps), 128 dwconv rows
+
+template <int C, int S>
+__global__ void __launch_bounds__(kUpDwThreads) upsample_cn_dwconv7_ln_kernel(const __grid_constant__ UpDwParams<C> p) {
+    constexpr int RB = 128, XR = RB + 6, PITCH = C + 4, CH = C / 4;
+    constexpr int YR = (XR + S - 1) / S + 2;                       // rows of y a tile interpolates between
+    extern __shared__ __align__(16) float updw_smem[];
+    float* ytile = updw_smem;                                        // YR x PITCH
+    float* xtile = updw_smem + YR * PITCH;                           // XR x PITCH
+    const int b = blockIdx.y, t0 = blockIdx.x * RB;
+    const int T = p.T, To = T * S;
+    const float* yb = p.y + (long long)b * T * C;
+    // source row of output j (exact integer form of floor((j + 0.5) / S - 0.5)); before row 0 the index clamps to 0
+    auto src_row = [](int j) { const int q = 2 * j + 1 - S; return q >= 0 ? q / (2 * S) : 0; };
+    const int j_first = t0 - 3 > 0 ? t0 - 3 : 0;
+    const int iy0 = src_row(j_first);
+    for (int i = threadIdx.x; i < YR * CH; i += kUpDwThreads) {
+        const int r = i / CH, c = i - r * CH;
+        int t = iy0 + r;
+        t = t > T - 1 ? T - 1 : t;
+        const uint32_t d32 = (uint32_t)__cvta_generic_to_shared(ytile + r * PITCH + 4 * c);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d32), "l"(yb + (long long)t * C + 4 * c) : "memory");
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    // ---- x_up rows t0 - 3 .. t0 + 130 -> xtile (zeros outside the clip: the conv's padding)
+    if (threadIdx.x < XR) {
+        const int r = threadIdx.x, j = t0 - 3 + r;
+        float* xrow = xtile + r * PITCH;
+        if (j < 0 || j >= To) {
+#pragma unroll
+            for (int g = 0; g < CH; ++g) *reinterpret_cast<float4*>(xrow + 4 * g) = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            const int q = 2 * j + 1 - S;
+            int i0 = q >= 0 ? q / (2 * S) : 0;
+            const float rscale = (float)(1.0 / (double)S);
+            const float src = fmaf(rscale, (float)j + 0.5f, -0.5f);            // ATen contracts this to one fma
+            float l1 = src - (float)i0;
+            if (q < 0 || src < 0.f) l1 = 0.f;                                   // clamped source index: weight 0 on row 0
+            int i1 = i0 + 1;
+            i0 = i0 > T - 1 ? T - 1 : i0;
+            i1 = i1 > T - 1 ? T - 1 : i1;
+            if (q < 0) i1 = 0;
+            const float w1 = l1, w0 = 1.0f - l1;
+            const float* r0 = ytile + (i0 - iy0) * PITCH;
+            const float* r1 = ytile + (i1 - iy0) * PITCH;
+            float v[C];
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int g = 0; g < CH; ++g) {
+                const float4 a0 = *reinterpret_cast<const float4*>(r0 + 4 * g), a1 = *reinterpret_cast<const float4*>(r1 + 4 * g);
+                v[4 * g] = __fmaf_rn(w1, a1.x, __fmul_rn(w0, a0.x));
+                v[4 * g + 1] = __fmaf_rn(w1, a1.y, __fmul_rn(w0, a0.y));
+                v[4 * g + 2] = __fmaf_rn(w1, a1.z, __fmul_rn(w0, a0.z));
+                v[4 * g + 3] = __fmaf_rn(w1, a1.w, __fmul_rn(w0, a0.w));
+                s0 += v[4 * g]; s1 += v[4 * g + 1]; s2 += v[4 * g + 2]; s3 += v[4 * g + 3];
+            }
+            const float inv_c = 1.0f / (float)C;
+            const float mean = ((s0 + s1) + (s2 + s3)) * inv_c;
+            s0 = s1 = s2 = s3 = 0.f;
+#pragma unroll
+            for (int g = 0; g < CH; ++g) {
+                v[4 * g] -= mean; v[4 * g + 1] -= mean; v[4 * g + 2] -= mean; v[4 * g + 3] -= mean;
+                s0 = fmaf(v[4 * g], v[4 * g], s0); s1 = fmaf(v[4 * g + 1], v[4 * g + 1], s1);
+                s2 = fmaf(v[4 * g + 2], v[4 * g + 2], s2); s3 = fmaf(v[4 * g + 3], v[4 * g + 3], s3);
+            }
+            const float rstd = rsqrt_nr(((s0 + s1) + (s2 + s3)) * inv_c + p.cn_eps);
+#pragma unroll
+            for (int g = 0; g < CH; ++g)
+                *reinterpret_cast<float4*>(xrow + 4 * g) =
+                    make_float4(v[4 * g] * rstd * p.cw[4 * g] + p.cb[4 * g], v[4 * g + 1] * rstd * p.cw[4 * g + 1] + p.cb[4 * g + 1],
+                                v[4 * g + 2] * rstd * p.cw[4 * g + 2] + p.cb[4 * g + 2], v[4 * g + 3] * rstd * p.cw[4 * g + 3] + p.cb[4 * g + 3]);
+        }
+    }
+    __syncthreads();
+    // ---- the tile's own rows of x_up -> HBM, coalesced (they are one contiguous block of the (B, To, C) tensor)
+    const int n_rows = To - t0 < RB ? To - t0 : RB;
+    {
+        float4* dst = reinterpret_cast<float4*>(p.xup + ((long long)b * To + t0) * C);
+        for (int i = threadIdx.x; i < n_rows * CH; i += kUpDwThreads) {
+            const int r = i / CH, c = i - r * CH;
+            dst[i] = *reinterpret_cast<const float4*>(xtile + (r + 3) * PITCH + 4 * c);
+        }
+    }
+    // ---- dwconv7 + LayerNorm, one thread per row (dwconv7_ln_thread_kernel)
+    const int r = threadIdx.x;
+    if (r >= n_rows) return;
+    float acc[C];
+    const float* row = xtile + r * PITCH;
+#pragma unroll
+    for (int g = 0; g < CH; ++g) {
+        float4 a = make_float4(p.b[4 * g], p.b[4 * g + 1], p.b[4 * g + 2], p.b[4 * g + 3]);
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            const float4 xv = *reinterpret_cast<const float4*>(row + j * PITCH + 4 * g);
+            a.x = fmaf(p.w[j][4 * g], xv.x, a.x);
+            a.y = fmaf(p.w[j][4 * g + 1], xv.y, a.y);
+            a.z = fmaf(p.w[j][4 * g + 2], xv.z, a.z);
+            a.w = fmaf(p.w[j][4 * g + 3], xv.w, a.w);
+        }
+        acc[4 * g] = a.x; acc[4 * g + 1] = a.y; acc[4 * g + 2] = a.z; acc[4 * g + 3] = a.w;
+    }
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int g = 0; g < CH; ++g) { s0 += acc[4 * g]; s1 += acc[4 * g + 1]; s2 += acc[4 * g + 2]; s3 += acc[4 * g + 3]; }
+    const float inv_c = 1.0f / (float)C;
+    const float mean = ((s0 + s1) + (s2 + s3)) * inv_c;
+    s0 = s1 = s2 = s3 = 0.f;
+#pragma unroll
+    for (int g = 0; g < CH; ++g) {
+        acc[4 * g] -= mean; acc[4 * g + 1] -= mean; acc[4 * g + 2] -= mean; acc[4 * g + 3] -= mean;
+        s0 = fmaf(acc[4 * g], acc[4 * g], s0); s1 = fmaf(acc[4 * g + 1], acc[4 * g + 1], s1);
+        s2 = fmaf(acc[4 * g + 2], acc[4 * g + 2], s2); s3 = fmaf(acc[4 * g + 3], acc[4 * g + 3], s3);
+    }
+    const float rstd = rsqrt_nr(((s0 + s1) + (s2 + s3)) * inv_c + p.ln_eps);
+    uint4* orow = reinterpret_cast<uint4*>(p.a + ((long long)b * To + t0 + r) * C);
+#pragma unroll
+    for (int k = 0; k < C / 8; ++k) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int e = 8 * k + 2 * i;
+            const __nv_bfloat162 h = __floats2bfloat162_rn(acc[e] * rstd * p.lw[e] + p.lb[e], acc[e + 1] * rstd * p.lw[e + 1] + p.lb[e + 1]);
+            pk[i] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        orow[k] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+}
+
 // Wide-channel vector variant (C % 128 == 0, C <= 512): one CTA of C/4 threads (one float4 of channels per thread, one
 // warp per 128 channels) handles R consecutive time steps.  The per-time-step statistics are a warp shuffle reduction
 // followed by one shared-memory exchange between the CTA's warps for all R steps at once (two exchanges: mean, then
@@ -1655,4 +1803,74 @@ extern "C" int l3ac_dwconv7_ln_plan(const l3ac_dwconv_plan* plan, const float* x
     L3AC_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0);
     if (plan->C == 48) return launch_dw_thread<48>(plan->p48, x, B, T, out, (cudaStream_t)stream);
     return launch_dw_thread<96>(plan->p96, x, B, T, out, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// Upsample + ChannelNorm + (next unit's) dwconv7 + LayerNorm through a plan (C = 48 / 96, scale 2 / 3, bf16 operand out).
+// ------------------------------------------------------------------------------------------
+struct l3ac_updw_plan {
+    int C, S;
+    l3ac::UpDwParams<48> p48;
+    l3ac::UpDwParams<96> p96;
+};
+
+template <int C>
+static void fill_updw_params(l3ac::UpDwParams<C>& p, int S, const float* cn_w, const float* cn_b, float cn_eps, const float* dw_w,
+                             const float* dw_b, const float* ln_w, const float* ln_b, float ln_eps) {
+    p.S = S;
+    p.cn_eps = cn_eps;
+    p.ln_eps = ln_eps;
+    for (int j = 0; j < 7; ++j)
+        for (int c = 0; c < C; ++c) p.w[j][c] = dw_w[j * C + c];
+    for (int c = 0; c < C; ++c) {
+        p.cw[c] = cn_w[c];
+        p.cb[c] = cn_b[c];
+        p.b[c] = dw_b[c];
+        p.lw[c] = ln_w[c];
+        p.lb[c] = ln_b[c];
+    }
+}
+
+extern "C" int l3ac_updw_plan_create(int C, int scale, const float* cn_w, const float* cn_b, float cn_eps, const float* dw_w,
+                                     const float* dw_b, const float* ln_w, const float* ln_b, float ln_eps, l3ac_updw_plan** plan_out) {
+    L3AC_CHECK_ARG(cn_w && cn_b && dw_w && dw_b && ln_w && ln_b && plan_out);
+    if ((C != 48 && C != 96) || (scale != 2 && scale != 3)) return L3AC_EUNSUPPORTED;
+    l3ac_updw_plan* plan = new (std::nothrow) l3ac_updw_plan();
+    if (!plan) return L3AC_EINVAL;
+    plan->C = C;
+    plan->S = scale;
+    if (C == 48) fill_updw_params(plan->p48, scale, cn_w, cn_b, cn_eps, dw_w, dw_b, ln_w, ln_b, ln_eps);
+    else fill_updw_params(plan->p96, scale, cn_w, cn_b, cn_eps, dw_w, dw_b, ln_w, ln_b, ln_eps);
+    *plan_out = plan;
+    return L3AC_OK;
+}
+
+extern "C" int l3ac_updw_plan_destroy(l3ac_updw_plan* plan) {
+    delete plan;
+    return L3AC_OK;
+}
+
+template <int C, int S>
+static int launch_updw(l3ac::UpDwParams<C> p, const float* y, int B, int T, float* xup, void* a, cudaStream_t st) {
+    using namespace l3ac;
+    p.y = y;
+    p.xup = xup;
+    p.a = static_cast<__nv_bfloat16*>(a);
+    p.B = B;
+    p.T = T;
+    constexpr int XR = 128 + 6, YR = (XR + S - 1) / S + 2;
+    constexpr int smem = (XR + YR) * (C + 4) * 4;
+    cudaError_t e = cudaFuncSetAttribute(upsample_cn_dwconv7_ln_kernel<C, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    upsample_cn_dwconv7_ln_kernel<C, S><<<dim3(l3ac_cdiv((long long)T * S, 128), B), kUpDwThreads, smem, st>>>(p);
+    return l3ac_launch_status();
+}
+
+extern "C" int l3ac_upsample_cn_dwconv7_ln(const l3ac_updw_plan* plan, const float* y, int B, int T, float* x_up, void* a_out,
+                                           l3ac_stream_t stream) {
+    L3AC_CHECK_ARG(plan && y && x_up && a_out && B > 0 && B <= 65535 && T > 0 && (long long)T * plan->S < (1LL << 30));
+    L3AC_CHECK_ARG(((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(x_up) | reinterpret_cast<uintptr_t>(a_out)) & 15) == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (plan->C == 48) return plan->S == 2 ? launch_updw<48, 2>(plan->p48, y, B, T, x_up, a_out, st) : launch_updw<48, 3>(plan->p48, y, B, T, x_up, a_out, st);
+    return plan->S == 2 ? launch_updw<96, 2>(plan->p96, y, B, T, x_up, a_out, st) : launch_updw<96, 3>(plan->p96, y, B, T, x_up, a_out, st);
 }

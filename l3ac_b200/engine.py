@@ -337,7 +337,7 @@ class Engine:
             return ops.split_bf16(x)
         return x.to(kind)
 
-    def _run_conv_unit(self, x, u, act_dtype, out_kind=torch.float32, ch0_out: Optional[list] = None):
+    def _run_conv_unit(self, x, u, act_dtype, out_kind=torch.float32, ch0_out: Optional[list] = None, a_pre=None):
         """Residual(ConvUnit) -- l3ac/modules.py:32-44.
 
         The 4C-wide hidden tensor is the largest activation of the path.  Optionally (``hidden_block_bytes`` > 0) the
@@ -367,7 +367,9 @@ class Engine:
         if C == 24 and act_dtype != torch.bfloat16:      # thin full-rate encoder stage: one fused fp32 kernel
             return ops.convunit_thin(x, u["dw_w"], u["dw_b"], u["ln_w"], u["ln_b"], EPS, u["pw1"].w32, u["pw1"].bias,
                                      u["alpha"], u["scale"], u["shift"], u["pw2"].w32, u["pw2"].bias, out_dtype=out_kind)
-        if act_dtype == torch.bfloat16 and C in (48, 96) and self.dwconv_rows and B <= 65535:
+        if a_pre is not None:
+            a = a_pre                        # (dwconv7 + LayerNorm already done by the fused up-layer kernel)
+        elif act_dtype == torch.bfloat16 and C in (48, 96) and self.dwconv_rows and B <= 65535:
             # decode side's thin stages: thread-per-row kernel, parameters in a plan (constant bank)
             if u.get("dw_plan") is None:
                 u["dw_plan"] = ops.DwconvPlan(u["dw_w"], u["dw_b"], u["ln_w"], u["ln_b"], EPS)
@@ -649,14 +651,25 @@ class Engine:
         adt = self.dec_dtype
         B, T, F = x.shape
         x = self._lin(self._as_operand(x, adt), self.dec_in, B, T, F, taps=3, tap_shift0=-1)   # Conv1d(k3, pad 1)
+        a_pre = None
         for si, st in enumerate(self.dec_stages):
             ch0 = []
             for ui, u in enumerate(st["units"]):
-                x = self._run_conv_unit(x, u, adt, ch0_out=ch0 if ui == len(st["units"]) - 1 else None)
+                x = self._run_conv_unit(x, u, adt, ch0_out=ch0 if ui == len(st["units"]) - 1 else None, a_pre=a_pre if ui == 0 else None)
+            a_pre = None
             B, T, C = x.shape
             a = ops.enhance(x, out_dtype=torch.float32 if adt == ops.SPLIT else adt, ch0=ch0[0] if ch0 else None, **st["enh"])    # EnhanceBlock
             y = self._lin(self._as_operand(a, adt), st["up"], B, T, C)              # Conv1d 1x1
-            x = ops.upsample_linear_cn(y, st["stride"], st["cn_w"], st["cn_b"], EPS)   # Upsample + ChannelNorm
+            nxt = self.dec_stages[si + 1]["units"] if si + 1 < len(self.dec_stages) else []
+            if (adt == torch.bfloat16 and self.dwconv_rows and nxt and y.shape[-1] in (48, 96) and st["stride"] in (2, 3) and B <= 65535
+                    and taps is None):
+                # Upsample + ChannelNorm fused with the next unit's dwconv7 + LayerNorm: x_up is written once, never re-read
+                if st.get("updw_plan") is None:
+                    u0 = nxt[0]
+                    st["updw_plan"] = ops.UpDwPlan(st["stride"], st["cn_w"], st["cn_b"], EPS, u0["dw_w"], u0["dw_b"], u0["ln_w"], u0["ln_b"], EPS)
+                x, a_pre = ops.upsample_cn_dwconv7_ln(y, st["updw_plan"])
+            else:
+                x = ops.upsample_linear_cn(y, st["stride"], st["cn_w"], st["cn_b"], EPS)   # Upsample + ChannelNorm
             if taps is not None:
                 taps[f"dec_up{si}"] = x
         B, T, C = x.shape

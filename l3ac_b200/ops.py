@@ -470,6 +470,42 @@ def upsample_linear_cn(x: torch.Tensor, scale: int, cn_w=None, cn_b=None, eps: f
     return out
 
 
+class UpDwPlan:
+    """Host-side parameters of the fused upsample + ChannelNorm + dwconv7 + LayerNorm kernel (``l3ac_updw_plan``)."""
+
+    def __init__(self, scale: int, cn_w, cn_b, cn_eps: float, dw_w, dw_b, ln_w, ln_b, ln_eps: float):
+        host = lambda t: t.detach().to("cpu", torch.float32).contiguous()
+        cw, cb, dw, db, lw, lb = (host(t) for t in (cn_w, cn_b, dw_w, dw_b, ln_w, ln_b))
+        self.C, self.scale = int(db.numel()), int(scale)
+        if tuple(dw.shape) != (7, self.C) or cw.numel() != self.C:
+            raise ValueError("UpDwPlan: dw_w (7, C) and cn_w (C) expected")
+        self.handle = C.c_void_p()
+        check(_lib.load().l3ac_updw_plan_create(self.C, self.scale, cw.data_ptr(), cb.data_ptr(), float(cn_eps), dw.data_ptr(), db.data_ptr(),
+                                                lw.data_ptr(), lb.data_ptr(), float(ln_eps), C.byref(self.handle)), "l3ac_updw_plan_create")
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            try:
+                _lib.load().l3ac_updw_plan_destroy(h)
+            except Exception:
+                pass
+
+
+def upsample_cn_dwconv7_ln(y: torch.Tensor, plan: UpDwPlan):
+    """y (B, T, C) fp32 -> (x_up (B, T*scale, C) fp32, a (B, T*scale, C) bf16): Upsample + ChannelNorm, then dwconv7 + LayerNorm."""
+    _chk(y, name="y")
+    B, T, Cc = y.shape
+    if Cc != plan.C:
+        raise ValueError(f"upsample_cn_dwconv7_ln: plan is for C = {plan.C}, got {Cc}")
+    xup = torch.empty((B, T * plan.scale, Cc), device=y.device, dtype=torch.float32)
+    a = torch.empty((B, T * plan.scale, Cc), device=y.device, dtype=torch.bfloat16)
+    _count()
+    with _hook("upsample_cn_dwconv7_ln", _nbytes(y, xup, a)), torch.cuda.device(y.device):
+        check(_lib.load().l3ac_upsample_cn_dwconv7_ln(plan.handle, _ptr(y), B, T, _ptr(xup), _ptr(a), _stream(y)), "l3ac_upsample_cn_dwconv7_ln")
+    return xup, a
+
+
 def enhance(x: torch.Tensor, conv_w, conv_b, in_w, in_b, merge_w, merge_b, out_dtype=torch.float32,
             stream_branches: bool = True, ch0: Optional[torch.Tensor] = None) -> torch.Tensor:
     """EnhanceBlock.  ``stream_branches``: the stats pass stores the four branch signals (B, T, 4) and the apply pass streams

@@ -97,6 +97,30 @@ def test_dwconv7_ln_plan(cuda_lib, C, T):
     assert float((diff > 0).float().mean()) < 2e-3 and float(diff.max()) <= 2 ** -7 * max(1.0, float(want.abs().max()))
 
 
+@pytest.mark.parametrize("C,S", [(48, 3), (96, 3), (48, 2), (96, 2)])
+@pytest.mark.parametrize("T", [1, 2, 43, 128, 1001, 8889])
+def test_upsample_cn_dwconv7_ln(cuda_lib, C, S, T):
+    """Fused Upsample + ChannelNorm + dwconv7 + LayerNorm (l3ac_upsample_cn_dwconv7_ln) against torch and against the two
+    kernels it replaces (l3ac_upsample_linear_cn, l3ac_dwconv7_ln_plan)."""
+    y = rnd(3, C, T, seed=1)
+    cw, cb = 1 + rnd(C, seed=2, scale=0.1), rnd(C, seed=3, scale=0.1)
+    w, b = rnd(C, 1, 7, seed=4, scale=0.3), rnd(C, seed=5, scale=0.1)
+    lw, lb = 1 + rnd(C, seed=6, scale=0.1), rnd(C, seed=7, scale=0.1)
+    up = F.interpolate(y, scale_factor=S, mode="linear", align_corners=False)
+    want_x = O.channel_norm_cf(up, cw, cb)                                                  # (3, C, T*S)
+    want_a = F.layer_norm(F.conv1d(want_x, w, b, padding=3, groups=C).permute(0, 2, 1), (C,), lw, lb, 1e-8)
+    wt = w[:, 0].t().contiguous()
+    xup, a = ops.upsample_cn_dwconv7_ln(cl(y), ops.UpDwPlan(S, cw, cb, 1e-8, wt, b, lw, lb, 1e-8))
+    assert xup.shape == (3, T * S, C) and a.dtype == torch.bfloat16
+    assert max_abs(cf(xup), want_x) < 2e-5
+    assert max_abs(a.float().cpu(), want_a) < 2 ** -8 * max(1.0, float(want_a.abs().max()))
+    x2 = ops.upsample_linear_cn(cl(y), S, cw.to(DEV), cb.to(DEV), 1e-8)
+    a2 = ops.dwconv7_ln_plan(x2, ops.DwconvPlan(wt, b, lw, lb, 1e-8))
+    assert max_abs(xup, x2) < 2e-6 * max(1.0, float(x2.abs().max()))                        # (statistics summed in a different order)
+    diff = (a.float() - a2.float()).abs()
+    assert float((diff > 0).float().mean()) < 5e-3 and float(diff.max()) <= 2 ** -7 * max(1.0, float(want_a.abs().max()))
+
+
 @pytest.mark.parametrize("C", [48, 128, 192])
 def test_layernorm_is_channel_norm(cuda_lib, C):
     x = rnd(2, C, 33, seed=1)
