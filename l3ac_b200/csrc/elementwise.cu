@@ -407,7 +407,7 @@ struct UpDwParams {
 constexpr int kUpDwThreads = 160;           // 134 tile rows in one pass (five warps), 128 dwconv rows
 
 template <int C, int S>
-__global__ void __launch_bounds__(kUpDwThreads) upsample_cn_dwconv7_ln_kernel(const __grid_constant__ UpDwParams<C> p) {
+__global__ void __launch_bounds__(kUpDwThreads, C >= 96 ? 3 : 5) upsample_cn_dwconv7_ln_kernel(const __grid_constant__ UpDwParams<C> p) {
     constexpr int RB = 128, XR = RB + 6, PITCH = C + 4, CH = C / 4;
     constexpr int YR = (XR + S - 1) / S + 2;                       // rows of y a tile interpolates between
     extern __shared__ __align__(16) float updw_smem[];
