@@ -272,6 +272,18 @@ int l3ac_enhance_apply(const float* x, int B, int T, int C, const float* conv_w,
                        const float* in_w, const float* in_b, const float* merge_w, const float* merge_b,
                        const float* partials, const float* branches, void* out, int out_dtype, l3ac_stream_t stream);
 
+/* EnhanceBlock gate + the up layer's 1x1 conv in one kernel for the thin decode stages ((C_in, C_out) = (48, 24) / (96, 48), bf16
+ * operands): out = bf16(x + y * x) . W^T + b with y from the stats pass' partials / branches (l3ac/tconv/__init__.py:40-44 ->
+ * l3ac/modules.py:161).  The gated activation goes straight into mma.sync fragments; it is never written to memory.  Plan from HOST
+ * arrays: in_w / in_b [4] (InstanceNorm affine), merge_w [C_in][4], merge_b [C_in], up_w [C_out][C_in] (folded), up_b [C_out].
+ * x (B,T,C_in) fp32, partials / branches as written by l3ac_enhance_stats, out (B,T,C_out) fp32; 16-byte aligned; B <= 65535. */
+typedef struct l3ac_enhup_plan l3ac_enhup_plan;
+int l3ac_enhup_plan_create(int C_in, int C_out, const float* in_w, const float* in_b, const float* merge_w, const float* merge_b,
+                           const float* up_w, const float* up_b, l3ac_enhup_plan** plan_out);
+int l3ac_enhup_plan_destroy(l3ac_enhup_plan* plan);
+int l3ac_enhance_up(const l3ac_enhup_plan* plan, const float* x, int B, int T, const float* partials, const float* branches,
+                    float* out, l3ac_stream_t stream);
+
 /* Decoder tail (l3ac/modules.py:192-194): Snake(C) -> Conv1d(C->1,k7,pad 3) -> tanh.
  * x (B,T,C) fp32 -> out (B,T) fp32.  w is [7][C] (tap-major). */
 int l3ac_tail_conv_tanh(const float* x, int B, int T, int C, const float* alpha, const float* w, float bias,

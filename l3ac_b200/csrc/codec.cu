@@ -170,6 +170,7 @@ struct DecStage {
     Lin up;
     size_t cn_w = kNone, cn_b = kNone;
     l3ac_updw_plan* updw = nullptr;      // Upsample + ChannelNorm fused with the next stage's first dwconv7 + LayerNorm
+    l3ac_enhup_plan* enhup = nullptr;    // EnhanceBlock gate + the 1x1 up conv in one kernel (thin stages)
     std::vector<float> h_cnw, h_cnb;
 };
 
@@ -435,6 +436,14 @@ void build(l3ac_codec* c, Dict& d) {
         st.merge_b = b.f32(d.get(e + ".merge_layer.1.bias", st.C_in), st.C_in);
         ++blk;
         st.up = pack_conv(b, d, "blocks." + std::to_string(blk) + ".0", st.C_out, st.C_in, 1, dk);
+        if (dk == kBf16 && ((st.C_in == 48 && st.C_out == 24) || (st.C_in == 96 && st.C_out == 48))) {
+            const std::string up = "blocks." + std::to_string(blk) + ".0";
+            std::vector<float> uw = d.folded(up, st.C_out, st.C_in);
+            int rc = l3ac_enhup_plan_create(st.C_in, st.C_out, d.get(e + ".merge_layer.0.weight", 4), d.get(e + ".merge_layer.0.bias", 4),
+                                            d.get(e + ".merge_layer.1.weight", (long long)st.C_in * 4), d.get(e + ".merge_layer.1.bias", st.C_in),
+                                            uw.data(), d.get(up + ".bias", st.C_out), &st.enhup);
+            if (rc != 0) fail(rc, "l3ac_enhup_plan_create");
+        }
         st.cn_w = b.f32(d.get("blocks." + std::to_string(blk) + ".2.weight", st.C_out), st.C_out);
         st.cn_b = b.f32(d.get("blocks." + std::to_string(blk) + ".2.bias", st.C_out), st.C_out);
         st.h_cnw = d.vec("blocks." + std::to_string(blk) + ".2.weight", st.C_out);
@@ -785,21 +794,29 @@ struct Run {
             const long long np = l3ac_enhance_partials_floats(B, T);
             float* partials = static_cast<float*>(ar.alloc((size_t)np * 4));
             float* branches = static_cast<float*>(ar.alloc((size_t)B * T * 4 * 4));
-            Act a = make(dk == kBf16 ? kBf16 : kF32, B, T, C);         // (split mode: fp32 out, split below)
+            const bool fused_up = s.enhup && B <= 65535;               // thin stages: gate + 1x1 up conv in one kernel
+            Act a, y;
+            if (fused_up) y = make(kF32, B, T, s.C_out);
+            else a = make(dk == kBf16 ? kBf16 : kF32, B, T, C);        // (split mode: fp32 out, split below)
             if (!dry) {
                 const float* xp = static_cast<const float*>(x.hi);
                 if (ch0.hi) ok(l3ac_enhance_stats(static_cast<const float*>(ch0.hi), B, T, 1, c->P(s.conv_w), c->P(s.conv_b), partials, branches, st), "l3ac_enhance_stats");
                 else ok(l3ac_enhance_stats(xp, B, T, C, c->P(s.conv_w), c->P(s.conv_b), partials, branches, st), "l3ac_enhance_stats");
-                ok(l3ac_enhance_apply(xp, B, T, C, c->P(s.conv_w), c->P(s.conv_b), c->P(s.in_w), c->P(s.in_b), c->P(s.merge_w),
-                                      c->P(s.merge_b), partials, branches, a.hi, a.kind, st), "l3ac_enhance_apply");
+                if (fused_up)
+                    ok(l3ac_enhance_up(s.enhup, xp, B, T, partials, branches, static_cast<float*>(y.hi), st), "l3ac_enhance_up");
+                else
+                    ok(l3ac_enhance_apply(xp, B, T, C, c->P(s.conv_w), c->P(s.conv_b), c->P(s.in_w), c->P(s.in_b), c->P(s.merge_w),
+                                          c->P(s.merge_b), partials, branches, a.hi, a.kind, st), "l3ac_enhance_apply");
             }
             ar.free(partials);
             ar.free(branches);
             if (ch0.hi) drop(ch0);
             drop(x);
-            a = as_operand(a, dk);
-            Act y = gemm(a, s.up, B, T, C, kF32);                                  // Conv1d 1x1
-            drop(a);
+            if (!fused_up) {
+                a = as_operand(a, dk);
+                y = gemm(a, s.up, B, T, C, kF32);                                  // Conv1d 1x1
+                drop(a);
+            }
             x = make(kF32, B, T * s.stride, s.C_out);                              // Upsample(linear) + ChannelNorm
             if (s.updw && B <= 65535) {                                            // ... + the next unit's dwconv7 + LayerNorm
                 a_pre = make(kBf16, B, T * s.stride, s.C_out);
@@ -924,6 +941,7 @@ extern "C" int l3ac_destroy(l3ac_codec* c) {
     for (DecStage& s : c->dec_stages) {
         free_units(s.units);
         if (s.updw) l3ac_updw_plan_destroy(s.updw);
+        if (s.enhup) l3ac_enhup_plan_destroy(s.enhup);
     }
     free_units(c->enc_last);
     if (c->stem) l3ac_stem_plan_destroy(c->stem);

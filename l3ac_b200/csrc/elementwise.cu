@@ -1874,3 +1874,211 @@ extern "C" int l3ac_upsample_cn_dwconv7_ln(const l3ac_updw_plan* plan, const flo
     if (plan->C == 48) return plan->S == 2 ? launch_updw<48, 2>(plan->p48, y, B, T, x_up, a_out, st) : launch_updw<48, 3>(plan->p48, y, B, T, x_up, a_out, st);
     return plan->S == 2 ? launch_updw<96, 2>(plan->p96, y, B, T, x_up, a_out, st) : launch_updw<96, 3>(plan->p96, y, B, T, x_up, a_out, st);
 }
+
+// ------------------------------------------------------------------------------------------
+// EnhanceBlock gate + the up layer's 1x1 conv in one kernel (decode side, bf16 operands; (C_in, C_out) = (48, 24) / (96, 48)):
+//   a = bf16(x + y(t, c) * x),  y = merge(InstanceNorm(branches))      (l3ac/tconv/__init__.py:40-44)
+//   out = a . W^T + b                                                   (l3ac/modules.py:161)
+// These two stages are HBM-bound row kernels around a tiny contraction (K = 48 / 96, N = 24 / 48: 0.15 % of the model's FLOPs):
+// the gated activation goes straight into mma.sync A fragments in registers -- every lane loads exactly the (row, k) pairs of
+// its fragment, 8 bytes at a time, a quad covering one 32-byte sector per row -- so the bf16 activation tensor is never
+// written or read; W sits in shared memory at a (K + 8)-element pitch (conflict-free fragment reads).
+// ------------------------------------------------------------------------------------------
+namespace l3ac {
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int kEnhUpTile = 2048;       // rows of one clip per block
+
+template <int CI, int CO>
+struct EnhUpBlob {                     // device blob, copied to shared memory by every block
+    __nv_bfloat16 w[CO][CI + 8];       // up conv weight, bf16
+    float4 mw[CI];                     // merge_layer.1 weight [c][0..3]
+    float mb[CI];                      // merge_layer.1 bias
+    float bias[CO];                    // up conv bias
+    float in_w[4], in_b[4];            // InstanceNorm affine
+};
+
+template <int CI, int CO>
+__global__ void __launch_bounds__(256) enhance_up_kernel(const float* __restrict__ x, int B, int T, const float* __restrict__ partials,
+                                                         int nchunk, const float4* __restrict__ branches,
+                                                         const EnhUpBlob<CI, CO>* __restrict__ blob, float* __restrict__ out) {
+    __shared__ __align__(16) EnhUpBlob<CI, CO> sb;
+    __shared__ float s_scale[4], s_shift[4];
+    const int b = blockIdx.y, t0 = blockIdx.x * kEnhUpTile;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(blob);
+        uint4* dst = reinterpret_cast<uint4*>(&sb);
+        for (int i = threadIdx.x; i < (int)(sizeof(EnhUpBlob<CI, CO>) / 16); i += 256) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {            // InstanceNorm statistics of the clip from the stats pass' partial sums (fp64)
+        double acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.0;
+        for (int c = threadIdx.x; c < nchunk; c += 32) {
+            const float4* pp = reinterpret_cast<const float4*>(partials + ((long long)b * nchunk + c) * 8);
+            const float4 p0 = __ldg(pp), p1 = __ldg(pp + 1);
+            acc[0] += p0.x; acc[1] += p0.y; acc[2] += p0.z; acc[3] += p0.w;
+            acc[4] += p1.x; acc[5] += p1.y; acc[6] += p1.z; acc[7] += p1.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+        if (threadIdx.x < 4) {
+            const int j = threadIdx.x;
+            const double sum = j == 0 ? acc[0] : j == 1 ? acc[2] : j == 2 ? acc[4] : acc[6];
+            const double sq = j == 0 ? acc[1] : j == 1 ? acc[3] : j == 2 ? acc[5] : acc[7];
+            const double mean = sum / (double)T;
+            double var = sq / (double)T - mean * mean;   // biased variance (InstanceNorm1d)
+            if (var < 0.0) var = 0.0;
+            const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+            const float gg = sb.in_w[j] * rstd;
+            s_scale[j] = gg;
+            s_shift[j] = sb.in_b[j] - (float)mean * gg;
+        }
+    }
+    __syncthreads();
+    const int nt = min(kEnhUpTile, T - t0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tig = lane & 3;
+    const float4 sc = make_float4(s_scale[0], s_scale[1], s_scale[2], s_scale[3]);
+    const float4 sh = make_float4(s_shift[0], s_shift[1], s_shift[2], s_shift[3]);
+    const float* xb = x + ((long long)b * T + t0) * CI;
+    const float4* yb = branches + (long long)b * T + t0;
+    float* ob = out + ((long long)b * T + t0) * CO;
+    constexpr int KK = CI / 16, NT = CO / 8;
+    for (int m0 = warp * 16; m0 < nt; m0 += 8 * 16) {
+        const int r_lo = m0 + g, r_hi = r_lo + 8;
+        const int l_lo = r_lo < nt ? r_lo : nt - 1, l_hi = r_hi < nt ? r_hi : nt - 1;       // (clamped loads, masked stores)
+        float2 xv[KK][4];
+#pragma unroll
+        for (int kk = 0; kk < KK; ++kk)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = 16 * kk + 8 * h + 2 * tig;
+                xv[kk][2 * h] = __ldg(reinterpret_cast<const float2*>(xb + (long long)l_lo * CI + c));
+                xv[kk][2 * h + 1] = __ldg(reinterpret_cast<const float2*>(xb + (long long)l_hi * CI + c));
+            }
+        const float4 b_lo = __ldg(yb + l_lo), b_hi = __ldg(yb + l_hi);
+        const float yl0 = fmaf(b_lo.x, sc.x, sh.x), yl1 = fmaf(b_lo.y, sc.y, sh.y), yl2 = fmaf(b_lo.z, sc.z, sh.z), yl3 = fmaf(b_lo.w, sc.w, sh.w);
+        const float yh0 = fmaf(b_hi.x, sc.x, sh.x), yh1 = fmaf(b_hi.y, sc.y, sh.y), yh2 = fmaf(b_hi.z, sc.z, sh.z), yh3 = fmaf(b_hi.w, sc.w, sh.w);
+        uint32_t a[KK][4];
+#pragma unroll
+        for (int kk = 0; kk < KK; ++kk)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = 16 * kk + 8 * h + 2 * tig;
+                const float4 m0w = sb.mw[c], m1w = sb.mw[c + 1];
+                const float mb0 = sb.mb[c], mb1 = sb.mb[c + 1];
+                // gate(t, c) = mb[c] + sum_k mw[c][k] y_k(t), nested like enhance_apply_stream_kernel; r = x + gate * x
+                const float gl0 = fmaf(m0w.w, yl3, fmaf(m0w.z, yl2, fmaf(m0w.y, yl1, fmaf(m0w.x, yl0, mb0))));
+                const float gl1 = fmaf(m1w.w, yl3, fmaf(m1w.z, yl2, fmaf(m1w.y, yl1, fmaf(m1w.x, yl0, mb1))));
+                const float gh0 = fmaf(m0w.w, yh3, fmaf(m0w.z, yh2, fmaf(m0w.y, yh1, fmaf(m0w.x, yh0, mb0))));
+                const float gh1 = fmaf(m1w.w, yh3, fmaf(m1w.z, yh2, fmaf(m1w.y, yh1, fmaf(m1w.x, yh0, mb1))));
+                const float2 xl = xv[kk][2 * h], xh = xv[kk][2 * h + 1];
+                const __nv_bfloat162 pl = __floats2bfloat162_rn(fmaf(gl0, xl.x, xl.x), fmaf(gl1, xl.y, xl.y));
+                const __nv_bfloat162 ph = __floats2bfloat162_rn(fmaf(gh0, xh.x, xh.x), fmaf(gh1, xh.y, xh.y));
+                a[kk][2 * h] = *reinterpret_cast<const uint32_t*>(&pl);          // a0 / a2: row g
+                a[kk][2 * h + 1] = *reinterpret_cast<const uint32_t*>(&ph);      // a1 / a3: row g + 8
+            }
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int kk = 0; kk < KK; ++kk) {
+                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&sb.w[8 * n + g][16 * kk + 2 * tig]);
+                const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&sb.w[8 * n + g][16 * kk + 8 + 2 * tig]);
+                mma_bf16_16816(d, a[kk], b0, b1);
+            }
+            const int col = 8 * n + 2 * tig;
+            const float bias0 = sb.bias[col], bias1 = sb.bias[col + 1];
+            if (r_lo < nt) *reinterpret_cast<float2*>(ob + (long long)r_lo * CO + col) = make_float2(d[0] + bias0, d[1] + bias1);
+            if (r_hi < nt) *reinterpret_cast<float2*>(ob + (long long)r_hi * CO + col) = make_float2(d[2] + bias0, d[3] + bias1);
+        }
+    }
+}
+
+}  // namespace l3ac
+
+struct l3ac_enhup_plan {
+    int C_in, C_out, device;
+    void* dev_blob;
+};
+
+template <int CI, int CO>
+static int make_enhup_blob(l3ac_enhup_plan* plan, const float* in_w, const float* in_b, const float* merge_w, const float* merge_b,
+                           const float* up_w, const float* up_b) {
+    using Blob = l3ac::EnhUpBlob<CI, CO>;
+    Blob* h = new (std::nothrow) Blob();
+    if (!h) return L3AC_EINVAL;
+    memset(h, 0, sizeof(Blob));
+    for (int n = 0; n < CO; ++n)
+        for (int k = 0; k < CI; ++k) h->w[n][k] = __float2bfloat16_rn(up_w[(size_t)n * CI + k]);
+    for (int c = 0; c < CI; ++c) {
+        h->mw[c] = make_float4(merge_w[4 * c], merge_w[4 * c + 1], merge_w[4 * c + 2], merge_w[4 * c + 3]);
+        h->mb[c] = merge_b[c];
+    }
+    for (int n = 0; n < CO; ++n) h->bias[n] = up_b[n];
+    for (int j = 0; j < 4; ++j) {
+        h->in_w[j] = in_w[j];
+        h->in_b[j] = in_b[j];
+    }
+    cudaError_t e = cudaMalloc(&plan->dev_blob, sizeof(Blob));
+    if (e == cudaSuccess) e = cudaMemcpy(plan->dev_blob, h, sizeof(Blob), cudaMemcpyHostToDevice);
+    delete h;
+    return e == cudaSuccess ? L3AC_OK : (int)e;
+}
+
+extern "C" int l3ac_enhup_plan_create(int C_in, int C_out, const float* in_w, const float* in_b, const float* merge_w, const float* merge_b,
+                                      const float* up_w, const float* up_b, l3ac_enhup_plan** plan_out) {
+    L3AC_CHECK_ARG(in_w && in_b && merge_w && merge_b && up_w && up_b && plan_out);
+    if (!((C_in == 48 && C_out == 24) || (C_in == 96 && C_out == 48))) return L3AC_EUNSUPPORTED;
+    l3ac_enhup_plan* plan = new (std::nothrow) l3ac_enhup_plan();
+    if (!plan) return L3AC_EINVAL;
+    plan->C_in = C_in;
+    plan->C_out = C_out;
+    plan->dev_blob = nullptr;
+    if (cudaGetDevice(&plan->device) != cudaSuccess) { delete plan; return L3AC_EDRIVER; }
+    const int rc = C_in == 48 ? make_enhup_blob<48, 24>(plan, in_w, in_b, merge_w, merge_b, up_w, up_b)
+                              : make_enhup_blob<96, 48>(plan, in_w, in_b, merge_w, merge_b, up_w, up_b);
+    if (rc != L3AC_OK) {
+        cudaFree(plan->dev_blob);
+        delete plan;
+        return rc;
+    }
+    *plan_out = plan;
+    return L3AC_OK;
+}
+
+extern "C" int l3ac_enhup_plan_destroy(l3ac_enhup_plan* plan) {
+    if (!plan) return L3AC_OK;
+    cudaFree(plan->dev_blob);
+    delete plan;
+    return L3AC_OK;
+}
+
+extern "C" int l3ac_enhance_up(const l3ac_enhup_plan* plan, const float* x, int B, int T, const float* partials, const float* branches,
+                               float* out, l3ac_stream_t stream) {
+    using namespace l3ac;
+    L3AC_CHECK_ARG(plan && x && partials && branches && out && B > 0 && B <= 65535 && T > 0);
+    L3AC_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(partials) | reinterpret_cast<uintptr_t>(branches) |
+                     reinterpret_cast<uintptr_t>(out)) & 15) == 0);
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) return L3AC_EDRIVER;
+    L3AC_CHECK_ARG(dev == plan->device);
+    const int nchunk = l3ac_cdiv(T, kEnhChunk);
+    dim3 grid(l3ac_cdiv(T, kEnhUpTile), B);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (plan->C_in == 48)
+        enhance_up_kernel<48, 24><<<grid, 256, 0, st>>>(x, B, T, partials, nchunk, reinterpret_cast<const float4*>(branches),
+                                                         static_cast<const EnhUpBlob<48, 24>*>(plan->dev_blob), out);
+    else
+        enhance_up_kernel<96, 48><<<grid, 256, 0, st>>>(x, B, T, partials, nchunk, reinterpret_cast<const float4*>(branches),
+                                                         static_cast<const EnhUpBlob<96, 48>*>(plan->dev_blob), out);
+    return l3ac_launch_status();
+}

@@ -658,8 +658,16 @@ class Engine:
                 x = self._run_conv_unit(x, u, adt, ch0_out=ch0 if ui == len(st["units"]) - 1 else None, a_pre=a_pre if ui == 0 else None)
             a_pre = None
             B, T, C = x.shape
-            a = ops.enhance(x, out_dtype=torch.float32 if adt == ops.SPLIT else adt, ch0=ch0[0] if ch0 else None, **st["enh"])    # EnhanceBlock
-            y = self._lin(self._as_operand(a, adt), st["up"], B, T, C)              # Conv1d 1x1
+            c_out = st["up"].w32.shape[0]
+            if adt == torch.bfloat16 and self.dwconv_rows and (C, c_out) in ((48, 24), (96, 48)) and B <= 65535:
+                # thin stages: EnhanceBlock gate + the 1x1 up conv in one kernel (the gated bf16 activation stays in registers)
+                if st.get("enhup_plan") is None:
+                    e = st["enh"]
+                    st["enhup_plan"] = ops.EnhUpPlan(e["in_w"], e["in_b"], e["merge_w"], e["merge_b"], st["up"].w32, st["up"].bias, self.device)
+                y = ops.enhance_up(x, st["enh"]["conv_w"], st["enh"]["conv_b"], st["enhup_plan"], ch0=ch0[0] if ch0 else None)
+            else:
+                a = ops.enhance(x, out_dtype=torch.float32 if adt == ops.SPLIT else adt, ch0=ch0[0] if ch0 else None, **st["enh"])    # EnhanceBlock
+                y = self._lin(self._as_operand(a, adt), st["up"], B, T, C)              # Conv1d 1x1
             nxt = self.dec_stages[si + 1]["units"] if si + 1 < len(self.dec_stages) else []
             if (adt == torch.bfloat16 and self.dwconv_rows and nxt and y.shape[-1] in (48, 96) and st["stride"] in (2, 3) and B <= 65535
                     and taps is None):

@@ -533,6 +533,51 @@ def enhance(x: torch.Tensor, conv_w, conv_b, in_w, in_b, merge_w, merge_b, out_d
     return out
 
 
+class EnhUpPlan:
+    """Weights of the fused EnhanceBlock gate + up 1x1 conv kernel (``l3ac_enhup_plan``; (C_in, C_out) = (48, 24) / (96, 48))."""
+
+    def __init__(self, in_w, in_b, merge_w, merge_b, up_w, up_b, device):
+        host = lambda t: t.detach().to("cpu", torch.float32).contiguous()
+        iw, ib, mw, mb, uw, ub = (host(t) for t in (in_w, in_b, merge_w, merge_b, up_w, up_b))
+        self.C_out, self.C_in = int(uw.shape[0]), int(uw.shape[1])
+        if tuple(mw.shape) != (self.C_in, 4) or mb.numel() != self.C_in or ub.numel() != self.C_out:
+            raise ValueError("EnhUpPlan: merge_w (C_in, 4), merge_b (C_in), up_w (C_out, C_in), up_b (C_out) expected")
+        self.handle = C.c_void_p()
+        self.device = torch.device(device)
+        with torch.cuda.device(self.device):
+            check(_lib.load().l3ac_enhup_plan_create(self.C_in, self.C_out, iw.data_ptr(), ib.data_ptr(), mw.data_ptr(), mb.data_ptr(),
+                                                     uw.data_ptr(), ub.data_ptr(), C.byref(self.handle)), "l3ac_enhup_plan_create")
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            try:
+                _lib.load().l3ac_enhup_plan_destroy(h)
+            except Exception:
+                pass
+
+
+def enhance_up(x: torch.Tensor, conv_w, conv_b, plan: EnhUpPlan, ch0: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """EnhanceBlock + the up layer's 1x1 conv: stats pass, then the fused gate + conv kernel.  x (B, T, C_in) fp32 -> (B, T, C_out) fp32."""
+    _chk(x, name="x")
+    B, T, Cc = x.shape
+    if Cc != plan.C_in:
+        raise ValueError(f"enhance_up: plan is for C_in = {plan.C_in}, got {Cc}")
+    lib = _lib.load()
+    partials = torch.empty(lib.l3ac_enhance_partials_floats(B, T), device=x.device, dtype=torch.float32)
+    branches = torch.empty((B, T, 4), device=x.device, dtype=torch.float32)
+    out = torch.empty((B, T, plan.C_out), device=x.device, dtype=torch.float32)
+    _count(2)
+    with _hook("enhance_up", 2 * B * T * 4 * 4 + _nbytes(x, out), 2.0 * B * T * plan.C_in * plan.C_out), torch.cuda.device(x.device):
+        st = _stream(x)
+        if ch0 is not None:
+            check(lib.l3ac_enhance_stats(_ptr(ch0), B, T, 1, _ptr(conv_w), _ptr(conv_b), _ptr(partials), _ptr(branches), st), "l3ac_enhance_stats")
+        else:
+            check(lib.l3ac_enhance_stats(_ptr(x), B, T, Cc, _ptr(conv_w), _ptr(conv_b), _ptr(partials), _ptr(branches), st), "l3ac_enhance_stats")
+        check(lib.l3ac_enhance_up(plan.handle, _ptr(x), B, T, _ptr(partials), _ptr(branches), _ptr(out), st), "l3ac_enhance_up")
+    return out
+
+
 def tail_conv_tanh(x: torch.Tensor, alpha, w, bias: float) -> torch.Tensor:
     _chk(x, name="x")
     B, T, Cc = x.shape

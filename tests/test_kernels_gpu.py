@@ -271,6 +271,36 @@ def test_enhance_block(cuda_lib, C, T):
     assert max_abs(got16.float(), got) < 2e-2 * float(got.abs().max())
 
 
+@pytest.mark.parametrize("CI,CO", [(48, 24), (96, 48)])
+@pytest.mark.parametrize("T", [2, 15, 16, 17, 300, 2049, 26667])
+def test_enhance_up(cuda_lib, CI, CO, T):
+    """Fused EnhanceBlock gate + 1x1 up conv (l3ac_enhance_up, mma.sync fragments) against the two kernels it replaces on the
+    same bf16 operands (bit-level arithmetic differs only in the fp32 accumulation order) and against the oracle."""
+    sd = {}
+    for k in range(4):
+        sd[f"e.blocks.{k}.1.weight"], sd[f"e.blocks.{k}.1.bias"] = rnd(1, 1, 7, seed=k, scale=0.4), rnd(1, seed=10 + k, scale=0.1)
+    sd["e.merge_layer.0.weight"], sd["e.merge_layer.0.bias"] = 1 + rnd(4, seed=20, scale=0.1), rnd(4, seed=21, scale=0.1)
+    sd["e.merge_layer.1.weight"], sd["e.merge_layer.1.bias"] = rnd(CI, 4, 1, seed=22, scale=0.3), rnd(CI, seed=23, scale=0.1)
+    up_w, up_b = rnd(CO, CI, seed=24, scale=CI ** -0.5), rnd(CO, seed=25, scale=0.1)
+    x = rnd(3, CI, T, seed=30)
+    conv_w = torch.stack([sd[f"e.blocks.{k}.1.weight"][0, 0] for k in range(4)]).contiguous().to(DEV)
+    conv_b = torch.cat([sd[f"e.blocks.{k}.1.bias"] for k in range(4)]).to(DEV)
+    in_w, in_b = sd["e.merge_layer.0.weight"].to(DEV), sd["e.merge_layer.0.bias"].to(DEV)
+    mw, mb = sd["e.merge_layer.1.weight"][:, :, 0].contiguous().to(DEV), sd["e.merge_layer.1.bias"].to(DEV)
+    plan = ops.EnhUpPlan(in_w, in_b, mw, mb, up_w, up_b, DEV)
+    got = ops.enhance_up(cl(x), conv_w, conv_b, plan)
+    a16 = ops.enhance(cl(x), conv_w, conv_b, in_w, in_b, mw, mb, out_dtype=torch.bfloat16)
+    two = ops.gemm(a16, up_w.to(torch.bfloat16).to(DEV), B=3, T=T, K=CI, bias=up_b.to(DEV))
+    want = F.conv1d(O.enhance_block(sd, "e", x), up_w[:, :, None], up_b)                     # exact fp32 reference
+    scale = max(1.0, float(want.abs().max()))
+    print(f"[enhance_up {CI}->{CO} T={T}] vs two kernels {max_abs(got, two):.2e}; vs oracle {max_abs(cf(got), want):.2e} (two kernels: {max_abs(cf(two), want):.2e})")
+    assert got.shape == (3, T, CO)
+    assert max_abs(got, two) < 1e-5 * scale                       # same bf16 operands, fp32 accumulation in a different order
+    assert max_abs(cf(got), want) < 2e-2 * scale
+    ch0 = cl(x)[..., 0].contiguous()
+    assert torch.equal(ops.enhance_up(cl(x), conv_w, conv_b, plan, ch0=ch0), got)
+
+
 def test_snake_and_tail(cuda_lib):
     C, T = 24, 700
     x = rnd(2, C, T, seed=1)
