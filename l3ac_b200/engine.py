@@ -106,8 +106,8 @@ class Engine:
         self._streams = None
         # Fused tcgen05 MLP kernel (mlp_fused.cu) for the bf16 (decode-side) ConvUnits: the 4C hidden activation stays in
         # TMEM / shared memory.  Bit-identical to the two-GEMM path.  Per 24-clip chunk on B200: C=48 288 vs 429 us, C=96
-        # 222 vs 298 us; at C=256 the fused kernel re-streams 1 MB of weights per 128-row tile and is L2-bound at parity
-        # (282 vs 280 us), so the two-GEMM path keeps that width.
+        # 222 vs 298 us, C=256 206 vs 278 us (it re-streams 1 MB of weights per 128-row tile out of L2);
+        # C=512 needs more TMEM columns than an SM has and stays on two GEMM launches.
         self.fused_mlp = True
         self.thin_tc = os.environ.get("L3AC_THIN_TC", "1") != "0"     # fused tensor-core ConvUnit for the C = 24 / 48 encoder stages
         # The same kernel with plain bf16 operands for the decode-side C = 48 unit: measured SLOWER than dwconv7_ln + the tcgen05
@@ -116,7 +116,9 @@ class Engine:
         self.thin_tc_decode = os.environ.get("L3AC_THIN_TC_DECODE", "0") != "0"
         self.thin_impl = os.environ.get("L3AC_THIN_IMPL", "tcgen05")  # "mma_sync": the register-level cross-check kernel
         self.fused_mlp_max_c = 256
-        self.dwconv_rows = os.environ.get("L3AC_DWCONV_ROWS", "1") != "0"   # thread-per-row dwconv7 + LN for the bf16 C = 48 / 96 units
+        # row-kernel fusions of the thin decode stages (bf16, C = 48 / 96): thread-per-row dwconv7 + LN, Upsample + ChannelNorm fused
+        # with the next unit's dwconv7 + LN, EnhanceBlock gate + 1x1 up conv in one kernel ("0": the separate kernels)
+        self.dwconv_rows = os.environ.get("L3AC_DWCONV_ROWS", "1") != "0"
         self.hidden_block_bytes = 0              # >0: L2-blocked ConvUnit MLP (measured slower, see _run_conv_unit)
         self.dec_dtype = {"bf16": torch.bfloat16, "split": ops.SPLIT, "fp32": torch.float32}[precision]
         self.enc_dtype = ops.SPLIT if encoder_precision == "split" else torch.float32
