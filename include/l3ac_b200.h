@@ -283,12 +283,6 @@ int l3ac_enhup_plan_create(int C_in, int C_out, const float* in_w, const float* 
 int l3ac_enhup_plan_destroy(l3ac_enhup_plan* plan);
 int l3ac_enhance_up(const l3ac_enhup_plan* plan, const float* x, int B, int T, const float* partials, const float* branches,
                     float* out, l3ac_stream_t stream);
-/* ... and with the up layer's Upsample (linear, x scale) + ChannelNorm appended (the last up layer, 48 -> 24, scale 2:
- * l3ac/modules.py:161-163): l3ac_enhup_plan_set_upsample registers scale and the ChannelNorm parameters (HOST arrays [C_out]);
- * l3ac_enhance_up_upsample_cn then writes out (B, T*scale, C_out) fp32 -- the conv output lives in shared memory only. */
-int l3ac_enhup_plan_set_upsample(l3ac_enhup_plan* plan, int scale, const float* cn_w, const float* cn_b, float eps);
-int l3ac_enhance_up_upsample_cn(const l3ac_enhup_plan* plan, const float* x, int B, int T, const float* partials,
-                                const float* branches, float* out, l3ac_stream_t stream);
 
 /* Decoder tail (l3ac/modules.py:192-194): Snake(C) -> Conv1d(C->1,k7,pad 3) -> tanh.
  * x (B,T,C) fp32 -> out (B,T) fp32.  w is [7][C] (tap-major). */

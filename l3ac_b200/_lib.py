@@ -83,8 +83,6 @@ PROTOTYPES = {
     "l3ac_enhup_plan_create": (_i, [_i, _i, _p, _p, _p, _p, _p, _p, C.POINTER(_p)]),
     "l3ac_enhup_plan_destroy": (_i, [_p]),
     "l3ac_enhance_up": (_i, [_p, _p, _i, _i, _p, _p, _p, _p]),
-    "l3ac_enhup_plan_set_upsample": (_i, [_p, _i, _p, _p, _f]),
-    "l3ac_enhance_up_upsample_cn": (_i, [_p, _p, _i, _i, _p, _p, _p, _p]),
     "l3ac_tail_conv_tanh": (_i, [_p, _i, _i, _i, _p, _p, _f, _p, _p]),
     "l3ac_decoder_tail": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, C.POINTER(_i), _p, _p, _f, _p, _p]),
     "l3ac_convunit_plan_create": (_i, [_i, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p, C.POINTER(_p)]),

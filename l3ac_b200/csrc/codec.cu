@@ -171,7 +171,6 @@ struct DecStage {
     size_t cn_w = kNone, cn_b = kNone;
     l3ac_updw_plan* updw = nullptr;      // Upsample + ChannelNorm fused with the next stage's first dwconv7 + LayerNorm
     l3ac_enhup_plan* enhup = nullptr;    // EnhanceBlock gate + the 1x1 up conv in one kernel (thin stages)
-    bool enhup_ups = false;              // ... + Upsample + ChannelNorm (the last up layer)
     std::vector<float> h_cnw, h_cnb;
 };
 
@@ -451,14 +450,6 @@ void build(l3ac_codec* c, Dict& d) {
         st.h_cnb = d.vec("blocks." + std::to_string(blk) + ".2.bias", st.C_out);
         ++blk;
         c->dec_stages.push_back(std::move(st));
-    }
-    if (!c->dec_stages.empty()) {                                // last up layer: gate + conv + Upsample + ChannelNorm in one kernel
-        DecStage& st = c->dec_stages.back();
-        if (st.enhup && st.C_in == 48 && st.C_out == 24 && st.stride == 2) {
-            int rc = l3ac_enhup_plan_set_upsample(st.enhup, 2, st.h_cnw.data(), st.h_cnb.data(), kCnEps);
-            if (rc != 0) fail(rc, "l3ac_enhup_plan_set_upsample");
-            st.enhup_ups = true;
-        }
     }
     for (size_t i = 0; i + 1 < c->dec_stages.size(); ++i) {      // up-layer tail + next unit's prologue in one kernel
         DecStage& st = c->dec_stages[i];
@@ -804,17 +795,14 @@ struct Run {
             float* partials = static_cast<float*>(ar.alloc((size_t)np * 4));
             float* branches = static_cast<float*>(ar.alloc((size_t)B * T * 4 * 4));
             const bool fused_up = s.enhup && B <= 65535;               // thin stages: gate + 1x1 up conv in one kernel
-            const bool fused_ups = fused_up && s.enhup_ups;            // ... + Upsample + ChannelNorm
             Act a, y;
-            if (fused_up) y = make(kF32, B, fused_ups ? T * s.stride : T, s.C_out);
+            if (fused_up) y = make(kF32, B, T, s.C_out);
             else a = make(dk == kBf16 ? kBf16 : kF32, B, T, C);        // (split mode: fp32 out, split below)
             if (!dry) {
                 const float* xp = static_cast<const float*>(x.hi);
                 if (ch0.hi) ok(l3ac_enhance_stats(static_cast<const float*>(ch0.hi), B, T, 1, c->P(s.conv_w), c->P(s.conv_b), partials, branches, st), "l3ac_enhance_stats");
                 else ok(l3ac_enhance_stats(xp, B, T, C, c->P(s.conv_w), c->P(s.conv_b), partials, branches, st), "l3ac_enhance_stats");
-                if (fused_ups)
-                    ok(l3ac_enhance_up_upsample_cn(s.enhup, xp, B, T, partials, branches, static_cast<float*>(y.hi), st), "l3ac_enhance_up_upsample_cn");
-                else if (fused_up)
+                if (fused_up)
                     ok(l3ac_enhance_up(s.enhup, xp, B, T, partials, branches, static_cast<float*>(y.hi), st), "l3ac_enhance_up");
                 else
                     ok(l3ac_enhance_apply(xp, B, T, C, c->P(s.conv_w), c->P(s.conv_b), c->P(s.in_w), c->P(s.in_b), c->P(s.merge_w),
@@ -828,10 +816,6 @@ struct Run {
                 a = as_operand(a, dk);
                 y = gemm(a, s.up, B, T, C, kF32);                                  // Conv1d 1x1
                 drop(a);
-            }
-            if (fused_ups) {
-                x = y;                                                             // already upsampled and normalised
-                continue;
             }
             x = make(kF32, B, T * s.stride, s.C_out);                              // Upsample(linear) + ChannelNorm
             if (s.updw && B <= 65535) {                                            // ... + the next unit's dwconv7 + LayerNorm

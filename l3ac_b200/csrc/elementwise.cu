@@ -7,8 +7,6 @@
 //   tail                     Snake -> Conv(C->1,k7) -> tanh   l3ac/modules.py:192-194
 #include "common.cuh"
 
-#include <cstddef>
-#include <cstring>
 #include <new>
 
 namespace l3ac {
@@ -1903,10 +1901,6 @@ struct EnhUpBlob {                     // device blob, copied to shared memory b
     float mb[CI];                      // merge_layer.1 bias
     float bias[CO];                    // up conv bias
     float in_w[4], in_b[4];            // InstanceNorm affine
-    float cn_w[CO], cn_b[CO];          // ChannelNorm after the up layer's Upsample (enhance_up_upsample_cn_kernel only)
-    float cn_eps;
-    int up_scale;                      // 0: not registered
-    float pad_[2];
 };
 
 template <int CI, int CO>
@@ -2009,167 +2003,10 @@ __global__ void __launch_bounds__(256) enhance_up_kernel(const float* __restrict
     }
 }
 
-// The same gate + 1x1 conv with the up layer's Upsample (x S, linear) + ChannelNorm appended (the last up layer, 48 -> 24, S = 2:
-// l3ac/modules.py:161-163): a block computes the conv output y for 512 rows of one clip (+ one row either side) into shared
-// memory, then one thread per OUTPUT row interpolates between two y rows (weights like ATen's upsample_linear1d), takes the
-// ChannelNorm statistics thread-locally and writes the row -- y (B, T, C_out) never exists in HBM.
-constexpr int kEnhUpUpRows = 512;
-
-template <int CI, int CO, int S>
-__global__ void __launch_bounds__(256) enhance_up_upsample_cn_kernel(const float* __restrict__ x, int B, int T, const float* __restrict__ partials,
-                                                                     int nchunk, const float4* __restrict__ branches,
-                                                                     const EnhUpBlob<CI, CO>* __restrict__ blob, float* __restrict__ out) {
-    extern __shared__ __align__(16) uint8_t enhup_smem[];
-    EnhUpBlob<CI, CO>& sb = *reinterpret_cast<EnhUpBlob<CI, CO>*>(enhup_smem);
-    float* ytile = reinterpret_cast<float*>(enhup_smem + sizeof(EnhUpBlob<CI, CO>));      // [kEnhUpUpRows + 2][CO]: rows t0 - 1 .. t0 + 512
-    __shared__ float s_scale[4], s_shift[4];
-    const int b = blockIdx.y, t0 = blockIdx.x * kEnhUpUpRows;
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(blob);
-        uint4* dst = reinterpret_cast<uint4*>(&sb);
-        for (int i = threadIdx.x; i < (int)(sizeof(EnhUpBlob<CI, CO>) / 16); i += 256) dst[i] = __ldg(src + i);
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        double acc[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = 0.0;
-        for (int c = threadIdx.x; c < nchunk; c += 32) {
-            const float4* pp = reinterpret_cast<const float4*>(partials + ((long long)b * nchunk + c) * 8);
-            const float4 p0 = __ldg(pp), p1 = __ldg(pp + 1);
-            acc[0] += p0.x; acc[1] += p0.y; acc[2] += p0.z; acc[3] += p0.w;
-            acc[4] += p1.x; acc[5] += p1.y; acc[6] += p1.z; acc[7] += p1.w;
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-        if (threadIdx.x < 4) {
-            const int j = threadIdx.x;
-            const double sum = j == 0 ? acc[0] : j == 1 ? acc[2] : j == 2 ? acc[4] : acc[6];
-            const double sq = j == 0 ? acc[1] : j == 1 ? acc[3] : j == 2 ? acc[5] : acc[7];
-            const double mean = sum / (double)T;
-            double var = sq / (double)T - mean * mean;
-            if (var < 0.0) var = 0.0;
-            const float rstd = (float)(1.0 / sqrt(var + 1e-5));
-            const float gg = sb.in_w[j] * rstd;
-            s_scale[j] = gg;
-            s_shift[j] = sb.in_b[j] - (float)mean * gg;
-        }
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tig = lane & 3;
-    const float4 sc = make_float4(s_scale[0], s_scale[1], s_scale[2], s_scale[3]);
-    const float4 sh = make_float4(s_shift[0], s_shift[1], s_shift[2], s_shift[3]);
-    const float* xb = x + (long long)b * T * CI;
-    const float4* yb = branches + (long long)b * T;
-    constexpr int KK = CI / 16, NT = CO / 8;
-    // ---- phase 1: y rows t0 - 1 .. t0 + 512 (inside the clip) -> ytile.  m16 tiles -1 .. 32; of the two halo tiles only one row is kept.
-    for (int mt = warp - 1; mt <= kEnhUpUpRows / 16; mt += 8) {
-        const int r_lo = t0 + 16 * mt + g, r_hi = r_lo + 8;                 // absolute rows of this lane's two fragment rows
-        const bool any = t0 + 16 * mt + 15 >= 0 && t0 + 16 * mt < T && (mt >= 0 || t0 > 0) && (mt < kEnhUpUpRows / 16 || t0 + kEnhUpUpRows < T);
-        if (!any) continue;                                                 // (warp-uniform)
-        const int l_lo = r_lo < 0 ? 0 : (r_lo > T - 1 ? T - 1 : r_lo), l_hi = r_hi < 0 ? 0 : (r_hi > T - 1 ? T - 1 : r_hi);
-        float2 xv[KK][4];
-#pragma unroll
-        for (int kk = 0; kk < KK; ++kk)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int c = 16 * kk + 8 * h + 2 * tig;
-                xv[kk][2 * h] = __ldg(reinterpret_cast<const float2*>(xb + (long long)l_lo * CI + c));
-                xv[kk][2 * h + 1] = __ldg(reinterpret_cast<const float2*>(xb + (long long)l_hi * CI + c));
-            }
-        const float4 b_lo = __ldg(yb + l_lo), b_hi = __ldg(yb + l_hi);
-        const float yl0 = fmaf(b_lo.x, sc.x, sh.x), yl1 = fmaf(b_lo.y, sc.y, sh.y), yl2 = fmaf(b_lo.z, sc.z, sh.z), yl3 = fmaf(b_lo.w, sc.w, sh.w);
-        const float yh0 = fmaf(b_hi.x, sc.x, sh.x), yh1 = fmaf(b_hi.y, sc.y, sh.y), yh2 = fmaf(b_hi.z, sc.z, sh.z), yh3 = fmaf(b_hi.w, sc.w, sh.w);
-        uint32_t a[KK][4];
-#pragma unroll
-        for (int kk = 0; kk < KK; ++kk)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int c = 16 * kk + 8 * h + 2 * tig;
-                const float4 m0w = sb.mw[c], m1w = sb.mw[c + 1];
-                const float mb0 = sb.mb[c], mb1 = sb.mb[c + 1];
-                const float gl0 = fmaf(m0w.w, yl3, fmaf(m0w.z, yl2, fmaf(m0w.y, yl1, fmaf(m0w.x, yl0, mb0))));
-                const float gl1 = fmaf(m1w.w, yl3, fmaf(m1w.z, yl2, fmaf(m1w.y, yl1, fmaf(m1w.x, yl0, mb1))));
-                const float gh0 = fmaf(m0w.w, yh3, fmaf(m0w.z, yh2, fmaf(m0w.y, yh1, fmaf(m0w.x, yh0, mb0))));
-                const float gh1 = fmaf(m1w.w, yh3, fmaf(m1w.z, yh2, fmaf(m1w.y, yh1, fmaf(m1w.x, yh0, mb1))));
-                const float2 xl = xv[kk][2 * h], xh = xv[kk][2 * h + 1];
-                const __nv_bfloat162 pl = __floats2bfloat162_rn(fmaf(gl0, xl.x, xl.x), fmaf(gl1, xl.y, xl.y));
-                const __nv_bfloat162 ph = __floats2bfloat162_rn(fmaf(gh0, xh.x, xh.x), fmaf(gh1, xh.y, xh.y));
-                a[kk][2 * h] = *reinterpret_cast<const uint32_t*>(&pl);
-                a[kk][2 * h + 1] = *reinterpret_cast<const uint32_t*>(&ph);
-            }
-        const int s_lo = r_lo - (t0 - 1), s_hi = r_hi - (t0 - 1);           // ytile row slots
-        const bool k_lo = s_lo >= 0 && s_lo < kEnhUpUpRows + 2 && r_lo >= 0 && r_lo < T;
-        const bool k_hi = s_hi >= 0 && s_hi < kEnhUpUpRows + 2 && r_hi >= 0 && r_hi < T;
-#pragma unroll
-        for (int n = 0; n < NT; ++n) {
-            float d[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int kk = 0; kk < KK; ++kk) {
-                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&sb.w[8 * n + g][16 * kk + 2 * tig]);
-                const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&sb.w[8 * n + g][16 * kk + 8 + 2 * tig]);
-                mma_bf16_16816(d, a[kk], b0, b1);
-            }
-            const int col = 8 * n + 2 * tig;
-            const float bias0 = sb.bias[col], bias1 = sb.bias[col + 1];
-            if (k_lo) *reinterpret_cast<float2*>(ytile + s_lo * CO + col) = make_float2(d[0] + bias0, d[1] + bias1);
-            if (k_hi) *reinterpret_cast<float2*>(ytile + s_hi * CO + col) = make_float2(d[2] + bias0, d[3] + bias1);
-        }
-    }
-    __syncthreads();
-    // ---- phase 2: output rows S * t0 .. S * (t0 + nt) - 1, one thread per row
-    const int nt = min(kEnhUpUpRows, T - t0);
-    const int To = T * S;
-    const float rscale = (float)(1.0 / (double)S);
-    float* ob = out + (long long)b * To * CO;
-    for (int jj = threadIdx.x; jj < S * nt; jj += 256) {
-        const int j = S * t0 + jj;
-        const int q = 2 * j + 1 - S;
-        int i0 = q >= 0 ? q / (2 * S) : 0;
-        const float src = fmaf(rscale, (float)j + 0.5f, -0.5f);
-        float l1 = src - (float)i0;
-        if (q < 0 || src < 0.f) l1 = 0.f;
-        int i1 = q < 0 ? 0 : i0 + 1;
-        i0 = i0 > T - 1 ? T - 1 : i0;
-        i1 = i1 > T - 1 ? T - 1 : i1;
-        const float w1 = l1, w0 = 1.0f - l1;
-        const float* r0 = ytile + (i0 - (t0 - 1)) * CO;
-        const float* r1 = ytile + (i1 - (t0 - 1)) * CO;
-        float v[CO];
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-        for (int c4 = 0; c4 < CO / 4; ++c4) {
-            const float4 a0 = *reinterpret_cast<const float4*>(r0 + 4 * c4), a1 = *reinterpret_cast<const float4*>(r1 + 4 * c4);
-            v[4 * c4] = __fmaf_rn(w1, a1.x, __fmul_rn(w0, a0.x));
-            v[4 * c4 + 1] = __fmaf_rn(w1, a1.y, __fmul_rn(w0, a0.y));
-            v[4 * c4 + 2] = __fmaf_rn(w1, a1.z, __fmul_rn(w0, a0.z));
-            v[4 * c4 + 3] = __fmaf_rn(w1, a1.w, __fmul_rn(w0, a0.w));
-            s0 += v[4 * c4]; s1 += v[4 * c4 + 1]; s2 += v[4 * c4 + 2]; s3 += v[4 * c4 + 3];
-        }
-        const float inv_c = 1.0f / (float)CO;
-        const float mean = ((s0 + s1) + (s2 + s3)) * inv_c;
-        s0 = s1 = s2 = s3 = 0.f;
-#pragma unroll
-        for (int c4 = 0; c4 < CO / 4; ++c4) {
-            v[4 * c4] -= mean; v[4 * c4 + 1] -= mean; v[4 * c4 + 2] -= mean; v[4 * c4 + 3] -= mean;
-            s0 = fmaf(v[4 * c4], v[4 * c4], s0); s1 = fmaf(v[4 * c4 + 1], v[4 * c4 + 1], s1);
-            s2 = fmaf(v[4 * c4 + 2], v[4 * c4 + 2], s2); s3 = fmaf(v[4 * c4 + 3], v[4 * c4 + 3], s3);
-        }
-        const float rstd = rsqrt_nr(((s0 + s1) + (s2 + s3)) * inv_c + sb.cn_eps);
-        float4* orow = reinterpret_cast<float4*>(ob + (long long)j * CO);
-#pragma unroll
-        for (int c4 = 0; c4 < CO / 4; ++c4)
-            orow[c4] = make_float4(v[4 * c4] * rstd * sb.cn_w[4 * c4] + sb.cn_b[4 * c4], v[4 * c4 + 1] * rstd * sb.cn_w[4 * c4 + 1] + sb.cn_b[4 * c4 + 1],
-                                   v[4 * c4 + 2] * rstd * sb.cn_w[4 * c4 + 2] + sb.cn_b[4 * c4 + 2], v[4 * c4 + 3] * rstd * sb.cn_w[4 * c4 + 3] + sb.cn_b[4 * c4 + 3]);
-    }
-}
-
 }  // namespace l3ac
 
 struct l3ac_enhup_plan {
-    int C_in, C_out, device, up_scale;
+    int C_in, C_out, device;
     void* dev_blob;
 };
 
@@ -2205,7 +2042,6 @@ extern "C" int l3ac_enhup_plan_create(int C_in, int C_out, const float* in_w, co
     if (!plan) return L3AC_EINVAL;
     plan->C_in = C_in;
     plan->C_out = C_out;
-    plan->up_scale = 0;
     plan->dev_blob = nullptr;
     if (cudaGetDevice(&plan->device) != cudaSuccess) { delete plan; return L3AC_EDRIVER; }
     const int rc = C_in == 48 ? make_enhup_blob<48, 24>(plan, in_w, in_b, merge_w, merge_b, up_w, up_b)
@@ -2224,49 +2060,6 @@ extern "C" int l3ac_enhup_plan_destroy(l3ac_enhup_plan* plan) {
     cudaFree(plan->dev_blob);
     delete plan;
     return L3AC_OK;
-}
-
-template <int CI, int CO>
-static int set_enhup_upsample(l3ac_enhup_plan* plan, int scale, const float* cn_w, const float* cn_b, float eps) {
-    using Blob = l3ac::EnhUpBlob<CI, CO>;
-    struct Tail { float cn_w[CO], cn_b[CO]; float cn_eps; int up_scale; } t;
-    for (int c = 0; c < CO; ++c) {
-        t.cn_w[c] = cn_w[c];
-        t.cn_b[c] = cn_b[c];
-    }
-    t.cn_eps = eps;
-    t.up_scale = scale;
-    cudaError_t e = cudaMemcpy(static_cast<uint8_t*>(plan->dev_blob) + offsetof(Blob, cn_w), &t, sizeof(t), cudaMemcpyHostToDevice);
-    return e == cudaSuccess ? L3AC_OK : (int)e;
-}
-
-extern "C" int l3ac_enhup_plan_set_upsample(l3ac_enhup_plan* plan, int scale, const float* cn_w, const float* cn_b, float eps) {
-    L3AC_CHECK_ARG(plan && cn_w && cn_b);
-    if (!(plan->C_in == 48 && plan->C_out == 24 && scale == 2)) return L3AC_EUNSUPPORTED;
-    int dev = -1;
-    if (cudaGetDevice(&dev) != cudaSuccess) return L3AC_EDRIVER;
-    L3AC_CHECK_ARG(dev == plan->device);
-    const int rc = set_enhup_upsample<48, 24>(plan, scale, cn_w, cn_b, eps);
-    if (rc == L3AC_OK) plan->up_scale = scale;
-    return rc;
-}
-
-extern "C" int l3ac_enhance_up_upsample_cn(const l3ac_enhup_plan* plan, const float* x, int B, int T, const float* partials,
-                                           const float* branches, float* out, l3ac_stream_t stream) {
-    using namespace l3ac;
-    L3AC_CHECK_ARG(plan && plan->up_scale == 2 && x && partials && branches && out && B > 0 && B <= 65535 && T > 0 && T < (1 << 29));
-    L3AC_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(partials) | reinterpret_cast<uintptr_t>(branches) |
-                     reinterpret_cast<uintptr_t>(out)) & 15) == 0);
-    int dev = -1;
-    if (cudaGetDevice(&dev) != cudaSuccess) return L3AC_EDRIVER;
-    L3AC_CHECK_ARG(dev == plan->device);
-    const int nchunk = l3ac_cdiv(T, kEnhChunk);
-    constexpr int smem = (int)sizeof(EnhUpBlob<48, 24>) + (kEnhUpUpRows + 2) * 24 * 4;
-    cudaError_t e = cudaFuncSetAttribute(enhance_up_upsample_cn_kernel<48, 24, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return (int)e;
-    enhance_up_upsample_cn_kernel<48, 24, 2><<<dim3(l3ac_cdiv(T, kEnhUpUpRows), B), 256, smem, (cudaStream_t)stream>>>(
-        x, B, T, partials, nchunk, reinterpret_cast<const float4*>(branches), static_cast<const EnhUpBlob<48, 24>*>(plan->dev_blob), out);
-    return l3ac_launch_status();
 }
 
 extern "C" int l3ac_enhance_up(const l3ac_enhup_plan* plan, const float* x, int B, int T, const float* partials, const float* branches,

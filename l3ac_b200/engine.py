@@ -666,12 +666,6 @@ class Engine:
                 if st.get("enhup_plan") is None:
                     e = st["enh"]
                     st["enhup_plan"] = ops.EnhUpPlan(e["in_w"], e["in_b"], e["merge_w"], e["merge_b"], st["up"].w32, st["up"].bias, self.device)
-                if si == len(self.dec_stages) - 1 and (C, c_out, st["stride"]) == (48, 24, 2) and taps is None:
-                    # last up layer: + Upsample + ChannelNorm in the same kernel (the conv output lives in shared memory only)
-                    if not getattr(st["enhup_plan"], "up_scale", 0):
-                        ops.enhup_plan_set_upsample(st["enhup_plan"], 2, st["cn_w"], st["cn_b"], EPS)
-                    x = ops.enhance_up(x, st["enh"]["conv_w"], st["enh"]["conv_b"], st["enhup_plan"], ch0=ch0[0] if ch0 else None, upsample=True)
-                    continue
                 y = ops.enhance_up(x, st["enh"]["conv_w"], st["enh"]["conv_b"], st["enhup_plan"], ch0=ch0[0] if ch0 else None)
             else:
                 a = ops.enhance(x, out_dtype=torch.float32 if adt == ops.SPLIT else adt, ch0=ch0[0] if ch0 else None, **st["enh"])    # EnhanceBlock

@@ -557,20 +557,8 @@ class EnhUpPlan:
                 pass
 
 
-def enhup_plan_set_upsample(plan: EnhUpPlan, scale: int, cn_w, cn_b, eps: float):
-    """Registers the up layer's Upsample scale and ChannelNorm parameters (enhance_up(..., upsample=True))."""
-    host = lambda t: t.detach().to("cpu", torch.float32).contiguous()
-    cw, cb = host(cn_w), host(cn_b)
-    if cw.numel() != plan.C_out or cb.numel() != plan.C_out:
-        raise ValueError("enhup_plan_set_upsample: ChannelNorm parameters of C_out channels expected")
-    with torch.cuda.device(plan.device):
-        check(_lib.load().l3ac_enhup_plan_set_upsample(plan.handle, int(scale), cw.data_ptr(), cb.data_ptr(), float(eps)), "l3ac_enhup_plan_set_upsample")
-    plan.up_scale = int(scale)
-
-
-def enhance_up(x: torch.Tensor, conv_w, conv_b, plan: EnhUpPlan, ch0: Optional[torch.Tensor] = None, upsample: bool = False) -> torch.Tensor:
-    """EnhanceBlock + the up layer's 1x1 conv: stats pass, then the fused gate + conv kernel.  x (B, T, C_in) fp32 -> (B, T, C_out) fp32;
-    ``upsample``: + Upsample + ChannelNorm (plan with enhup_plan_set_upsample) -> (B, T * scale, C_out)."""
+def enhance_up(x: torch.Tensor, conv_w, conv_b, plan: EnhUpPlan, ch0: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """EnhanceBlock + the up layer's 1x1 conv: stats pass, then the fused gate + conv kernel.  x (B, T, C_in) fp32 -> (B, T, C_out) fp32."""
     _chk(x, name="x")
     B, T, Cc = x.shape
     if Cc != plan.C_in:
@@ -578,19 +566,15 @@ def enhance_up(x: torch.Tensor, conv_w, conv_b, plan: EnhUpPlan, ch0: Optional[t
     lib = _lib.load()
     partials = torch.empty(lib.l3ac_enhance_partials_floats(B, T), device=x.device, dtype=torch.float32)
     branches = torch.empty((B, T, 4), device=x.device, dtype=torch.float32)
-    if upsample and not getattr(plan, "up_scale", 0):
-        raise ValueError("enhance_up(upsample=True) needs a plan with enhup_plan_set_upsample")
-    out = torch.empty((B, T * plan.up_scale if upsample else T, plan.C_out), device=x.device, dtype=torch.float32)
+    out = torch.empty((B, T, plan.C_out), device=x.device, dtype=torch.float32)
     _count(2)
-    with _hook("enhance_up_upsample_cn" if upsample else "enhance_up", 2 * B * T * 4 * 4 + _nbytes(x, out), 2.0 * B * T * plan.C_in * plan.C_out), \
-            torch.cuda.device(x.device):
+    with _hook("enhance_up", 2 * B * T * 4 * 4 + _nbytes(x, out), 2.0 * B * T * plan.C_in * plan.C_out), torch.cuda.device(x.device):
         st = _stream(x)
         if ch0 is not None:
             check(lib.l3ac_enhance_stats(_ptr(ch0), B, T, 1, _ptr(conv_w), _ptr(conv_b), _ptr(partials), _ptr(branches), st), "l3ac_enhance_stats")
         else:
             check(lib.l3ac_enhance_stats(_ptr(x), B, T, Cc, _ptr(conv_w), _ptr(conv_b), _ptr(partials), _ptr(branches), st), "l3ac_enhance_stats")
-        fn = lib.l3ac_enhance_up_upsample_cn if upsample else lib.l3ac_enhance_up
-        check(fn(plan.handle, _ptr(x), B, T, _ptr(partials), _ptr(branches), _ptr(out), st), "l3ac_enhance_up")
+        check(lib.l3ac_enhance_up(plan.handle, _ptr(x), B, T, _ptr(partials), _ptr(branches), _ptr(out), st), "l3ac_enhance_up")
     return out
 
 

@@ -272,7 +272,7 @@ def test_enhance_block(cuda_lib, C, T):
 
 
 @pytest.mark.parametrize("CI,CO", [(48, 24), (96, 48)])
-@pytest.mark.parametrize("T", [2, 15, 16, 17, 300, 511, 512, 513, 2049, 26667])
+@pytest.mark.parametrize("T", [2, 15, 16, 17, 300, 2049, 26667])
 def test_enhance_up(cuda_lib, CI, CO, T):
     """Fused EnhanceBlock gate + 1x1 up conv (l3ac_enhance_up, mma.sync fragments) against the two kernels it replaces on the
     same bf16 operands (bit-level arithmetic differs only in the fp32 accumulation order) and against the oracle."""
@@ -299,13 +299,6 @@ def test_enhance_up(cuda_lib, CI, CO, T):
     assert max_abs(cf(got), want) < 2e-2 * scale
     ch0 = cl(x)[..., 0].contiguous()
     assert torch.equal(ops.enhance_up(cl(x), conv_w, conv_b, plan, ch0=ch0), got)
-    if (CI, CO) == (48, 24):      # the last up layer: + Upsample(x2) + ChannelNorm in the same kernel
-        cw, cb = 1 + rnd(CO, seed=40, scale=0.1), rnd(CO, seed=41, scale=0.1)
-        ops.enhup_plan_set_upsample(plan, 2, cw, cb, 1e-8)
-        up = ops.enhance_up(cl(x), conv_w, conv_b, plan, upsample=True)
-        ref = ops.upsample_linear_cn(got, 2, cw.to(DEV), cb.to(DEV), 1e-8)
-        assert up.shape == (3, 2 * T, CO)
-        assert max_abs(up, ref) < 2e-6 * max(1.0, float(ref.abs().max()))                   # (ChannelNorm statistics summed in a different order)
 
 
 def test_snake_and_tail(cuda_lib):
