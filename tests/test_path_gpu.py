@@ -96,7 +96,7 @@ def test_split_mode_is_fp32_class(cuda_lib, name):
     err = max_abs(wav.cpu()[:, ::stride], ref_wav)
     print(f"[{name}] split: index agreement {agree:.5f}  wav snr {snr:.1f} dB  max-abs {err:.3e}")
     assert agree >= 0.999
-    assert snr > 55.0 and err < 5e-3
+    assert snr > 65.0 and err < 1e-3
 
 
 def test_api_surface_and_invariants(cuda_lib):
