@@ -558,6 +558,14 @@ class Engine:
         ops.LAUNCHES += n_kernels                                    # the kernels of this library inside the replayed graph
         return tuple(o.clone() for o in outs)
 
+    def _chunk_graphs(self, n_chunks: int, taps) -> bool:
+        """Per-micro-batch CUDA graphs pay when PYTHON issues the ~120 launches of a micro-batch (10.9 -> 6.2 ms of host time per
+        64 x 10 s step).  The step-level C ABI issues them in ~1 ms, so with it the micro-batches are launched directly (a
+        256 x 30 s batch = 24 + 24 micro-batches would otherwise thrash the graph cache: every miss is a warm-up run, a capture
+        and an instantiation).  On the Python path graphs are used only while every slot of the call fits the cache."""
+        return (self.graph_chunks and not self._use_native() and n_chunks > 1 and 2 * n_chunks + 8 <= self.graph_cache_size
+                and taps is None and ops.OP_HOOK is None and not torch.cuda.is_current_stream_capturing())
+
     def _run_chunks(self, fn, chunks):
         """Runs ``fn(lo, hi)`` for every micro-batch, round-robin over ``num_streams`` side streams; returns the results
         in order.  All side streams are joined back into the caller's stream before returning."""
@@ -613,8 +621,7 @@ class Engine:
         n_all = audio.shape[0]
 
         chunks = self._chunks(*audio.shape)
-        use_graphs = (self.graph_chunks and len(chunks) > 1 and taps is None and ops.OP_HOOK is None
-                      and not torch.cuda.is_current_stream_capturing())
+        use_graphs = self._chunk_graphs(len(chunks), taps)
 
         def run(lo, hi):
             if use_graphs:
@@ -780,8 +787,7 @@ class Engine:
                 return finish(self._graphed(("dec", B, T_tok), lambda f: (self.decode_features(f),), feat)[0])
         chunks = self._chunks(B, T_tok * self.mc.hop_length)
 
-        use_graphs = (self.graph_chunks and len(chunks) > 1 and taps is None and ops.OP_HOOK is None
-                      and not torch.cuda.is_current_stream_capturing())
+        use_graphs = self._chunk_graphs(len(chunks), taps)
 
         def run(lo, hi):
             if use_graphs:

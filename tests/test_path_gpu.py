@@ -260,12 +260,17 @@ def test_pinned_host_input_is_uploaded_per_micro_batch(cuda_lib):
         codec.decode_audio(indices=idx0["indices"], out=torch.empty(tuple(wav.shape)))   # not pinned
 
 
-def test_micro_batch_graphs_match_eager(cuda_lib):
-    """Large batches: each micro-batch is captured into its own CUDA graph on its second appearance and replayed on its stream
-    (pinned host input uploaded straight into the graph's input); results must be bit-identical to the eager launch sequence."""
+@pytest.mark.parametrize("engine_kind", ["python", "native"])
+def test_micro_batch_graphs_match_eager(cuda_lib, engine_kind, monkeypatch):
+    """Large batches on the operator-level (Python) path: each micro-batch is captured into its own CUDA graph on its second
+    appearance and replayed on its stream (pinned host input uploaded straight into the graph's input); results must be
+    bit-identical to the eager launch sequence.  With the step-level C ABI underneath (native) the micro-batches are launched
+    directly -- no graphs -- and the same invariants hold."""
+    monkeypatch.setenv("L3AC_ENGINE", engine_kind)
     codec = l3ac_b200.get_model("1kbps", pretrained=False)
     codec.network.cuda()
     eng = codec.network.engine
+    assert (eng.native is not None) == (engine_kind == "native")
     eng.max_chunk_samples = 16000 * 12                            # 4 micro-batches for 7 clips of 5 s
     eng.graph_max_samples = 0
     a, b = make_audio(7, 5.0, seed=51), make_audio(7, 5.0, seed=52).pin_memory()
@@ -284,10 +289,13 @@ def test_micro_batch_graphs_match_eager(cuda_lib):
                 q, idx = codec.encode_audio(x)
                 w = codec.decode_audio(indices=idx["indices"])
                 assert torch.equal(q, q0) and torch.equal(idx["indices"], i0) and torch.equal(w, w0), rep
-        assert len(eng._graphs) == 2 * len(eng._chunks(7, 80000)) >= 6      # micro-batch slots x (encode, decode)
-        # replayed kernels are counted like launched ones: 1 eager call + the capture's warm-up run + 5 replays (the few kernels
-        # outside the graphs -- dequantize -- are not repeated by the warm-up run)
-        assert abs((ops.LAUNCHES - launches0) - 7 * per_call) <= 8
+        if engine_kind == "python":
+            assert len(eng._graphs) == 2 * len(eng._chunks(7, 80000)) >= 6      # micro-batch slots x (encode, decode)
+            # replayed kernels are counted like launched ones: 1 eager call + the capture's warm-up run + 5 replays (the few
+            # kernels outside the graphs -- dequantize -- are not repeated by the warm-up run)
+            assert abs((ops.LAUNCHES - launches0) - 7 * per_call) <= 8
+        else:
+            assert len(eng._graphs) == 0 and ops.LAUNCHES - launches0 == 6 * per_call
 
 
 def test_cuda_graph_path_matches_eager(cuda_lib):
